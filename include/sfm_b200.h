@@ -1,0 +1,192 @@
+/* sfm_b200 — C ABI of the B200-native two-view geometry hot path.
+ *
+ * Drop-in acceleration boundary for Bazs/structure_from_motion's
+ *   RANSAC essential-matrix estimation -> cheirality vote -> linear triangulation.
+ * The reference is pure Python and has no FFI of its own; the boundary it exposes is the
+ * set of Python callables in lib/ransac/ransac.py and lib/epipolar/*.py.  Each entry point
+ * below names the reference callable (file:line) whose work it replaces; the Python
+ * mirror in structure_from_motion_b200/ (re-exported under the reference's import paths
+ * in lib/) binds these with ctypes — see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; all pointers are HOST memory unless the parameter name ends in _d
+ *   - every function returns 0 on success, a negative sfm_status otherwise;
+ *     sfm_last_error() gives the message for the calling thread
+ *   - a context owns one CUDA device, one stream and grow-only device buffers; calls on
+ *     one context are serialised by the caller (the reference is single-threaded)
+ *   - "correspondence" = one matched feature pair (xa, ya) <-> (xb, yb) in pixel
+ *     coordinates; "hypothesis" = one RANSAC iteration (one minimal sample of 8
+ *     correspondences and the essential matrix fitted to it)
+ */
+#ifndef SFM_B200_H
+#define SFM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sfm_ctx sfm_ctx;
+
+enum sfm_status {
+    SFM_OK = 0,
+    SFM_ERR_ARG = -1,      /* bad argument                                  */
+    SFM_ERR_CUDA = -2,     /* CUDA runtime error (see sfm_last_error)        */
+    SFM_ERR_STATE = -3,    /* call order violated (e.g. score before fit)   */
+    SFM_ERR_NO_DEVICE = -4 /* no usable CUDA device                         */
+};
+
+/* lib/ransac/ransac.py:12-16  ErrorAggregationMethod */
+enum sfm_aggregation { SFM_AGG_SUM = 0, SFM_AGG_SQUARE = 1, SFM_AGG_MEAN = 2, SFM_AGG_RMS = 3 };
+/* lib/ransac/ransac.py:83 selects by minimum aggregated error (default); max-inliers is an extra. */
+enum sfm_selection { SFM_SELECT_MIN_ERROR = 0, SFM_SELECT_MAX_INLIERS = 1 };
+/* scoring kernel variant: screened (12 FP64 slots per evaluation + exact re-check of
+ * candidates) or full two-sided decision (21 slots + exact re-check).  Same results. */
+enum sfm_score_variant { SFM_SCORE_SCREEN = 0, SFM_SCORE_FULL = 1 };
+
+/* ---- context ------------------------------------------------------------------------ */
+int sfm_version(void);
+const char *sfm_last_error(void);
+int sfm_device_count(void);
+int sfm_create(int device, sfm_ctx **out);
+int sfm_destroy(sfm_ctx *ctx);
+/* Use an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the
+ * context's own stream. */
+int sfm_set_stream(sfm_ctx *ctx, void *cuda_stream);
+int sfm_synchronize(sfm_ctx *ctx);
+int sfm_set_score_variant(sfm_ctx *ctx, int variant, int hyps_per_thread /* 1 or 2, 0 = default */);
+/* Pinned host memory for the caller's buffers (so that H2D/D2H copies are true async DMA). */
+int sfm_host_alloc(uint64_t bytes, void **out);
+int sfm_host_free(void *p);
+
+/* ---- sampling ----------------------------------------------------------------------- */
+/* lib/ransac/ransac.py:62-63 — `random.shuffle(data); data[:8]`, cumulative over iterations,
+ * restated for CPython's MT19937 + Fisher-Yates (random.py shuffle/_randbelow_with_getrandbits).
+ * state: the 625 words of random.getstate()[1] (624 MT words + position), updated in place so
+ * the caller can random.setstate() it back.  table: int32[h][8].  If perm_at >= 0,
+ * perm_out[n] receives the full permutation after iteration perm_at (the reference returns
+ * the inliers in that order, ransac.py:70-76).  Host-only; needs no context. */
+int sfm_mt_shuffle_table(uint32_t *state625, int64_t n, int64_t h, int32_t *table, int64_t perm_at,
+                         int32_t *perm_out);
+/* Upload a sample table (h x 8 indices into the correspondences). */
+int sfm_set_table(sfm_ctx *ctx, const int32_t *table, int64_t h);
+/* Device sampler (Philox4x32-10 keyed by seed/stream/global hypothesis index): 8 distinct
+ * uniform indices per hypothesis; hyp_offset shifts the global index for hypothesis-sharded
+ * runs so that the union over ranks equals the single-GPU table. */
+int sfm_sample_device(sfm_ctx *ctx, uint64_t seed, uint64_t stream, int64_t hyp_offset, int64_t h);
+int sfm_get_table(sfm_ctx *ctx, int32_t *table, int64_t h);
+
+/* ---- correspondences ---------------------------------------------------------------- */
+/* lib/epipolar/eight_point.py:127-133 (to_normalized_image_coords), applied once on the
+ * device.  xa/ya/xb/yb: pixel coordinates, element i at ptr[i*stride] (stride 1 = four
+ * separate arrays; stride 2 = two interleaved [n][2] arrays with ya = xa + 1).
+ * K: row-major 3x3; only fx, fy, cx, cy are used, as in the reference. */
+int sfm_upload_pairs(sfm_ctx *ctx, const double *xa, const double *ya, const double *xb,
+                     const double *yb, int64_t stride, int64_t n, const double *K);
+/* Same, inputs already in device memory. */
+int sfm_upload_pairs_d(sfm_ctx *ctx, const double *xa_d, const double *ya_d, const double *xb_d,
+                       const double *yb_d, int64_t stride, int64_t n, const double *K);
+/* Read back the K-normalised records: out[n][4] = (xa, ya, xb, yb). */
+int sfm_get_normalised(sfm_ctx *ctx, double *out, int64_t n);
+
+/* ---- model fitting ------------------------------------------------------------------- */
+/* lib/epipolar/epipolar_ransac.py:28-42 (eight_point_model_fitter) ->
+ * lib/epipolar/eight_point.py:99-170 for every row of the current sample table.
+ * E_out: double[h][9] or NULL; valid_out: uint8[h] or NULL (0 = the reference would raise
+ * EightPointCalculationError, eight_point.py:414-421); eig_out: double[h][9] or NULL
+ * (eigenvalues of Y^T Y, diagnostics). */
+int sfm_fit(sfm_ctx *ctx, double *E_out, uint8_t *valid_out, double *eig_out);
+/* Replace the fitted models by caller-supplied ones (scorer-only parity tests). */
+int sfm_set_models(sfm_ctx *ctx, const double *E, const uint8_t *valid /* or NULL */, int64_t h);
+
+/* ---- scoring + selection ------------------------------------------------------------- */
+/* lib/ransac/ransac.py:66-86 + :96-108 with lib/epipolar/epipolar_ransac.py:18-25 /
+ * lib/epipolar/sed.py:7-30 as the scorer.  use_table != 0 applies the sample rule of
+ * ransac.py:63-64,76 with the current table.  Outputs (each may be NULL):
+ * count_extra int32[h] (-1 for invalid hypotheses), S1/S2 double[h] (sum of sed / sed^2 over
+ * samples + extra inliers), err double[h] (+inf when not a candidate). */
+int sfm_score(sfm_ctx *ctx, double threshold, double min_extra, int aggregation, int selection,
+              int use_table, int64_t idx_offset, int32_t *count_extra, double *S1, double *S2,
+              double *err);
+
+typedef struct sfm_best {
+    double err;            /* aggregated error of the winner                          */
+    int64_t index;         /* global hypothesis index, -1 if no candidate              */
+    int32_t count_extra;   /* inliers beyond the 8 samples                             */
+    int32_t reserved;
+    int64_t num_invalid;   /* hypotheses the reference would have raised on           */
+    int64_t first_invalid; /* lowest such index, -1 if none                            */
+    double E[9];           /* the winning model (row-major), E[8] == 1                 */
+} sfm_best;
+/* Winner of the last sfm_score (ransac.py:83: minimum error, earliest iteration on ties). */
+int sfm_get_best(sfm_ctx *ctx, sfm_best *out);
+/* Tell the context which hypothesis won (hypothesis-sharded runs: after the cross-rank
+ * merge).  local_index < 0 = the winner lives on another rank; E then supplies the model. */
+int sfm_set_winner(sfm_ctx *ctx, int64_t local_index, const double *E);
+/* Inlier mask (sed <= threshold) and SED value of every correspondence under the current
+ * winner.  mask uint8[n], sed double[n]; either may be NULL. */
+int sfm_inlier_mask(sfm_ctx *ctx, double threshold, uint8_t *mask, double *sed);
+
+/* One call for the whole estimate (lib/epipolar/epipolar_ransac.py:45-70): fit -> score ->
+ * select -> mask of the winner, no host round trip in between. */
+int sfm_ransac_essential(sfm_ctx *ctx, double threshold, double min_extra, int aggregation,
+                         int selection, sfm_best *best, uint8_t *mask, double *sed);
+
+/* ---- pose + triangulation ------------------------------------------------------------ */
+typedef struct sfm_poses {
+    double R[4][9];      /* (R1,t) (R1,-t) (R2,t) (R2,-t)  — eight_point.py:210-212 order */
+    double t[4][3];
+    double sv[3];        /* singular values of E, descending                             */
+    int64_t counts[4];   /* cheirality votes (index-0 quirk of eight_point.py:228-230)   */
+    int32_t best;        /* np.argmax(counts) (eight_point.py:237), -1 before the vote    */
+    int32_t reserved;
+} sfm_poses;
+/* lib/epipolar/eight_point.py:245-280 (_recover_all_r_t) on the device. */
+int sfm_decompose_essential(sfm_ctx *ctx, const double *E, sfm_poses *out);
+/* lib/epipolar/eight_point.py:181-242 (_recover_r_t): decomposition + 4-pose cheirality vote
+ * (eight_point.py:449-488) over m correspondences given in K-NORMALISED coordinates
+ * (element i at ptr[i*stride]).  pass4: uint8[m], bit p set = passes pose p. */
+int sfm_recover_pose(sfm_ctx *ctx, const double *E, const double *xa, const double *ya,
+                     const double *xb, const double *yb, int64_t stride, int64_t m,
+                     double distance_threshold, sfm_poses *out, uint8_t *pass4);
+/* lib/epipolar/triangulation.py:9-62: DLT triangulation of m correspondences (pixel
+ * coordinates) with 3x4 row-major camera matrices P1, P2.  X: double[m][3]. */
+int sfm_triangulate(sfm_ctx *ctx, const double *P1, const double *P2, const double *xa,
+                    const double *ya, const double *xb, const double *yb, int64_t stride, int64_t m,
+                    double *X);
+/* Fused tail of the pipeline for the current winner (apps/sfm.py:110-186): inliers of the
+ * winner -> decomposition -> cheirality vote -> triangulation of the passing inliers with
+ * P1 = K[I|0], P2 = K[R|t], all on the device.  inlier_idx int64[cap] receives the indices
+ * (ascending) of the winner's inliers, pass uint8[cap] the vote result per inlier, X
+ * double[cap][3] the points (NaN rows where pass == 0). */
+int sfm_pose_and_triangulate(sfm_ctx *ctx, double threshold, double distance_threshold,
+                             sfm_poses *poses, int64_t cap, int64_t *num_inliers,
+                             int64_t *inlier_idx, uint8_t *pass, double *X);
+
+/* ---- batched image pairs (pair-sharded workloads) ------------------------------------ */
+/* P independent pairs; pair p owns correspondences [offsets[p], offsets[p+1]) of the
+ * concatenated arrays, its own K (Ks[p][9]) and h hypotheses drawn by the device sampler
+ * (stream = pair_id0 + p).  Outputs per pair: E[p][9], best_index[p] (-1 = none),
+ * best_err[p], count_extra[p], num_invalid[p].  Degenerate samples are skipped. */
+int sfm_batch_ransac(sfm_ctx *ctx, const double *xa, const double *ya, const double *xb,
+                     const double *yb, int64_t stride, const int64_t *offsets, int64_t npairs,
+                     const double *Ks, int64_t h, uint64_t seed, uint64_t pair_id0, double threshold,
+                     double min_extra, int aggregation, int selection, double *E, int64_t *best_index,
+                     double *best_err, int32_t *count_extra, int64_t *num_invalid);
+
+/* ---- measurement --------------------------------------------------------------------- */
+/* Per-stage device times (CUDA events on the context's stream) of the most recent
+ * pipeline call: ms[0]=upload+normalise ms[1]=sample ms[2]=fit ms[3]=score ms[4]=finalise+select
+ * ms[5]=mask ms[6]=pose ms[7]=triangulate.  launches = kernels launched by this library since
+ * the context was created. */
+int sfm_enable_timing(sfm_ctx *ctx, int on);
+int sfm_get_timing(sfm_ctx *ctx, float ms[8], int64_t *launches);
+/* FP64 FMA throughput microbenchmark (denominator of the FP64 roofline): returns achieved
+ * DFMA/s over the whole device. */
+int sfm_measure_fp64_peak(sfm_ctx *ctx, double *dfma_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFM_B200_H */

@@ -1,0 +1,396 @@
+"""ctypes binding of include/sfm_b200.h and the per-process engine.
+
+There is NO CPU fallback: if the shared library is missing or no sm_100 device is visible
+the calls raise ``NativeUnavailableError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsfm_b200.so")
+
+AGG = {"sum": 0, "square": 1, "mean": 2, "rms": 3}
+SELECT = {"min_error": 0, "max_inliers": 1}
+VARIANT = {"screen": 0, "full": 1}
+
+
+class NativeUnavailableError(RuntimeError):
+    """libsfm_b200.so is missing / not loadable, or there is no B200 to run it on."""
+
+
+class NativeError(RuntimeError):
+    """A C-ABI call returned a non-zero status."""
+
+
+class Best(C.Structure):
+    _fields_ = [("err", C.c_double), ("index", C.c_int64), ("count_extra", C.c_int32),
+                ("reserved", C.c_int32), ("num_invalid", C.c_int64), ("first_invalid", C.c_int64),
+                ("E", C.c_double * 9)]
+
+
+class Poses(C.Structure):
+    _fields_ = [("R", (C.c_double * 9) * 4), ("t", (C.c_double * 3) * 4), ("sv", C.c_double * 3),
+                ("counts", C.c_int64 * 4), ("best", C.c_int32), ("reserved", C.c_int32)]
+
+
+_P = C.c_void_p
+_SIGNATURES = {
+    "sfm_version": (C.c_int, []),
+    "sfm_last_error": (C.c_char_p, []),
+    "sfm_device_count": (C.c_int, []),
+    "sfm_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "sfm_destroy": (C.c_int, [_P]),
+    "sfm_set_stream": (C.c_int, [_P, _P]),
+    "sfm_synchronize": (C.c_int, [_P]),
+    "sfm_set_score_variant": (C.c_int, [_P, C.c_int, C.c_int]),
+    "sfm_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(_P)]),
+    "sfm_host_free": (C.c_int, [_P]),
+    "sfm_mt_shuffle_table": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int64, _P]),
+    "sfm_set_table": (C.c_int, [_P, _P, C.c_int64]),
+    "sfm_sample_device": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64]),
+    "sfm_get_table": (C.c_int, [_P, _P, C.c_int64]),
+    "sfm_upload_pairs": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P]),
+    "sfm_upload_pairs_d": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P]),
+    "sfm_get_normalised": (C.c_int, [_P, _P, C.c_int64]),
+    "sfm_fit": (C.c_int, [_P, _P, _P, _P]),
+    "sfm_set_models": (C.c_int, [_P, _P, _P, C.c_int64]),
+    "sfm_score": (C.c_int, [_P, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int64, _P, _P, _P, _P]),
+    "sfm_get_best": (C.c_int, [_P, C.POINTER(Best)]),
+    "sfm_set_winner": (C.c_int, [_P, C.c_int64, _P]),
+    "sfm_inlier_mask": (C.c_int, [_P, C.c_double, _P, _P]),
+    "sfm_ransac_essential": (C.c_int, [_P, C.c_double, C.c_double, C.c_int, C.c_int, C.POINTER(Best), _P, _P]),
+    "sfm_decompose_essential": (C.c_int, [_P, _P, C.POINTER(Poses)]),
+    "sfm_recover_pose": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_double, C.POINTER(Poses), _P]),
+    "sfm_triangulate": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P]),
+    "sfm_pose_and_triangulate": (C.c_int, [_P, C.c_double, C.c_double, C.POINTER(Poses), C.c_int64,
+                                           C.POINTER(C.c_int64), _P, _P, _P]),
+    "sfm_batch_ransac": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P, C.c_int64, _P, C.c_int64, C.c_uint64,
+                                   C.c_uint64, C.c_double, C.c_double, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
+    "sfm_enable_timing": (C.c_int, [_P, C.c_int]),
+    "sfm_get_timing": (C.c_int, [_P, _P, C.POINTER(C.c_int64)]),
+    "sfm_measure_fp64_peak": (C.c_int, [_P, C.POINTER(C.c_double)]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library():
+    """Load libsfm_b200.so and declare every prototype of include/sfm_b200.h."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise NativeUnavailableError(
+                f"{LIB_PATH} is missing — build it with `python -m structure_from_motion_b200.build` "
+                "(or __graft_entry__.build()); there is no CPU fallback.")
+        try:
+            lib = C.CDLL(LIB_PATH)
+        except OSError as exc:  # pragma: no cover
+            raise NativeUnavailableError(f"cannot load {LIB_PATH}: {exc}") from exc
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    return a.ctypes.data_as(_P)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _split_xy(pa):
+    """Accept [n,2] arrays (interleaved, stride 2) and return (x_ptr_array, y_view, stride)."""
+    pa = _f64(pa)
+    if pa.ndim != 2 or pa.shape[1] != 2:
+        raise ValueError(f"expected an [n,2] coordinate array, got shape {pa.shape}")
+    return pa
+
+
+class Engine:
+    """One context (one GPU, one stream).  Thin, stateful mirror of the C ABI."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = _P()
+        rc = self.lib.sfm_create(int(device), C.byref(h))
+        if rc != 0:
+            msg = self.lib.sfm_last_error().decode()
+            if rc == -4:
+                raise NativeUnavailableError(f"sfm_create(device={device}): {msg}; there is no CPU fallback.")
+            raise NativeError(f"sfm_create(device={device}) -> {rc}: {msg}")
+        self.h = h
+        self.device = int(device)
+        self._keep = None  # host arrays referenced by the last upload
+        self.n = 0
+
+    # -- helpers -------------------------------------------------------------------------
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise NativeError(f"{what} -> {rc}: {self.lib.sfm_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sfm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self.lib.sfm_set_stream(self.h, _P(cuda_stream_ptr) if cuda_stream_ptr else None), "sfm_set_stream")
+
+    def synchronize(self):
+        self._ck(self.lib.sfm_synchronize(self.h), "sfm_synchronize")
+
+    def set_score_variant(self, variant="screen", hyps_per_thread=0):
+        self._ck(self.lib.sfm_set_score_variant(self.h, VARIANT[variant], int(hyps_per_thread)), "sfm_set_score_variant")
+
+    # -- correspondences ------------------------------------------------------------------
+    def upload_pairs(self, pts_a, pts_b, K):
+        """pts_a, pts_b: [n,2] pixel coordinates; K: 3x3."""
+        pa, pb = _split_xy(pts_a), _split_xy(pts_b)
+        if pa.shape != pb.shape:
+            raise ValueError("pts_a and pts_b must have the same shape")
+        K = _f64(K).reshape(3, 3)
+        n = pa.shape[0]
+        base_a, base_b = pa.ctypes.data, pb.ctypes.data
+        self._ck(self.lib.sfm_upload_pairs(self.h, _P(base_a), _P(base_a + 8), _P(base_b), _P(base_b + 8), 2, n,
+                                           _ptr(K)), "sfm_upload_pairs")
+        self.n = n
+
+    def upload_pairs_soa(self, xa, ya, xb, yb, K):
+        xa, ya, xb, yb = (_f64(v).reshape(-1) for v in (xa, ya, xb, yb))
+        K = _f64(K).reshape(3, 3)
+        n = xa.shape[0]
+        self._ck(self.lib.sfm_upload_pairs(self.h, _ptr(xa), _ptr(ya), _ptr(xb), _ptr(yb), 1, n, _ptr(K)),
+                 "sfm_upload_pairs")
+        self.n = n
+
+    def upload_pairs_device(self, xa_ptr, ya_ptr, xb_ptr, yb_ptr, stride, n, K):
+        K = _f64(K).reshape(3, 3)
+        self._ck(self.lib.sfm_upload_pairs_d(self.h, _P(xa_ptr), _P(ya_ptr), _P(xb_ptr), _P(yb_ptr), int(stride),
+                                             int(n), _ptr(K)), "sfm_upload_pairs_d")
+        self.n = int(n)
+
+    def get_normalised(self):
+        out = np.empty((self.n, 4), dtype=np.float64)
+        self._ck(self.lib.sfm_get_normalised(self.h, _ptr(out), self.n), "sfm_get_normalised")
+        return out
+
+    # -- sampling -------------------------------------------------------------------------
+    def set_table(self, table):
+        table = np.ascontiguousarray(table, dtype=np.int32).reshape(-1, 8)
+        self._ck(self.lib.sfm_set_table(self.h, _ptr(table), table.shape[0]), "sfm_set_table")
+        self.h_count = table.shape[0]
+
+    def sample_device(self, seed, h, stream=0, hyp_offset=0):
+        self._ck(self.lib.sfm_sample_device(self.h, int(seed), int(stream), int(hyp_offset), int(h)),
+                 "sfm_sample_device")
+        self.h_count = int(h)
+
+    def get_table(self, h=None):
+        h = self.h_count if h is None else h
+        out = np.empty((h, 8), dtype=np.int32)
+        self._ck(self.lib.sfm_get_table(self.h, _ptr(out), h), "sfm_get_table")
+        return out
+
+    # -- fit / score ----------------------------------------------------------------------
+    def fit(self, want_E=True, want_eig=False):
+        h = self.h_count
+        E = np.empty((h, 3, 3), dtype=np.float64) if want_E else None
+        valid = np.empty(h, dtype=np.uint8)
+        eig = np.empty((h, 9), dtype=np.float64) if want_eig else None
+        self._ck(self.lib.sfm_fit(self.h, _ptr(E), _ptr(valid), _ptr(eig)), "sfm_fit")
+        return E, valid.astype(bool), eig
+
+    def set_models(self, E, valid=None):
+        E = _f64(E).reshape(-1, 9)
+        v = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint8)
+        self._ck(self.lib.sfm_set_models(self.h, _ptr(E), _ptr(v), E.shape[0]), "sfm_set_models")
+        self.h_count = E.shape[0]
+
+    def score(self, threshold, min_extra=0.0, aggregation="rms", selection="min_error", use_table=True,
+              idx_offset=0, want_arrays=True):
+        h = self.h_count
+        if want_arrays:
+            cnt = np.empty(h, dtype=np.int32)
+            s1 = np.empty(h, dtype=np.float64)
+            s2 = np.empty(h, dtype=np.float64)
+            err = np.empty(h, dtype=np.float64)
+        else:
+            cnt = s1 = s2 = err = None
+        self._ck(self.lib.sfm_score(self.h, float(threshold), float(min_extra), AGG[aggregation], SELECT[selection],
+                                    1 if use_table else 0, int(idx_offset), _ptr(cnt), _ptr(s1), _ptr(s2), _ptr(err)),
+                 "sfm_score")
+        return cnt, s1, s2, err
+
+    def get_best(self):
+        b = Best()
+        self._ck(self.lib.sfm_get_best(self.h, C.byref(b)), "sfm_get_best")
+        return b
+
+    def set_winner(self, local_index, E=None):
+        Ea = None if E is None else _f64(E).reshape(9)
+        self._ck(self.lib.sfm_set_winner(self.h, int(local_index), _ptr(Ea)), "sfm_set_winner")
+
+    def inlier_mask(self, threshold, want_sed=True):
+        mask = np.empty(self.n, dtype=np.uint8)
+        sed = np.empty(self.n, dtype=np.float64) if want_sed else None
+        self._ck(self.lib.sfm_inlier_mask(self.h, float(threshold), _ptr(mask), _ptr(sed)), "sfm_inlier_mask")
+        return mask.astype(bool), sed
+
+    def ransac_essential(self, threshold, min_extra=0.0, aggregation="rms", selection="min_error",
+                         want_mask=True, want_sed=True, mask_out=None, sed_out=None):
+        b = Best()
+        mask = mask_out if mask_out is not None else (np.empty(self.n, dtype=np.uint8) if want_mask else None)
+        sed = sed_out if sed_out is not None else (np.empty(self.n, dtype=np.float64) if want_sed else None)
+        self._ck(self.lib.sfm_ransac_essential(self.h, float(threshold), float(min_extra), AGG[aggregation],
+                                               SELECT[selection], C.byref(b), _ptr(mask), _ptr(sed)),
+                 "sfm_ransac_essential")
+        return b, mask, sed
+
+    # -- pose / triangulation ---------------------------------------------------------------
+    def decompose_essential(self, E):
+        E = _f64(E).reshape(9)
+        p = Poses()
+        self._ck(self.lib.sfm_decompose_essential(self.h, _ptr(E), C.byref(p)), "sfm_decompose_essential")
+        return p
+
+    def recover_pose(self, E, norm_a, norm_b, distance_threshold=50.0):
+        """norm_a, norm_b: [m,2] K-normalised coordinates."""
+        E = _f64(E).reshape(9)
+        na, nb = _split_xy(norm_a), _split_xy(norm_b)
+        m = na.shape[0]
+        p = Poses()
+        pass4 = np.zeros(m, dtype=np.uint8)
+        a, b = na.ctypes.data, nb.ctypes.data
+        self._ck(self.lib.sfm_recover_pose(self.h, _ptr(E), _P(a), _P(a + 8), _P(b), _P(b + 8), 2, m,
+                                           float(distance_threshold), C.byref(p), _ptr(pass4)), "sfm_recover_pose")
+        return p, pass4
+
+    def triangulate(self, P1, P2, pts_a, pts_b):
+        P1 = _f64(np.asarray(P1)[:3, :]).reshape(12)
+        P2 = _f64(np.asarray(P2)[:3, :]).reshape(12)
+        pa, pb = _split_xy(pts_a), _split_xy(pts_b)
+        m = pa.shape[0]
+        X = np.empty((m, 3), dtype=np.float64)
+        a, b = pa.ctypes.data, pb.ctypes.data
+        self._ck(self.lib.sfm_triangulate(self.h, _ptr(P1), _ptr(P2), _P(a), _P(a + 8), _P(b), _P(b + 8), 2, m,
+                                          _ptr(X)), "sfm_triangulate")
+        return X
+
+    def pose_and_triangulate(self, threshold, distance_threshold=50.0, cap=None):
+        cap = self.n if cap is None else int(cap)
+        p = Poses()
+        num = C.c_int64(0)
+        idx = np.empty(cap, dtype=np.int64)
+        ok = np.empty(cap, dtype=np.uint8)
+        X = np.empty((cap, 3), dtype=np.float64)
+        self._ck(self.lib.sfm_pose_and_triangulate(self.h, float(threshold), float(distance_threshold), C.byref(p),
+                                                   cap, C.byref(num), _ptr(idx), _ptr(ok), _ptr(X)),
+                 "sfm_pose_and_triangulate")
+        m = min(int(num.value), cap)
+        return p, int(num.value), idx[:m], ok[:m], X[:m]
+
+    # -- batches ----------------------------------------------------------------------------
+    def batch_ransac(self, pts_a, pts_b, offsets, Ks, h, seed, threshold, min_extra=0.0, aggregation="rms",
+                     selection="min_error", pair_id0=0):
+        pa, pb = _split_xy(pts_a), _split_xy(pts_b)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        P = offsets.shape[0] - 1
+        Ks = _f64(Ks).reshape(P, 9)
+        E = np.empty((P, 3, 3), dtype=np.float64)
+        bi = np.empty(P, dtype=np.int64)
+        be = np.empty(P, dtype=np.float64)
+        ce = np.empty(P, dtype=np.int32)
+        ni = np.empty(P, dtype=np.int64)
+        a, b = pa.ctypes.data, pb.ctypes.data
+        self._ck(self.lib.sfm_batch_ransac(self.h, _P(a), _P(a + 8), _P(b), _P(b + 8), 2, _ptr(offsets), P, _ptr(Ks),
+                                           int(h), int(seed), int(pair_id0), float(threshold), float(min_extra),
+                                           AGG[aggregation], SELECT[selection], _ptr(E), _ptr(bi), _ptr(be), _ptr(ce),
+                                           _ptr(ni)), "sfm_batch_ransac")
+        return dict(E=E, best_index=bi, best_err=be, count_extra=ce, num_invalid=ni)
+
+    # -- measurement ------------------------------------------------------------------------
+    def enable_timing(self, on=True):
+        self._ck(self.lib.sfm_enable_timing(self.h, 1 if on else 0), "sfm_enable_timing")
+
+    def get_timing(self):
+        ms = (C.c_float * 8)()
+        n = C.c_int64(0)
+        self._ck(self.lib.sfm_get_timing(self.h, C.cast(ms, _P), C.byref(n)), "sfm_get_timing")
+        names = ["upload", "sample", "fit", "score", "select", "mask", "pose", "triangulate"]
+        return {k: float(v) for k, v in zip(names, ms)}, int(n.value)
+
+    def measure_fp64_peak(self):
+        v = C.c_double(0)
+        self._ck(self.lib.sfm_measure_fp64_peak(self.h, C.byref(v)), "sfm_measure_fp64_peak")
+        return float(v.value)
+
+
+def mt_shuffle_table(state625: np.ndarray, n: int, h: int, perm_at: int = -1):
+    """CPython-exact sampler (host).  state625 is updated in place.  Returns (table, perm|None)."""
+    lib = load_library()
+    st = np.ascontiguousarray(state625, dtype=np.uint32)
+    assert st.shape == (625,)
+    table = np.empty((h, 8), dtype=np.int32)
+    perm = np.empty(n, dtype=np.int32) if perm_at >= 0 else None
+    rc = lib.sfm_mt_shuffle_table(_ptr(st), int(n), int(h), _ptr(table), int(perm_at), _ptr(perm))
+    if rc != 0:
+        raise NativeError(f"sfm_mt_shuffle_table -> {rc}: {lib.sfm_last_error().decode()}")
+    if st is not state625:
+        state625[...] = st
+    return table, perm
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array backed by pinned (page-locked) host memory from sfm_host_alloc."""
+    lib = load_library()
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    p = _P()
+    rc = lib.sfm_host_alloc(max(nbytes, 1), C.byref(p))
+    if rc != 0:
+        raise NativeError(f"sfm_host_alloc -> {rc}: {lib.sfm_last_error().decode()}")
+    buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[arr.ctypes.data] = p
+    return arr
+
+
+_PINNED: dict = {}
+_engines: dict = {}
+_engine_lock = threading.Lock()
+
+
+def default_device() -> int:
+    return int(os.environ.get("SFM_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+
+
+def get_engine(device: int | None = None) -> Engine:
+    """Process-wide engine for a device (created on first use)."""
+    dev = default_device() if device is None else int(device)
+    with _engine_lock:
+        eng = _engines.get(dev)
+        if eng is None:
+            eng = Engine(dev)
+            _engines[dev] = eng
+        return eng

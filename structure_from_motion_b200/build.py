@@ -1,0 +1,52 @@
+"""Build the sm_100a shared library in-tree (nvcc cross-compiles without a GPU)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "csrc", "sfm_api.cu")
+SO = os.path.join(HERE, "libsfm_b200.so")
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; cannot build libsfm_b200.so")
+
+
+def sources():
+    d = os.path.join(HERE, "csrc")
+    return [os.path.join(d, f) for f in sorted(os.listdir(d))] + [
+        os.path.join(HERE, "..", "include", "sfm_b200.h")
+    ]
+
+
+def is_stale() -> bool:
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    return any(os.path.getmtime(s) > t for s in sources() if os.path.exists(s))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not is_stale():
+        return SO
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", SO + ".tmp", SRC]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+    subprocess.check_call(cmd)
+    os.replace(SO + ".tmp", SO)
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,952 @@
+// C ABI (include/sfm_b200.h) over the sm_100a kernels.  Host side: context, grow-only
+// device buffers, launch geometry, and the CPython-compatible MT19937 sampler.
+#include "../../include/sfm_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "sfm_device.cuh"
+#include "sfm_fit.cuh"
+#include "sfm_linalg.cuh"
+#include "sfm_score.cuh"
+#include "sfm_pose.cuh"
+#include "sfm_misc.cuh"
+
+using namespace sfm;
+
+static_assert(sizeof(Corr) == 32, "Corr must be 32 bytes");
+static_assert(sizeof(PoseSet) == sizeof(sfm_poses), "PoseSet/sfm_poses layout mismatch");
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(SFM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                        __LINE__);                                                                 \
+    } while (0)
+
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) return fail(SFM_ERR_CUDA, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        cap = want;
+        return 0;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+enum { T_UPLOAD = 0, T_SAMPLE, T_FIT, T_SCORE, T_SELECT, T_MASK, T_POSE, T_TRI, T_COUNT };
+
+}  // namespace
+
+struct sfm_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    // data
+    Buf raw, pts, offsets, Ks, table, E, valid, eig;
+    Buf pcount, ps1, ps2, count_extra, S1, S2, err, blocks, best, invalid, winnerE;
+    Buf mask, sed, poses, pass, X, idx, scan, tmp;
+    long long n = 0, h = 0, npairs = 1;
+    long long raw_stride = 1;
+    bool batched = false, has_pts = false, has_table = false, has_models = false, has_score = false;
+    long long winner_local = -1;  // index into E of the current winner, -1 = use winnerE
+    bool winner_set = false;
+    long long last_idx_offset = 0;
+    double Khost[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    // config
+    int variant = SFM_SCORE_SCREEN, hpt = 2;
+    // timing
+    bool timing = false;
+    cudaEvent_t ev0[T_COUNT], ev1[T_COUNT];
+    bool ev_used[T_COUNT];
+    long long launches = 0;
+    // pinned scratch for small results
+    void* hpin = nullptr;
+    size_t hpin_cap = 0;
+
+    void tic(int s) {
+        if (timing) { cudaEventRecord(ev0[s], stream); }
+    }
+    void toc(int s) {
+        if (timing) { cudaEventRecord(ev1[s], stream); ev_used[s] = true; }
+    }
+};
+
+namespace {
+
+int ensure_pinned(sfm_ctx* c, size_t bytes) {
+    if (bytes <= c->hpin_cap) return 0;
+    if (c->hpin) cudaFreeHost(c->hpin);
+    c->hpin = nullptr;
+    c->hpin_cap = 0;
+    CU(cudaMallocHost(&c->hpin, bytes + 4096));
+    c->hpin_cap = bytes + 4096;
+    return 0;
+}
+
+int use(sfm_ctx* c) {
+    if (!c) return fail(SFM_ERR_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    return 0;
+}
+
+int check_launch(sfm_ctx* c, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(SFM_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    c->launches += 1;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// CPython random: MT19937 + shuffle()  (lib/ransac/ransac.py:62 uses random.shuffle)
+// ---------------------------------------------------------------------------------------
+struct PyMT {
+    uint32_t mt[624];
+    int pos;
+    uint32_t next() {
+        if (pos >= 624) {
+            for (int k = 0; k < 624; ++k) {
+                uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+                mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            pos = 0;
+        }
+        uint32_t y = mt[pos++];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
+    }
+    // Random._randbelow_with_getrandbits(n): k = n.bit_length(); r = getrandbits(k) until r < n
+    uint32_t below(uint32_t n) {
+        int k = 32 - __builtin_clz(n);
+        uint32_t r = next() >> (32 - k);
+        while (r >= n) r = next() >> (32 - k);
+        return r;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+int sfm_version(void) { return 100; }
+const char* sfm_last_error(void) { return g_err.c_str(); }
+
+int sfm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int sfm_create(int device, sfm_ctx** out) {
+    if (!out) return fail(SFM_ERR_ARG, "out is null");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(SFM_ERR_NO_DEVICE, "no CUDA device available (%s)",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= n) return fail(SFM_ERR_ARG, "device %d out of range [0,%d)", device, n);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(SFM_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    sfm_ctx* c = new sfm_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    for (int i = 0; i < T_COUNT; ++i) {
+        CU(cudaEventCreate(&c->ev0[i]));
+        CU(cudaEventCreate(&c->ev1[i]));
+        c->ev_used[i] = false;
+    }
+    CU(cudaFuncSetAttribute(k_fit, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(kFitThreads * kFitSmemDoubles * sizeof(double))));
+    *out = c;
+    return 0;
+}
+
+int sfm_destroy(sfm_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    Buf* bufs[] = {&c->raw, &c->pts, &c->offsets, &c->Ks, &c->table, &c->E, &c->valid, &c->eig, &c->pcount,
+                   &c->ps1, &c->ps2, &c->count_extra, &c->S1, &c->S2, &c->err, &c->blocks, &c->best,
+                   &c->invalid, &c->winnerE, &c->mask, &c->sed, &c->poses, &c->pass, &c->X, &c->idx,
+                   &c->scan, &c->tmp};
+    for (Buf* b : bufs) b->release();
+    for (int i = 0; i < T_COUNT; ++i) {
+        cudaEventDestroy(c->ev0[i]);
+        cudaEventDestroy(c->ev1[i]);
+    }
+    if (c->hpin) cudaFreeHost(c->hpin);
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+    return 0;
+}
+
+int sfm_set_stream(sfm_ctx* c, void* s) {
+    if (int r = use(c)) return r;
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return 0;
+}
+
+int sfm_synchronize(sfm_ctx* c) {
+    if (int r = use(c)) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int sfm_set_score_variant(sfm_ctx* c, int variant, int hpt) {
+    if (!c) return fail(SFM_ERR_ARG, "null context");
+    if (variant != SFM_SCORE_SCREEN && variant != SFM_SCORE_FULL) return fail(SFM_ERR_ARG, "bad variant %d", variant);
+    if (hpt != 0 && hpt != 1 && hpt != 2) return fail(SFM_ERR_ARG, "hyps_per_thread must be 1 or 2");
+    c->variant = variant;
+    if (hpt) c->hpt = hpt;
+    return 0;
+}
+
+int sfm_host_alloc(uint64_t bytes, void** out) {
+    if (!out) return fail(SFM_ERR_ARG, "out is null");
+    CU(cudaMallocHost(out, bytes ? bytes : 1));
+    return 0;
+}
+int sfm_host_free(void* p) {
+    if (p) CU(cudaFreeHost(p));
+    return 0;
+}
+
+// ---- sampling ---------------------------------------------------------------------------
+int sfm_mt_shuffle_table(uint32_t* state625, int64_t n, int64_t h, int32_t* table, int64_t perm_at,
+                         int32_t* perm_out) {
+    if (!state625 || !table) return fail(SFM_ERR_ARG, "null argument");
+    if (n < 8 || n > 0x7fffffff) return fail(SFM_ERR_ARG, "need 8 <= n < 2^31 correspondences, got %lld", (long long)n);
+    if (h < 0) return fail(SFM_ERR_ARG, "negative hypothesis count");
+    PyMT g;
+    memcpy(g.mt, state625, 624 * sizeof(uint32_t));
+    g.pos = (int)state625[624];
+    if (g.pos < 0 || g.pos > 624) return fail(SFM_ERR_ARG, "bad MT position %d", g.pos);
+    std::vector<int32_t> perm((size_t)n);
+    for (int64_t i = 0; i < n; ++i) perm[(size_t)i] = (int32_t)i;
+    for (int64_t it = 0; it < h; ++it) {
+        // random.shuffle: for i in reversed(range(1, len(x))): j = randbelow(i + 1); swap
+        for (int64_t i = n - 1; i >= 1; --i) {
+            const uint32_t j = g.below((uint32_t)(i + 1));
+            const int32_t t = perm[(size_t)i];
+            perm[(size_t)i] = perm[j];
+            perm[j] = t;
+        }
+        memcpy(table + 8 * it, perm.data(), 8 * sizeof(int32_t));
+        if (perm_out && it == perm_at) memcpy(perm_out, perm.data(), (size_t)n * sizeof(int32_t));
+    }
+    memcpy(state625, g.mt, 624 * sizeof(uint32_t));
+    state625[624] = (uint32_t)g.pos;
+    return 0;
+}
+
+int sfm_set_table(sfm_ctx* c, const int32_t* table, int64_t h) {
+    if (int r = use(c)) return r;
+    if (!table || h <= 0) return fail(SFM_ERR_ARG, "bad table");
+    if (!c->has_pts) return fail(SFM_ERR_STATE, "upload correspondences before the sample table");
+    for (int64_t i = 0; i < 8 * h; ++i)
+        if (table[i] < 0 || table[i] >= c->n) return fail(SFM_ERR_ARG, "table[%lld] = %d out of range", (long long)i, table[i]);
+    if (int r = c->table.reserve((size_t)h * 32)) return r;
+    CU(cudaMemcpyAsync(c->table.p, table, (size_t)h * 32, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->h = h;
+    c->npairs = 1;
+    c->has_table = true;
+    c->has_models = false;
+    c->has_score = false;
+    return 0;
+}
+
+static int sample_device(sfm_ctx* c, uint64_t seed, uint64_t stream, int64_t hyp_offset, int64_t h) {
+    if (h <= 0) return fail(SFM_ERR_ARG, "need h > 0");
+    if (!c->has_pts) return fail(SFM_ERR_STATE, "upload correspondences before sampling");
+    if (!c->batched && c->n < 8) return fail(SFM_ERR_ARG, "need at least 8 correspondences");
+    if (int r = c->table.reserve((size_t)h * c->npairs * 32)) return r;
+    c->tic(T_SAMPLE);
+    dim3 grid((unsigned)((h + 127) / 128), (unsigned)c->npairs);
+    k_sample<<<grid, 128, 0, c->stream>>>(seed, stream, hyp_offset, h, c->n,
+                                          c->batched ? c->offsets.as<long long>() : nullptr,
+                                          c->table.as<int32_t>());
+    if (int r = check_launch(c, "k_sample")) return r;
+    c->toc(T_SAMPLE);
+    c->h = h;
+    c->has_table = true;
+    c->has_models = false;
+    c->has_score = false;
+    return 0;
+}
+
+int sfm_sample_device(sfm_ctx* c, uint64_t seed, uint64_t stream, int64_t hyp_offset, int64_t h) {
+    if (int r = use(c)) return r;
+    return sample_device(c, seed, stream, hyp_offset, h);
+}
+
+int sfm_get_table(sfm_ctx* c, int32_t* table, int64_t h) {
+    if (int r = use(c)) return r;
+    if (!c->has_table || h > c->h * c->npairs) return fail(SFM_ERR_STATE, "no table of that size");
+    CU(cudaMemcpyAsync(table, c->table.p, (size_t)h * 32, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- correspondences --------------------------------------------------------------------
+static int normalise_from(sfm_ctx* c, const double* xa, const double* ya, const double* xb, const double* yb,
+                          int64_t stride, int64_t n, int64_t max_len) {
+    if (int r = c->pts.reserve((size_t)n * sizeof(Corr))) return r;
+    dim3 grid((unsigned)((max_len + 255) / 256), (unsigned)c->npairs);
+    k_normalise<<<grid, 256, 0, c->stream>>>(xa, ya, xb, yb, stride, n,
+                                             c->batched ? c->offsets.as<long long>() : nullptr,
+                                             c->Ks.as<double>(), c->pts.as<Corr>());
+    return check_launch(c, "k_normalise");
+}
+
+static int stage_raw(sfm_ctx* c, const double* xa, const double* ya, const double* xb, const double* yb,
+                     int64_t stride, int64_t n, const double** dxa, const double** dya, const double** dxb,
+                     const double** dyb) {
+    if (int r = c->raw.reserve((size_t)n * 4 * sizeof(double))) return r;
+    double* d = c->raw.as<double>();
+    if (stride == 1) {
+        const double* src[4] = {xa, ya, xb, yb};
+        for (int k = 0; k < 4; ++k)
+            CU(cudaMemcpyAsync(d + (size_t)k * n, src[k], (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        *dxa = d; *dya = d + n; *dxb = d + 2 * n; *dyb = d + 3 * n;
+    } else if (stride == 2 && ya == xa + 1 && yb == xb + 1) {
+        CU(cudaMemcpyAsync(d, xa, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(d + 2 * n, xb, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        *dxa = d; *dya = d + 1; *dxb = d + 2 * n; *dyb = d + 2 * n + 1;
+    } else {
+        return fail(SFM_ERR_ARG, "unsupported layout: stride must be 1 (four arrays) or 2 (two interleaved [n][2] arrays)");
+    }
+    c->raw_stride = stride;
+    return 0;
+}
+
+int sfm_upload_pairs(sfm_ctx* c, const double* xa, const double* ya, const double* xb, const double* yb,
+                     int64_t stride, int64_t n, const double* K) {
+    if (int r = use(c)) return r;
+    if (!xa || !ya || !xb || !yb || !K) return fail(SFM_ERR_ARG, "null argument");
+    if (n <= 0 || (uint64_t)n >= kMaxPoints) return fail(SFM_ERR_ARG, "need 0 < n < 2^26 correspondences, got %lld", (long long)n);
+    c->tic(T_UPLOAD);
+    c->batched = false;
+    c->npairs = 1;
+    const double *dxa, *dya, *dxb, *dyb;
+    if (int r = stage_raw(c, xa, ya, xb, yb, stride, n, &dxa, &dya, &dxb, &dyb)) return r;
+    if (int r = c->Ks.reserve(9 * sizeof(double))) return r;
+    memcpy(c->Khost, K, sizeof c->Khost);
+    CU(cudaMemcpyAsync(c->Ks.p, K, 9 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    c->n = n;
+    if (int r = normalise_from(c, dxa, dya, dxb, dyb, stride, n, n)) return r;
+    c->toc(T_UPLOAD);
+    // K is read from caller memory by the async copy: finish before returning
+    CU(cudaStreamSynchronize(c->stream));
+    c->has_pts = true;
+    c->has_table = c->has_models = c->has_score = false;
+    c->winner_set = false;
+    return 0;
+}
+
+int sfm_upload_pairs_d(sfm_ctx* c, const double* xa, const double* ya, const double* xb, const double* yb,
+                       int64_t stride, int64_t n, const double* K) {
+    if (int r = use(c)) return r;
+    if (!xa || !ya || !xb || !yb || !K) return fail(SFM_ERR_ARG, "null argument");
+    if (n <= 0 || (uint64_t)n >= kMaxPoints) return fail(SFM_ERR_ARG, "need 0 < n < 2^26 correspondences, got %lld", (long long)n);
+    c->tic(T_UPLOAD);
+    c->batched = false;
+    c->npairs = 1;
+    if (int r = c->Ks.reserve(9 * sizeof(double))) return r;
+    memcpy(c->Khost, K, sizeof c->Khost);
+    CU(cudaMemcpyAsync(c->Ks.p, K, 9 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    c->n = n;
+    // keep a device copy of the pixel coordinates for the triangulation tail
+    if (int r = c->raw.reserve((size_t)n * 4 * sizeof(double))) return r;
+    double* d = c->raw.as<double>();
+    const double* src[4] = {xa, ya, xb, yb};
+    for (int k = 0; k < 4; ++k)
+        CU(cudaMemcpy2DAsync(d + (size_t)k * n, sizeof(double), src[k], (size_t)stride * sizeof(double),
+                             sizeof(double), (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
+    c->raw_stride = 1;
+    if (int r = normalise_from(c, d, d + n, d + 2 * n, d + 3 * n, 1, n, n)) return r;
+    c->toc(T_UPLOAD);
+    CU(cudaStreamSynchronize(c->stream));
+    c->has_pts = true;
+    c->has_table = c->has_models = c->has_score = false;
+    c->winner_set = false;
+    return 0;
+}
+
+int sfm_get_normalised(sfm_ctx* c, double* out, int64_t n) {
+    if (int r = use(c)) return r;
+    if (!c->has_pts || n > c->n) return fail(SFM_ERR_STATE, "no correspondences of that size");
+    CU(cudaMemcpyAsync(out, c->pts.p, (size_t)n * sizeof(Corr), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- fit ----------------------------------------------------------------------------------
+static int fit_launch(sfm_ctx* c, bool want_eig) {
+    if (!c->has_pts || !c->has_table) return fail(SFM_ERR_STATE, "fit needs correspondences and a sample table");
+    const size_t H = (size_t)c->h * c->npairs;
+    if (int r = c->E.reserve(H * 9 * sizeof(double))) return r;
+    if (int r = c->valid.reserve(H)) return r;
+    if (want_eig)
+        if (int r = c->eig.reserve(H * 9 * sizeof(double))) return r;
+    c->tic(T_FIT);
+    dim3 grid((unsigned)((c->h + kFitThreads - 1) / kFitThreads), (unsigned)c->npairs);
+    k_fit<<<grid, kFitThreads, kFitThreads * kFitSmemDoubles * sizeof(double), c->stream>>>(
+        c->pts.as<Corr>(), c->batched ? c->offsets.as<long long>() : nullptr, c->table.as<int32_t>(), c->h,
+        c->E.as<double>(), c->valid.as<uint8_t>(), want_eig ? c->eig.as<double>() : nullptr);
+    if (int r = check_launch(c, "k_fit")) return r;
+    c->toc(T_FIT);
+    c->has_models = true;
+    c->has_score = false;
+    return 0;
+}
+
+int sfm_fit(sfm_ctx* c, double* E_out, uint8_t* valid_out, double* eig_out) {
+    if (int r = use(c)) return r;
+    if (int r = fit_launch(c, eig_out != nullptr)) return r;
+    const size_t H = (size_t)c->h * c->npairs;
+    if (E_out) CU(cudaMemcpyAsync(E_out, c->E.p, H * 72, cudaMemcpyDeviceToHost, c->stream));
+    if (valid_out) CU(cudaMemcpyAsync(valid_out, c->valid.p, H, cudaMemcpyDeviceToHost, c->stream));
+    if (eig_out) CU(cudaMemcpyAsync(eig_out, c->eig.p, H * 72, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int sfm_set_models(sfm_ctx* c, const double* E, const uint8_t* valid, int64_t h) {
+    if (int r = use(c)) return r;
+    if (!E || h <= 0) return fail(SFM_ERR_ARG, "bad models");
+    if (c->batched) return fail(SFM_ERR_STATE, "set_models is a single-pair call");
+    if (c->has_table && h != c->h) return fail(SFM_ERR_ARG, "model count %lld != table rows %lld", (long long)h, c->h);
+    if (int r = c->E.reserve((size_t)h * 72)) return r;
+    if (int r = c->valid.reserve((size_t)h)) return r;
+    CU(cudaMemcpyAsync(c->E.p, E, (size_t)h * 72, cudaMemcpyHostToDevice, c->stream));
+    if (valid) CU(cudaMemcpyAsync(c->valid.p, valid, (size_t)h, cudaMemcpyHostToDevice, c->stream));
+    else CU(cudaMemsetAsync(c->valid.p, 1, (size_t)h, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->h = h;
+    c->has_models = true;
+    c->has_score = false;
+    return 0;
+}
+
+// ---- score + select ---------------------------------------------------------------------
+static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int mode, bool use_table,
+                        long long idx_offset, long long max_len) {
+    if (!c->has_pts || !c->has_models) return fail(SFM_ERR_STATE, "score needs correspondences and fitted models");
+    if (use_table && !c->has_table) return fail(SFM_ERR_STATE, "sample rule requested but no table is loaded");
+    if (agg < 0 || agg > 3) return fail(SFM_ERR_ARG, "bad aggregation %d", agg);
+    if (mode != 0 && mode != 1) return fail(SFM_ERR_ARG, "bad selection %d", mode);
+    if (!(thr >= 0.0)) return fail(SFM_ERR_ARG, "threshold must be >= 0");
+    const long long h = c->h, P = c->npairs;
+    const int hpt = c->hpt;
+    const long long hblocks = (h + (long long)kScoreThreads * hpt - 1) / ((long long)kScoreThreads * hpt);
+    // split the correspondences so that the grid covers the machine several times over
+    const long long target_blocks = (long long)c->sm_count * 32;
+    const long long tiles = (max_len + kTile - 1) / kTile;
+    long long nsplit = (target_blocks + hblocks * P - 1) / (hblocks * P);
+    if (nsplit > tiles) nsplit = tiles;
+    if (nsplit > 1024) nsplit = 1024;
+    if (nsplit < 1) nsplit = 1;
+    long long chunk = ((tiles + nsplit - 1) / nsplit) * kTile;
+    nsplit = (max_len + chunk - 1) / chunk;
+    if (nsplit < 1) nsplit = 1;
+    const size_t np = (size_t)P * nsplit * h;
+    if (int r = c->pcount.reserve(np * 4)) return r;
+    if (int r = c->ps1.reserve(np * 8)) return r;
+    if (int r = c->ps2.reserve(np * 8)) return r;
+    const size_t H = (size_t)h * P;
+    if (int r = c->count_extra.reserve(H * 4)) return r;
+    if (int r = c->S1.reserve(H * 8)) return r;
+    if (int r = c->S2.reserve(H * 8)) return r;
+    if (int r = c->err.reserve(H * 8)) return r;
+    const int fblocks = (int)((h + 255) / 256);
+    if (int r = c->blocks.reserve((size_t)fblocks * P * sizeof(Best))) return r;
+    if (int r = c->best.reserve((size_t)P * sizeof(Best))) return r;
+    if (int r = c->invalid.reserve((size_t)P * 16)) return r;
+
+    ScoreArgs a;
+    a.pts = c->pts.as<Corr>();
+    a.n = c->n;
+    a.offsets = c->batched ? c->offsets.as<long long>() : nullptr;
+    a.E = c->E.as<double>();
+    a.h = h;
+    a.thr = thr;
+    // rounding guard of the screening tests: relative slack + an absolute term that covers a
+    // cancelling residual r at the 1-ulp level (only matters for thr -> 0)
+    a.thr_pre = thr * (1.0 + 1e-9) + 1e-22;
+    a.chunk = chunk;
+    a.pcount = c->pcount.as<int32_t>();
+    a.ps1 = c->ps1.as<double>();
+    a.ps2 = c->ps2.as<double>();
+    dim3 grid((unsigned)hblocks, (unsigned)nsplit, (unsigned)P);
+    c->tic(T_SCORE);
+    if (c->variant == SFM_SCORE_SCREEN) {
+        if (hpt == 2) k_score<2, true><<<grid, kScoreThreads, 0, c->stream>>>(a);
+        else k_score<1, true><<<grid, kScoreThreads, 0, c->stream>>>(a);
+    } else {
+        if (hpt == 2) k_score<2, false><<<grid, kScoreThreads, 0, c->stream>>>(a);
+        else k_score<1, false><<<grid, kScoreThreads, 0, c->stream>>>(a);
+    }
+    if (int r = check_launch(c, "k_score")) return r;
+    c->toc(T_SCORE);
+
+    c->tic(T_SELECT);
+    FinalArgs f;
+    f.pts = a.pts;
+    f.offsets = a.offsets;
+    f.E = a.E;
+    f.valid = c->valid.as<uint8_t>();
+    f.table = use_table ? c->table.as<int32_t>() : nullptr;
+    f.h = h;
+    f.idx_offset = idx_offset;
+    f.nsplit = (int)nsplit;
+    f.pcount = a.pcount;
+    f.ps1 = a.ps1;
+    f.ps2 = a.ps2;
+    f.thr = thr;
+    f.min_extra = min_extra;
+    f.agg = agg;
+    f.mode = mode;
+    f.count_extra = c->count_extra.as<int32_t>();
+    f.S1 = c->S1.as<double>();
+    f.S2 = c->S2.as<double>();
+    f.err = c->err.as<double>();
+    f.block_out = c->blocks.as<Best>();
+    k_finalise<<<dim3((unsigned)fblocks, (unsigned)P), 256, 0, c->stream>>>(f);
+    if (int r = check_launch(c, "k_finalise")) return r;
+    k_select<<<(unsigned)P, 256, 0, c->stream>>>(c->blocks.as<Best>(), fblocks, mode, c->valid.as<uint8_t>(), h,
+                                                  idx_offset, c->best.as<Best>(), c->invalid.as<long long>());
+    if (int r = check_launch(c, "k_select")) return r;
+    c->toc(T_SELECT);
+    c->has_score = true;
+    c->last_idx_offset = idx_offset;
+    c->winner_set = false;
+    return 0;
+}
+
+int sfm_score(sfm_ctx* c, double thr, double min_extra, int agg, int mode, int use_table, int64_t idx_offset,
+              int32_t* count_extra, double* S1, double* S2, double* err) {
+    if (int r = use(c)) return r;
+    if (c->batched) return fail(SFM_ERR_STATE, "sfm_score is a single-pair call; use sfm_batch_ransac");
+    if (int r = score_launch(c, thr, min_extra, agg, mode, use_table != 0, idx_offset, c->n)) return r;
+    const size_t H = (size_t)c->h;
+    if (count_extra) CU(cudaMemcpyAsync(count_extra, c->count_extra.p, H * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (S1) CU(cudaMemcpyAsync(S1, c->S1.p, H * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (S2) CU(cudaMemcpyAsync(S2, c->S2.p, H * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (err) CU(cudaMemcpyAsync(err, c->err.p, H * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int fetch_best(sfm_ctx* c, sfm_best* out) {
+    if (int r = ensure_pinned(c, sizeof(Best) + 16 + 72)) return r;
+    char* hp = (char*)c->hpin;
+    CU(cudaMemcpyAsync(hp, c->best.p, sizeof(Best), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(hp + sizeof(Best), c->invalid.p, 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    Best b;
+    memcpy(&b, hp, sizeof b);
+    long long inv[2];
+    memcpy(inv, hp + sizeof(Best), 16);
+    out->err = b.err;
+    out->index = b.idx;
+    out->count_extra = b.count;
+    out->reserved = 0;
+    out->num_invalid = inv[0];
+    out->first_invalid = inv[1];
+    for (int k = 0; k < 9; ++k) out->E[k] = 0.0;
+    if (b.idx >= 0) {
+        const long long local = b.idx - c->last_idx_offset;
+        CU(cudaMemcpyAsync(hp, c->E.as<double>() + 9 * local, 72, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        memcpy(out->E, hp, 72);
+        c->winner_local = local;
+        c->winner_set = true;
+    } else {
+        out->err = __builtin_inf();
+    }
+    return 0;
+}
+
+int sfm_get_best(sfm_ctx* c, sfm_best* out) {
+    if (int r = use(c)) return r;
+    if (!out) return fail(SFM_ERR_ARG, "out is null");
+    if (!c->has_score || c->batched) return fail(SFM_ERR_STATE, "no single-pair score to read");
+    return fetch_best(c, out);
+}
+
+int sfm_set_winner(sfm_ctx* c, int64_t local_index, const double* E) {
+    if (int r = use(c)) return r;
+    if (local_index >= 0) {
+        if (!c->has_models || local_index >= c->h) return fail(SFM_ERR_ARG, "winner index out of range");
+        c->winner_local = local_index;
+    } else {
+        if (!E) return fail(SFM_ERR_ARG, "need the winning model when it lives on another rank");
+        if (int r = c->winnerE.reserve(72)) return r;
+        CU(cudaMemcpyAsync(c->winnerE.p, E, 72, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->winner_local = -1;
+    }
+    c->winner_set = true;
+    return 0;
+}
+
+static const double* winner_E_dev(sfm_ctx* c) {
+    return c->winner_local >= 0 ? c->E.as<double>() + 9 * c->winner_local : c->winnerE.as<double>();
+}
+
+static int mask_launch(sfm_ctx* c, double thr, const Best* best_dev) {
+    if (int r = c->mask.reserve((size_t)c->n)) return r;
+    if (int r = c->sed.reserve((size_t)c->n * 8)) return r;
+    c->tic(T_MASK);
+    const double* E = best_dev ? c->E.as<double>() : winner_E_dev(c);
+    k_inlier_mask<<<(unsigned)((c->n + 255) / 256), 256, 0, c->stream>>>(
+        c->pts.as<Corr>(), c->n, E, best_dev, c->last_idx_offset, 0, thr, c->mask.as<uint8_t>(), c->sed.as<double>());
+    if (int r = check_launch(c, "k_inlier_mask")) return r;
+    c->toc(T_MASK);
+    return 0;
+}
+
+int sfm_inlier_mask(sfm_ctx* c, double thr, uint8_t* mask, double* sed) {
+    if (int r = use(c)) return r;
+    if (!c->has_pts || c->batched) return fail(SFM_ERR_STATE, "no single-pair correspondences loaded");
+    if (!c->winner_set) return fail(SFM_ERR_STATE, "no winner: call sfm_get_best or sfm_set_winner first");
+    if (int r = mask_launch(c, thr, nullptr)) return r;
+    if (mask) CU(cudaMemcpyAsync(mask, c->mask.p, (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
+    if (sed) CU(cudaMemcpyAsync(sed, c->sed.p, (size_t)c->n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int sfm_ransac_essential(sfm_ctx* c, double thr, double min_extra, int agg, int mode, sfm_best* best,
+                         uint8_t* mask, double* sed) {
+    if (int r = use(c)) return r;
+    if (!best) return fail(SFM_ERR_ARG, "best is null");
+    if (c->batched) return fail(SFM_ERR_STATE, "single-pair call on a batched context");
+    if (int r = fit_launch(c, false)) return r;
+    if (int r = score_launch(c, thr, min_extra, agg, mode, true, 0, c->n)) return r;
+    if (mask || sed) {
+        if (int r = mask_launch(c, thr, c->best.as<Best>())) return r;
+        if (mask) CU(cudaMemcpyAsync(mask, c->mask.p, (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
+        if (sed) CU(cudaMemcpyAsync(sed, c->sed.p, (size_t)c->n * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    return fetch_best(c, best);
+}
+
+// ---- pose + triangulation ---------------------------------------------------------------
+int sfm_decompose_essential(sfm_ctx* c, const double* E, sfm_poses* out) {
+    if (int r = use(c)) return r;
+    if (!E || !out) return fail(SFM_ERR_ARG, "null argument");
+    if (int r = c->tmp.reserve(72)) return r;
+    if (int r = c->poses.reserve(sizeof(PoseSet))) return r;
+    CU(cudaMemcpyAsync(c->tmp.p, E, 72, cudaMemcpyHostToDevice, c->stream));
+    k_decompose<<<1, 32, 0, c->stream>>>(c->tmp.as<double>(), nullptr, 0, c->poses.as<PoseSet>(), 1);
+    if (int r = check_launch(c, "k_decompose")) return r;
+    CU(cudaMemcpyAsync(out, c->poses.p, sizeof(PoseSet), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int sfm_recover_pose(sfm_ctx* c, const double* E, const double* xa, const double* ya, const double* xb,
+                     const double* yb, int64_t stride, int64_t m, double dist_thr, sfm_poses* out,
+                     uint8_t* pass4) {
+    if (int r = use(c)) return r;
+    if (!E || !out) return fail(SFM_ERR_ARG, "null argument");
+    if (m < 0) return fail(SFM_ERR_ARG, "negative count");
+    if (int r = c->tmp.reserve(72 + 9 * 8 + (size_t)m * 4 * 8 + (size_t)m * sizeof(Corr) + 64)) return r;
+    if (int r = c->poses.reserve(sizeof(PoseSet))) return r;
+    if (int r = c->pass.reserve((size_t)m + 1)) return r;
+    c->tic(T_POSE);
+    double* dE = c->tmp.as<double>();
+    double* dK = dE + 9;
+    double* draw = dK + 9;
+    Corr* dpts = reinterpret_cast<Corr*>(((uintptr_t)(draw + 4 * m) + 31) & ~(uintptr_t)31);
+    CU(cudaMemcpyAsync(dE, E, 72, cudaMemcpyHostToDevice, c->stream));
+    k_decompose<<<1, 32, 0, c->stream>>>(dE, nullptr, 0, c->poses.as<PoseSet>(), 1);
+    if (int r = check_launch(c, "k_decompose")) return r;
+    if (m > 0) {
+        if (!xa || !ya || !xb || !yb) return fail(SFM_ERR_ARG, "null coordinates");
+        // inputs are already K-normalised: pack them into Corr records with an identity K
+        const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        CU(cudaMemcpyAsync(dK, I, 72, cudaMemcpyHostToDevice, c->stream));
+        const double *sxa, *sya, *sxb, *syb;
+        if (stride == 1) {
+            const double* src[4] = {xa, ya, xb, yb};
+            for (int k = 0; k < 4; ++k)
+                CU(cudaMemcpyAsync(draw + (size_t)k * m, src[k], (size_t)m * 8, cudaMemcpyHostToDevice, c->stream));
+            sxa = draw; sya = draw + m; sxb = draw + 2 * m; syb = draw + 3 * m;
+        } else if (stride == 2 && ya == xa + 1 && yb == xb + 1) {
+            CU(cudaMemcpyAsync(draw, xa, (size_t)m * 16, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(draw + 2 * m, xb, (size_t)m * 16, cudaMemcpyHostToDevice, c->stream));
+            sxa = draw; sya = draw + 1; sxb = draw + 2 * m; syb = draw + 2 * m + 1;
+        } else {
+            return fail(SFM_ERR_ARG, "unsupported layout: stride must be 1 or 2");
+        }
+        k_normalise<<<dim3((unsigned)((m + 255) / 256), 1), 256, 0, c->stream>>>(sxa, sya, sxb, syb, stride, m, nullptr, dK, dpts);
+        if (int r = check_launch(c, "k_normalise")) return r;
+        k_cheirality<<<(unsigned)((m + 127) / 128), 128, 0, c->stream>>>(dpts, m, nullptr, nullptr, c->poses.as<PoseSet>(),
+                                                                        dist_thr, c->pass.as<uint8_t>(), nullptr);
+        if (int r = check_launch(c, "k_cheirality")) return r;
+    }
+    k_vote<<<1, 32, 0, c->stream>>>(c->poses.as<PoseSet>());
+    if (int r = check_launch(c, "k_vote")) return r;
+    c->toc(T_POSE);
+    CU(cudaMemcpyAsync(out, c->poses.p, sizeof(PoseSet), cudaMemcpyDeviceToHost, c->stream));
+    if (pass4 && m > 0) CU(cudaMemcpyAsync(pass4, c->pass.p, (size_t)m, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int sfm_triangulate(sfm_ctx* c, const double* P1, const double* P2, const double* xa, const double* ya,
+                    const double* xb, const double* yb, int64_t stride, int64_t m, double* X) {
+    if (int r = use(c)) return r;
+    if (!P1 || !P2 || !X) return fail(SFM_ERR_ARG, "null argument");
+    if (m <= 0) return m == 0 ? 0 : fail(SFM_ERR_ARG, "negative count");
+    if (!xa || !ya || !xb || !yb) return fail(SFM_ERR_ARG, "null coordinates");
+    if (int r = c->tmp.reserve(24 * 8 + (size_t)m * 4 * 8)) return r;
+    if (int r = c->X.reserve((size_t)m * 24)) return r;
+    c->tic(T_TRI);
+    double* dP = c->tmp.as<double>();
+    double* draw = dP + 24;
+    CU(cudaMemcpyAsync(dP, P1, 96, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(dP + 12, P2, 96, cudaMemcpyHostToDevice, c->stream));
+    const double *sxa, *sya, *sxb, *syb;
+    if (stride == 1) {
+        const double* src[4] = {xa, ya, xb, yb};
+        for (int k = 0; k < 4; ++k)
+            CU(cudaMemcpyAsync(draw + (size_t)k * m, src[k], (size_t)m * 8, cudaMemcpyHostToDevice, c->stream));
+        sxa = draw; sya = draw + m; sxb = draw + 2 * m; syb = draw + 3 * m;
+    } else if (stride == 2 && ya == xa + 1 && yb == xb + 1) {
+        CU(cudaMemcpyAsync(draw, xa, (size_t)m * 16, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(draw + 2 * m, xb, (size_t)m * 16, cudaMemcpyHostToDevice, c->stream));
+        sxa = draw; sya = draw + 1; sxb = draw + 2 * m; syb = draw + 2 * m + 1;
+    } else {
+        return fail(SFM_ERR_ARG, "unsupported layout: stride must be 1 or 2");
+    }
+    k_triangulate<<<(unsigned)((m + 127) / 128), 128, 0, c->stream>>>(sxa, sya, sxb, syb, stride, m, nullptr, dP, dP + 12,
+                                                                      nullptr, nullptr, nullptr, 0, c->X.as<double>());
+    if (int r = check_launch(c, "k_triangulate")) return r;
+    c->toc(T_TRI);
+    CU(cudaMemcpyAsync(X, c->X.p, (size_t)m * 24, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int sfm_pose_and_triangulate(sfm_ctx* c, double thr, double dist_thr, sfm_poses* poses, int64_t cap,
+                             int64_t* num_inliers, int64_t* inlier_idx, uint8_t* pass, double* X) {
+    if (int r = use(c)) return r;
+    if (!poses || !num_inliers) return fail(SFM_ERR_ARG, "null argument");
+    if (!c->has_pts || c->batched) return fail(SFM_ERR_STATE, "no single-pair correspondences loaded");
+    if (!c->winner_set) return fail(SFM_ERR_STATE, "no winner: run sfm_ransac_essential / sfm_get_best first");
+    const long long n = c->n;
+    if (int r = mask_launch(c, thr, nullptr)) return r;
+    const bool have_row = c->has_table && c->winner_local >= 0;
+    if (have_row) {
+        k_mark_samples<<<1, 32, 0, c->stream>>>(c->table.as<int32_t>() + 8 * c->winner_local, c->mask.as<uint8_t>());
+        if (int r = check_launch(c, "k_mark_samples")) return r;
+    }
+    // compact the winner's inliers (ascending index): block counts -> scan -> scatter
+    const int cblocks = (int)((n + 1023) / 1024);
+    if (int r = c->scan.reserve((size_t)(cblocks + 2) * 8)) return r;
+    if (int r = c->idx.reserve((size_t)n * 8)) return r;
+    if (int r = c->poses.reserve(sizeof(PoseSet))) return r;
+    if (int r = c->pass.reserve((size_t)n + 1)) return r;
+    if (int r = c->X.reserve((size_t)n * 24)) return r;
+    c->tic(T_POSE);
+    k_compact_count<<<cblocks, 256, 0, c->stream>>>(c->mask.as<uint8_t>(), n, c->scan.as<long long>());
+    if (int r = check_launch(c, "k_compact_count")) return r;
+    k_compact_scan<<<1, 1024, 0, c->stream>>>(c->scan.as<long long>(), cblocks);
+    if (int r = check_launch(c, "k_compact_scan")) return r;
+    k_compact_scatter<<<cblocks, 256, 0, c->stream>>>(c->mask.as<uint8_t>(), n, c->scan.as<long long>(), c->idx.as<long long>());
+    if (int r = check_launch(c, "k_compact_scatter")) return r;
+    k_decompose<<<1, 32, 0, c->stream>>>(winner_E_dev(c), nullptr, 0, c->poses.as<PoseSet>(), 1);
+    if (int r = check_launch(c, "k_decompose")) return r;
+    // the number of inliers stays on the device: launch over n and let threads beyond it exit
+    const long long* cnt_dev = c->scan.as<long long>() + cblocks;
+    k_cheirality<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(
+        c->pts.as<Corr>(), -1, c->idx.as<long long>(), cnt_dev, c->poses.as<PoseSet>(), dist_thr, c->pass.as<uint8_t>(),
+        have_row ? c->table.as<int32_t>() + 8 * c->winner_local : nullptr);
+    if (int r = check_launch(c, "k_cheirality")) return r;
+    k_vote<<<1, 32, 0, c->stream>>>(c->poses.as<PoseSet>());
+    if (int r = check_launch(c, "k_vote")) return r;
+    c->toc(T_POSE);
+    c->tic(T_TRI);
+    const double* d = c->raw.as<double>();
+    const double *sxa, *sya, *sxb, *syb;
+    if (c->raw_stride == 1) { sxa = d; sya = d + n; sxb = d + 2 * n; syb = d + 3 * n; }
+    else { sxa = d; sya = d + 1; sxb = d + 2 * n; syb = d + 2 * n + 1; }
+    k_triangulate<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(sxa, sya, sxb, syb, c->raw_stride, -1, cnt_dev,
+                                                                      nullptr, nullptr, c->Ks.as<double>(),
+                                                                      c->poses.as<PoseSet>(), c->pass.as<uint8_t>(), 1,
+                                                                      c->X.as<double>(), c->idx.as<long long>());
+    if (int r = check_launch(c, "k_triangulate")) return r;
+    c->toc(T_TRI);
+    if (int r = ensure_pinned(c, 64)) return r;
+    CU(cudaMemcpyAsync(c->hpin, cnt_dev, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(poses, c->poses.p, sizeof(PoseSet), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    long long m;
+    memcpy(&m, c->hpin, 8);
+    *num_inliers = m;
+    const long long take = m < cap ? m : cap;
+    if (take > 0) {
+        if (inlier_idx) CU(cudaMemcpyAsync(inlier_idx, c->idx.p, (size_t)take * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (pass) CU(cudaMemcpyAsync(pass, c->pass.p, (size_t)take, cudaMemcpyDeviceToHost, c->stream));
+        if (X) CU(cudaMemcpyAsync(X, c->X.p, (size_t)take * 24, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+// ---- batched pairs ------------------------------------------------------------------------
+int sfm_batch_ransac(sfm_ctx* c, const double* xa, const double* ya, const double* xb, const double* yb,
+                     int64_t stride, const int64_t* offsets, int64_t npairs, const double* Ks, int64_t h,
+                     uint64_t seed, uint64_t pair_id0, double thr, double min_extra, int agg, int mode, double* E,
+                     int64_t* best_index, double* best_err, int32_t* count_extra, int64_t* num_invalid) {
+    if (int r = use(c)) return r;
+    if (!xa || !ya || !xb || !yb || !offsets || !Ks) return fail(SFM_ERR_ARG, "null argument");
+    if (npairs <= 0 || npairs > 65535) return fail(SFM_ERR_ARG, "need 1 <= npairs <= 65535 per call");
+    if (h <= 0) return fail(SFM_ERR_ARG, "need h > 0");
+    const long long n = offsets[npairs];
+    if (offsets[0] != 0 || n <= 0 || (uint64_t)n >= kMaxPoints) return fail(SFM_ERR_ARG, "bad offsets (total %lld)", n);
+    long long max_len = 0;
+    for (int64_t p = 0; p < npairs; ++p) {
+        const long long len = offsets[p + 1] - offsets[p];
+        if (len < 0) return fail(SFM_ERR_ARG, "offsets must be non-decreasing");
+        if (len > max_len) max_len = len;
+    }
+    c->tic(T_UPLOAD);
+    c->batched = true;
+    c->npairs = npairs;
+    c->n = n;
+    if (int r = c->offsets.reserve((size_t)(npairs + 1) * 8)) return r;
+    if (int r = c->Ks.reserve((size_t)npairs * 72)) return r;
+    CU(cudaMemcpyAsync(c->offsets.p, offsets, (size_t)(npairs + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->Ks.p, Ks, (size_t)npairs * 72, cudaMemcpyHostToDevice, c->stream));
+    const double *dxa, *dya, *dxb, *dyb;
+    if (int r = stage_raw(c, xa, ya, xb, yb, stride, n, &dxa, &dya, &dxb, &dyb)) return r;
+    if (int r = normalise_from(c, dxa, dya, dxb, dyb, stride, n, max_len)) return r;
+    c->toc(T_UPLOAD);
+    c->has_pts = true;
+    if (int r = sample_device(c, seed, pair_id0, 0, h)) return r;
+    if (int r = fit_launch(c, false)) return r;
+    if (int r = score_launch(c, thr, min_extra, agg, mode, true, 0, max_len)) return r;
+    // gather per-pair winners
+    if (int r = c->tmp.reserve((size_t)npairs * 72)) return r;
+    k_gather_winners<<<(unsigned)((npairs + 127) / 128), 128, 0, c->stream>>>(c->best.as<Best>(), c->E.as<double>(), h,
+                                                                              (int)npairs, c->tmp.as<double>());
+    if (int r = check_launch(c, "k_gather_winners")) return r;
+    const size_t bytes = (size_t)npairs * (sizeof(Best) + 16 + 72);
+    if (int r = ensure_pinned(c, bytes)) return r;
+    char* hp = (char*)c->hpin;
+    CU(cudaMemcpyAsync(hp, c->best.p, (size_t)npairs * sizeof(Best), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(hp + npairs * sizeof(Best), c->invalid.p, (size_t)npairs * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(hp + npairs * (sizeof(Best) + 16), c->tmp.p, (size_t)npairs * 72, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const Best* hb = reinterpret_cast<const Best*>(hp);
+    const long long* hinv = reinterpret_cast<const long long*>(hp + npairs * sizeof(Best));
+    const double* hE = reinterpret_cast<const double*>(hp + npairs * (sizeof(Best) + 16));
+    for (int64_t p = 0; p < npairs; ++p) {
+        if (best_index) best_index[p] = hb[p].idx;
+        if (best_err) best_err[p] = hb[p].idx >= 0 ? hb[p].err : __builtin_inf();
+        if (count_extra) count_extra[p] = hb[p].idx >= 0 ? hb[p].count : -1;
+        if (num_invalid) num_invalid[p] = hinv[2 * p];
+        if (E) memcpy(E + 9 * p, hE + 9 * p, 72);
+    }
+    c->has_score = false;  // per-hypothesis single-pair getters do not apply to batches
+    c->winner_set = false;
+    return 0;
+}
+
+// ---- measurement ----------------------------------------------------------------------------
+int sfm_enable_timing(sfm_ctx* c, int on) {
+    if (!c) return fail(SFM_ERR_ARG, "null context");
+    c->timing = on != 0;
+    for (int i = 0; i < T_COUNT; ++i) c->ev_used[i] = false;
+    return 0;
+}
+
+int sfm_get_timing(sfm_ctx* c, float ms[8], int64_t* launches) {
+    if (int r = use(c)) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < T_COUNT; ++i) {
+        ms[i] = 0.f;
+        if (c->timing && c->ev_used[i]) CU(cudaEventElapsedTime(&ms[i], c->ev0[i], c->ev1[i]));
+    }
+    if (launches) *launches = c->launches;
+    return 0;
+}
+
+int sfm_measure_fp64_peak(sfm_ctx* c, double* dfma_per_s) {
+    if (int r = use(c)) return r;
+    if (!dfma_per_s) return fail(SFM_ERR_ARG, "null argument");
+    if (int r = c->tmp.reserve(1 << 20)) return r;
+    const int blocks = c->sm_count * 8, threads = 256, iters = 4096;
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CU(cudaEventRecord(a, c->stream));
+        k_fp64_peak<<<blocks, threads, 0, c->stream>>>(c->tmp.as<double>(), iters, 1.0000001);
+        if (int r = check_launch(c, "k_fp64_peak")) return r;
+        CU(cudaEventRecord(b, c->stream));
+        CU(cudaEventSynchronize(b));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, a, b));
+        const double rate = (double)blocks * threads * iters * 16.0 / (ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *dfma_per_s = best;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,269 @@
+// K0 (K-normalisation), the device sampler and K1 (batched eight-point fitter).
+#pragma once
+#include "sfm_device.cuh"
+#include "sfm_linalg.cuh"
+
+namespace sfm {
+
+// ------------------------------------------------------------------------------------
+// K0 — to_normalized_image_coords (lib/epipolar/eight_point.py:127-133) once per
+// correspondence instead of twice per evaluation (lib/epipolar/epipolar_ransac.py:21-22).
+// IEEE subtract + divide, bit-identical to the reference.  Packs SoA/strided pixel input
+// into the 32-byte Corr records every other kernel consumes.
+// ------------------------------------------------------------------------------------
+// Batched form: blockIdx.y = image pair; pair p owns records [offsets[p], offsets[p+1]) and
+// its own intrinsics Ks[p] (row-major 3x3).  offsets == nullptr means one pair of n records.
+__global__ void k_normalise(const double* __restrict__ xa, const double* __restrict__ ya,
+                            const double* __restrict__ xb, const double* __restrict__ yb,
+                            long long stride, long long n, const long long* __restrict__ offsets,
+                            const double* __restrict__ Ks, Corr* __restrict__ out) {
+    const long long base = offsets ? offsets[blockIdx.y] : 0;
+    const long long len = offsets ? offsets[blockIdx.y + 1] - base : n;
+    const long long li = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (li >= len) return;
+    const long long i = base + li;
+    const double* K = Ks + 9 * (long long)blockIdx.y;
+    const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+    Corr c;
+    c.xa = __ddiv_rn(__dsub_rn(xa[i * stride], cx), fx);
+    c.ya = __ddiv_rn(__dsub_rn(ya[i * stride], cy), fy);
+    c.xb = __ddiv_rn(__dsub_rn(xb[i * stride], cx), fx);
+    c.yb = __ddiv_rn(__dsub_rn(yb[i * stride], cy), fy);
+    out[i] = c;
+}
+
+// ------------------------------------------------------------------------------------
+// Device sampler: table[h] = 8 distinct indices in [0, n) from Philox keyed by
+// (seed, stream=pair, global hypothesis index) — independent of how hypotheses are
+// sharded over GPUs.  Replaces the O(N) random.shuffle per iteration of
+// lib/ransac/ransac.py:62 for the large configurations (documented deviation; the
+// faithful sampler is sfm_mt_shuffle_table on the host).
+// ------------------------------------------------------------------------------------
+__global__ void k_sample(unsigned long long seed, unsigned long long stream0,
+                         long long hyp_offset, long long h, long long n,
+                         const long long* __restrict__ offsets, int32_t* __restrict__ table) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= h) return;
+    const long long len = offsets ? offsets[blockIdx.y + 1] - offsets[blockIdx.y] : n;
+    int32_t idx[8];
+    if (len >= 8) {
+        philox_sample8(seed, stream0 + blockIdx.y, (unsigned long long)(hyp_offset + i), (unsigned)len, idx);
+    } else {
+        for (int k = 0; k < 8; ++k) idx[k] = 0;
+    }
+    int4* t = reinterpret_cast<int4*>(table + 8 * ((long long)blockIdx.y * h + i));
+    t[0] = make_int4(idx[0], idx[1], idx[2], idx[3]);
+    t[1] = make_int4(idx[4], idx[5], idx[6], idx[7]);
+}
+
+// ------------------------------------------------------------------------------------
+// K1 — eight-point fit, one thread per hypothesis.
+//
+// Restates estimate_fundamental_mat (lib/epipolar/eight_point.py:136-170):
+//   Hartley normalisation (:308-338) -> Y^T Y (:363-393) -> eigenvector of the smallest
+//   |eigenvalue| with the "only one small eigenvalue" validity test (:396-427) -> rank-2
+//   projection (:430-446) -> E = T2^T F T1 (:163) -> E /= E[2,2] (:166).
+//
+// The 9x9 symmetric eigenproblem is solved by cyclic Jacobi with the matrix and the
+// eigenvector matrix in shared memory, element-major ([element][thread]) so that a warp's
+// accesses are conflict-free; one thread owns one hypothesis, which keeps all 32 lanes of
+// a warp doing rotations (a warp-per-hypothesis mapping would idle most lanes in the
+// scalar rotation-angle computation and costs ~20x more issue slots per fit).
+// The rank-2 projection avoids a full SVD: F' = F - (F v3) v3^T with v3 the eigenvector of
+// the smallest eigenvalue of F^T F (3x3 Jacobi in registers).
+// ------------------------------------------------------------------------------------
+constexpr int kFitThreads = 64;
+constexpr int kFitSmemDoubles = 162;  // A[81] + V[81] per thread
+
+__device__ __forceinline__ void hartley(const double (&x)[8], const double (&y)[8], double (&nx)[8],
+                                        double (&ny)[8], double& scale, double& cx, double& cy) {
+    // np.mean(coords, axis=0): rows added in order (eight_point.py:320)
+    double sx = x[0], sy = y[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+        sx = __dadd_rn(sx, x[i]);
+        sy = __dadd_rn(sy, y[i]);
+    }
+    cx = sx / 8.0;
+    cy = sy / 8.0;
+    double nrm[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        nx[i] = __dsub_rn(x[i], cx);
+        ny[i] = __dsub_rn(y[i], cy);
+        nrm[i] = sqrt(__dadd_rn(__dmul_rn(nx[i], nx[i]), __dmul_rn(ny[i], ny[i])));  // :323
+    }
+    // np.mean over 8 contiguous values: numpy's pairwise tree (eight_point.py:324)
+    const double s = __dadd_rn(__dadd_rn(__dadd_rn(nrm[0], nrm[1]), __dadd_rn(nrm[2], nrm[3])),
+                               __dadd_rn(__dadd_rn(nrm[4], nrm[5]), __dadd_rn(nrm[6], nrm[7])));
+    scale = sqrt(2.0) / (s / 8.0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        nx[i] = __dmul_rn(nx[i], scale);
+        ny[i] = __dmul_rn(ny[i], scale);
+    }
+}
+
+// Fit one hypothesis from 8 correspondences.  sm points at this thread's column of the
+// element-major shared scratch (stride = kFitThreads doubles).  Returns validity.
+__device__ inline bool eight_point_fit(const Corr (&c)[8], double* sm, double (&E)[9],
+                                       double* eig_out /* 9 or nullptr */) {
+    constexpr int S = kFitThreads;
+#define A_(i, j) sm[((i) * 9 + (j)) * S]
+#define V_(i, j) sm[(81 + (i) * 9 + (j)) * S]
+    double s1, c1x, c1y, s2, c2x, c2y;
+    {
+        double xa[8], ya[8], xb[8], yb[8], nxa[8], nya[8], nxb[8], nyb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            xa[i] = c[i].xa; ya[i] = c[i].ya; xb[i] = c[i].xb; yb[i] = c[i].yb;
+        }
+        hartley(xa, ya, nxa, nya, s1, c1x, c1y);
+        hartley(xb, yb, nxb, nyb, s2, c2x, c2y);
+        // Y^T Y = sum_k y_k y_k^T, products rounded then accumulated in point order (:363-375)
+        for (int i = 0; i < 9; ++i)
+            for (int j = i; j < 9; ++j) A_(i, j) = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            double y[9];
+            y[0] = __dmul_rn(nxb[k], nxa[k]); y[1] = __dmul_rn(nxb[k], nya[k]); y[2] = nxb[k];
+            y[3] = __dmul_rn(nyb[k], nxa[k]); y[4] = __dmul_rn(nyb[k], nya[k]); y[5] = nyb[k];
+            y[6] = nxa[k]; y[7] = nya[k]; y[8] = 1.0;
+#pragma unroll
+            for (int i = 0; i < 9; ++i)
+#pragma unroll
+                for (int j = i; j < 9; ++j) A_(i, j) = __dadd_rn(A_(i, j), __dmul_rn(y[i], y[j]));
+        }
+    }
+    for (int i = 0; i < 9; ++i)
+        for (int j = 0; j < 9; ++j) V_(i, j) = (i == j) ? 1.0 : 0.0;
+
+    // cyclic Jacobi on the upper triangle
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < 9; ++i) {
+            diag += fabs(A_(i, i));
+            for (int j = i + 1; j < 9; ++j) off += fabs(A_(i, j));
+        }
+        if (off <= 1e-300 || off <= 1e-24 * diag) break;
+        for (int p = 0; p < 8; ++p) {
+            for (int q = p + 1; q < 9; ++q) {
+                const double apq = A_(p, q);
+                if (apq == 0.0) continue;
+                const double app = A_(p, p), aqq = A_(q, q);
+                const double g = 1e3 * fabs(apq);
+                if (fabs(app) + g == fabs(app) && fabs(aqq) + g == fabs(aqq)) {
+                    A_(p, q) = 0.0;
+                    continue;
+                }
+                double cs, sn, t;
+                sym_schur(app, aqq, apq, cs, sn, t);
+                A_(p, p) = fma(-t, apq, app);
+                A_(q, q) = fma(t, apq, aqq);
+                A_(p, q) = 0.0;
+                for (int k = 0; k < p; ++k) {
+                    const double x = A_(k, p), y = A_(k, q);
+                    A_(k, p) = fma(cs, x, -sn * y);
+                    A_(k, q) = fma(sn, x, cs * y);
+                }
+                for (int k = p + 1; k < q; ++k) {
+                    const double x = A_(p, k), y = A_(k, q);
+                    A_(p, k) = fma(cs, x, -sn * y);
+                    A_(k, q) = fma(sn, x, cs * y);
+                }
+                for (int k = q + 1; k < 9; ++k) {
+                    const double x = A_(p, k), y = A_(q, k);
+                    A_(p, k) = fma(cs, x, -sn * y);
+                    A_(q, k) = fma(sn, x, cs * y);
+                }
+                for (int k = 0; k < 9; ++k) {
+                    const double x = V_(k, p), y = V_(k, q);
+                    V_(k, p) = fma(cs, x, -sn * y);
+                    V_(k, q) = fma(sn, x, cs * y);
+                }
+            }
+        }
+    }
+    // validity (:414-421): after sorting, every eigenvalue but the smallest must exceed 1e-10
+    int nsmall = 0, imin = 0;
+    double wmin = fabs(A_(0, 0));
+    for (int i = 0; i < 9; ++i) {
+        const double w = A_(i, i);
+        if (eig_out) eig_out[i] = w;
+        nsmall += (w <= kVerySmall) ? 1 : 0;
+        if (fabs(w) < wmin) { wmin = fabs(w); imin = i; }  // np.argmin(np.abs(w)) (:423)
+    }
+    const bool valid = nsmall <= 1;
+    double F[9];
+    for (int i = 0; i < 9; ++i) F[i] = V_(i, imin);  // v_min.reshape((3,3)) (:424-425)
+#undef A_
+#undef V_
+    // rank-2 projection (:430-446)
+    double M[9], W[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            M[i * 3 + j] = fma(F[6 + i], F[6 + j], fma(F[3 + i], F[3 + j], F[i] * F[j]));
+    jacobi_eig_reg<3>(M, W, 20);
+    int k3 = 0;
+    if (M[4] < M[k3 * 4]) k3 = 1;
+    if (M[8] < M[k3 * 4]) k3 = 2;
+    double v3[3] = {k3 == 0 ? W[0] : (k3 == 1 ? W[1] : W[2]), k3 == 0 ? W[3] : (k3 == 1 ? W[4] : W[5]),
+                    k3 == 0 ? W[6] : (k3 == 1 ? W[7] : W[8])};
+    {
+        const double inv = rsqrt(fma(v3[2], v3[2], fma(v3[1], v3[1], v3[0] * v3[0])));
+        v3[0] *= inv; v3[1] *= inv; v3[2] *= inv;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double fv = fma(F[i * 3 + 2], v3[2], fma(F[i * 3 + 1], v3[1], F[i * 3] * v3[0]));
+#pragma unroll
+        for (int j = 0; j < 3; ++j) F[i * 3 + j] = fma(-fv, v3[j], F[i * 3 + j]);
+    }
+    // E = T2^T F T1 (:163), T = [[s,0,-s cx],[0,s,-s cy],[0,0,1]] (:329-336)
+    const double T1[9] = {s1, 0.0, -s1 * c1x, 0.0, s1, -s1 * c1y, 0.0, 0.0, 1.0};
+    const double T2t[9] = {s2, 0.0, 0.0, 0.0, s2, 0.0, -s2 * c2x, -s2 * c2y, 1.0};
+    double tmp[9];
+    mat3_mul(T2t, F, tmp);
+    mat3_mul(tmp, T1, E);
+    const double e22 = E[8];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) E[i] = E[i] / e22;  // (:166)
+    return valid;
+}
+
+__global__ void __launch_bounds__(kFitThreads)
+k_fit(const Corr* __restrict__ pts, const long long* __restrict__ offsets,
+      const int32_t* __restrict__ table, long long h, double* __restrict__ E_out,
+      uint8_t* __restrict__ valid_out, double* __restrict__ eig_out) {
+    extern __shared__ double fit_smem[];
+    const long long li = blockIdx.x * (long long)kFitThreads + threadIdx.x;
+    if (li >= h) return;
+    const long long i = (long long)blockIdx.y * h + li;  // blockIdx.y = image pair
+    bool enough = true;
+    if (offsets) {
+        enough = offsets[blockIdx.y + 1] - offsets[blockIdx.y] >= 8;
+        pts += offsets[blockIdx.y];
+    }
+    if (!enough) {
+        for (int k = 0; k < 9; ++k) E_out[9 * i + k] = 0.0;
+        valid_out[i] = 0;
+        return;
+    }
+    Corr c[8];
+    const int4 t0 = reinterpret_cast<const int4*>(table + 8 * i)[0];
+    const int4 t1 = reinterpret_cast<const int4*>(table + 8 * i)[1];
+    const int idx[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) c[k] = pts[idx[k]];
+    double E[9], eig[9];
+    const bool valid = eight_point_fit(c, fit_smem + threadIdx.x, E, eig_out ? eig : nullptr);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) E_out[9 * i + k] = valid ? E[k] : 0.0;
+    valid_out[i] = valid ? 1 : 0;
+    if (eig_out)
+        for (int k = 0; k < 9; ++k) eig_out[9 * i + k] = eig[k];
+}
+
+}  // namespace sfm

@@ -1,0 +1,297 @@
+"""Array-native entry points of the two-view hot path (numpy in, numpy out).
+
+These are the twins of the reference's list-of-dataclass callables:
+marshalling 10^5..10^6 ``Feature`` objects costs more than the GPU work, so the
+list-based mirrors in ``ransac/`` and ``epipolar/`` convert once and call these.
+Everything numeric happens in libsfm_b200.so (CUDA, sm_100a); there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import dataclasses
+import random
+from math import inf
+from typing import Optional
+
+import numpy as np
+
+from . import _native
+from .errors import EIGHT_POINT_ERROR_MESSAGE, EightPointCalculationError
+from .ransac.ransac import ErrorAggregationMethod
+
+
+@dataclasses.dataclass
+class RansacResult:
+    E: np.ndarray                 # (3,3), E[2,2] == 1
+    best_index: int               # winning iteration (global hypothesis index)
+    error: float                  # aggregated error of the winner
+    count_extra: int              # inliers beyond the 8 samples
+    inlier_indices: np.ndarray    # int64; reference order (samples, then permuted rest) with the
+                                  # reference sampler, else samples then ascending
+    mask: np.ndarray              # bool[n]: sed <= threshold under the winner
+    sed: np.ndarray               # float64[n]
+    sample: np.ndarray            # int32[8] the winner's minimal sample
+    num_invalid: int
+    first_invalid: int
+
+
+def _agg_name(method) -> str:
+    if method is None:
+        return "rms"  # ransac.py:50-51
+    return method.value if isinstance(method, ErrorAggregationMethod) else str(method)
+
+
+def _get_state_words():
+    version, words, gauss = random.getstate()
+    return version, np.array(words, dtype=np.uint32), gauss
+
+
+def _set_state_words(version, words, gauss):
+    random.setstate((version, tuple(int(w) for w in words), gauss))
+
+
+def ransac_essential_arrays(
+    camera_matrix,
+    pts_a,
+    pts_b,
+    threshold: float,
+    min_num_extra_inliers=None,
+    error_aggregation_method=None,
+    max_iterations: Optional[int] = None,
+    *,
+    sampler: str = "reference",
+    seed: int = 0,
+    hyp_offset: int = 0,
+    on_degenerate: str = "raise",
+    selection: str = "min_error",
+    engine: Optional[_native.Engine] = None,
+    table: Optional[np.ndarray] = None,
+) -> RansacResult:
+    """estimate_essential_mat_with_ransac (lib/epipolar/epipolar_ransac.py:45-70) on arrays.
+
+    pts_a, pts_b: [n,2] matched pixel coordinates (row i of each is one correspondence).
+    sampler: "reference" — CPython random.shuffle semantics on the process-global state
+             (lib/ransac/ransac.py:62), the state advances exactly as in the reference;
+             "device" — Philox sampler on the GPU (seed), for sizes where the reference's
+             O(N) shuffle per iteration is infeasible; "table" — use the given table.
+    """
+    if max_iterations is None:
+        max_iterations = 100  # ransac.py:48-49
+    if min_num_extra_inliers is None:
+        min_num_extra_inliers = 0  # ransac.py:52-53
+    agg = _agg_name(error_aggregation_method)
+    eng = engine or _native.get_engine()
+    pts_a = np.ascontiguousarray(pts_a, dtype=np.float64).reshape(-1, 2)
+    pts_b = np.ascontiguousarray(pts_b, dtype=np.float64).reshape(-1, 2)
+    n = pts_a.shape[0]
+    H = int(max_iterations)
+
+    def no_model():
+        return ValueError(f"No model could be found with at least {min_num_extra_inliers + 8} inliers.")
+
+    if H <= 0:
+        raise no_model()  # ransac.py:88-91 (loop never ran)
+    if n < 8:
+        if sampler == "reference":
+            random.shuffle(list(range(n)))  # the reference shuffles once before the fitter raises
+        raise ValueError("Eight feature pairs are expected.")  # epipolar_ransac.py:31-32
+
+    state0 = None
+    if sampler == "reference":
+        version, words, gauss = _get_state_words()
+        state0 = words.copy()
+        table, _ = _native.mt_shuffle_table(words, n, H)
+    elif sampler == "table":
+        table = np.ascontiguousarray(table, dtype=np.int32).reshape(-1, 8)
+        H = table.shape[0]
+
+    eng.upload_pairs(pts_a, pts_b, camera_matrix)
+    if sampler == "device":
+        eng.sample_device(seed, H, hyp_offset=hyp_offset)
+    else:
+        eng.set_table(table)
+    best, mask, sed = eng.ransac_essential(threshold, float(min_num_extra_inliers), agg, selection)
+
+    if sampler == "reference":
+        if best.num_invalid > 0 and on_degenerate == "raise":
+            # the reference aborts inside iteration first_invalid: only that many shuffles happened
+            w = state0.copy()
+            _native.mt_shuffle_table(w, n, int(best.first_invalid) + 1)
+            _set_state_words(version, w, gauss)
+        else:
+            _set_state_words(version, words, gauss)
+    if best.num_invalid > 0 and on_degenerate == "raise":
+        raise EightPointCalculationError(EIGHT_POINT_ERROR_MESSAGE)  # eight_point.py:417-421
+    if best.index < 0:
+        raise no_model()
+
+    mask = mask.astype(bool)
+    local = int(best.index)
+    sample = eng.get_table()[local] if sampler == "device" else table[local]
+    is_sample = np.zeros(n, dtype=bool)
+    is_sample[sample] = True
+    if sampler == "reference":
+        # inliers in the reference's order: samples, then the rest of that iteration's permutation
+        w = state0.copy()
+        _, perm = _native.mt_shuffle_table(w, n, int(best.index) + 1, perm_at=int(best.index))
+        rest = perm[8:].astype(np.int64)
+        extra = rest[mask[rest]]
+    else:
+        extra = np.nonzero(mask & ~is_sample)[0]
+    inliers = np.concatenate([np.asarray(sample, dtype=np.int64), extra])
+    return RansacResult(
+        E=np.array(best.E, dtype=np.float64).reshape(3, 3),
+        best_index=int(best.index) + (hyp_offset if sampler == "device" else 0),
+        error=float(best.err),
+        count_extra=int(best.count_extra),
+        inlier_indices=inliers,
+        mask=mask,
+        sed=sed,
+        sample=np.asarray(sample, dtype=np.int32),
+        num_invalid=int(best.num_invalid),
+        first_invalid=int(best.first_invalid),
+    )
+
+
+def eight_point_arrays(pts_a, pts_b, camera_matrix=None, engine=None) -> np.ndarray:
+    """estimate_essential_mat / estimate_fundamental_mat on 8 gathered pairs ([8,2] arrays).
+
+    lib/epipolar/eight_point.py:99-170; camera_matrix None = fundamental matrix (pixel coords).
+    """
+    pts_a = np.ascontiguousarray(pts_a, dtype=np.float64).reshape(-1, 2)
+    pts_b = np.ascontiguousarray(pts_b, dtype=np.float64).reshape(-1, 2)
+    if pts_a.shape[0] != 8 or pts_b.shape[0] != 8:
+        raise ValueError("Exactly eight matches are needed")  # eight_point.py:151-152
+    eng = engine or _native.get_engine()
+    K = np.eye(3) if camera_matrix is None else camera_matrix
+    eng.upload_pairs(pts_a, pts_b, K)
+    eng.set_table(np.arange(8, dtype=np.int32).reshape(1, 8))
+    E, valid, _ = eng.fit()
+    if not valid[0]:
+        raise EightPointCalculationError(EIGHT_POINT_ERROR_MESSAGE)
+    return E[0]
+
+
+def sed_arrays(e, norm_a, norm_b, engine=None) -> np.ndarray:
+    """calculate_symmetric_epipolar_distance (lib/epipolar/sed.py:7-30) for [n,2] arrays of
+    K-normalised coordinates and one E."""
+    eng = engine or _native.get_engine()
+    na = np.ascontiguousarray(norm_a, dtype=np.float64).reshape(-1, 2)
+    nb = np.ascontiguousarray(norm_b, dtype=np.float64).reshape(-1, 2)
+    eng.upload_pairs(na, nb, np.eye(3))
+    eng.set_models(np.asarray(e, dtype=np.float64).reshape(1, 9))
+    eng.set_winner(0)
+    _, sed = eng.inlier_mask(inf)
+    return sed
+
+
+@dataclasses.dataclass
+class PoseResult:
+    R: np.ndarray
+    t: np.ndarray
+    passing_indices: np.ndarray  # int64 indices of correspondences passing the chosen pose
+    counts: np.ndarray           # votes per candidate (with the reference's index-0 quirk)
+    candidates: list             # [(R, t)] * 4 in the reference's enumeration order
+    singular_values: np.ndarray
+
+
+def _check_decomposition(p):
+    # lib/epipolar/eight_point.py:268-271 — np.isclose(0.0, s[-1]) with default tolerances
+    if not np.isclose(0.0, p.sv[2]):
+        raise EightPointCalculationError(
+            "The smallest singular value of the Essential matrix is expected to be ~0")
+
+
+def recover_all_r_t_arrays(e, engine=None):
+    """_recover_all_r_t (lib/epipolar/eight_point.py:245-280) -> (R1, R2, t1)."""
+    eng = engine or _native.get_engine()
+    p = eng.decompose_essential(e)
+    _check_decomposition(p)
+    R = np.array(p.R, dtype=np.float64).reshape(4, 3, 3)
+    t = np.array(p.t, dtype=np.float64).reshape(4, 3)
+    return R[0], R[2], t[0]
+
+
+def recover_pose_arrays(e, norm_a, norm_b, distance_threshold=None, engine=None) -> PoseResult:
+    """_recover_r_t (lib/epipolar/eight_point.py:181-242) on [m,2] K-normalised arrays."""
+    if distance_threshold is None:
+        distance_threshold = 50.0  # eight_point.py:469-470
+    eng = engine or _native.get_engine()
+    na = np.ascontiguousarray(norm_a, dtype=np.float64).reshape(-1, 2)
+    nb = np.ascontiguousarray(norm_b, dtype=np.float64).reshape(-1, 2)
+    p, pass4 = eng.recover_pose(e, na, nb, distance_threshold)
+    _check_decomposition(p)
+    counts = np.array(p.counts, dtype=np.int64)
+    if 0 == np.count_nonzero(counts):
+        raise EightPointCalculationError("None of the transformations pass the cheirality check.")
+    R = np.array(p.R, dtype=np.float64).reshape(4, 3, 3)
+    t = np.array(p.t, dtype=np.float64).reshape(4, 3)
+    b = int(p.best)
+    idx = np.nonzero((pass4 >> b) & 1)[0].astype(np.int64)
+    return PoseResult(R=R[b].copy(), t=t[b].copy(), passing_indices=idx, counts=counts,
+                      candidates=[(R[i], t[i]) for i in range(4)], singular_values=np.array(p.sv))
+
+
+def k_normalise_arrays(pts, camera_matrix):
+    """to_normalized_image_coords (lib/epipolar/eight_point.py:127-133) for an [n,2] array.
+
+    Host arithmetic on purpose: two IEEE operations per coordinate, used only to prepare the
+    arguments of the list-based pose API; the RANSAC path normalises on the device (K0).
+    """
+    K = np.asarray(camera_matrix, dtype=np.float64)
+    pts = np.asarray(pts, dtype=np.float64).reshape(-1, 2)
+    out = np.empty_like(pts)
+    out[:, 0] = (pts[:, 0] - K[0][2]) / K[0][0]
+    out[:, 1] = (pts[:, 1] - K[1][2]) / K[1][1]
+    return out
+
+
+def triangulate_arrays(pts_a, pts_b, P1, P2, engine=None) -> np.ndarray:
+    """triangulate_point_correspondence over arrays (lib/epipolar/triangulation.py:9-39)."""
+    eng = engine or _native.get_engine()
+    return eng.triangulate(P1, P2, pts_a, pts_b)
+
+
+def camera_matrices(intrinsic_camera_matrix, cam2_T_cam1_Tmat):
+    """P1 = K[I|0], P2 = K[R|t] as lib/epipolar/triangulation.py:52-56 builds them."""
+    K = np.asarray(intrinsic_camera_matrix, dtype=np.float64)
+    if (3, 3) != K.shape:
+        raise ValueError(f"Camera intrinsic matrix is not 3x3, actual shape: {K.shape}")
+    K_ext = np.hstack((K, np.zeros((3, 1))))
+    P1 = K_ext @ np.eye(4)
+    P2 = K_ext @ (np.asarray(cam2_T_cam1_Tmat, dtype=np.float64) @ np.eye(4))
+    return P1, P2
+
+
+@dataclasses.dataclass
+class TwoViewResult:
+    ransac: RansacResult
+    R: np.ndarray
+    t: np.ndarray
+    inlier_indices: np.ndarray   # ascending indices of the winner's inliers (samples included)
+    passing: np.ndarray          # bool per inlier: passed the cheirality vote
+    points: np.ndarray           # [m,3] triangulated points (NaN where not passing)
+    counts: np.ndarray
+
+
+def two_view_arrays(camera_matrix, pts_a, pts_b, threshold, min_num_extra_inliers=None,
+                    error_aggregation_method=None, max_iterations=None, distance_threshold=None,
+                    **kw) -> TwoViewResult:
+    """The whole hot path of apps/sfm.py:110-186 in one call: RANSAC E -> cheirality vote ->
+    triangulation of the passing inliers.  Correspondences are uploaded once; only results
+    come back."""
+    if distance_threshold is None:
+        distance_threshold = 50.0
+    eng = kw.get("engine") or _native.get_engine()
+    kw["engine"] = eng
+    res = ransac_essential_arrays(camera_matrix, pts_a, pts_b, threshold, min_num_extra_inliers,
+                                  error_aggregation_method, max_iterations, **kw)
+    p, num, idx, ok, X = eng.pose_and_triangulate(threshold, distance_threshold)
+    _check_decomposition(p)
+    counts = np.array(p.counts, dtype=np.int64)
+    if 0 == np.count_nonzero(counts):
+        raise EightPointCalculationError("None of the transformations pass the cheirality check.")
+    b = int(p.best)
+    R = np.array(p.R, dtype=np.float64).reshape(4, 3, 3)[b].copy()
+    t = np.array(p.t, dtype=np.float64).reshape(4, 3)[b].copy()
+    return TwoViewResult(ransac=res, R=R, t=t, inlier_indices=idx, passing=((ok >> b) & 1).astype(bool),
+                         points=X, counts=counts)

@@ -1,0 +1,259 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star):
+  * inlier masks bit-identical except for correspondences within 1e-9 relative of the threshold
+  * best E within 1e-6 (up to scale and sign)
+  * triangulated points within 1e-6 relative
+All fp64.  The scorer is additionally required to be *bit-exact* against oracle/sed_exact.c
+(which is bit-exact against the reference's numpy evaluation, tests/test_oracle.py).
+"""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import csed
+from oracle import restatement as o
+from structure_from_motion_b200 import two_view
+from structure_from_motion_b200.scenes import make_scene
+
+pytestmark = pytest.mark.gpu
+
+THR = 1.5e-6  # apps/config/config.yaml:7
+BAND = 1e-9
+
+
+def _norm(K, x1, x2):
+    nxa, nya = o.k_normalise(x1[:, 0], x1[:, 1], K)
+    nxb, nyb = o.k_normalise(x2[:, 0], x2[:, 1], K)
+    return nxa, nya, nxb, nyb
+
+
+def _e_close(a, b, tol=1e-6):
+    a = a.reshape(-1) / np.linalg.norm(a)
+    b = b.reshape(-1) / np.linalg.norm(b)
+    return min(np.abs(a - b).max(), np.abs(a + b).max()) <= tol
+
+
+def test_k_normalise_bit_exact(engine):
+    K, x1, x2, *_ = make_scene(1000, 0.3, seed=11)
+    engine.upload_pairs(x1, x2, K)
+    got = engine.get_normalised()
+    nxa, nya, nxb, nyb = _norm(K, x1, x2)
+    assert np.array_equal(got, np.stack([nxa, nya, nxb, nyb], axis=1))
+
+
+def test_sampler_table_roundtrip(engine):
+    K, x1, x2, *_ = make_scene(500, 0.3, seed=0)
+    engine.upload_pairs(x1, x2, K)
+    engine.sample_device(seed=7, h=4096)
+    t = engine.get_table()
+    assert t.shape == (4096, 8) and t.min() >= 0 and t.max() < 500
+    assert all(len(set(row)) == 8 for row in t.tolist())
+    # same (seed, global index) => same rows, however the hypotheses are sharded
+    engine.sample_device(seed=7, h=1024, hyp_offset=2048)
+    assert np.array_equal(engine.get_table(), t[2048:3072])
+    # roughly uniform
+    counts = np.bincount(t.reshape(-1), minlength=500)
+    assert counts.min() > 20 and counts.max() < 130
+
+
+@pytest.mark.parametrize("variant,hpt", [("screen", 2), ("screen", 1), ("full", 2), ("full", 1)])
+def test_scorer_bit_exact_against_oracle(engine, variant, hpt):
+    """K2+K3 with oracle-supplied E's: counts equal, sums within 1e-12 (different summation order)."""
+    n, h = 3000, 700
+    K, x1, x2, *_ = make_scene(n, 0.4, seed=2)
+    nxa, nya, nxb, nyb = _norm(K, x1, x2)
+    rng = np.random.default_rng(5)
+    table = np.stack([rng.choice(n, 8, replace=False) for _ in range(h)]).astype(np.int32)
+    ca, cb = np.stack([nxa, nya], 1), np.stack([nxb, nyb], 1)
+    E = np.stack([o.eight_point(ca[s], cb[s]) for s in table])
+    cnt_o, s1_o, s2_o = csed.score_batch(E, nxa, nya, nxb, nyb, THR, table=table, nthreads=8)
+
+    engine.set_score_variant(variant, hpt)
+    try:
+        engine.upload_pairs(x1, x2, K)
+        engine.set_table(table)
+        engine.set_models(E)
+        cnt, s1, s2, err = engine.score(THR, min_extra=10, aggregation="rms")
+    finally:
+        engine.set_score_variant("screen", 2)
+    assert np.array_equal(cnt, cnt_o)
+    np.testing.assert_allclose(s1, s1_o, rtol=1e-12, atol=0)
+    np.testing.assert_allclose(s2, s2_o, rtol=1e-12, atol=0)
+    n_tot = 8 + cnt_o
+    err_o = np.where(cnt_o >= 10, np.sqrt(s2_o / n_tot), np.inf)
+    np.testing.assert_allclose(err, err_o, rtol=1e-12)
+    best = engine.get_best()
+    assert best.index == int(np.argmin(err_o))
+    # K4: mask + SED values of the winner are bit-identical to the exact oracle scorer
+    mask, sed = engine.inlier_mask(THR)
+    sed_o = csed.sed_exact_many(E[best.index], nxa, nya, nxb, nyb)
+    assert np.array_equal(sed, sed_o)
+    assert np.array_equal(mask, sed_o <= THR)
+
+
+@pytest.mark.parametrize("agg", ["sum", "square", "mean", "rms"])
+def test_aggregation_methods(engine, agg):
+    n, h = 800, 300
+    K, x1, x2, *_ = make_scene(n, 0.3, seed=4)
+    nxa, nya, nxb, nyb = _norm(K, x1, x2)
+    rng = np.random.default_rng(1)
+    table = np.stack([rng.choice(n, 8, replace=False) for _ in range(h)]).astype(np.int32)
+    engine.upload_pairs(x1, x2, K)
+    engine.set_table(table)
+    E, valid, _ = engine.fit()
+    assert valid.all()
+    cnt, s1, s2, err = engine.score(THR, min_extra=5.5, aggregation=agg)
+    cnt_o, s1_o, s2_o = csed.score_batch(E, nxa, nya, nxb, nyb, THR, table=table, nthreads=4)
+    assert np.array_equal(cnt, cnt_o)
+    ntot = 8 + cnt_o
+    exp = {"sum": s1_o, "square": s2_o, "mean": s1_o / ntot, "rms": np.sqrt(s2_o / ntot)}[agg]
+    exp = np.where(cnt_o >= 5.5, exp, np.inf)  # fractional min_num_extra_inliers (test_ransac.py:109)
+    np.testing.assert_allclose(err, exp, rtol=1e-12)
+
+
+def test_fitter_against_oracle(engine):
+    """K1 per hypothesis vs the reference's eig/svd route; tolerance scaled by conditioning."""
+    n, h = 5000, 2000
+    K, x1, x2, *_ = make_scene(n, 0.4, seed=9)
+    nxa, nya, nxb, nyb = _norm(K, x1, x2)
+    rng = np.random.default_rng(3)
+    table = np.stack([rng.choice(n, 8, replace=False) for _ in range(h)]).astype(np.int32)
+    engine.upload_pairs(x1, x2, K)
+    engine.set_table(table)
+    E, valid, eig = engine.fit(want_eig=True)
+    assert valid.all()
+    ca, cb = np.stack([nxa, nya], 1), np.stack([nxb, nyb], 1)
+    worst = 0.0
+    for i in range(h):
+        s = table[i]
+        e_o = o.eight_point(ca[s], cb[s])
+        w_o = o.eight_point_eigenvalues(ca[s], cb[s])
+        w = np.sort(eig[i])
+        np.testing.assert_allclose(w[1:], w_o[1:], rtol=1e-9, atol=1e-13)
+        d = np.linalg.norm(E[i] - e_o) / np.linalg.norm(e_o)
+        # both solvers are accurate to ~eps * lambda_max / lambda_2 in the null vector
+        tol = 2e-14 * w_o[-1] / w_o[1] + 1e-12
+        worst = max(worst, d / tol)
+        assert d <= tol, (i, d, tol, w_o[:3])
+        assert E[i][2, 2] == 1.0
+
+
+def test_degenerate_sample_is_flagged(engine):
+    """Two coplanar rectangles (tests/golden degenerate fixture analogue): valid == 0."""
+    # 8 points on a plane seen by two cameras: the 9x9 system has a 2-dimensional null space
+    rng = np.random.default_rng(0)
+    X = np.column_stack([rng.uniform(-1, 1, 8), rng.uniform(-1, 1, 8), np.full(8, 5.0)])
+    K = np.array([[500.0, 0, 320], [0, 500.0, 240], [0, 0, 1]])
+    R = np.eye(3)
+    t = np.array([-0.5, 0.0, 0.0])
+    x1 = (K @ X.T).T
+    x1 = x1[:, :2] / x1[:, 2:]
+    X2 = X @ R.T + t
+    x2 = (K @ X2.T).T
+    x2 = x2[:, :2] / x2[:, 2:]
+    with pytest.raises(two_view.EightPointCalculationError):
+        two_view.eight_point_arrays(x1, x2, K, engine=engine)
+
+
+@pytest.mark.parametrize("n,h,frac,seed", [(500, 200, 0.3, 0), (2000, 500, 0.4, 1)])
+def test_ransac_end_to_end_reference_sampler(engine, n, h, frac, seed):
+    K, x1, x2, *_ = make_scene(n, frac, seed=seed)
+    random.seed(5)
+    ref = o.ransac_essential(K, x1[:, 0], x1[:, 1], x2[:, 0], x2[:, 1], THR, 10, "rms", h, return_all=True)
+    state_after = random.getstate()
+    random.seed(5)
+    res = two_view.ransac_essential_arrays(K, x1, x2, THR, 10, "rms", h, engine=engine)
+    assert random.getstate() == state_after  # the global RNG advanced exactly as in the reference
+    assert res.best_index == ref["best_index"]
+    assert _e_close(res.E, ref["E"])
+    assert abs(res.error - ref["error"]) <= 1e-9 * ref["error"]
+    # inlier list: same order, identical outside the guard band
+    nxa, nya, nxb, nyb = _norm(K, x1, x2)
+    sed_o = csed.sed_exact_many(ref["E"], nxa, nya, nxb, nyb)
+    in_band = np.abs(sed_o - THR) <= BAND * THR
+    a, b = list(res.inlier_indices), list(ref["inlier_indices"])
+    if a != b:
+        diff = set(a) ^ set(b)
+        assert all(in_band[i] for i in diff), diff
+    assert res.inlier_indices[:8].tolist() == ref["inlier_indices"][:8].tolist()
+
+
+def test_selection_tie_and_no_candidate(engine):
+    K, x1, x2, *_ = make_scene(300, 0.3, seed=5)
+    random.seed(1)
+    with pytest.raises(ValueError, match="No model could be found with at least 298 inliers"):
+        two_view.ransac_essential_arrays(K, x1, x2, THR, 290, "rms", 20, engine=engine)
+    # duplicated rows in the table: identical errors, the earliest index must win (ransac.py:83)
+    rng = np.random.default_rng(2)
+    row = rng.choice(300, 8, replace=False).astype(np.int32)
+    table = np.stack([rng.choice(300, 8, replace=False).astype(np.int32) for _ in range(64)])
+    engine.upload_pairs(x1, x2, K)
+    engine.set_table(table)
+    E, valid, _ = engine.fit()
+    cnt, s1, s2, err = engine.score(THR, 0, "rms")
+    w = int(np.argmin(err))
+    table2 = table.copy()
+    table2[w + 3 if w + 3 < 64 else w - 3] = table[w]  # a duplicate of the winner elsewhere
+    dup = w + 3 if w + 3 < 64 else w - 3
+    engine.set_table(table2)
+    engine.fit()
+    cnt2, _, _, err2 = engine.score(THR, 0, "rms")
+    assert err2[dup] == err2[w]
+    assert engine.get_best().index == min(w, dup)
+    # max-inliers selection (non-default)
+    engine.score(THR, 0, "rms", selection="max_inliers")
+    b = engine.get_best()
+    assert b.count_extra == cnt2.max() and b.index == int(np.argmax(cnt2))
+
+
+def test_pose_and_triangulation_against_oracle(engine):
+    n = 600
+    K, x1, x2, R_true, t_true, out_idx = make_scene(n, 0.0, seed=8, noise_px=0.05)
+    nxa, nya, nxb, nyb = _norm(K, x1, x2)
+    s = np.arange(8) * 50
+    e = o.eight_point(np.stack([nxa[s], nya[s]], 1), np.stack([nxb[s], nyb[s]], 1))
+    Rr, tr, idx_o, counts_o = o.recover_r_t(nxa, nya, nxb, nyb, e)
+    res = two_view.recover_pose_arrays(e, np.stack([nxa, nya], 1), np.stack([nxb, nyb], 1), engine=engine)
+    np.testing.assert_allclose(res.R, Rr, atol=1e-9)
+    np.testing.assert_allclose(res.t, tr, atol=1e-9)
+    assert np.array_equal(res.passing_indices, idx_o)
+    assert sorted(res.counts.tolist()) == sorted(int(c) for c in counts_o)
+    # the direction of t and R agree with the ground truth of the scene
+    assert abs(np.dot(res.t, t_true / np.linalg.norm(t_true))) > 0.999
+    np.testing.assert_allclose(res.R, R_true, atol=5e-3)
+    # triangulation in pixel coordinates
+    T = o.tmat(Rr, tr)
+    X_o = o.triangulate_points(x1[:, 0], x1[:, 1], x2[:, 0], x2[:, 1], K, T)
+    P1, P2 = two_view.camera_matrices(K, T)
+    X = two_view.triangulate_arrays(x1, x2, P1, P2, engine=engine)
+    rel = np.linalg.norm(X - X_o, axis=1) / np.linalg.norm(X_o, axis=1)
+    assert rel.max() <= 1e-6, rel.max()
+
+
+def test_two_view_pipeline(engine):
+    K, x1, x2, R_true, t_true, _ = make_scene(3000, 0.4, seed=12)
+    res = two_view.two_view_arrays(K, x1, x2, THR, 10, "rms", 2000, sampler="device", seed=3,
+                                   on_degenerate="skip", engine=engine)
+    r = res.ransac
+    # oracle on the same table
+    nxa, nya, nxb, nyb = _norm(K, x1, x2)
+    table = engine.get_table()
+    ref = o.ransac_essential(K, x1[:, 0], x1[:, 1], x2[:, 0], x2[:, 1], THR, 10, "rms", 2000, table=table,
+                             on_degenerate="skip")
+    assert r.best_index == ref["best_index"]
+    assert _e_close(r.E, ref["E"])
+    inl = np.sort(ref["inlier_indices"])
+    assert np.array_equal(res.inlier_indices, inl)
+    Rr, tr, idx_o, _ = o.recover_r_t(nxa[inl], nya[inl], nxb[inl], nyb[inl], ref["E"])
+    np.testing.assert_allclose(res.R, Rr, atol=1e-6)
+    np.testing.assert_allclose(res.t, tr, atol=1e-6)
+    # fused path: position 0 of the reference's list is the first sample, not the lowest index —
+    # the vote can differ by that one correspondence only
+    assert abs(int(res.passing.sum()) - len(idx_o)) <= 1
+    X_o = o.triangulate_points(x1[inl, 0], x1[inl, 1], x2[inl, 0], x2[inl, 1], K, o.tmat(Rr, tr))
+    ok = res.passing
+    rel = np.linalg.norm(res.points[ok] - X_o[ok], axis=1) / np.linalg.norm(X_o[ok], axis=1)
+    assert rel.max() <= 1e-6
+    assert np.isnan(res.points[~ok]).all()

@@ -1,0 +1,451 @@
+#!/usr/bin/env python
+"""bench.py — the reference's headline metric on B200: fp64 hypothesis x correspondence
+evaluations per second of RANSAC essential-matrix estimation (+ cheirality vote and
+triangulation of the inliers), BASELINE.json configs[2]: 100k correspondences x 64k hypotheses.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload ...]
+
+One "step" = one complete estimate on a synthetic two-view scene (40 % outliers): device
+sampler -> eight-point fit of every hypothesis -> scoring -> selection -> inlier mask of the
+winner -> decomposition + cheirality vote -> triangulation of the passing inliers.
+
+* ``value``     whole-step throughput, correspondences already resident in HBM.
+* ``e2e``       the same estimate through the public Python API (two_view.two_view_arrays) from
+                pinned HOST arrays: H2D of the correspondences and D2H of every result are inside
+                the timed region.
+* ``roofline``  the scoring kernel (k_score) against the FP64 pipe: algorithmic work
+                (35 flop per evaluation) / its CUDA-event duration, against an FP64
+                FMA peak measured on this GPU in this run (MEASURED_PEAKS.json has no fp64 entry).
+* ``cpu_baseline`` the oracle port (numpy eight-point + threaded C scorer) on the host cores, on a
+                bounded sample of the same workload.
+N > 1 (torchrun): hypotheses are sharded — every rank scores its own 64k hypotheses of the same
+pair (weak scaling), winners merged by one 96-byte-per-rank NCCL all-gather.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "hyp x point evals/sec (fp64)"
+UNIT = "evals/s"
+THR, MIN_EXTRA, AGG = 1.5e-6, 10, "rms"  # apps/config/config.yaml:6-9, apps/sfm.py:116
+FLOP_PER_EVAL = 35.0                      # 14 DFMA + 7 DMUL/DADD
+BYTES_PER_CORR = 32.0
+
+WORKLOADS = {
+    # name: (correspondences, hypotheses per GPU, outlier fraction)
+    "config2": (10_000, 16_384, 0.4),
+    "config3": (100_000, 65_536, 0.4),
+    "config5": (1_048_576, 1_048_576, 0.4),  # hypotheses are split over the ranks (strong scaling)
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="config3", choices=list(WORKLOADS) + ["config4"])
+    ap.add_argument("--variant", default=os.environ.get("SFM_SCORE_VARIANT", "screen"), choices=["screen", "full"])
+    ap.add_argument("--hpt", type=int, default=int(os.environ.get("SFM_SCORE_HPT", "2")))
+    ap.add_argument("--pairs", type=int, default=512, help="config4: image pairs per GPU per step")
+    ap.add_argument("--cpu-sample-hyps", type=int, default=2048)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks (nvidia-smi sampled DURING the timed region)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.path = tempfile.mktemp(prefix="sfm_clocks_", suffix=".csv")
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    sm.append(float(f[0]))
+                    mx.append(float(f[1]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU legs (oracle port; the only places bench.py executes oracle/)
+# ----------------------------------------------------------------------------------------------
+def cpu_port_rate(K, x1, x2, hyps: int, seed: int, threads: int):
+    """Evaluations/s of the oracle port on `hyps` hypotheses x all correspondences: numpy
+    eight-point fit per hypothesis (oracle/restatement.py) + threaded exact C scorer
+    (oracle/sed_exact.c) + numpy selection.  Returns (evals_per_s, seconds)."""
+    from oracle import csed
+    from oracle import restatement as o
+
+    n = x1.shape[0]
+    nxa, nya = o.k_normalise(x1[:, 0], x1[:, 1], K)
+    nxb, nyb = o.k_normalise(x2[:, 0], x2[:, 1], K)
+    ca, cb = np.stack([nxa, nya], 1), np.stack([nxb, nyb], 1)
+    rng = np.random.default_rng(seed)
+    csed.lib()
+    t0 = time.perf_counter()
+    table = np.stack([rng.choice(n, 8, replace=False) for _ in range(hyps)]).astype(np.int32)
+    E = np.zeros((hyps, 9))
+    valid = np.ones(hyps, dtype=np.uint8)
+    for i in range(hyps):
+        try:
+            E[i] = o.eight_point(ca[table[i]], cb[table[i]]).reshape(9)
+        except o.OracleEightPointError:
+            valid[i] = 0
+    cnt, s1, s2 = csed.score_batch(E, nxa, nya, nxb, nyb, THR, table=table, valid=valid, nthreads=threads)
+    err = np.where((cnt >= MIN_EXTRA) & (valid > 0), np.sqrt(s2 / (8 + cnt)), np.inf)
+    int(np.argmin(err))
+    dt = time.perf_counter() - t0
+    return hyps * n / dt, dt
+
+
+def run_reference_arm(args):
+    """--impl reference: the CPU implementation of the path on the host cores.  The reference is
+    pure Python (2.5e4 evals/s) and cannot travel to the GPU box; the arm times the
+    oracle port (numpy fit + threaded C scorer), which is ~3 orders of magnitude faster than the
+    reference itself — a generous CPU baseline."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from structure_from_motion_b200.scenes import make_scene
+
+    wl = args.workload if args.workload in WORKLOADS else "config3"
+    n, h, frac = WORKLOADS[wl]
+    threads = os.cpu_count() or 1
+    K, x1, x2, *_ = make_scene(n, frac, seed=0)
+    sample_h = max(64, min(args.cpu_sample_hyps, h) // 4)
+    for w in range(args.warmup):
+        cpu_port_rate(K, x1, x2, max(8, sample_h // 8), seed=100 + w, threads=threads)
+    secs, evals = 0.0, 0.0
+    for s in range(args.steps):
+        rate, dt = cpu_port_rate(K, x1, x2, sample_h, seed=s, threads=threads)
+        secs += dt
+        evals += sample_h * n
+    value = evals / secs
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{wl}: {n} correspondences x {h} hypotheses, 40% outliers (each step a sample of "
+                               f"{sample_h} hypotheses x all correspondences)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample_h} of {h} hypotheses x {n} correspondences per step"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# native arm
+# ----------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from structure_from_motion_b200 import _native, distributed, two_view
+    from structure_from_motion_b200.scenes import make_scene
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the native arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng = _native.get_engine(local_rank)
+    eng.set_score_variant(args.variant, args.hpt)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def flush_l2():
+        flush_buf.zero_()
+
+    if args.workload == "config4":
+        return bench_pairs(args, eng, world, rank, barrier, flush_l2, torch, dist)
+
+    n, h_cfg, frac = WORKLOADS[args.workload]
+    strong = args.workload == "config5"
+    h_rank = h_cfg // world if strong else h_cfg
+    K, x1, x2, *_ = make_scene(n, frac, seed=0)
+    # pinned host copies for the e2e leg
+    pa = _native.pinned_empty((n, 2))
+    pb = _native.pinned_empty((n, 2))
+    pa[...] = x1
+    pb[...] = x2
+
+    eng.upload_pairs(pa, pb, K)  # resident correspondences for the `value` leg
+    fp64_peak_dfma = eng.measure_fp64_peak()
+
+    def step_resident(seed):
+        r = distributed.ransac_essential_sharded(K, None, None, THR, MIN_EXTRA, AGG, h_rank, seed, engine=eng,
+                                                 rank=rank, world=world, resident=True)
+        if r["owner"] < 0:
+            raise RuntimeError("no model found")
+        poses, num, idx, ok, X = eng.pose_and_triangulate(THR, 50.0)
+        return r, num
+
+    def step_e2e(seed):
+        if world == 1:
+            res = two_view.two_view_arrays(K, pa, pb, THR, MIN_EXTRA, AGG, h_rank, sampler="device", seed=seed,
+                                           on_degenerate="skip", engine=eng)
+            return res.points.shape[0]
+        r = distributed.ransac_essential_sharded(K, pa, pb, THR, MIN_EXTRA, AGG, h_rank, seed, engine=eng,
+                                                 rank=rank, world=world, resident=False)
+        mask, sed = eng.inlier_mask(THR)
+        poses, num, idx, ok, X = eng.pose_and_triangulate(THR, 50.0)
+        return num
+
+    # ---- warm-up -------------------------------------------------------------------------------
+    for w in range(max(args.warmup, 3)):
+        step_resident(1000 + w)
+    barrier()
+
+    # ---- timed: resident ---------------------------------------------------------------------
+    eng.enable_timing(True)
+    _, launches0 = eng.get_timing()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    stage_ms = {}
+    num_inl = 0
+    barrier()
+    for s in range(args.steps):
+        flush_l2()
+        ev[s][0].record(stream)
+        _, num_inl = step_resident(s)
+        ev[s][1].record(stream)
+        t, _ = eng.get_timing()
+        for k, v in t.items():
+            stage_ms[k] = stage_ms.get(k, 0.0) + v
+    barrier()
+    clk = clocks.stop()
+    _, launches1 = eng.get_timing()
+    ms_total = sum(a.elapsed_time(b) for a, b in ev)
+    eng.enable_timing(False)
+
+    # ---- timed: end to end through the public API (host buffers) ---------------------------------
+    e2e_ms = None
+    if not args.no_e2e:
+        for w in range(2):
+            step_e2e(2000 + w)
+        barrier()
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for s in range(args.steps):
+            flush_l2()
+            ev2[s][0].record(stream)
+            m = step_e2e(s)
+            ev2[s][1].record(stream)
+        barrier()
+        e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
+
+    # ---- max over ranks ----------------------------------------------------------------------------
+    vals = torch.tensor([ms_total, e2e_ms if e2e_ms is not None else 0.0, stage_ms.get("score", 0.0)],
+                        dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    ms_total, e2e_max, score_ms = (float(v) for v in vals.cpu())
+
+    if rank == 0:
+        evals_per_step = float(n) * h_rank * world
+        value = evals_per_step * args.steps / (ms_total * 1e-3)
+        score_ms_per_launch = score_ms / args.steps
+        kern_evals = float(n) * h_rank / (score_ms_per_launch * 1e-3)
+        fp64_peak_tflops = 2.0 * fp64_peak_dfma / 1e12
+        achieved_tflops = kern_evals * FLOP_PER_EVAL / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "k_score_dram_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(args.workload)
+            except Exception:
+                traffic = None
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        algo_bytes = BYTES_PER_CORR * n * ((h_rank + 255) // 256) + 72.0 * h_rank
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"{args.workload}: {n} correspondences x {h_rank} hypotheses per GPU "
+                            f"({h_rank * world} total), 40% outliers, thr 1.5e-6, RMS, min_extra 10, + cheirality "
+                            f"vote + triangulation of the {num_inl} inliers",
+                "sampler": "device (Philox)", "score_variant": args.variant, "hyps_per_thread": args.hpt,
+                "l2": "flushed (256 MiB memset) between timed steps",
+                "parallelism": f"hypothesis-sharded x{world}, one 96 B/rank all-gather" if world > 1 else "single GPU",
+            },
+            "ms_per_estimate": ms_total / args.steps,
+            "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+            "kernel_evals_per_s": kern_evals,
+            "roofline": {
+                "bound": "fp64", "kernel": "k_score", "achieved": achieved_tflops, "peak": fp64_peak_tflops,
+                "unit": "TFLOP/s", "frac": achieved_tflops / fp64_peak_tflops if fp64_peak_tflops else None,
+                "traffic": traffic,
+                "peak_source": "DFMA microbenchmark in this run (sfm_measure_fp64_peak); MEASURED_PEAKS.json has no fp64 entry",
+                "algorithmic_flop_per_eval": FLOP_PER_EVAL,
+                "executed_fp64_slots_per_eval": 12.0 if args.variant == "screen" else 21.0,
+                "fp64_pipe_busy_frac_est": kern_evals * (12.0 if args.variant == "screen" else 21.0) / fp64_peak_dfma,
+                "hbm_achieved_gbs": algo_bytes / (score_ms_per_launch * 1e-3) / 1e9,
+                "hbm_peak_gbs": peaks.get("hbm_gbs"),
+            },
+            "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"],
+                       "samples": clk["samples"]},
+            "gpu_launches": launches1 - launches0,
+        }
+        if e2e_ms is not None:
+            d2h = 8 + 72 + 48 + n * 1 + n * 8 + num_inl * (8 + 1 + 24) + 392
+            line["e2e"] = {"value": evals_per_step * args.steps / (e2e_max * 1e-3), "unit": UNIT,
+                           "ms_per_step": e2e_max / args.steps,
+                           "h2d_bytes_per_step": int(n * 32 + 72), "d2h_bytes_per_step": int(d2h)}
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            sh = min(args.cpu_sample_hyps, h_rank)
+            rate, dt = cpu_port_rate(K, x1, x2, sh, seed=0, threads=threads)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{sh} of {h_rank} hypotheses x {n} correspondences ({dt:.1f} s)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_pairs(args, eng, world, rank, barrier, flush_l2, torch, dist):
+    """config4: a batch of independent image pairs, sharded by pair, no communication."""
+    from structure_from_motion_b200 import _native
+    from structure_from_motion_b200.scenes import make_scene
+
+    P, n, h = args.pairs, 2000, 2000
+    xs1, xs2, Ks = [], [], []
+    base = make_scene(n, 0.4, seed=0)
+    rng = np.random.default_rng(rank)
+    for p in range(P):  # cheap per-pair variation of one scene (generation is not what is measured)
+        perm = rng.permutation(n)
+        xs1.append(base[1][perm])
+        xs2.append(base[2][perm])
+        Ks.append(base[0])
+    pa = _native.pinned_empty((P * n, 2))
+    pb = _native.pinned_empty((P * n, 2))
+    pa[...] = np.concatenate(xs1)
+    pb[...] = np.concatenate(xs2)
+    offsets = np.arange(P + 1, dtype=np.int64) * n
+    Ks = np.stack(Ks)
+    stream = torch.cuda.current_stream()
+
+    def step(seed):
+        return eng.batch_ransac(pa, pb, offsets, Ks, h, seed, THR, MIN_EXTRA, AGG, pair_id0=rank * P)
+
+    for w in range(max(args.warmup, 3)):
+        step(100 + w)
+    barrier()
+    eng.enable_timing(True)
+    _, l0 = eng.get_timing()
+    clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    stage = {}
+    for s in range(args.steps):
+        flush_l2()
+        ev[s][0].record(stream)
+        out = step(s)
+        ev[s][1].record(stream)
+        t, _ = eng.get_timing()
+        for k, v in t.items():
+            stage[k] = stage.get(k, 0.0) + v
+    barrier()
+    clk = clocks.stop()
+    _, l1 = eng.get_timing()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    vals = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    ms = float(vals.cpu()[0])
+    if rank == 0:
+        evals = float(P) * n * h * world * args.steps
+        found = int((out["best_index"] >= 0).sum())
+        line = {
+            "metric": METRIC, "value": evals / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"config4: {P} image pairs per GPU x {n} correspondences x {h} hypotheses, "
+                                   f"pair-sharded, host buffers (H2D inside the timed region), models found {found}/{P}",
+                       "l2": "flushed between timed steps", "parallelism": f"pair-sharded x{world}, no collective"},
+            "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
+            "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
+            "gpu_launches": l1 - l0,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

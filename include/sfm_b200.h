@@ -75,7 +75,8 @@ int sfm_set_table(sfm_ctx *ctx, const int32_t *table, int64_t h);
  * uniform indices per hypothesis; hyp_offset shifts the global index for hypothesis-sharded
  * runs so that the union over ranks equals the single-GPU table. */
 int sfm_sample_device(sfm_ctx *ctx, uint64_t seed, uint64_t stream, int64_t hyp_offset, int64_t h);
-int sfm_get_table(sfm_ctx *ctx, int32_t *table, int64_t h);
+/* Read back rows [first, first + h) of the current table. */
+int sfm_get_table(sfm_ctx *ctx, int32_t *table, int64_t first, int64_t h);
 
 /* ---- correspondences ---------------------------------------------------------------- */
 /* lib/epipolar/eight_point.py:127-133 (to_normalized_image_coords), applied once on the
@@ -178,8 +179,8 @@ int sfm_batch_ransac(sfm_ctx *ctx, const double *xa, const double *ya, const dou
 /* ---- measurement --------------------------------------------------------------------- */
 /* Per-stage device times (CUDA events on the context's stream) of the most recent
  * pipeline call: ms[0]=upload+normalise ms[1]=sample ms[2]=fit ms[3]=score ms[4]=finalise+select
- * ms[5]=mask ms[6]=pose ms[7]=triangulate.  launches = kernels launched by this library since
- * the context was created. */
+ * ms[5]=mask ms[6]=pose ms[7]=triangulate (a stage is reported once, then reads 0 until it runs
+ * again).  launches = kernels launched by this library since the context was created. */
 int sfm_enable_timing(sfm_ctx *ctx, int on);
 int sfm_get_timing(sfm_ctx *ctx, float ms[8], int64_t *launches);
 /* FP64 FMA throughput microbenchmark (denominator of the FP64 roofline): returns achieved

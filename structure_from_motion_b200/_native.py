@@ -53,7 +53,7 @@ _SIGNATURES = {
     "sfm_mt_shuffle_table": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int64, _P]),
     "sfm_set_table": (C.c_int, [_P, _P, C.c_int64]),
     "sfm_sample_device": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64]),
-    "sfm_get_table": (C.c_int, [_P, _P, C.c_int64]),
+    "sfm_get_table": (C.c_int, [_P, _P, C.c_int64, C.c_int64]),
     "sfm_upload_pairs": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P]),
     "sfm_upload_pairs_d": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P]),
     "sfm_get_normalised": (C.c_int, [_P, _P, C.c_int64]),
@@ -206,10 +206,10 @@ class Engine:
                  "sfm_sample_device")
         self.h_count = int(h)
 
-    def get_table(self, h=None):
-        h = self.h_count if h is None else h
+    def get_table(self, h=None, first=0):
+        h = self.h_count - first if h is None else h
         out = np.empty((h, 8), dtype=np.int32)
-        self._ck(self.lib.sfm_get_table(self.h, _ptr(out), h), "sfm_get_table")
+        self._ck(self.lib.sfm_get_table(self.h, _ptr(out), int(first), int(h)), "sfm_get_table")
         return out
 
     # -- fit / score ----------------------------------------------------------------------

@@ -326,10 +326,11 @@ int sfm_sample_device(sfm_ctx* c, uint64_t seed, uint64_t stream, int64_t hyp_of
     return sample_device(c, seed, stream, hyp_offset, h);
 }
 
-int sfm_get_table(sfm_ctx* c, int32_t* table, int64_t h) {
+int sfm_get_table(sfm_ctx* c, int32_t* table, int64_t first, int64_t h) {
     if (int r = use(c)) return r;
-    if (!c->has_table || h > c->h * c->npairs) return fail(SFM_ERR_STATE, "no table of that size");
-    CU(cudaMemcpyAsync(table, c->table.p, (size_t)h * 32, cudaMemcpyDeviceToHost, c->stream));
+    if (!c->has_table || first < 0 || h < 0 || first + h > c->h * c->npairs)
+        return fail(SFM_ERR_STATE, "no table rows [%lld, %lld)", (long long)first, (long long)(first + h));
+    CU(cudaMemcpyAsync(table, c->table.as<int32_t>() + 8 * first, (size_t)h * 32, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -918,6 +919,7 @@ int sfm_get_timing(sfm_ctx* c, float ms[8], int64_t* launches) {
     for (int i = 0; i < T_COUNT; ++i) {
         ms[i] = 0.f;
         if (c->timing && c->ev_used[i]) CU(cudaEventElapsedTime(&ms[i], c->ev0[i], c->ev1[i]));
+        c->ev_used[i] = false;  // each stage is reported once
     }
     if (launches) *launches = c->launches;
     return 0;

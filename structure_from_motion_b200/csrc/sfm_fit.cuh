@@ -69,8 +69,7 @@ __global__ void k_sample(unsigned long long seed, unsigned long long stream0,
 // accesses are conflict-free; one thread owns one hypothesis, which keeps all 32 lanes of
 // a warp doing rotations (a warp-per-hypothesis mapping would idle most lanes in the
 // scalar rotation-angle computation and costs ~20x more issue slots per fit).
-// The rank-2 projection avoids a full SVD: F' = F - (F v3) v3^T with v3 the eigenvector of
-// the smallest eigenvalue of F^T F (3x3 Jacobi in registers).
+// The rank-2 projection uses a one-sided Jacobi SVD of the 3x3 estimate in registers.
 // ------------------------------------------------------------------------------------
 constexpr int kFitThreads = 64;
 constexpr int kFitSmemDoubles = 162;  // A[81] + V[81] per thread
@@ -198,28 +197,29 @@ __device__ inline bool eight_point_fit(const Corr (&c)[8], double* sm, double (&
     for (int i = 0; i < 9; ++i) F[i] = V_(i, imin);  // v_min.reshape((3,3)) (:424-425)
 #undef A_
 #undef V_
-    // rank-2 projection (:430-446)
-    double M[9], W[9];
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-            M[i * 3 + j] = fma(F[6 + i], F[6 + j], fma(F[3 + i], F[3 + j], F[i] * F[j]));
-    jacobi_eig_reg<3>(M, W, 20);
-    int k3 = 0;
-    if (M[4] < M[k3 * 4]) k3 = 1;
-    if (M[8] < M[k3 * 4]) k3 = 2;
-    double v3[3] = {k3 == 0 ? W[0] : (k3 == 1 ? W[1] : W[2]), k3 == 0 ? W[3] : (k3 == 1 ? W[4] : W[5]),
-                    k3 == 0 ? W[6] : (k3 == 1 ? W[7] : W[8])};
+    // rank-2 projection (:430-446): one-sided Jacobi SVD of F; the column of F V with the
+    // smallest norm is sigma_3 u_3, so F' = F - (sigma_3 u_3) v_3^T zeroes the smallest
+    // singular value without ever dividing by it.
     {
-        const double inv = rsqrt(fma(v3[2], v3[2], fma(v3[1], v3[1], v3[0] * v3[0])));
-        v3[0] *= inv; v3[1] *= inv; v3[2] *= inv;
-    }
+        double G[9], W[9];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const double fv = fma(F[i * 3 + 2], v3[2], fma(F[i * 3 + 1], v3[1], F[i * 3] * v3[0]));
+        for (int i = 0; i < 9; ++i) G[i] = F[i];
+        jacobi_svd_onesided<3, 3>(G, W, 30);
+        double nrm[3];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) F[i * 3 + j] = fma(-fv, v3[j], F[i * 3 + j]);
+        for (int j = 0; j < 3; ++j) nrm[j] = fma(G[6 + j], G[6 + j], fma(G[3 + j], G[3 + j], G[j] * G[j]));
+        int k3 = 0;
+        if (nrm[1] < nrm[0]) k3 = 1;
+        if (nrm[2] < (k3 == 0 ? nrm[0] : nrm[1])) k3 = 2;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double g = (k3 == 0) ? G[i * 3] : ((k3 == 1) ? G[i * 3 + 1] : G[i * 3 + 2]);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const double w = (k3 == 0) ? W[j * 3] : ((k3 == 1) ? W[j * 3 + 1] : W[j * 3 + 2]);
+                F[i * 3 + j] = fma(-g, w, F[i * 3 + j]);
+            }
+        }
     }
     // E = T2^T F T1 (:163), T = [[s,0,-s cx],[0,s,-s cy],[0,0,1]] (:329-336)
     const double T1[9] = {s1, 0.0, -s1 * c1x, 0.0, s1, -s1 * c1y, 0.0, 0.0, 1.0};

@@ -1,0 +1,115 @@
+"""Multi-GPU plumbing for the two shardings of the path.
+
+* hypothesis-sharded (one large pair): correspondences replicated, rank r evaluates the
+  global hypothesis indices [r*H, (r+1)*H); the per-rank winners are merged by ONE tiny
+  collective (an all-gather of 12 doubles per rank) and every rank applies the reference's
+  selection rule (lib/ransac/ransac.py:83: smallest error, earliest iteration on ties).
+* pair-sharded (batches of independent pairs): no data-path communication at all.
+
+torch.distributed is plumbing only (NCCL on the GPUs, gloo in the CPU tests); the merge
+itself is a dozen scalar comparisons.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Sequence
+
+import numpy as np
+
+
+def shard_range(total: int, rank: int, world: int):
+    """Contiguous, balanced partition of ``total`` items: returns (start, stop) for ``rank``."""
+    base, rem = divmod(int(total), int(world))
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def pack_local_best(err: float, index: int, count: int, E) -> np.ndarray:
+    """12 doubles: err, global index (exact in a double up to 2^53), count, E[9]."""
+    out = np.empty(12, dtype=np.float64)
+    out[0] = err if index >= 0 else math.inf
+    out[1] = float(index)
+    out[2] = float(count)
+    out[3:] = np.asarray(E, dtype=np.float64).reshape(9) if index >= 0 else 0.0
+    return out
+
+
+def merge_best(rows: np.ndarray, selection: str = "min_error"):
+    """Pick the global winner from per-rank rows (see pack_local_best).
+
+    min_error: smallest error, lowest global index on ties (ransac.py:83 keeps the earliest
+    iteration).  max_inliers: largest count, lowest index on ties.  Returns
+    (owner_rank, err, index, count, E) or (-1, inf, -1, -1, None) when no rank has a candidate.
+    """
+    rows = np.asarray(rows, dtype=np.float64).reshape(-1, 12)
+    best = -1
+    for r in range(rows.shape[0]):
+        if rows[r, 1] < 0:
+            continue
+        if best < 0:
+            best = r
+            continue
+        if selection == "max_inliers":
+            better = (rows[r, 2], -rows[r, 1]) > (rows[best, 2], -rows[best, 1])
+        else:
+            better = (rows[r, 0], rows[r, 1]) < (rows[best, 0], rows[best, 1])
+        if better:
+            best = r
+    if best < 0:
+        return -1, math.inf, -1, -1, None
+    return best, float(rows[best, 0]), int(rows[best, 1]), int(rows[best, 2]), rows[best, 3:].reshape(3, 3).copy()
+
+
+def all_gather_best(local: np.ndarray, group=None, device=None) -> np.ndarray:
+    """The one collective of the hypothesis-sharded mode: all-gather of 12 doubles per rank."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return np.asarray(local, dtype=np.float64).reshape(1, 12)
+    world = dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
+                                             if backend == "nccl" else torch.device("cpu"))
+    t = torch.from_numpy(np.asarray(local, dtype=np.float64).reshape(12)).to(dev)
+    if backend == "nccl":
+        out = torch.empty(world * 12, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(out, t, group=group)
+        return out.view(world, 12).cpu().numpy()
+    parts = [torch.empty(12, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(parts, t, group=group)
+    return torch.stack(parts).numpy()
+
+
+def ransac_essential_sharded(camera_matrix, pts_a, pts_b, threshold, min_num_extra_inliers, aggregation,
+                             hyps_per_rank: int, seed: int, *, engine, rank: int, world: int,
+                             selection: str = "min_error", group=None, resident: bool = False):
+    """One estimate with hypotheses sharded over ``world`` GPUs (device sampler).
+
+    Every rank holds the full correspondence set (``resident=True``: already uploaded to
+    ``engine``) and scores its own ``hyps_per_rank`` hypotheses; one all-gather merges the
+    winners; every rank then adopts the global winner (so the inlier mask / pose /
+    triangulation tail can run anywhere).  Returns dict(err, index, count, E, owner).
+    """
+    if not resident:
+        engine.upload_pairs(pts_a, pts_b, camera_matrix)
+    engine.sample_device(seed, hyps_per_rank, hyp_offset=rank * hyps_per_rank)
+    best, _, _ = engine.ransac_essential(threshold, float(min_num_extra_inliers or 0), aggregation, selection,
+                                         want_mask=False, want_sed=False)
+    gidx = int(best.index) + rank * hyps_per_rank if best.index >= 0 else -1
+    rows = all_gather_best(pack_local_best(best.err, gidx, best.count_extra, list(best.E)), group=group)
+    owner, err, index, count, E = merge_best(rows, selection)
+    if owner >= 0:
+        if owner == rank:
+            engine.set_winner(int(best.index))
+        else:
+            engine.set_winner(-1, E)
+    return dict(err=err, index=index, count=count, E=E, owner=owner,
+                num_invalid=int(best.num_invalid))
+
+
+def shard_pairs(offsets: Sequence[int], rank: int, world: int):
+    """Pair-sharded mode: the pairs [p0, p1) this rank owns and their re-based offsets."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    p0, p1 = shard_range(len(offsets) - 1, rank, world)
+    return p0, p1, offsets[p0:p1 + 1] - offsets[p0]

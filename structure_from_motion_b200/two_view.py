@@ -79,7 +79,6 @@ def ransac_essential_arrays(
     if min_num_extra_inliers is None:
         min_num_extra_inliers = 0  # ransac.py:52-53
     agg = _agg_name(error_aggregation_method)
-    eng = engine or _native.get_engine()
     pts_a = np.ascontiguousarray(pts_a, dtype=np.float64).reshape(-1, 2)
     pts_b = np.ascontiguousarray(pts_b, dtype=np.float64).reshape(-1, 2)
     n = pts_a.shape[0]
@@ -94,6 +93,7 @@ def ransac_essential_arrays(
         if sampler == "reference":
             random.shuffle(list(range(n)))  # the reference shuffles once before the fitter raises
         raise ValueError("Eight feature pairs are expected.")  # epipolar_ransac.py:31-32
+    eng = engine or _native.get_engine()
 
     state0 = None
     if sampler == "reference":
@@ -126,7 +126,7 @@ def ransac_essential_arrays(
 
     mask = mask.astype(bool)
     local = int(best.index)
-    sample = eng.get_table()[local] if sampler == "device" else table[local]
+    sample = eng.get_table(1, first=local)[0] if sampler == "device" else table[local]
     is_sample = np.zeros(n, dtype=bool)
     is_sample[sample] = True
     if sampler == "reference":

@@ -125,20 +125,25 @@ def test_fitter_against_oracle(engine):
     E, valid, eig = engine.fit(want_eig=True)
     assert valid.all()
     ca, cb = np.stack([nxa, nya], 1), np.stack([nxb, nyb], 1)
-    worst = 0.0
+    rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)  # noqa: E731
+    ratios = []
     for i in range(h):
         s = table[i]
         e_o = o.eight_point(ca[s], cb[s])
         w_o, sv = o.eight_point_conditioning(ca[s], cb[s])
         w = np.sort(eig[i])
         np.testing.assert_allclose(w[1:], w_o[1:], rtol=1e-9, atol=1e-13)
-        d = np.linalg.norm(E[i] - e_o) / np.linalg.norm(e_o)
-        # two correct solvers may differ by ~eps * lambda_max / lambda_2 in the null vector and by
-        # ~eps * sigma_1 / (sigma_2 - sigma_3) in the rank-2 projection
-        tol = 2e-14 * w_o[-1] / w_o[1] + 2e-14 * sv[0] / (sv[1] - sv[2]) + 1e-12
-        worst = max(worst, d / tol)
-        assert d <= tol, (i, d, tol, w_o[:3])
+        d = rel(E[i], e_o)
+        # How well-determined is E on this sample?  Measure it: the reference's own route (LAPACK
+        # dgeev + dgesdd) against two other correct CPU solvers.  The GPU result must be as close to
+        # the reference as those are (x4), with a conditioning-scaled floor.
+        alt = max(rel(a, e_o) for a in o.eight_point_alternatives(ca[s], cb[s]))
+        tol = max(4.0 * alt, 2e-14 * w_o[-1] / w_o[1] + 1e-12)
+        ratios.append(d / tol)
+        assert d <= tol, (i, d, tol, alt, w_o[:3], sv)
+        assert d <= 1e-6  # the north_star bound, far above anything seen
         assert E[i][2, 2] == 1.0
+    assert np.median(ratios) < 0.5
 
 
 def test_degenerate_sample_is_flagged(engine):

@@ -60,7 +60,8 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="config3", choices=list(WORKLOADS) + ["config4"])
     ap.add_argument("--variant", default=os.environ.get("SFM_SCORE_VARIANT", "screen"), choices=["screen", "full"])
-    ap.add_argument("--hpt", type=int, default=int(os.environ.get("SFM_SCORE_HPT", "2")))
+    ap.add_argument("--hpt", type=int, default=int(os.environ.get("SFM_SCORE_HPT", "1")))
+    ap.add_argument("--group", type=int, default=int(os.environ.get("SFM_SCORE_GROUP", "4")))
     ap.add_argument("--pairs", type=int, default=512, help="config4: image pairs per GPU per step")
     ap.add_argument("--cpu-sample-hyps", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -213,7 +214,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = _native.get_engine(local_rank)
-    eng.set_score_variant(args.variant, args.hpt)
+    eng.set_score_variant(args.variant, args.hpt, args.group)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
 
@@ -331,7 +332,7 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        algo_bytes = BYTES_PER_CORR * n * ((h_rank + 255) // 256) + 72.0 * h_rank
+        algo_bytes = BYTES_PER_CORR * n * ((h_rank + 127) // 128) + 72.0 * h_rank
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -340,7 +341,7 @@ def main():
                 "workload": f"{args.workload}: {n} correspondences x {h_rank} hypotheses per GPU "
                             f"({h_rank * world} total), 40% outliers, thr 1.5e-6, RMS, min_extra 10, + cheirality "
                             f"vote + triangulation of the {num_inl} inliers",
-                "sampler": "device (Philox)", "score_variant": args.variant, "hyps_per_thread": args.hpt,
+                "sampler": "device (Philox)", "score_variant": args.variant, "hyps_per_thread": args.hpt, "group": args.group,
                 "l2": "flushed (256 MiB memset) between timed steps",
                 "parallelism": f"hypothesis-sharded x{world}, one 96 B/rank all-gather" if world > 1 else "single GPU",
             },

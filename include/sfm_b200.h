@@ -55,7 +55,9 @@ int sfm_destroy(sfm_ctx *ctx);
  * context's own stream. */
 int sfm_set_stream(sfm_ctx *ctx, void *cuda_stream);
 int sfm_synchronize(sfm_ctx *ctx);
-int sfm_set_score_variant(sfm_ctx *ctx, int variant, int hyps_per_thread /* 1 or 2, 0 = default */);
+/* hyps_per_thread: essential matrices per thread (1 or 2); group: correspondences evaluated
+ * per step (1, 2, 4, 8); 0 keeps the current value. */
+int sfm_set_score_variant(sfm_ctx *ctx, int variant, int hyps_per_thread, int group);
 /* Pinned host memory for the caller's buffers (so that H2D/D2H copies are true async DMA). */
 int sfm_host_alloc(uint64_t bytes, void **out);
 int sfm_host_free(void *p);

@@ -47,7 +47,7 @@ _SIGNATURES = {
     "sfm_destroy": (C.c_int, [_P]),
     "sfm_set_stream": (C.c_int, [_P, _P]),
     "sfm_synchronize": (C.c_int, [_P]),
-    "sfm_set_score_variant": (C.c_int, [_P, C.c_int, C.c_int]),
+    "sfm_set_score_variant": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     "sfm_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(_P)]),
     "sfm_host_free": (C.c_int, [_P]),
     "sfm_mt_shuffle_table": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int64, _P]),
@@ -160,8 +160,9 @@ class Engine:
     def synchronize(self):
         self._ck(self.lib.sfm_synchronize(self.h), "sfm_synchronize")
 
-    def set_score_variant(self, variant="screen", hyps_per_thread=0):
-        self._ck(self.lib.sfm_set_score_variant(self.h, VARIANT[variant], int(hyps_per_thread)), "sfm_set_score_variant")
+    def set_score_variant(self, variant="screen", hyps_per_thread=0, group=0):
+        self._ck(self.lib.sfm_set_score_variant(self.h, VARIANT[variant], int(hyps_per_thread), int(group)),
+                 "sfm_set_score_variant")
 
     # -- correspondences ------------------------------------------------------------------
     def upload_pairs(self, pts_a, pts_b, K):

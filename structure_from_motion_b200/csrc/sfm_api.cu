@@ -2,6 +2,7 @@
 // device buffers, launch geometry, and the CPython-compatible MT19937 sampler.
 #include "../../include/sfm_b200.h"
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -75,7 +76,7 @@ struct sfm_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     // data
     Buf raw, pts, offsets, Ks, table, E, valid, eig;
-    Buf pcount, ps1, ps2, count_extra, S1, S2, err, blocks, best, invalid, winnerE;
+    Buf acc, count_extra, S1, S2, err, blocks, best, invalid, winnerE;
     Buf mask, sed, poses, pass, X, idx, scan, tmp;
     long long n = 0, h = 0, npairs = 1;
     long long raw_stride = 1;
@@ -85,7 +86,7 @@ struct sfm_ctx {
     long long last_idx_offset = 0;
     double Khost[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     // config
-    int variant = SFM_SCORE_SCREEN, hpt = 2;
+    int variant = SFM_SCORE_SCREEN, hpt = 1, group = 4;
     // timing
     bool timing = false;
     cudaEvent_t ev0[T_COUNT], ev1[T_COUNT];
@@ -126,6 +127,20 @@ int check_launch(sfm_ctx* c, const char* what) {
     if (e != cudaSuccess) return fail(SFM_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
     c->launches += 1;
     return 0;
+}
+
+const void* score_kernel(int variant, int hpt, int group) {
+#define SFM_K(H, G, S) reinterpret_cast<const void*>(&k_score<H, G, S>)
+    const bool scr = variant == SFM_SCORE_SCREEN;
+    if (hpt == 1 && group == 4) return scr ? SFM_K(1, 4, true) : SFM_K(1, 4, false);
+    if (hpt == 1 && group == 2) return scr ? SFM_K(1, 2, true) : SFM_K(1, 2, false);
+    if (hpt == 1 && group == 1) return scr ? SFM_K(1, 1, true) : SFM_K(1, 1, false);
+    if (hpt == 1 && group == 8) return scr ? SFM_K(1, 8, true) : SFM_K(1, 8, false);
+    if (hpt == 2 && group == 4) return scr ? SFM_K(2, 4, true) : SFM_K(2, 4, false);
+    if (hpt == 2 && group == 2) return scr ? SFM_K(2, 2, true) : SFM_K(2, 2, false);
+    if (hpt == 2 && group == 1) return scr ? SFM_K(2, 1, true) : SFM_K(2, 1, false);
+#undef SFM_K
+    return nullptr;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -211,8 +226,8 @@ int sfm_destroy(sfm_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    Buf* bufs[] = {&c->raw, &c->pts, &c->offsets, &c->Ks, &c->table, &c->E, &c->valid, &c->eig, &c->pcount,
-                   &c->ps1, &c->ps2, &c->count_extra, &c->S1, &c->S2, &c->err, &c->blocks, &c->best,
+    Buf* bufs[] = {&c->raw, &c->pts, &c->offsets, &c->Ks, &c->table, &c->E, &c->valid, &c->eig, &c->acc,
+                   &c->count_extra, &c->S1, &c->S2, &c->err, &c->blocks, &c->best,
                    &c->invalid, &c->winnerE, &c->mask, &c->sed, &c->poses, &c->pass, &c->X, &c->idx,
                    &c->scan, &c->tmp};
     for (Buf* b : bufs) b->release();
@@ -238,12 +253,15 @@ int sfm_synchronize(sfm_ctx* c) {
     return 0;
 }
 
-int sfm_set_score_variant(sfm_ctx* c, int variant, int hpt) {
+int sfm_set_score_variant(sfm_ctx* c, int variant, int hpt, int group) {
     if (!c) return fail(SFM_ERR_ARG, "null context");
     if (variant != SFM_SCORE_SCREEN && variant != SFM_SCORE_FULL) return fail(SFM_ERR_ARG, "bad variant %d", variant);
-    if (hpt != 0 && hpt != 1 && hpt != 2) return fail(SFM_ERR_ARG, "hyps_per_thread must be 1 or 2");
+    const int nh = hpt ? hpt : c->hpt, ng = group ? group : c->group;
+    if (!score_kernel(variant, nh, ng))
+        return fail(SFM_ERR_ARG, "unsupported combination: hyps_per_thread %d, group %d", nh, ng);
     c->variant = variant;
-    if (hpt) c->hpt = hpt;
+    c->hpt = nh;
+    c->group = ng;
     return 0;
 }
 
@@ -484,24 +502,29 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
     if (agg < 0 || agg > 3) return fail(SFM_ERR_ARG, "bad aggregation %d", agg);
     if (mode != 0 && mode != 1) return fail(SFM_ERR_ARG, "bad selection %d", mode);
     if (!(thr >= 0.0)) return fail(SFM_ERR_ARG, "threshold must be >= 0");
+    if (thr > 1e100) return fail(SFM_ERR_ARG, "threshold too large for the fixed-point accumulators");
     const long long h = c->h, P = c->npairs;
-    const int hpt = c->hpt;
+    const int hpt = c->hpt, G = c->group;
     const long long hblocks = (h + (long long)kScoreThreads * hpt - 1) / ((long long)kScoreThreads * hpt);
-    // split the correspondences so that the grid covers the machine several times over
-    const long long target_blocks = (long long)c->sm_count * 32;
+    // persistent grid: one wave of resident blocks; items = (pair, split, hypothesis block)
+    const void* fn = score_kernel(c->variant, hpt, G);
+    if (!fn) return fail(SFM_ERR_ARG, "unsupported scoring configuration (variant %d, hpt %d, group %d)", c->variant, hpt, G);
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kScoreThreads, 0));
+    if (occ < 1) occ = 1;
+    const long long grid_blocks = (long long)c->sm_count * occ;
     const long long tiles = (max_len + kTile - 1) / kTile;
-    long long nsplit = (target_blocks + hblocks * P - 1) / (hblocks * P);
-    if (nsplit > tiles) nsplit = tiles;
-    if (nsplit > 1024) nsplit = 1024;
+    const long long target_items = grid_blocks * 12;
+    long long nsplit = (target_items + hblocks * P - 1) / (hblocks * P);
+    const long long max_split = tiles / 8 > 0 ? tiles / 8 : 1;  // keep >= 8 tiles per item
+    if (nsplit > max_split) nsplit = max_split;
     if (nsplit < 1) nsplit = 1;
-    long long chunk = ((tiles + nsplit - 1) / nsplit) * kTile;
+    const long long chunk = ((tiles + nsplit - 1) / nsplit) * kTile;
     nsplit = (max_len + chunk - 1) / chunk;
     if (nsplit < 1) nsplit = 1;
-    const size_t np = (size_t)P * nsplit * h;
-    if (int r = c->pcount.reserve(np * 4)) return r;
-    if (int r = c->ps1.reserve(np * 8)) return r;
-    if (int r = c->ps2.reserve(np * 8)) return r;
+    const long long total_items = hblocks * nsplit * P;
     const size_t H = (size_t)h * P;
+    if (int r = c->acc.reserve(H * kAccWords * 8 + 64)) return r;
     if (int r = c->count_extra.reserve(H * 4)) return r;
     if (int r = c->S1.reserve(H * 8)) return r;
     if (int r = c->S2.reserve(H * 8)) return r;
@@ -511,6 +534,9 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
     if (int r = c->best.reserve((size_t)P * sizeof(Best))) return r;
     if (int r = c->invalid.reserve((size_t)P * 16)) return r;
 
+    int e2 = 0;
+    if (thr > 0.0) (void)frexp(thr, &e2);  // thr = m * 2^e2, m in [0.5, 1)  =>  thr < 2^e2
+    if (e2 < -400) e2 = -400;
     ScoreArgs a;
     a.pts = c->pts.as<Corr>();
     a.n = c->n;
@@ -521,19 +547,21 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
     // rounding guard of the screening tests: relative slack + an absolute term that covers a
     // cancelling residual r at the 1-ulp level (only matters for thr -> 0)
     a.thr_pre = thr * (1.0 + 1e-9) + 1e-22;
+    a.scale1 = ldexp(1.0, 23 - e2);
+    a.scale2 = ldexp(1.0, 23 - 2 * e2);
     a.chunk = chunk;
-    a.pcount = c->pcount.as<int32_t>();
-    a.ps1 = c->ps1.as<double>();
-    a.ps2 = c->ps2.as<double>();
-    dim3 grid((unsigned)hblocks, (unsigned)nsplit, (unsigned)P);
+    a.hblocks = (int)hblocks;
+    a.nsplit = (int)nsplit;
+    a.total_items = total_items;
+    a.htotal = (long long)H;
+    // accumulator planes followed by the work counter, zeroed together
+    a.acc = c->acc.as<unsigned long long>();
+    a.work_counter = reinterpret_cast<unsigned*>(a.acc + H * kAccWords);
     c->tic(T_SCORE);
-    if (c->variant == SFM_SCORE_SCREEN) {
-        if (hpt == 2) k_score<2, true><<<grid, kScoreThreads, 0, c->stream>>>(a);
-        else k_score<1, true><<<grid, kScoreThreads, 0, c->stream>>>(a);
-    } else {
-        if (hpt == 2) k_score<2, false><<<grid, kScoreThreads, 0, c->stream>>>(a);
-        else k_score<1, false><<<grid, kScoreThreads, 0, c->stream>>>(a);
-    }
+    CU(cudaMemsetAsync(c->acc.p, 0, H * kAccWords * 8 + 64, c->stream));
+    const long long launch_blocks = grid_blocks < total_items ? grid_blocks : total_items;
+    void* kargs[] = {(void*)&a};
+    CU(cudaLaunchKernel(fn, dim3((unsigned)launch_blocks), dim3(kScoreThreads), kargs, 0, c->stream));
     if (int r = check_launch(c, "k_score")) return r;
     c->toc(T_SCORE);
 
@@ -546,10 +574,10 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
     f.table = use_table ? c->table.as<int32_t>() : nullptr;
     f.h = h;
     f.idx_offset = idx_offset;
-    f.nsplit = (int)nsplit;
-    f.pcount = a.pcount;
-    f.ps1 = a.ps1;
-    f.ps2 = a.ps2;
+    f.htotal = (long long)H;
+    f.acc = a.acc;
+    f.inv_scale1 = ldexp(1.0, e2 - 69);
+    f.inv_scale2 = ldexp(1.0, 2 * e2 - 69);
     f.thr = thr;
     f.min_extra = min_extra;
     f.agg = agg;

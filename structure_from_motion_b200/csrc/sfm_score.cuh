@@ -1,5 +1,7 @@
 // K2 (scoring), K3 (finalise + select) and K4 (inlier mask of one hypothesis).
 #pragma once
+#include <type_traits>
+
 #include "sfm_device.cuh"
 
 namespace sfm {
@@ -54,176 +56,258 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 // Mapping: lane = hypothesis.  Each thread keeps HPT essential matrices in registers and
 // streams correspondences from shared-memory tiles (every lane of a warp reads the same
 // 32-byte record: a broadcast, conflict-free).  Tiles are filled by 1-D bulk async copies
-// (TMA) into a two-stage ring, signalled through mbarriers, so loads overlap the FP64
-// work.  Accumulators are private to the owning lane: no atomics, no floating-point
-// shuffles, and a fixed summation order (point order) => run-to-run deterministic.
+// (TMA) into a kStages-deep ring signalled through mbarriers; a stage is refilled by
+// whichever warp finishes it last, so no warp ever waits for a slower one (warps may drift
+// kStages-1 tiles apart) and there is no block barrier in the loop.
 //
-// Two-level evaluation: a cheap division-free test (SCREEN: 12 FP64 issue slots using only
-// the image-A distance, a necessary condition; FULL: the 21-slot two-sided decision) runs
-// for every (hypothesis, correspondence).  Candidates (typically < 1 %) are appended to a
-// per-warp queue and processed 32 at a time by all lanes (dense, no divergence): the exact
-// reference-order SED is evaluated, compared with thr, and the result is routed back to
-// the owning lane in queue order.
+// Persistent blocks: the grid is one wave (SMs x resident blocks); work items
+// (pair, correspondence split, hypothesis block) are claimed from an atomic counter, which
+// balances the uneven cost of "good" hypotheses.
+//
+// Two-level evaluation.  G correspondences are evaluated per step with a cheap
+// division-free test (SCREEN: 12 FP64 issue slots using only the image-A distance, a
+// necessary condition; FULL: the 21-slot two-sided decision).  Candidates (~1 %) are pushed
+// to a per-warp ring and processed 32 at a time by all lanes (dense, no divergence): the
+// exact reference-order SED is evaluated and compared with thr.
+//
+// Exact accumulation.  An inlier's sed (and sed^2) is split into three 23-bit chunks of a
+// fixed-point number scaled so that thr < 2^0 maps below 2^69; chunks are added with native
+// 32-bit shared-memory atomics, folded into 64-bit registers of the owning lane, and finally
+// into 64-bit global accumulators.  Integer addition is associative, so the sums are EXACT
+// (every double s >= thr*2^-16 is represented without rounding) and independent of warp
+// scheduling, split count and GPU count — run-to-run deterministic by construction, and
+// closer to the true sum than any floating-point summation order (numpy's included).
 // ------------------------------------------------------------------------------------
 constexpr int kScoreThreads = 128;
-constexpr int kTile = 256;
+constexpr int kScoreWarps = kScoreThreads / 32;
+constexpr int kTile = 128;    // correspondences per stage (4 KB)
+constexpr int kStages = 4;
 constexpr unsigned kMaxPoints = 1u << 26;
+constexpr int kAccWords = 7;  // count, 3 chunks of sum(sed), 3 chunks of sum(sed^2)
+constexpr int kFlushEvery = 8;
 
 struct ScoreArgs {
     const Corr* pts;
     long long n;
     const long long* offsets;  // [npairs+1] or null (single pair of n records)
-    const double* E;  // [npairs][h][9]
+    const double* E;           // [npairs][h][9]
     long long h;
     double thr, thr_pre;
-    long long chunk;  // correspondences per split (multiple of kTile)
-    int32_t* pcount;  // [npairs][nsplit][h]
-    double* ps1;
-    double* ps2;
+    double scale1, scale2;     // 2^(23-e), 2^(23-2e) with thr < 2^e
+    long long chunk;           // correspondences per split (multiple of kTile)
+    int hblocks, nsplit;
+    long long total_items;
+    long long htotal;          // npairs * h
+    unsigned* work_counter;
+    unsigned long long* acc;   // [kAccWords][npairs*h] exact integer accumulators (pre-zeroed)
 };
 
-template <int HPT, bool SCREEN>
+__device__ __forceinline__ unsigned atom_add_acq_rel_shared(unsigned* p, unsigned v) {
+    unsigned old;
+    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+    return old;
+}
+
+// three 23-bit chunks of floor(x * 2^46), x in [0, 2^23)
+__device__ __forceinline__ void chunks23(double x, unsigned& c2, unsigned& c1, unsigned& c0) {
+    c2 = __double2uint_rz(x);
+    const double r1 = (x - (double)c2) * 8388608.0;
+    c1 = __double2uint_rz(r1);
+    const double r0 = (r1 - (double)c1) * 8388608.0;
+    c0 = __double2uint_rn(r0);
+}
+
+template <int HPT, int G, bool SCREEN>
 __global__ void __launch_bounds__(kScoreThreads) k_score(const ScoreArgs a) {
-    __shared__ __align__(128) Corr tile[2][kTile];
-    __shared__ __align__(8) unsigned long long full_bar[2];
-    __shared__ unsigned queue[kScoreThreads / 32][64];
+    constexpr int RING = 64 * HPT * G;  // >= 32*HPT*G new + 31 pending
+    __shared__ __align__(128) Corr tile[kStages][kTile];
+    __shared__ __align__(8) unsigned long long full_bar[kStages];
+    __shared__ unsigned done[kStages];
+    __shared__ unsigned ring[kScoreWarps][RING];
+    __shared__ unsigned ring_tail[kScoreWarps];
+    __shared__ unsigned sacc[kScoreWarps][HPT][kAccWords][32];
+    __shared__ unsigned s_item;
 
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const long long hyp_base = (long long)blockIdx.x * (kScoreThreads * HPT) + threadIdx.x;
-    // blockIdx.z = image pair, blockIdx.y = split of that pair's correspondences
-    const long long pbase = a.offsets ? a.offsets[blockIdx.z] : 0;
-    const long long plen = a.offsets ? a.offsets[blockIdx.z + 1] - pbase : a.n;
-    long long begin = (long long)blockIdx.y * a.chunk;
-    if (begin > plen) begin = plen;
-    const long long end = pbase + ((begin + a.chunk < plen) ? begin + a.chunk : plen);
-    begin += pbase;
-    const int ntiles = (int)((end - begin + kTile - 1) / kTile);
-    const double* Ep = a.E + 9 * (long long)blockIdx.z * a.h;
 
-    double e[HPT][9];
-#pragma unroll
-    for (int j = 0; j < HPT; ++j) {
-        const long long hyp = hyp_base + (long long)j * kScoreThreads;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) e[j][k] = (hyp < a.h) ? Ep[9 * hyp + k] : 0.0;
-    }
-    int cnt[HPT];
-    double s1[HPT], s2[HPT];
-#pragma unroll
-    for (int j = 0; j < HPT; ++j) { cnt[j] = 0; s1[j] = 0.0; s2[j] = 0.0; }
-
-    auto issue = [&](int t) {
-        const int s = t & 1;
-        const long long first = begin + (long long)t * kTile;
-        const long long rem = end - first;
-        const uint32_t bytes = (uint32_t)((rem < kTile ? rem : kTile) * sizeof(Corr));
-        mbar_expect_tx(&full_bar[s], bytes);
-        bulk_g2s(&tile[s][0], a.pts + first, bytes, &full_bar[s]);
-    };
     if (threadIdx.x == 0) {
-        mbar_init(&full_bar[0], 1);
-        mbar_init(&full_bar[1], 1);
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); done[s] = 0; }
         mbar_fence_init();
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (ntiles > 0) issue(0);
-        if (ntiles > 1) issue(1);
-    }
-
-    unsigned qhead = 0, qn = 0;
-    unsigned* q = queue[warp];
-
-    // Process m (<= 32) queued candidates with all 32 lanes.
-    auto drain = [&](unsigned m) {
-        __syncwarp();
-        const unsigned ent = (lane < (int)m) ? q[(qhead + lane) & 63u] : ((unsigned)lane << 27);
-        const int owner = (int)(ent >> 27);
-        const int slot = (int)((ent >> 26) & 1u);
-        const unsigned gi = ent & (kMaxPoints - 1u);
-        double eo[9];
+    if (lane == 0) ring_tail[warp] = 0;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            double v = __shfl_sync(full, e[0][k], owner);
-            if (HPT == 2) {
-                const double v1 = __shfl_sync(full, e[HPT - 1][k], owner);
-                v = slot ? v1 : v;
-            }
-            eo[k] = v;
+    for (int j = 0; j < HPT; ++j)
+#pragma unroll
+        for (int k = 0; k < kAccWords; ++k) sacc[warp][j][k][lane] = 0;
+    unsigned* q = ring[warp];
+    unsigned head = 0;        // entries consumed so far (warp-uniform, monotone)
+    unsigned gt = 0;          // tiles consumed so far by this block (drives stage + parity)
+
+    for (;;) {
+        __syncthreads();  // previous item completely finished; s_item free
+        if (threadIdx.x == 0) s_item = atomicAdd(a.work_counter, 1u);
+        __syncthreads();
+        const unsigned item = s_item;
+        if (item >= a.total_items) break;
+        const int hb = (int)(item % (unsigned)a.hblocks);
+        const unsigned rest = item / (unsigned)a.hblocks;
+        const int split = (int)(rest % (unsigned)a.nsplit);
+        const int pair = (int)(rest / (unsigned)a.nsplit);
+
+        const long long pbase = a.offsets ? a.offsets[pair] : 0;
+        const long long plen = a.offsets ? a.offsets[pair + 1] - pbase : a.n;
+        long long begin = (long long)split * a.chunk;
+        if (begin > plen) begin = plen;
+        const long long end = pbase + ((begin + a.chunk < plen) ? begin + a.chunk : plen);
+        begin += pbase;
+        const int ntiles = (int)((end - begin + kTile - 1) / kTile);
+        const long long hyp_base = (long long)hb * (kScoreThreads * HPT) + threadIdx.x;
+        const double* Ep = a.E + 9 * (long long)pair * a.h;
+
+        auto issue = [&](int t) {
+            const int s = (int)((gt + (unsigned)t) % kStages);
+            const long long first = begin + (long long)t * kTile;
+            const long long rem = end - first;
+            const uint32_t bytes = (uint32_t)((rem < kTile ? rem : kTile) * sizeof(Corr));
+            mbar_expect_tx(&full_bar[s], bytes);
+            bulk_g2s(&tile[s][0], a.pts + first, bytes, &full_bar[s]);
+        };
+        if (threadIdx.x == 0)
+            for (int t = 0; t < kStages && t < ntiles; ++t) issue(t);
+
+        double e[HPT][9];
+#pragma unroll
+        for (int j = 0; j < HPT; ++j) {
+            const long long hyp = hyp_base + (long long)j * kScoreThreads;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) e[j][k] = (hyp < a.h) ? Ep[9 * hyp + k] : 0.0;
         }
-        const Corr c = a.pts[gi];
-        const double sv = sed_exact(eo, c.xa, c.ya, c.xb, c.yb);
-        const bool inl = (lane < (int)m) && (sv <= a.thr);  // ransac.py:73  score <= threshold
-        unsigned mask = __ballot_sync(full, inl);
-        while (mask) {
-            const int src = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const unsigned oe = __shfl_sync(full, ent, src);
-            const double v = __shfl_sync(full, sv, src);
-            const bool mine = ((int)(oe >> 27) == lane);
-            const int sl = (int)((oe >> 26) & 1u);
+        unsigned long long tot[HPT][kAccWords];
 #pragma unroll
-            for (int j = 0; j < HPT; ++j) {
-                if (mine && sl == j) {
-                    cnt[j] += 1;
-                    s1[j] = __dadd_rn(s1[j], v);
-                    s2[j] = __dadd_rn(s2[j], __dmul_rn(v, v));
+        for (int j = 0; j < HPT; ++j)
+#pragma unroll
+            for (int k = 0; k < kAccWords; ++k) tot[j][k] = 0ull;
+        int drains = 0;
+
+        // fold the warp's shared 32-bit chunk sums into the owning lanes' 64-bit registers
+        auto flush = [&]() {
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < HPT; ++j)
+#pragma unroll
+                for (int k = 0; k < kAccWords; ++k) {
+                    tot[j][k] += sacc[warp][j][k][lane];
+                    sacc[warp][j][k][lane] = 0;
+                }
+            __syncwarp();
+            drains = 0;
+        };
+
+        // exact evaluation of m (<= 32) queued candidates by all 32 lanes
+        auto drain = [&](unsigned m) {
+            const unsigned ent = (lane < (int)m) ? q[(head + lane) & (RING - 1)] : ((unsigned)lane << 27);
+            const int owner = (int)(ent >> 27);
+            const int slot = (int)((ent >> 26) & 1u);
+            const unsigned gi = ent & (kMaxPoints - 1u);
+            double eo[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                double v = __shfl_sync(full, e[0][k], owner);
+                if (HPT == 2) {
+                    const double v1 = __shfl_sync(full, e[HPT - 1][k], owner);
+                    v = slot ? v1 : v;
+                }
+                eo[k] = v;
+            }
+            const Corr c = a.pts[gi];
+            const double sv = sed_exact(eo, c.xa, c.ya, c.xb, c.yb);
+            if ((lane < (int)m) && (sv <= a.thr)) {  // ransac.py:73  score <= threshold
+                unsigned c2, c1, c0;
+                unsigned* dst = &sacc[warp][HPT == 2 ? slot : 0][0][owner];
+                atomicAdd(dst, 1u);
+                chunks23(sv * a.scale1, c2, c1, c0);
+                atomicAdd(dst + 32, c2);
+                atomicAdd(dst + 64, c1);
+                atomicAdd(dst + 96, c0);
+                chunks23(__dmul_rn(sv, sv) * a.scale2, c2, c1, c0);
+                atomicAdd(dst + 128, c2);
+                atomicAdd(dst + 160, c1);
+                atomicAdd(dst + 192, c0);
+            }
+            head += m;
+            if (++drains >= kFlushEvery) flush();
+        };
+
+        // one step: G correspondences starting at tile record p (global index gi0)
+        auto step = [&](const Corr* tp, int p, unsigned gi0, auto gtag) {
+            constexpr int GG = decltype(gtag)::value;
+            Corr c[GG];
+#pragma unroll
+            for (int g = 0; g < GG; ++g) c[g] = tp[p + g];
+            unsigned pm = 0;
+#pragma unroll
+            for (int j = 0; j < HPT; ++j)
+#pragma unroll
+                for (int g = 0; g < GG; ++g) {
+                    const double d = SCREEN ? sed_screen(e[j], c[g].xa, c[g].ya, c[g].xb, c[g].yb, a.thr_pre)
+                                            : sed_full_decision(e[j], c[g].xa, c[g].ya, c[g].xb, c[g].yb, a.thr_pre);
+                    pm |= ((unsigned)__double2hiint(d) >> 31) << (j * GG + g);
+                }
+            if (__any_sync(full, pm != 0u)) {
+                unsigned mbits = pm;
+                while (mbits) {  // usually one bit in one or two lanes
+                    const int k = __ffs(mbits) - 1;
+                    mbits &= mbits - 1;
+                    const unsigned pos = atomicAdd(&ring_tail[warp], 1u);
+                    q[pos & (RING - 1)] = ((unsigned)lane << 27) | ((unsigned)(k / GG) << 26) | (gi0 + (unsigned)(k % GG));
+                }
+                __syncwarp();
+                const unsigned tail = *(volatile unsigned*)&ring_tail[warp];
+                while (tail - head >= 32u) drain(32u);
+            }
+        };
+
+        for (int t = 0; t < ntiles; ++t) {
+            const unsigned gti = gt + (unsigned)t;
+            const int s = (int)(gti % kStages);
+            mbar_wait(&full_bar[s], (gti / kStages) & 1u);
+            const long long first = begin + (long long)t * kTile;
+            const int np = (int)((end - first < kTile) ? (end - first) : kTile);
+            const Corr* tp = tile[s];
+            int p = 0;
+            for (; p + G <= np; p += G) step(tp, p, (unsigned)(first + p), std::integral_constant<int, G>{});
+            for (; p < np; ++p) step(tp, p, (unsigned)(first + p), std::integral_constant<int, 1>{});
+            // release the stage: the last warp to finish it refills it (nobody waits)
+            __syncwarp();
+            if (lane == 0) {
+                const unsigned old = atom_add_acq_rel_shared(&done[s], 1u);
+                if (old == kScoreWarps - 1) {
+                    done[s] = 0;
+                    if (t + kStages < ntiles) issue(t + kStages);
                 }
             }
         }
-        qhead = (qhead + m) & 63u;
-        qn -= m;
-        __syncwarp();
-    };
+        gt += (unsigned)ntiles;
 
-    for (int t = 0; t < ntiles; ++t) {
-        const int s = t & 1;
-        mbar_wait(&full_bar[s], (uint32_t)((t >> 1) & 1));
-        const long long first = begin + (long long)t * kTile;
-        const int np = (int)((end - first < kTile) ? (end - first) : kTile);
-        const Corr* tp = tile[s];
-#pragma unroll 4
-        for (int p = 0; p < np; ++p) {
-            const Corr c = tp[p];
-            bool pass[HPT];
-            bool any = false;
-#pragma unroll
-            for (int j = 0; j < HPT; ++j) {
-                const double d = SCREEN ? sed_screen(e[j], c.xa, c.ya, c.xb, c.yb, a.thr_pre)
-                                        : sed_full_decision(e[j], c.xa, c.ya, c.xb, c.yb, a.thr_pre);
-                pass[j] = __double2hiint(d) < 0;
-                any |= pass[j];
-            }
-            if (__any_sync(full, any)) {
-                const unsigned gi = (unsigned)(first + p);
-#pragma unroll
-                for (int j = 0; j < HPT; ++j) {
-                    const unsigned b = __ballot_sync(full, pass[j]);
-                    if (b) {
-                        if (pass[j])
-                            q[(qhead + qn + __popc(b & lt_mask)) & 63u] =
-                                ((unsigned)lane << 27) | ((unsigned)j << 26) | gi;
-                        qn += __popc(b);
-                        if (qn >= 32u) drain(32u);
-                    }
-                }
-            }
+        // tail of the queue, then publish this item's exact sums
+        {
+            __syncwarp();
+            const unsigned tail = *(volatile unsigned*)&ring_tail[warp];
+            while (tail != head) drain(tail - head < 32u ? tail - head : 32u);
+            flush();
         }
-        __syncthreads();  // every warp is done reading stage s
-        if (threadIdx.x == 0 && t + 2 < ntiles) issue(t + 2);
-    }
-    while (qn > 0u) drain(qn < 32u ? qn : 32u);
-
 #pragma unroll
-    for (int j = 0; j < HPT; ++j) {
-        const long long hyp = hyp_base + (long long)j * kScoreThreads;
-        if (hyp < a.h) {
-            const long long o = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * a.h + hyp;
-            a.pcount[o] = cnt[j];
-            a.ps1[o] = s1[j];
-            a.ps2[o] = s2[j];
+        for (int j = 0; j < HPT; ++j) {
+            const long long hyp = hyp_base + (long long)j * kScoreThreads;
+            if (hyp < a.h && tot[j][0]) {
+                const long long HT = a.htotal;
+                unsigned long long* dst = a.acc + (long long)pair * a.h + hyp;
+#pragma unroll
+                for (int k = 0; k < kAccWords; ++k)
+                    if (tot[j][k]) atomicAdd(dst + (long long)k * HT, tot[j][k]);
+            }
         }
     }
 }
@@ -294,6 +378,14 @@ __device__ __forceinline__ Best block_best(Best b, int mode, Best* sm /* 32 */) 
     return b;  // valid in thread 0
 }
 
+// (c2 * 2^46 + c1 * 2^23 + c0) as a double; the chunk sums are < 2^49 each, the total < 2^96.
+__device__ __forceinline__ double fixed69_to_double(unsigned long long c2, unsigned long long c1,
+                                                    unsigned long long c0) {
+    const unsigned __int128 v = ((unsigned __int128)c2 << 46) + ((unsigned __int128)c1 << 23) + c0;
+    const unsigned long long hi = (unsigned long long)(v >> 64), lo = (unsigned long long)v;
+    return fma((double)hi, 18446744073709551616.0, (double)lo);
+}
+
 struct FinalArgs {
     const Corr* pts;
     const long long* offsets;
@@ -302,10 +394,9 @@ struct FinalArgs {
     const int32_t* table;  // may be null: no sample rule
     long long h;
     long long idx_offset;  // global index of hypothesis 0 (hypothesis-sharded runs)
-    int nsplit;
-    const int32_t* pcount;
-    const double* ps1;
-    const double* ps2;
+    long long htotal;                 // npairs * h (stride of the accumulator planes)
+    const unsigned long long* acc;    // [kAccWords][htotal] exact sums from K2
+    double inv_scale1, inv_scale2;    // 2^(e-69), 2^(2e-69)
     double thr, min_extra;
     int agg, mode;
     int32_t* count_extra;
@@ -323,14 +414,10 @@ __global__ void __launch_bounds__(256) k_finalise(const FinalArgs a) {
     Best b;
     b.err = 0.0; b.idx = -1; b.count = 0; b.pad = 0;
     if (li < a.h) {
-        long long cnt = 0;
-        double s1 = 0.0, s2 = 0.0;
-        for (int s = 0; s < a.nsplit; ++s) {
-            const long long o = ((long long)blockIdx.y * a.nsplit + s) * a.h + li;
-            cnt += a.pcount[o];
-            s1 = __dadd_rn(s1, a.ps1[o]);
-            s2 = __dadd_rn(s2, a.ps2[o]);
-        }
+        // exact integer sums -> one rounding each
+        long long cnt = (long long)a.acc[i];
+        double s1 = fixed69_to_double(a.acc[1 * a.htotal + i], a.acc[2 * a.htotal + i], a.acc[3 * a.htotal + i]) * a.inv_scale1;
+        double s2 = fixed69_to_double(a.acc[4 * a.htotal + i], a.acc[5 * a.htotal + i], a.acc[6 * a.htotal + i]) * a.inv_scale2;
         const bool valid = a.valid ? (a.valid[i] != 0) : true;
         if (a.table && valid) {
             double e[9];

@@ -58,8 +58,9 @@ def test_sampler_table_roundtrip(engine):
     assert counts.min() > 20 and counts.max() < 130
 
 
-@pytest.mark.parametrize("variant,hpt", [("screen", 2), ("screen", 1), ("full", 2), ("full", 1)])
-def test_scorer_bit_exact_against_oracle(engine, variant, hpt):
+@pytest.mark.parametrize("variant,hpt,group", [("screen", 1, 4), ("screen", 2, 4), ("full", 1, 4), ("screen", 1, 1),
+                                               ("full", 2, 2), ("screen", 1, 8), ("screen", 2, 1)])
+def test_scorer_bit_exact_against_oracle(engine, variant, hpt, group):
     """K2+K3 with oracle-supplied E's: counts equal, sums within 1e-12 (different summation order)."""
     n, h = 3000, 700
     K, x1, x2, *_ = make_scene(n, 0.4, seed=2)
@@ -70,14 +71,14 @@ def test_scorer_bit_exact_against_oracle(engine, variant, hpt):
     E = np.stack([o.eight_point(ca[s], cb[s]) for s in table])
     cnt_o, s1_o, s2_o = csed.score_batch(E, nxa, nya, nxb, nyb, THR, table=table, nthreads=8)
 
-    engine.set_score_variant(variant, hpt)
+    engine.set_score_variant(variant, hpt, group)
     try:
         engine.upload_pairs(x1, x2, K)
         engine.set_table(table)
         engine.set_models(E)
         cnt, s1, s2, err = engine.score(THR, min_extra=10, aggregation="rms")
     finally:
-        engine.set_score_variant("screen", 2)
+        engine.set_score_variant("screen", 1, 4)
     assert np.array_equal(cnt, cnt_o)
     np.testing.assert_allclose(s1, s1_o, rtol=1e-12, atol=0)
     np.testing.assert_allclose(s2, s2_o, rtol=1e-12, atol=0)

@@ -10,9 +10,10 @@ n, h = {"config2": (10_000, 16_384), "config3": (100_000, 65_536)}[sys.argv[1] i
 variant = sys.argv[2] if len(sys.argv) > 2 else "screen"
 hpt = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 2
+group = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 K, x1, x2, *_ = make_scene(n, 0.4, seed=0)
 eng = _native.get_engine(0)
-eng.set_score_variant(variant, hpt)
+eng.set_score_variant(variant, hpt, group)
 eng.upload_pairs(x1, x2, K)
 for r in range(reps):
     eng.sample_device(r, h)

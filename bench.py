@@ -59,7 +59,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="config3", choices=list(WORKLOADS) + ["config4"])
-    ap.add_argument("--variant", default=os.environ.get("SFM_SCORE_VARIANT", "screen"), choices=["screen", "full"])
+    ap.add_argument("--variant", default=os.environ.get("SFM_SCORE_VARIANT", "screen"), choices=["screen", "full", "screen_ring", "full_ring"])
     ap.add_argument("--hpt", type=int, default=int(os.environ.get("SFM_SCORE_HPT", "1")))
     ap.add_argument("--group", type=int, default=int(os.environ.get("SFM_SCORE_GROUP", "4")))
     ap.add_argument("--pairs", type=int, default=512, help="config4: image pairs per GPU per step")
@@ -354,8 +354,8 @@ def main():
                 "traffic": traffic,
                 "peak_source": "DFMA microbenchmark in this run (sfm_measure_fp64_peak); MEASURED_PEAKS.json has no fp64 entry",
                 "algorithmic_flop_per_eval": FLOP_PER_EVAL,
-                "executed_fp64_slots_per_eval": 12.0 if args.variant == "screen" else 21.0,
-                "fp64_pipe_busy_frac_est": kern_evals * (12.0 if args.variant == "screen" else 21.0) / fp64_peak_dfma,
+                "executed_fp64_slots_per_eval": 12.0 if args.variant.startswith("screen") else 21.0,
+                "fp64_pipe_busy_frac_est": kern_evals * (12.0 if args.variant.startswith("screen") else 21.0) / fp64_peak_dfma,
                 "hbm_achieved_gbs": algo_bytes / (score_ms_per_launch * 1e-3) / 1e9,
                 "hbm_peak_gbs": peaks.get("hbm_gbs"),
             },

@@ -42,8 +42,9 @@ enum sfm_aggregation { SFM_AGG_SUM = 0, SFM_AGG_SQUARE = 1, SFM_AGG_MEAN = 2, SF
 /* lib/ransac/ransac.py:83 selects by minimum aggregated error (default); max-inliers is an extra. */
 enum sfm_selection { SFM_SELECT_MIN_ERROR = 0, SFM_SELECT_MAX_INLIERS = 1 };
 /* scoring kernel variant: screened (12 FP64 slots per evaluation + exact re-check of
- * candidates) or full two-sided decision (21 slots + exact re-check).  Same results. */
-enum sfm_score_variant { SFM_SCORE_SCREEN = 0, SFM_SCORE_FULL = 1 };
+ * candidates) or full two-sided decision (21 slots + exact re-check); resident-range data
+ * movement (default) or the tile-ring form (+2).  All four give identical results. */
+enum sfm_score_variant { SFM_SCORE_SCREEN = 0, SFM_SCORE_FULL = 1, SFM_SCORE_SCREEN_RING = 2, SFM_SCORE_FULL_RING = 3 };
 
 /* ---- context ------------------------------------------------------------------------ */
 int sfm_version(void);

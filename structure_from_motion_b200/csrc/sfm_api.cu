@@ -76,7 +76,7 @@ struct sfm_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     // data
     Buf raw, pts, offsets, Ks, table, E, valid, eig;
-    Buf acc, units, count_extra, S1, S2, err, blocks, best, invalid, winnerE;
+    Buf acc, count_extra, S1, S2, err, blocks, best, invalid, winnerE;
     Buf mask, sed, poses, pass, X, idx, scan, tmp;
     long long n = 0, h = 0, npairs = 1;
     long long raw_stride = 1;
@@ -86,17 +86,12 @@ struct sfm_ctx {
     long long last_idx_offset = 0;
     double Khost[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     // config
-    int variant = SFM_SCORE_SCREEN, hpt = 1, group = 4;
+    int variant = SFM_SCORE_SCREEN, hpt = 4, group = 1;
     // timing
     bool timing = false;
     cudaEvent_t ev0[T_COUNT], ev1[T_COUNT];
     bool ev_used[T_COUNT];
     long long launches = 0;
-    // cached range-unit table of the resident scoring kernel
-    long long unit_sig[6] = {-1, -1, -1, -1, -1, -1};
-    int nunits = 0, unit_replicas = 1, unit_maxcount = 0;
-    void* hunits = nullptr;
-    size_t hunits_cap = 0;
     // pinned scratch for small results
     void* hpin = nullptr;
     size_t hpin_cap = 0;
@@ -134,30 +129,13 @@ int check_launch(sfm_ctx* c, const char* what) {
     return 0;
 }
 
-const void* score_res_kernel(int variant, int hpt, int group) {
-#define SFM_R(H, G, S) reinterpret_cast<const void*>(&k_score_res<H, G, S>)
-    const bool scr = (variant & 1) == SFM_SCORE_SCREEN;
-    if (hpt == 1 && group == 1) return scr ? SFM_R(1, 1, true) : SFM_R(1, 1, false);
-    if (hpt == 1 && group == 2) return scr ? SFM_R(1, 2, true) : SFM_R(1, 2, false);
-    if (hpt == 1 && group == 4) return scr ? SFM_R(1, 4, true) : SFM_R(1, 4, false);
-    if (hpt == 1 && group == 8) return scr ? SFM_R(1, 8, true) : SFM_R(1, 8, false);
-    if (hpt == 2 && group == 1) return scr ? SFM_R(2, 1, true) : SFM_R(2, 1, false);
-    if (hpt == 2 && group == 2) return scr ? SFM_R(2, 2, true) : SFM_R(2, 2, false);
-    if (hpt == 2 && group == 4) return scr ? SFM_R(2, 4, true) : SFM_R(2, 4, false);
-#undef SFM_R
-    return nullptr;
-}
-
 const void* score_kernel(int variant, int hpt, int group) {
-#define SFM_K(H, G, S) reinterpret_cast<const void*>(&k_score<H, G, S>)
-    const bool scr = (variant & 1) == SFM_SCORE_SCREEN;
-    if (hpt == 1 && group == 4) return scr ? SFM_K(1, 4, true) : SFM_K(1, 4, false);
-    if (hpt == 1 && group == 2) return scr ? SFM_K(1, 2, true) : SFM_K(1, 2, false);
-    if (hpt == 1 && group == 1) return scr ? SFM_K(1, 1, true) : SFM_K(1, 1, false);
-    if (hpt == 1 && group == 8) return scr ? SFM_K(1, 8, true) : SFM_K(1, 8, false);
-    if (hpt == 2 && group == 4) return scr ? SFM_K(2, 4, true) : SFM_K(2, 4, false);
-    if (hpt == 2 && group == 2) return scr ? SFM_K(2, 2, true) : SFM_K(2, 2, false);
-    if (hpt == 2 && group == 1) return scr ? SFM_K(2, 1, true) : SFM_K(2, 1, false);
+#define SFM_K(H, G) if (hpt == H && group == G) return scr ? reinterpret_cast<const void*>(&k_score<H, G, true>) \
+                                                           : reinterpret_cast<const void*>(&k_score<H, G, false>)
+    const bool scr = variant == SFM_SCORE_SCREEN;
+    SFM_K(1, 1); SFM_K(1, 2); SFM_K(1, 4); SFM_K(1, 8);
+    SFM_K(2, 1); SFM_K(2, 2); SFM_K(2, 4);
+    SFM_K(4, 1); SFM_K(4, 2);
 #undef SFM_K
     return nullptr;
 }
@@ -245,7 +223,7 @@ int sfm_destroy(sfm_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    Buf* bufs[] = {&c->raw, &c->pts, &c->offsets, &c->Ks, &c->table, &c->E, &c->valid, &c->eig, &c->acc, &c->units,
+    Buf* bufs[] = {&c->raw, &c->pts, &c->offsets, &c->Ks, &c->table, &c->E, &c->valid, &c->eig, &c->acc,
                    &c->count_extra, &c->S1, &c->S2, &c->err, &c->blocks, &c->best,
                    &c->invalid, &c->winnerE, &c->mask, &c->sed, &c->poses, &c->pass, &c->X, &c->idx,
                    &c->scan, &c->tmp};
@@ -255,7 +233,6 @@ int sfm_destroy(sfm_ctx* c) {
         cudaEventDestroy(c->ev1[i]);
     }
     if (c->hpin) cudaFreeHost(c->hpin);
-    if (c->hunits) cudaFreeHost(c->hunits);
     cudaStreamDestroy(c->own_stream);
     delete c;
     return 0;
@@ -275,9 +252,9 @@ int sfm_synchronize(sfm_ctx* c) {
 
 int sfm_set_score_variant(sfm_ctx* c, int variant, int hpt, int group) {
     if (!c) return fail(SFM_ERR_ARG, "null context");
-    if (variant < 0 || variant > 3) return fail(SFM_ERR_ARG, "bad variant %d", variant);
+    if (variant != SFM_SCORE_SCREEN && variant != SFM_SCORE_FULL) return fail(SFM_ERR_ARG, "bad variant %d", variant);
     const int nh = hpt ? hpt : c->hpt, ng = group ? group : c->group;
-    if (!((variant & 2) ? score_kernel(variant, nh, ng) : score_res_kernel(variant, nh, ng)))
+    if (!score_kernel(variant, nh, ng))
         return fail(SFM_ERR_ARG, "unsupported combination: hyps_per_thread %d, group %d", nh, ng);
     c->variant = variant;
     c->hpt = nh;
@@ -541,11 +518,10 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
     // rounding guard of the screening tests: relative slack + an absolute term that covers a
     // cancelling residual r at the 1-ulp level (only matters for thr -> 0)
     const double thr_pre = thr * (1.0 + 1e-9) + 1e-22;
-    const double scale1 = ldexp(1.0, 23 - e2), scale2 = ldexp(1.0, 23 - 2 * e2);
+    const double scale1 = ldexp(1.0, 14 - e2), scale2 = ldexp(1.0, 14 - 2 * e2);
     unsigned long long* acc_dev = nullptr;
-
-    if (c->variant & 2) {
-        // ---- legacy ring kernel: persistent blocks over (pair, split, hypothesis block) items ----
+    {
+        // persistent blocks over (pair, split, hypothesis block) items
         const void* fn = score_kernel(c->variant, hpt, G);
         if (!fn) return fail(SFM_ERR_ARG, "unsupported scoring configuration (variant %d, hpt %d, group %d)", c->variant, hpt, G);
         int occ = 0;
@@ -557,6 +533,8 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         long long nsplit = (target_items + hblocks * P - 1) / (hblocks * P);
         const long long max_split = tiles / 8 > 0 ? tiles / 8 : 1;  // keep >= 8 tiles per item
         if (nsplit > max_split) nsplit = max_split;
+        const long long min_split = (max_len + kMaxItemPoints - 1) / kMaxItemPoints;  // 32-bit chunk sums cannot overflow
+        if (nsplit < min_split) nsplit = min_split;
         if (nsplit < 1) nsplit = 1;
         const long long chunk = ((tiles + nsplit - 1) / nsplit) * kTile;
         nsplit = (max_len + chunk - 1) / chunk;
@@ -588,116 +566,6 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         CU(cudaLaunchKernel(fn, dim3((unsigned)launch_blocks), dim3(kScoreThreads), kargs, 0, c->stream));
         if (int r = check_launch(c, "k_score")) return r;
         c->toc(T_SCORE);
-    } else {
-        // ---- resident-range kernel (default) ----
-        const void* fn = score_res_kernel(c->variant, hpt, G);
-        if (!fn) return fail(SFM_ERR_ARG, "unsupported scoring configuration (variant %d, hpt %d, group %d)", c->variant, hpt, G);
-        const size_t max_smem = (size_t)kMaxRange * sizeof(Corr);
-        CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-        int occ = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kScoreThreads, max_smem));
-        if (occ < 1) occ = 1;
-        const long long grid_blocks = (long long)c->sm_count * occ;
-        const long long nsets = (h + 32 * hpt - 1) / (32 * hpt);
-        const long long sig[6] = {c->batched ? -2 : c->n, P, h, hpt, grid_blocks, c->batched ? -2 : 0};
-        bool reuse = !c->batched && memcmp(sig, c->unit_sig, sizeof sig) == 0;
-        if (!reuse) {
-            // ranges ("units") of <= kMaxRange correspondences
-            std::vector<RangeUnit> units;
-            int replicas = 1;
-            if (!c->batched) {
-                const long long n = c->n;
-                long long need = (n + kMaxRange - 1) / kMaxRange;
-                const long long for_sets = (64 * grid_blocks + nsets - 1) / nsets;  // >= 16 sets per warp
-                if (for_sets > need) need = for_sets;
-                long long cap = n / 64 > 0 ? n / 64 : 1;                            // >= 64 records per range
-                if (need > cap) need = cap;
-                if (need < (n + kMaxRange - 1) / kMaxRange) need = (n + kMaxRange - 1) / kMaxRange;
-                // smallest count >= need that tiles the grid exactly: a divisor or a multiple of it
-                long long nu = -1;
-                for (long long d = need; d <= grid_blocks; ++d)
-                    if (grid_blocks % d == 0) { nu = d; break; }
-                if (nu < 0) nu = ((need + grid_blocks - 1) / grid_blocks) * grid_blocks;
-                if (nu > n) nu = n;
-                replicas = nu <= grid_blocks ? (int)(grid_blocks / nu) : 1;
-                const long long base = n / nu, rem = n % nu;
-                long long first = 0;
-                for (long long k = 0; k < nu; ++k) {
-                    const int cnt = (int)(base + (k < rem ? 1 : 0));
-                    units.push_back(RangeUnit{first, cnt, 0});
-                    first += cnt;
-                }
-            } else {
-                std::vector<long long> off((size_t)P + 1);
-                CU(cudaMemcpyAsync(off.data(), c->offsets.p, (size_t)(P + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
-                CU(cudaStreamSynchronize(c->stream));
-                for (long long p = 0; p < P; ++p) {
-                    const long long len = off[(size_t)p + 1] - off[(size_t)p];
-                    if (len <= 0) continue;
-                    const long long r = (len + kMaxRange - 1) / kMaxRange;
-                    const long long base = len / r, rem = len % r;
-                    long long first = off[(size_t)p];
-                    for (long long k = 0; k < r; ++k) {
-                        const int cnt = (int)(base + (k < rem ? 1 : 0));
-                        units.push_back(RangeUnit{first, cnt, (int)p});
-                        first += cnt;
-                    }
-                }
-                // replicas k minimise idle time: 2k/nsets (warps waiting at the end of a slot)
-                // + grid/(2 nunits k) (blocks idle at the end of the launch)
-                const double kopt = sqrt((double)grid_blocks * (double)nsets / (4.0 * (double)(units.size() ? units.size() : 1)));
-                replicas = (int)(kopt + 0.5);
-                if (replicas < 1) replicas = 1;
-                if (replicas > 8) replicas = 8;
-            }
-            const size_t ub = units.size() * sizeof(RangeUnit);
-            if (ub > c->hunits_cap) {
-                if (c->hunits) cudaFreeHost(c->hunits);
-                c->hunits = nullptr;
-                CU(cudaMallocHost(&c->hunits, ub + 4096));
-                c->hunits_cap = ub + 4096;
-            }
-            if (int r = c->units.reserve(ub + 16)) return r;
-            CU(cudaStreamSynchronize(c->stream));  // the previous table upload has been consumed
-            int maxc = 0;
-            for (const RangeUnit& ru : units) maxc = ru.count > maxc ? ru.count : maxc;
-            if (ub) {
-                memcpy(c->hunits, units.data(), ub);
-                CU(cudaMemcpyAsync(c->units.p, c->hunits, ub, cudaMemcpyHostToDevice, c->stream));
-            }
-            c->nunits = (int)units.size();
-            c->unit_replicas = replicas;
-            c->unit_maxcount = maxc;
-            memcpy(c->unit_sig, sig, sizeof sig);
-        }
-        const size_t counters = ((size_t)c->nunits + 1) * 4 + 60;
-        if (int r = c->acc.reserve(H * kAccWords * 8 + counters)) return r;
-        ScoreResArgs a;
-        a.pts = c->pts.as<Corr>();
-        a.E = c->E.as<double>();
-        a.h = h;
-        a.htotal = (long long)H;
-        a.thr = thr;
-        a.thr_pre = thr_pre;
-        a.scale1 = scale1;
-        a.scale2 = scale2;
-        a.units = c->units.as<RangeUnit>();
-        a.nunits = c->nunits;
-        a.total_slots = (unsigned)((long long)c->nunits * c->unit_replicas);
-        a.acc = c->acc.as<unsigned long long>();
-        a.slot_counter = reinterpret_cast<unsigned*>(a.acc + H * kAccWords);
-        a.set_counters = a.slot_counter + 1;
-        acc_dev = a.acc;
-        c->tic(T_SCORE);
-        CU(cudaMemsetAsync(c->acc.p, 0, H * kAccWords * 8 + counters, c->stream));
-        if (c->nunits > 0) {
-            const long long launch_blocks = grid_blocks < (long long)a.total_slots ? grid_blocks : (long long)a.total_slots;
-            void* kargs[] = {(void*)&a};
-            CU(cudaLaunchKernel(fn, dim3((unsigned)launch_blocks), dim3(kScoreThreads), kargs,
-                                (size_t)c->unit_maxcount * sizeof(Corr), c->stream));
-            if (int r = check_launch(c, "k_score_res")) return r;
-        }
-        c->toc(T_SCORE);
     }
 
     c->tic(T_SELECT);
@@ -711,8 +579,8 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
     f.idx_offset = idx_offset;
     f.htotal = (long long)H;
     f.acc = acc_dev;
-    f.inv_scale1 = ldexp(1.0, e2 - 69);
-    f.inv_scale2 = ldexp(1.0, 2 * e2 - 69);
+    f.inv_scale1 = ldexp(1.0, e2 - 70);
+    f.inv_scale2 = ldexp(1.0, 2 * e2 - 70);
     f.thr = thr;
     f.min_extra = min_extra;
     f.agg = agg;

@@ -34,7 +34,8 @@ __device__ __forceinline__ double sed_exact(const double (&e)[9], double xa, dou
     const double r = __dadd_rn(__fma_rn(lb1, ya, __dmul_rn(lb0, xa)), lb2);
     const double na = __dadd_rn(__dmul_rn(la0, la0), __dmul_rn(la1, la1));
     const double nb = __dadd_rn(__dmul_rn(lb0, lb0), __dmul_rn(lb1, lb1));
-    return __dmul_rn(__dadd_rn(__ddiv_rn(1.0, na), __ddiv_rn(1.0, nb)), __dmul_rn(r, r));
+    // __drcp_rn is the correctly rounded reciprocal: bit-identical to the IEEE division 1.0 / x
+    return __dmul_rn(__dadd_rn(__drcp_rn(na), __drcp_rn(nb)), __dmul_rn(r, r));
 }
 
 // Screening form: 12 FP64 issue slots.  Returns d = r^2 - thr_pre * nb; a correspondence

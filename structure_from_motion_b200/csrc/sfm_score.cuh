@@ -53,38 +53,42 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 // point here; K3 applies the "samples are not thresholded but always counted in the
 // error" rule of ransac.py:63-64,76.)
 //
-// Mapping: lane = hypothesis.  Each thread keeps HPT essential matrices in registers and
-// streams correspondences from shared-memory tiles (every lane of a warp reads the same
-// 32-byte record: a broadcast, conflict-free).  Tiles are filled by 1-D bulk async copies
-// (TMA) into a kStages-deep ring signalled through mbarriers; a stage is refilled by
-// whichever warp finishes it last, so no warp ever waits for a slower one (warps may drift
-// kStages-1 tiles apart) and there is no block barrier in the loop.
+// Mapping: lane = hypothesis.  Each thread keeps HPT essential matrices in registers
+// (HPT = 4 by default: one broadcast read of a 32-byte correspondence from shared memory
+// feeds 4 x 32 evaluations, which keeps the shared-memory pipe at ~1/4 of the FP64 pipe's
+// appetite) and streams correspondences from shared-memory tiles.  Tiles are filled by
+// 1-D bulk async copies (TMA) into a kStages-deep ring signalled through mbarriers; a stage
+// is refilled by whichever warp finishes it last, so no warp ever waits for a slower one
+// (warps may drift kStages-1 tiles apart) and there is no block barrier in the loop.
 //
 // Persistent blocks: the grid is one wave (SMs x resident blocks); work items
-// (pair, correspondence split, hypothesis block) are claimed from an atomic counter, which
-// balances the uneven cost of "good" hypotheses.
+// (pair, correspondence split, hypothesis block) are claimed from an atomic counter.
 //
-// Two-level evaluation.  G correspondences are evaluated per step with a cheap
-// division-free test (SCREEN: 12 FP64 issue slots using only the image-A distance, a
-// necessary condition; FULL: the 21-slot two-sided decision).  Candidates (~1 %) are pushed
+// Two-level evaluation.  Every (hypothesis, correspondence) gets a cheap division-free test
+// (SCREEN: 12 FP64 issue slots using only the image-A distance, a necessary condition;
+// FULL: the 21-slot two-sided decision).  The screen is written hypothesis-innermost so that
+// consecutive DFMAs share the correspondence operand (operand-reuse cache: a DFMA with three
+// fresh 64-bit register operands issues at 2/3 rate on sm_100).  Survivors (~1 %) are pushed
 // to a per-warp ring and processed 32 at a time by all lanes (dense, no divergence): the
 // exact reference-order SED is evaluated and compared with thr.
 //
-// Exact accumulation.  An inlier's sed (and sed^2) is split into three 23-bit chunks of a
-// fixed-point number scaled so that thr < 2^0 maps below 2^69; chunks are added with native
-// 32-bit shared-memory atomics, folded into 64-bit registers of the owning lane, and finally
-// into 64-bit global accumulators.  Integer addition is associative, so the sums are EXACT
-// (every double s >= thr*2^-16 is represented without rounding) and independent of warp
-// scheduling, split count and GPU count — run-to-run deterministic by construction, and
-// closer to the true sum than any floating-point summation order (numpy's included).
+// Exact accumulation.  An inlier's sed (and sed^2) is split into five 14-bit chunks of a
+// fixed-point number scaled so that thr < 2^e maps below 2^70; chunks are added with native
+// 32-bit shared-memory atomics (a word cannot overflow within an item of <= 2^17
+// correspondences) and folded into 64-bit global accumulators at the end of the item.
+// Integer addition is associative, so the sums are EXACT (every double s >= thr*2^-17 is
+// represented without rounding) and independent of warp scheduling, split count and GPU
+// count — run-to-run deterministic by construction, and closer to the true sum than any
+// floating-point summation order (numpy's included).
 // ------------------------------------------------------------------------------------
 constexpr int kScoreThreads = 128;
 constexpr int kScoreWarps = kScoreThreads / 32;
 constexpr int kTile = 128;    // correspondences per stage (4 KB)
 constexpr int kStages = 4;
-constexpr unsigned kMaxPoints = 1u << 26;
-constexpr int kAccWords = 7;  // count, 3 chunks of sum(sed), 3 chunks of sum(sed^2)
-constexpr int kFlushEvery = 8;
+constexpr unsigned kMaxPoints = 1u << 25;
+constexpr int kChunks = 5;             // 14-bit chunks per exact sum
+constexpr int kAccWords = 1 + 2 * kChunks;  // count, sum(sed), sum(sed^2)
+constexpr long long kMaxItemPoints = 1ll << 17;  // 2^17 adds of <= 2^14 cannot overflow a 32-bit word
 
 struct ScoreArgs {
     const Corr* pts;
@@ -93,13 +97,13 @@ struct ScoreArgs {
     const double* E;           // [npairs][h][9]
     long long h;
     double thr, thr_pre;
-    double scale1, scale2;     // 2^(23-e), 2^(23-2e) with thr < 2^e
+    double scale1, scale2;     // 2^(14-e), 2^(14-2e) with thr < 2^e
     long long chunk;           // correspondences per split (multiple of kTile)
     int hblocks, nsplit;
     long long total_items;
     long long htotal;          // npairs * h
     unsigned* work_counter;
-    unsigned long long* acc;   // [kAccWords][npairs*h] exact integer accumulators (pre-zeroed)
+    unsigned long long* acc;   // [kAccWords][htotal] exact integer accumulators (pre-zeroed)
 };
 
 __device__ __forceinline__ unsigned atom_add_acq_rel_shared(unsigned* p, unsigned v) {
@@ -108,18 +112,21 @@ __device__ __forceinline__ unsigned atom_add_acq_rel_shared(unsigned* p, unsigne
     return old;
 }
 
-// three 23-bit chunks of floor(x * 2^46), x in [0, 2^23)
-__device__ __forceinline__ void chunks23(double x, unsigned& c2, unsigned& c1, unsigned& c0) {
-    c2 = __double2uint_rz(x);
-    const double r1 = (x - (double)c2) * 8388608.0;
-    c1 = __double2uint_rz(r1);
-    const double r0 = (r1 - (double)c1) * 8388608.0;
-    c0 = __double2uint_rn(r0);
+// five 14-bit chunks of floor(x * 2^56), x in [0, 2^14): c[4] is the most significant
+__device__ __forceinline__ void chunks14(double x, unsigned (&c)[kChunks]) {
+#pragma unroll
+    for (int k = kChunks - 1; k > 0; --k) {
+        c[k] = __double2uint_rz(x);
+        x = (x - (double)c[k]) * 16384.0;
+    }
+    c[0] = __double2uint_rn(x);
 }
 
 template <int HPT, int G, bool SCREEN>
 __global__ void __launch_bounds__(kScoreThreads) k_score(const ScoreArgs a) {
-    constexpr int RING = (HPT * G >= 8) ? 512 : 64 * HPT * G;  // >= new entries of one push slice + 31 pending
+    constexpr int NB = HPT * G;  // survivor bits per step
+    static_assert(NB <= 16, "at most 16 evaluations per lane and step");
+    constexpr int RING = 64 * NB;  // >= 32*NB new + 31 pending
     __shared__ __align__(128) Corr tile[kStages][kTile];
     __shared__ __align__(8) unsigned long long full_bar[kStages];
     __shared__ unsigned done[kStages];
@@ -163,7 +170,8 @@ __global__ void __launch_bounds__(kScoreThreads) k_score(const ScoreArgs a) {
         const long long end = pbase + ((begin + a.chunk < plen) ? begin + a.chunk : plen);
         begin += pbase;
         const int ntiles = (int)((end - begin + kTile - 1) / kTile);
-        const long long hyp_base = (long long)hb * (kScoreThreads * HPT) + threadIdx.x;
+        // this warp's hypotheses: lane l, slot j  ->  hyp_w + 32*j + l
+        const long long hyp_w = (long long)hb * (kScoreThreads * HPT) + (long long)warp * (32 * HPT);
         const double* Ep = a.E + 9 * (long long)pair * a.h;
 
         auto issue = [&](int t) {
@@ -180,96 +188,92 @@ __global__ void __launch_bounds__(kScoreThreads) k_score(const ScoreArgs a) {
         double e[HPT][9];
 #pragma unroll
         for (int j = 0; j < HPT; ++j) {
-            const long long hyp = hyp_base + (long long)j * kScoreThreads;
+            const long long hyp = hyp_w + 32 * j + lane;
 #pragma unroll
             for (int k = 0; k < 9; ++k) e[j][k] = (hyp < a.h) ? Ep[9 * hyp + k] : 0.0;
         }
-        unsigned long long tot[HPT][kAccWords];
-#pragma unroll
-        for (int j = 0; j < HPT; ++j)
-#pragma unroll
-            for (int k = 0; k < kAccWords; ++k) tot[j][k] = 0ull;
-        int drains = 0;
 
-        // fold the warp's shared 32-bit chunk sums into the owning lanes' 64-bit registers
-        auto flush = [&]() {
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < HPT; ++j)
-#pragma unroll
-                for (int k = 0; k < kAccWords; ++k) {
-                    tot[j][k] += sacc[warp][j][k][lane];
-                    sacc[warp][j][k][lane] = 0;
-                }
-            __syncwarp();
-            drains = 0;
-        };
-
-        // exact evaluation of m (<= 32) queued candidates by all 32 lanes
+        // exact evaluation of m (<= 32) queued candidates by all 32 lanes; the candidate's E
+        // comes from global memory (L1/L2 hits), its correspondence by index
         auto drain = [&](unsigned m) {
-            const unsigned ent = (lane < (int)m) ? q[(head + lane) & (RING - 1)] : ((unsigned)lane << 27);
+            const unsigned ent = (lane < (int)m) ? q[(head + lane) & (RING - 1)] : 0u;
             const int owner = (int)(ent >> 27);
-            const int slot = (int)((ent >> 26) & 1u);
+            const int slot = (int)((ent >> 25) & 3u);
             const unsigned gi = ent & (kMaxPoints - 1u);
+            long long hyp = hyp_w + 32 * slot + owner;
+            hyp = (hyp < a.h) ? hyp : 0;
             double eo[9];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                double v = __shfl_sync(full, e[0][k], owner);
-                if (HPT == 2) {
-                    const double v1 = __shfl_sync(full, e[HPT - 1][k], owner);
-                    v = slot ? v1 : v;
-                }
-                eo[k] = v;
-            }
-            const Corr c = a.pts[gi];
+            for (int k = 0; k < 9; ++k) eo[k] = __ldg(Ep + 9 * hyp + k);
+            const Corr c = a.pts[(lane < (int)m) ? gi : (unsigned)begin];
             const double sv = sed_exact(eo, c.xa, c.ya, c.xb, c.yb);
             if ((lane < (int)m) && (sv <= a.thr)) {  // ransac.py:73  score <= threshold
-                unsigned c2, c1, c0;
-                unsigned* dst = &sacc[warp][HPT == 2 ? slot : 0][0][owner];
+                unsigned ch[kChunks];
+                unsigned* dst = &sacc[warp][slot][0][owner];
                 atomicAdd(dst, 1u);
-                chunks23(sv * a.scale1, c2, c1, c0);
-                atomicAdd(dst + 32, c2);
-                atomicAdd(dst + 64, c1);
-                atomicAdd(dst + 96, c0);
-                chunks23(__dmul_rn(sv, sv) * a.scale2, c2, c1, c0);
-                atomicAdd(dst + 128, c2);
-                atomicAdd(dst + 160, c1);
-                atomicAdd(dst + 192, c0);
+                chunks14(sv * a.scale1, ch);
+#pragma unroll
+                for (int k = 0; k < kChunks; ++k) atomicAdd(dst + 32 * (1 + k), ch[k]);
+                chunks14(__dmul_rn(sv, sv) * a.scale2, ch);
+#pragma unroll
+                for (int k = 0; k < kChunks; ++k) atomicAdd(dst + 32 * (1 + kChunks + k), ch[k]);
             }
             head += m;
-            if (++drains >= kFlushEvery) flush();
         };
 
-        // one step: G correspondences starting at tile record p (global index gi0)
+        // one step: GG correspondences x HPT hypotheses per lane
         auto step = [&](const Corr* tp, int p, unsigned gi0, auto gtag) {
             constexpr int GG = decltype(gtag)::value;
-            Corr c[GG];
+            unsigned pm = 0;  // survivor bits; evaluation i = g*HPT + j ends up at bit GG*HPT-1-i
 #pragma unroll
-            for (int g = 0; g < GG; ++g) c[g] = tp[p + g];
-            unsigned pm = 0;
+            for (int g = 0; g < GG; ++g) {
+                const Corr c = tp[p + g];
+                double d[HPT];
+                if (SCREEN) {
+                    // hypothesis-innermost: consecutive DFMAs share c.yb / c.xb / c.ya / c.xa
+                    double t0[HPT], t1[HPT], t2[HPT];
 #pragma unroll
-            for (int j = 0; j < HPT; ++j)
-#pragma unroll
-                for (int g = 0; g < GG; ++g) {
-                    const double d = SCREEN ? sed_screen(e[j], c[g].xa, c[g].ya, c[g].xb, c[g].yb, a.thr_pre)
-                                            : sed_full_decision(e[j], c[g].xa, c[g].ya, c[g].xb, c[g].yb, a.thr_pre);
-                    pm |= ((unsigned)__double2hiint(d) >> 31) << (j * GG + g);
-                }
-            // push in slices of <= 8 bit positions (<= 256 new entries) so that the ring never overflows
-#pragma unroll
-            for (int c0 = 0; c0 < HPT * GG; c0 += 8) {
-                unsigned mbits = (pm >> c0) & 0xffu;
-                if (__any_sync(full, mbits != 0u)) {
-                    while (mbits) {  // usually one bit in a few lanes
-                        const int k = c0 + __ffs(mbits) - 1;
-                        mbits &= mbits - 1;
-                        const unsigned pos = atomicAdd(&ring_tail[warp], 1u);
-                        q[pos & (RING - 1)] = ((unsigned)lane << 27) | ((unsigned)(k / GG) << 26) | (gi0 + (unsigned)(k % GG));
+                    for (int j = 0; j < HPT; ++j) {
+                        t0[j] = fma(c.yb, e[j][3], e[j][6]);
+                        t1[j] = fma(c.yb, e[j][4], e[j][7]);
+                        t2[j] = fma(c.yb, e[j][5], e[j][8]);
                     }
-                    __syncwarp();
-                    const unsigned tail = *(volatile unsigned*)&ring_tail[warp];
-                    while (tail - head >= 32u) drain(32u);
+#pragma unroll
+                    for (int j = 0; j < HPT; ++j) {
+                        t0[j] = fma(c.xb, e[j][0], t0[j]);  // lb0
+                        t1[j] = fma(c.xb, e[j][1], t1[j]);  // lb1
+                        t2[j] = fma(c.xb, e[j][2], t2[j]);  // lb2
+                    }
+#pragma unroll
+                    for (int j = 0; j < HPT; ++j) t2[j] = fma(c.ya, t1[j], t2[j]);
+#pragma unroll
+                    for (int j = 0; j < HPT; ++j) t2[j] = fma(c.xa, t0[j], t2[j]);  // r
+#pragma unroll
+                    for (int j = 0; j < HPT; ++j) t1[j] = t1[j] * t1[j];
+#pragma unroll
+                    for (int j = 0; j < HPT; ++j) t1[j] = fma(t0[j], t0[j], t1[j]);  // nb
+#pragma unroll
+                    for (int j = 0; j < HPT; ++j) t1[j] = t1[j] * a.thr_pre;
+#pragma unroll
+                    for (int j = 0; j < HPT; ++j) d[j] = fma(t2[j], t2[j], -t1[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < HPT; ++j) d[j] = sed_full_decision(e[j], c.xa, c.ya, c.xb, c.yb, a.thr_pre);
                 }
+#pragma unroll
+                for (int j = 0; j < HPT; ++j) pm = __funnelshift_l((unsigned)__double2hiint(d[j]), pm, 1);
+            }
+            if (__any_sync(full, pm != 0u)) {
+                while (pm) {  // usually one bit in a few lanes
+                    const int b = __ffs(pm) - 1;
+                    pm &= pm - 1;
+                    const int i = GG * HPT - 1 - b;
+                    const unsigned pos = atomicAdd(&ring_tail[warp], 1u);
+                    q[pos & (RING - 1)] = ((unsigned)lane << 27) | ((unsigned)(i % HPT) << 25) | (gi0 + (unsigned)(i / HPT));
+                }
+                __syncwarp();
+                const unsigned tail = *(volatile unsigned*)&ring_tail[warp];
+                while (tail - head >= 32u) drain(32u);
             }
         };
 
@@ -300,232 +304,23 @@ __global__ void __launch_bounds__(kScoreThreads) k_score(const ScoreArgs a) {
             __syncwarp();
             const unsigned tail = *(volatile unsigned*)&ring_tail[warp];
             while (tail != head) drain(tail - head < 32u ? tail - head : 32u);
-            flush();
+            __syncwarp();
         }
 #pragma unroll
         for (int j = 0; j < HPT; ++j) {
-            const long long hyp = hyp_base + (long long)j * kScoreThreads;
-            if (hyp < a.h && tot[j][0]) {
-                const long long HT = a.htotal;
+            const long long hyp = hyp_w + 32 * j + lane;
+            const unsigned cnt = sacc[warp][j][0][lane];
+            if (cnt) {  // only real hypotheses can have inliers
                 unsigned long long* dst = a.acc + (long long)pair * a.h + hyp;
+                atomicAdd(dst, (unsigned long long)cnt);
+                sacc[warp][j][0][lane] = 0;
 #pragma unroll
-                for (int k = 0; k < kAccWords; ++k)
-                    if (tot[j][k]) atomicAdd(dst + (long long)k * HT, tot[j][k]);
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------
-// K2, resident-range form (the default).
-//
-// Same evaluation, queue and exact accumulation as k_score above, different data movement:
-// a block keeps ONE range of correspondences (<= kMaxRange records, one TMA bulk copy)
-// resident in shared memory and its four warps independently claim sets of 32*HPT
-// hypotheses from a per-range global counter until the range has met every hypothesis.
-// No per-tile mbarrier waits, no stage hand-off, no block barrier inside a range, and warps
-// that draw expensive ("good") hypotheses do not hold the others back; several blocks can
-// share a range (their sets come from the same counter), which is how a single large pair
-// fills the machine.  Range "units" and their (pair, first, count) live in a small table
-// built by the host; blocks claim (unit, replica) slots from a global counter.
-// ------------------------------------------------------------------------------------
-constexpr int kMaxRange = 1344;  // 42 KB of Corr: four blocks per SM
-
-struct RangeUnit {
-    long long first;  // global record index
-    int count;
-    int pair;
-};
-
-struct ScoreResArgs {
-    const Corr* pts;
-    const double* E;  // [npairs][h][9]
-    long long h;
-    long long htotal;
-    double thr, thr_pre, scale1, scale2;
-    const RangeUnit* units;
-    int nunits;
-    unsigned total_slots;      // nunits * replicas
-    unsigned* slot_counter;    // 1
-    unsigned* set_counters;    // [nunits]
-    unsigned long long* acc;   // [kAccWords][htotal]
-};
-
-template <int HPT, int G, bool SCREEN>
-__global__ void __launch_bounds__(kScoreThreads) k_score_res(const ScoreResArgs a) {
-    constexpr int RING = 512 * HPT;  // one push slice adds <= 256*HPT entries to <= 31 pending
-    extern __shared__ __align__(128) unsigned char res_smem[];
-    Corr* range = reinterpret_cast<Corr*>(res_smem);
-    __shared__ __align__(8) unsigned long long full_bar;
-    __shared__ unsigned ring[kScoreWarps][RING];
-    __shared__ unsigned ring_tail[kScoreWarps];
-    __shared__ unsigned sacc[kScoreWarps][HPT][kAccWords][32];
-    __shared__ unsigned s_slot;
-
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) {
-        mbar_init(&full_bar, 1);
-        mbar_fence_init();
-    }
-    if (lane == 0) ring_tail[warp] = 0;
-#pragma unroll
-    for (int j = 0; j < HPT; ++j)
-#pragma unroll
-        for (int k = 0; k < kAccWords; ++k) sacc[warp][j][k][lane] = 0;
-    unsigned* q = ring[warp];
-    unsigned head = 0;
-    const unsigned nsets = (unsigned)((a.h + 32 * HPT - 1) / (32 * HPT));
-
-    for (unsigned round = 0;; ++round) {
-        __syncthreads();  // every warp is done with the resident range
-        if (threadIdx.x == 0) s_slot = atomicAdd(a.slot_counter, 1u);
-        __syncthreads();
-        const unsigned slot = s_slot;
-        if (slot >= a.total_slots) break;
-        const int unit = (int)(slot % (unsigned)a.nunits);
-        const RangeUnit u = a.units[unit];
-        if (threadIdx.x == 0) {
-            const uint32_t bytes = (uint32_t)u.count * (uint32_t)sizeof(Corr);
-            mbar_expect_tx(&full_bar, bytes);
-            bulk_g2s(range, a.pts + u.first, bytes, &full_bar);
-        }
-        mbar_wait(&full_bar, round & 1u);
-        const double* Ep = a.E + 9 * (long long)u.pair * a.h;
-        const int np = u.count;
-
-        for (;;) {
-            unsigned set = 0;
-            if (lane == 0) set = atomicAdd(&a.set_counters[unit], 1u);
-            set = __shfl_sync(full, set, 0);
-            if (set >= nsets) break;
-            const long long hyp0 = (long long)set * (32 * HPT) + lane;
-
-            double e[HPT][9];
-#pragma unroll
-            for (int j = 0; j < HPT; ++j) {
-                const long long hyp = hyp0 + 32 * j;
-#pragma unroll
-                for (int k = 0; k < 9; ++k) e[j][k] = (hyp < a.h) ? Ep[9 * hyp + k] : 0.0;
-            }
-            unsigned long long tot[HPT][kAccWords];
-#pragma unroll
-            for (int j = 0; j < HPT; ++j)
-#pragma unroll
-                for (int k = 0; k < kAccWords; ++k) tot[j][k] = 0ull;
-            int drains = 0;
-
-            // fold the warp's shared 32-bit chunk sums into the owning lanes' 64-bit registers
-            auto flush = [&]() {
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < HPT; ++j)
-#pragma unroll
-                    for (int k = 0; k < kAccWords; ++k) {
-                        tot[j][k] += sacc[warp][j][k][lane];
+                for (int k = 1; k < kAccWords; ++k) {
+                    const unsigned v = sacc[warp][j][k][lane];
+                    if (v) {
+                        atomicAdd(dst + (long long)k * a.htotal, (unsigned long long)v);
                         sacc[warp][j][k][lane] = 0;
                     }
-                __syncwarp();
-                drains = 0;
-            };
-
-            // exact evaluation of m (<= 32) queued candidates by all 32 lanes
-            auto drain = [&](unsigned m) {
-                const unsigned ent = (lane < (int)m) ? q[(head + lane) & (RING - 1)] : ((unsigned)lane << 27);
-                const int owner = (int)(ent >> 27);
-                const int slot_j = (int)((ent >> 26) & 1u);
-                const unsigned pi = ent & 0xffffu;  // index into the resident range
-                double eo[9];
-#pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    double v = __shfl_sync(full, e[0][k], owner);
-                    if (HPT == 2) {
-                        const double v1 = __shfl_sync(full, e[HPT - 1][k], owner);
-                        v = slot_j ? v1 : v;
-                    }
-                    eo[k] = v;
-                }
-                const Corr c = range[pi];
-                const double sv = sed_exact(eo, c.xa, c.ya, c.xb, c.yb);
-                if ((lane < (int)m) && (sv <= a.thr)) {  // ransac.py:73  score <= threshold
-                    unsigned c2, c1, c0;
-                    unsigned* dst = &sacc[warp][HPT == 2 ? slot_j : 0][0][owner];
-                    atomicAdd(dst, 1u);
-                    chunks23(sv * a.scale1, c2, c1, c0);
-                    atomicAdd(dst + 32, c2);
-                    atomicAdd(dst + 64, c1);
-                    atomicAdd(dst + 96, c0);
-                    chunks23(__dmul_rn(sv, sv) * a.scale2, c2, c1, c0);
-                    atomicAdd(dst + 128, c2);
-                    atomicAdd(dst + 160, c1);
-                    atomicAdd(dst + 192, c0);
-                }
-                head += m;
-                if (++drains >= kFlushEvery) flush();
-            };
-
-            // 32 correspondences per chunk: screen them G at a time into per-lane bit masks,
-            // then push the survivors of the whole chunk in one go
-            for (int p0 = 0; p0 < np; p0 += 32) {
-                const int nv = (np - p0 < 32) ? (np - p0) : 32;
-                unsigned pm[HPT];
-#pragma unroll
-                for (int j = 0; j < HPT; ++j) pm[j] = 0u;
-#pragma unroll 1
-                for (int g0 = 0; g0 < nv; g0 += G) {
-#pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        int pi = p0 + g0 + g;
-                        pi = (pi < np) ? pi : (np - 1);  // clamped duplicates are masked off below
-                        const Corr c = range[pi];
-#pragma unroll
-                        for (int j = 0; j < HPT; ++j) {
-                            const double d = SCREEN ? sed_screen(e[j], c.xa, c.ya, c.xb, c.yb, a.thr_pre)
-                                                    : sed_full_decision(e[j], c.xa, c.ya, c.xb, c.yb, a.thr_pre);
-                            pm[j] |= ((unsigned)__double2hiint(d) >> 31) << (g0 + g);
-                        }
-                    }
-                }
-                const unsigned vmask = (nv == 32) ? 0xffffffffu : ((1u << nv) - 1u);
-                bool any = false;
-#pragma unroll
-                for (int j = 0; j < HPT; ++j) {
-                    pm[j] &= vmask;
-                    any |= pm[j] != 0u;
-                }
-                if (__any_sync(full, any)) {
-#pragma unroll 1
-                    for (int c0 = 0; c0 < 32; c0 += 8) {  // slices of 8 bit positions bound the ring
-#pragma unroll
-                        for (int j = 0; j < HPT; ++j) {
-                            unsigned mbits = (pm[j] >> c0) & 0xffu;
-                            while (mbits) {
-                                const int k = c0 + __ffs(mbits) - 1;
-                                mbits &= mbits - 1;
-                                const unsigned pos = atomicAdd(&ring_tail[warp], 1u);
-                                q[pos & (RING - 1)] = ((unsigned)lane << 27) | ((unsigned)j << 26) | (unsigned)(p0 + k);
-                            }
-                        }
-                        __syncwarp();
-                        const unsigned tail = *(volatile unsigned*)&ring_tail[warp];
-                        while (tail - head >= 32u) drain(32u);
-                    }
-                }
-            }
-            {
-                __syncwarp();
-                const unsigned tail = *(volatile unsigned*)&ring_tail[warp];
-                while (tail != head) drain(tail - head < 32u ? tail - head : 32u);
-                flush();
-            }
-#pragma unroll
-            for (int j = 0; j < HPT; ++j) {
-                const long long hyp = hyp0 + 32 * j;
-                if (hyp < a.h && tot[j][0]) {
-                    unsigned long long* dst = a.acc + (long long)u.pair * a.h + hyp;
-#pragma unroll
-                    for (int k = 0; k < kAccWords; ++k)
-                        if (tot[j][k]) atomicAdd(dst + (long long)k * a.htotal, tot[j][k]);
                 }
             }
         }
@@ -598,10 +393,11 @@ __device__ __forceinline__ Best block_best(Best b, int mode, Best* sm /* 32 */) 
     return b;  // valid in thread 0
 }
 
-// (c2 * 2^46 + c1 * 2^23 + c0) as a double; the chunk sums are < 2^49 each, the total < 2^96.
-__device__ __forceinline__ double fixed69_to_double(unsigned long long c2, unsigned long long c1,
-                                                    unsigned long long c0) {
-    const unsigned __int128 v = ((unsigned __int128)c2 << 46) + ((unsigned __int128)c1 << 23) + c0;
+// sum_k plane[k] * 2^(14k) as a double; plane sums are < 2^40 each, the total < 2^96.
+__device__ __forceinline__ double fixed70_to_double(const unsigned long long* acc, long long stride) {
+    unsigned __int128 v = 0;
+#pragma unroll
+    for (int k = kChunks - 1; k >= 0; --k) v = (v << 14) + acc[(long long)k * stride];
     const unsigned long long hi = (unsigned long long)(v >> 64), lo = (unsigned long long)v;
     return fma((double)hi, 18446744073709551616.0, (double)lo);
 }
@@ -616,7 +412,7 @@ struct FinalArgs {
     long long idx_offset;  // global index of hypothesis 0 (hypothesis-sharded runs)
     long long htotal;                 // npairs * h (stride of the accumulator planes)
     const unsigned long long* acc;    // [kAccWords][htotal] exact sums from K2
-    double inv_scale1, inv_scale2;    // 2^(e-69), 2^(2e-69)
+    double inv_scale1, inv_scale2;    // 2^(e-70), 2^(2e-70)
     double thr, min_extra;
     int agg, mode;
     int32_t* count_extra;
@@ -636,8 +432,8 @@ __global__ void __launch_bounds__(256) k_finalise(const FinalArgs a) {
     if (li < a.h) {
         // exact integer sums -> one rounding each
         long long cnt = (long long)a.acc[i];
-        double s1 = fixed69_to_double(a.acc[1 * a.htotal + i], a.acc[2 * a.htotal + i], a.acc[3 * a.htotal + i]) * a.inv_scale1;
-        double s2 = fixed69_to_double(a.acc[4 * a.htotal + i], a.acc[5 * a.htotal + i], a.acc[6 * a.htotal + i]) * a.inv_scale2;
+        double s1 = fixed70_to_double(a.acc + 1 * a.htotal + i, a.htotal) * a.inv_scale1;
+        double s2 = fixed70_to_double(a.acc + (1 + kChunks) * a.htotal + i, a.htotal) * a.inv_scale2;
         const bool valid = a.valid ? (a.valid[i] != 0) : true;
         if (a.table && valid) {
             double e[9];

@@ -58,9 +58,9 @@ def test_sampler_table_roundtrip(engine):
     assert counts.min() > 20 and counts.max() < 130
 
 
-@pytest.mark.parametrize("variant,hpt,group", [("screen", 1, 4), ("screen", 2, 4), ("full", 1, 4), ("screen", 1, 1),
-                                               ("full", 2, 2), ("screen", 1, 8), ("screen", 2, 1), ("screen", 1, 2),
-                                               ("screen_ring", 1, 4), ("full_ring", 2, 2), ("screen_ring", 2, 1)])
+@pytest.mark.parametrize("variant,hpt,group", [("screen", 4, 1), ("screen", 4, 2), ("screen", 2, 4), ("screen", 2, 2),
+                                               ("screen", 1, 8), ("screen", 1, 1), ("full", 4, 1), ("full", 2, 2),
+                                               ("full", 1, 4), ("screen", 2, 1), ("screen", 1, 2)])
 def test_scorer_bit_exact_against_oracle(engine, variant, hpt, group):
     """K2+K3 with oracle-supplied E's: counts equal, sums within 1e-12 (different summation order)."""
     n, h = 3000, 700
@@ -79,7 +79,7 @@ def test_scorer_bit_exact_against_oracle(engine, variant, hpt, group):
         engine.set_models(E)
         cnt, s1, s2, err = engine.score(THR, min_extra=10, aggregation="rms")
     finally:
-        engine.set_score_variant("screen", 1, 4)
+        engine.set_score_variant("screen", 4, 1)
     assert np.array_equal(cnt, cnt_o)
     np.testing.assert_allclose(s1, s1_o, rtol=1e-12, atol=0)
     np.testing.assert_allclose(s2, s2_o, rtol=1e-12, atol=0)

@@ -55,7 +55,7 @@ WORKLOADS = {
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="config3", choices=list(WORKLOADS) + ["config4"])
@@ -63,7 +63,9 @@ def parse():
     ap.add_argument("--hpt", type=int, default=int(os.environ.get("SFM_SCORE_HPT", "4")))
     ap.add_argument("--group", type=int, default=int(os.environ.get("SFM_SCORE_GROUP", "1")))
     ap.add_argument("--pairs", type=int, default=512, help="config4: image pairs per GPU per step")
-    ap.add_argument("--cpu-sample-hyps", type=int, default=2048)
+    ap.add_argument("--cpu-sample-hyps", type=int, default=0, help="reference arm: hypotheses per step (0 = auto)")
+    ap.add_argument("--cpu-step-seconds", type=float, default=2.0, help="reference arm: target seconds per step")
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0, help="native arm: cpu_baseline sample length")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -73,7 +75,9 @@ def parse():
 # clocks (nvidia-smi sampled DURING the timed region)
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi polled every 20 ms from before the warm-up; only samples whose timestamp falls
+    inside [mark_begin, mark_end] (the timed region) are reported."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -81,17 +85,26 @@ class ClockSampler:
         self.path = tempfile.mktemp(prefix="sfm_clocks_", suffix=".csv")
         self.proc = None
         self.index = index
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", "20"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        import datetime
+
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "power_w_max": None}
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -99,66 +112,106 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
-                if len(f) < 7:
+                if len(f) < 8:
                     continue
                 try:
-                    sm.append(float(f[0]))
-                    mx.append(float(f[1]))
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((ts, float(f[1]), float(f[2]), float(f[3]),
+                                 [nm for nm, v in zip(names, f[4:8]) if v.lower().startswith("active")]))
                 except ValueError:
                     continue
-                for nm, v in zip(names, f[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        inside = [r for r in rows if self.t0 is not None and self.t0 <= r[0] <= (self.t1 or 1e30)]
+        window = "timed region"
+        if not inside:  # timestamps unusable (time zone / clock skew): fall back to every sample of the run
+            inside, window = rows, "whole run"
+        if inside:
+            out.update(sm_mhz=statistics.median(r[1] for r in inside), sm_max_mhz=max(r[2] for r in inside),
+                       power_w_max=max(r[3] for r in inside), reasons=sorted({x for r in inside for x in r[4]}),
+                       samples=len(inside), window=window)
         return out
 
 
 # ----------------------------------------------------------------------------------------------
 # CPU legs (oracle port; the only places bench.py executes oracle/)
 # ----------------------------------------------------------------------------------------------
-def cpu_port_rate(K, x1, x2, hyps: int, seed: int, threads: int):
-    """Evaluations/s of the oracle port on `hyps` hypotheses x all correspondences: numpy
-    eight-point fit per hypothesis (oracle/restatement.py) + threaded exact C scorer
-    (oracle/sed_exact.c) + numpy selection.  Returns (evals_per_s, seconds)."""
+_CPU_CTX = {}
+
+
+def _cpu_worker_init(K, x1, x2):
     from oracle import csed
     from oracle import restatement as o
 
-    n = x1.shape[0]
     nxa, nya = o.k_normalise(x1[:, 0], x1[:, 1], K)
     nxb, nyb = o.k_normalise(x2[:, 0], x2[:, 1], K)
-    ca, cb = np.stack([nxa, nya], 1), np.stack([nxb, nyb], 1)
-    rng = np.random.default_rng(seed)
+    _CPU_CTX.update(nxa=nxa, nya=nya, nxb=nxb, nyb=nyb, ca=np.stack([nxa, nya], 1), cb=np.stack([nxb, nyb], 1))
     csed.lib()
-    t0 = time.perf_counter()
+
+
+def _cpu_worker(job):
+    """One shard of hypotheses on one host core: numpy eight-point fit per hypothesis
+    (oracle/restatement.py: np.linalg.eig 9x9 + svd 3x3, as the reference) + exact C scorer
+    (oracle/sed_exact.c) over all correspondences + the candidate/error rule."""
+    from oracle import csed
+    from oracle import restatement as o
+
+    seed, hyps = job
+    c = _CPU_CTX
+    n = len(c["nxa"])
+    rng = np.random.default_rng(seed)
     table = np.stack([rng.choice(n, 8, replace=False) for _ in range(hyps)]).astype(np.int32)
     E = np.zeros((hyps, 9))
     valid = np.ones(hyps, dtype=np.uint8)
     for i in range(hyps):
         try:
-            E[i] = o.eight_point(ca[table[i]], cb[table[i]]).reshape(9)
+            E[i] = o.eight_point(c["ca"][table[i]], c["cb"][table[i]]).reshape(9)
         except o.OracleEightPointError:
             valid[i] = 0
-    cnt, s1, s2 = csed.score_batch(E, nxa, nya, nxb, nyb, THR, table=table, valid=valid, nthreads=threads)
+    cnt, s1, s2 = csed.score_batch(E, c["nxa"], c["nya"], c["nxb"], c["nyb"], THR, table=table, valid=valid, nthreads=1)
     err = np.where((cnt >= MIN_EXTRA) & (valid > 0), np.sqrt(s2 / (8 + cnt)), np.inf)
-    int(np.argmin(err))
-    dt = time.perf_counter() - t0
-    return hyps * n / dt, dt
+    j = int(np.argmin(err))
+    return float(err[j]), j
+
+
+class CpuPort:
+    """The oracle port, hypothesis-sharded over all host cores (one process per core; the path has
+    no exchange step other than picking the minimum-error winner)."""
+
+    def __init__(self, K, x1, x2, procs: int):
+        import multiprocessing as mp
+
+        self.n = x1.shape[0]
+        self.procs = procs
+        self.pool = mp.get_context("fork").Pool(procs, initializer=_cpu_worker_init, initargs=(K, x1, x2))
+
+    def rate(self, hyps: int, seed: int):
+        per = max(1, hyps // self.procs)
+        jobs = [(seed * 100003 + p, per) for p in range(self.procs)]
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_worker, jobs)
+        min(res)
+        dt = time.perf_counter() - t0
+        return per * self.procs, dt
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
 
 
 def run_reference_arm(args):
     """--impl reference: the CPU implementation of the path on the host cores.  The reference is
-    pure Python (2.5e4 evals/s) and cannot travel to the GPU box; the arm times the
-    oracle port (numpy fit + threaded C scorer), which is ~3 orders of magnitude faster than the
-    reference itself — a generous CPU baseline."""
+    pure Python (2.5e4 evals/s on one core), has nothing to compile into oracle/_ref,
+    and cannot travel to the GPU box; the arm times the oracle port (numpy eight-point fit + exact C
+    scorer, one process per host core), which is ~4 orders of magnitude faster than the reference
+    itself — a generous CPU baseline.  Each step = a bounded sample of the workload's hypotheses
+    against ALL its correspondences."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -166,28 +219,50 @@ def run_reference_arm(args):
 
     wl = args.workload if args.workload in WORKLOADS else "config3"
     n, h, frac = WORKLOADS[wl]
-    threads = os.cpu_count() or 1
+    procs = os.cpu_count() or 1
     K, x1, x2, *_ = make_scene(n, frac, seed=0)
-    sample_h = max(64, min(args.cpu_sample_hyps, h) // 4)
-    for w in range(args.warmup):
-        cpu_port_rate(K, x1, x2, max(8, sample_h // 8), seed=100 + w, threads=threads)
+    port = CpuPort(K, x1, x2, procs)
+    # size a step to ~args.cpu_step_seconds from a short calibration run (also the warm-up)
+    hyps0 = 16 * procs
+    done, dt = port.rate(hyps0, seed=999)
+    for w in range(max(0, args.warmup - 1)):
+        done, dt = port.rate(hyps0, seed=1000 + w)
+    sample_h = args.cpu_sample_hyps or int(done / dt * args.cpu_step_seconds)
+    sample_h = max(procs, min(sample_h, h))
     secs, evals = 0.0, 0.0
     for s in range(args.steps):
-        rate, dt = cpu_port_rate(K, x1, x2, sample_h, seed=s, threads=threads)
+        done, dt = port.rate(sample_h, seed=s)
         secs += dt
-        evals += sample_h * n
+        evals += float(done) * n
+    port.close()
     value = evals / secs
+    sample_h = done
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{wl}: {n} correspondences x {h} hypotheses, 40% outliers (each step a sample of "
-                               f"{sample_h} hypotheses x all correspondences)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample_h} of {h} hypotheses x {n} correspondences per step"},
+        "config": {"workload": f"{wl}: {n} correspondences x {h} hypotheses, 40% outliers, thr 1.5e-6, RMS, "
+                               f"min_extra 10 (each step a sample of {sample_h} hypotheses x all correspondences)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
+                         "sample": f"{sample_h} of {h} hypotheses x {n} correspondences per step, "
+                                   f"{args.steps} steps, {secs:.1f} s"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+    return line
+
+
+def cpu_baseline_subprocess(args, workload):
+    """cpu_baseline leg of the native arm: the reference arm in a fresh process (no CUDA context to
+    fork), one step of ~args.cpu_baseline_seconds."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload, "--steps", "1",
+           "--warmup", "1", "--cpu-step-seconds", str(args.cpu_baseline_seconds)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+    for ln in reversed(out.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            return json.loads(ln)["cpu_baseline"]
+    raise RuntimeError("cpu baseline failed: " + out.stderr[-2000:])
 
 
 # ----------------------------------------------------------------------------------------------
@@ -264,6 +339,8 @@ def main():
         return num
 
     # ---- warm-up -------------------------------------------------------------------------------
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     for w in range(max(args.warmup, 3)):
         step_resident(1000 + w)
     barrier()
@@ -271,12 +348,11 @@ def main():
     # ---- timed: resident ---------------------------------------------------------------------
     eng.enable_timing(True)
     _, launches0 = eng.get_timing()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     stage_ms = {}
     num_inl = 0
     barrier()
+    clocks.mark_begin()
     for s in range(args.steps):
         flush_l2()
         ev[s][0].record(stream)
@@ -286,6 +362,7 @@ def main():
         for k, v in t.items():
             stage_ms[k] = stage_ms.get(k, 0.0) + v
     barrier()
+    clocks.mark_end()
     clk = clocks.stop()
     _, launches1 = eng.get_timing()
     ms_total = sum(a.elapsed_time(b) for a, b in ev)
@@ -359,8 +436,7 @@ def main():
                 "hbm_achieved_gbs": algo_bytes / (score_ms_per_launch * 1e-3) / 1e9,
                 "hbm_peak_gbs": peaks.get("hbm_gbs"),
             },
-            "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"],
-                       "samples": clk["samples"]},
+            "clocks": clk,
             "gpu_launches": launches1 - launches0,
         }
         if e2e_ms is not None:
@@ -369,11 +445,7 @@ def main():
                            "ms_per_step": e2e_max / args.steps,
                            "h2d_bytes_per_step": int(n * 32 + 72), "d2h_bytes_per_step": int(d2h)}
         if not args.no_cpu_baseline and world == 1:
-            threads = os.cpu_count() or 1
-            sh = min(args.cpu_sample_hyps, h_rank)
-            rate, dt = cpu_port_rate(K, x1, x2, sh, seed=0, threads=threads)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"{sh} of {h_rank} hypotheses x {n} correspondences ({dt:.1f} s)"}
+            line["cpu_baseline"] = cpu_baseline_subprocess(args, args.workload)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -404,13 +476,14 @@ def bench_pairs(args, eng, world, rank, barrier, flush_l2, torch, dist):
     def step(seed):
         return eng.batch_ransac(pa, pb, offsets, Ks, h, seed, THR, MIN_EXTRA, AGG, pair_id0=rank * P)
 
+    clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    clocks.start()
     for w in range(max(args.warmup, 3)):
         step(100 + w)
     barrier()
     eng.enable_timing(True)
     _, l0 = eng.get_timing()
-    clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
-    clocks.start()
+    clocks.mark_begin()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     stage = {}
     for s in range(args.steps):
@@ -422,6 +495,7 @@ def bench_pairs(args, eng, world, rank, barrier, flush_l2, torch, dist):
         for k, v in t.items():
             stage[k] = stage.get(k, 0.0) + v
     barrier()
+    clocks.mark_end()
     clk = clocks.stop()
     _, l1 = eng.get_timing()
     ms = sum(a.elapsed_time(b) for a, b in ev)
@@ -440,7 +514,7 @@ def bench_pairs(args, eng, world, rank, barrier, flush_l2, torch, dist):
                                    f"pair-sharded, host buffers (H2D inside the timed region), models found {found}/{P}",
                        "l2": "flushed between timed steps", "parallelism": f"pair-sharded x{world}, no collective"},
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
-            "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
+            "clocks": clk,
             "gpu_launches": l1 - l0,
         }
         print(json.dumps(line), flush=True)

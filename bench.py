@@ -60,8 +60,8 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="config3", choices=list(WORKLOADS) + ["config4"])
     ap.add_argument("--variant", default=os.environ.get("SFM_SCORE_VARIANT", "screen"), choices=["screen", "full"])
-    ap.add_argument("--hpt", type=int, default=int(os.environ.get("SFM_SCORE_HPT", "4")))
-    ap.add_argument("--group", type=int, default=int(os.environ.get("SFM_SCORE_GROUP", "1")))
+    ap.add_argument("--hpt", type=int, default=int(os.environ.get("SFM_SCORE_HPT", "0")))
+    ap.add_argument("--group", type=int, default=int(os.environ.get("SFM_SCORE_GROUP", "0")))
     ap.add_argument("--pairs", type=int, default=512, help="config4: image pairs per GPU per step")
     ap.add_argument("--cpu-sample-hyps", type=int, default=0, help="reference arm: hypotheses per step (0 = auto)")
     ap.add_argument("--cpu-step-seconds", type=float, default=2.0, help="reference arm: target seconds per step")

@@ -76,7 +76,7 @@ struct sfm_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     // data
     Buf raw, pts, offsets, Ks, table, E, valid, eig;
-    Buf acc, count_extra, S1, S2, err, blocks, best, invalid, winnerE;
+    Buf acc, count_extra, S1, S2, err, blocks, best, invalid, winnerE, spts, bounds;
     Buf mask, sed, poses, pass, X, idx, scan, tmp;
     long long n = 0, h = 0, npairs = 1;
     long long raw_stride = 1;
@@ -86,7 +86,7 @@ struct sfm_ctx {
     long long last_idx_offset = 0;
     double Khost[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     // config
-    int variant = SFM_SCORE_SCREEN, hpt = 4, group = 1;
+    int variant = SFM_SCORE_SCREEN, hpt = 2, group = 16;
     // timing
     bool timing = false;
     cudaEvent_t ev0[T_COUNT], ev1[T_COUNT];
@@ -133,9 +133,9 @@ const void* score_kernel(int variant, int hpt, int group) {
 #define SFM_K(H, G) if (hpt == H && group == G) return scr ? reinterpret_cast<const void*>(&k_score<H, G, true>) \
                                                            : reinterpret_cast<const void*>(&k_score<H, G, false>)
     const bool scr = variant == SFM_SCORE_SCREEN;
-    SFM_K(1, 1); SFM_K(1, 2); SFM_K(1, 4); SFM_K(1, 8);
-    SFM_K(2, 1); SFM_K(2, 2); SFM_K(2, 4);
-    SFM_K(4, 1); SFM_K(4, 2);
+    SFM_K(1, 16); SFM_K(1, 32);
+    SFM_K(2, 4); SFM_K(2, 8); SFM_K(2, 16);
+    SFM_K(4, 2); SFM_K(4, 4); SFM_K(4, 8);
 #undef SFM_K
     return nullptr;
 }
@@ -226,7 +226,7 @@ int sfm_destroy(sfm_ctx* c) {
     Buf* bufs[] = {&c->raw, &c->pts, &c->offsets, &c->Ks, &c->table, &c->E, &c->valid, &c->eig, &c->acc,
                    &c->count_extra, &c->S1, &c->S2, &c->err, &c->blocks, &c->best,
                    &c->invalid, &c->winnerE, &c->mask, &c->sed, &c->poses, &c->pass, &c->X, &c->idx,
-                   &c->scan, &c->tmp};
+                   &c->scan, &c->tmp, &c->spts, &c->bounds};
     for (Buf* b : bufs) b->release();
     for (int i = 0; i < T_COUNT; ++i) {
         cudaEventDestroy(c->ev0[i]);
@@ -517,7 +517,12 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
     if (e2 < -400) e2 = -400;
     // rounding guard of the screening tests: relative slack + an absolute term that covers a
     // cancelling residual r at the 1-ulp level (only matters for thr -> 0)
-    const double thr_pre = thr * (1.0 + 1e-9) + 1e-22;
+    const bool screen = c->variant == SFM_SCORE_SCREEN;
+    // SCREEN: relative guard here, absolute guard = kappa_h inside the kernel (see sfm_score.cuh);
+    // FULL: relative guard + an absolute term that covers a cancelling residual at the 1-ulp level
+    double thr_pre = screen ? thr * (1.0 + 1e-9) : thr * (1.0 + 1e-9) + 1e-22;
+    if (screen && thr_pre < 1e-280) thr_pre = 1e-280;  // keeps s = sqrt(thr') and 1/s normal; only widens the screen
+    const double s_scale = sqrt(thr_pre);
     const double scale1 = ldexp(1.0, 14 - e2), scale2 = ldexp(1.0, 14 - 2 * e2);
     unsigned long long* acc_dev = nullptr;
     {
@@ -541,8 +546,15 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         if (nsplit < 1) nsplit = 1;
         const long long total_items = hblocks * nsplit * P;
         if (int r = c->acc.reserve(H * kAccWords * 8 + 64)) return r;
+        const long long npts = c->n;  // total records (all pairs)
+        if (int r = c->bounds.reserve(16)) return r;
+        if (screen) { if (int r = c->spts.reserve((size_t)npts * sizeof(Corr))) return r; }
         ScoreArgs a;
         a.pts = c->pts.as<Corr>();
+        a.spts = screen ? c->spts.as<Corr>() : c->pts.as<Corr>();
+        a.bounds = c->bounds.as<double>();
+        a.s = s_scale;
+        a.kappa_coef = kKappaCoef * (1.0 + thr);
         a.n = c->n;
         a.offsets = c->batched ? c->offsets.as<long long>() : nullptr;
         a.E = c->E.as<double>();
@@ -561,6 +573,12 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         acc_dev = a.acc;
         c->tic(T_SCORE);
         CU(cudaMemsetAsync(c->acc.p, 0, H * kAccWords * 8 + 64, c->stream));
+        if (screen) {
+            CU(cudaMemsetAsync(c->bounds.p, 0, 16, c->stream));
+            k_screen_pts<<<(unsigned)((npts + 255) / 256), 256, 0, c->stream>>>(
+                c->pts.as<Corr>(), npts, 1.0 / s_scale, c->spts.as<Corr>(), c->bounds.as<unsigned long long>());
+            if (int r = check_launch(c, "k_screen_pts")) return r;
+        }
         const long long launch_blocks = grid_blocks < total_items ? grid_blocks : total_items;
         void* kargs[] = {(void*)&a};
         CU(cudaLaunchKernel(fn, dim3((unsigned)launch_blocks), dim3(kScoreThreads), kargs, 0, c->stream));

@@ -53,24 +53,40 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 // point here; K3 applies the "samples are not thresholded but always counted in the
 // error" rule of ransac.py:63-64,76.)
 //
-// Mapping: lane = hypothesis.  Each thread keeps HPT essential matrices in registers
-// (HPT = 4 by default: one broadcast read of a 32-byte correspondence from shared memory
-// feeds 4 x 32 evaluations, which keeps the shared-memory pipe at ~1/4 of the FP64 pipe's
-// appetite) and streams correspondences from shared-memory tiles.  Tiles are filled by
-// 1-D bulk async copies (TMA) into a kStages-deep ring signalled through mbarriers; a stage
-// is refilled by whichever warp finishes it last, so no warp ever waits for a slower one
-// (warps may drift kStages-1 tiles apart) and there is no block barrier in the loop.
+// Mapping: lane = hypothesis.  Each thread keeps HPT essential matrices in registers and
+// streams correspondences from shared-memory tiles (every lane reads the same 32-byte record:
+// two broadcast LDS.128).  Tiles are filled by 1-D bulk async copies (TMA) into a
+// kStages-deep ring signalled through mbarriers; a stage is refilled by whichever warp
+// finishes it last, so no warp ever waits for a slower one (warps may drift kStages-1 tiles
+// apart) and there is no block barrier in the loop.
 //
 // Persistent blocks: the grid is one wave (SMs x resident blocks); work items
 // (pair, correspondence split, hypothesis block) are claimed from an atomic counter.
 //
-// Two-level evaluation.  Every (hypothesis, correspondence) gets a cheap division-free test
-// (SCREEN: 12 FP64 issue slots using only the image-A distance, a necessary condition;
-// FULL: the 21-slot two-sided decision).  The screen is written hypothesis-innermost so that
-// consecutive DFMAs share the correspondence operand (operand-reuse cache: a DFMA with three
-// fresh 64-bit register operands issues at 2/3 rate on sm_100).  Survivors (~1 %) are pushed
-// to a per-warp ring and processed 32 at a time by all lanes (dense, no divergence): the
-// exact reference-order SED is evaluated and compared with thr.
+// Two-level evaluation.  Every (hypothesis, correspondence) gets a cheap division-free
+// test; the sign bits of a BATCH of HPT*G (<= 32) tests are collected in one register per
+// lane and the warp votes once per batch.  Survivors (~1 %) are compacted with
+// ballot/popc into a 64-entry per-warp ring (positions are warp-uniform registers: no
+// atomics) and processed 32 at a time by all lanes (dense, no divergence): the exact
+// reference-order SED is evaluated and compared with thr.
+//
+//   SCREEN (default), 11 FP64 issue slots per evaluation.  sed <= thr implies
+//   r^2 <= thr * nb  (drop the image-A term), nb = lb0^2 + lb1^2, lb = E^T b, r = lb . a.
+//   With s = sqrt(thr'), the kernel keeps E with columns 0 and 1 pre-multiplied by s and
+//   streams a copy of the correspondences with (xa, ya) pre-divided by s, so that
+//       lb0' = s lb0, lb1' = s lb1, lb2   (6 DFMA)      r = lb0' xa' + lb1' ya' + lb2   (2 DFMA)
+//       m = lb1'^2 + kappa ; m = lb0'^2 + m   (2 DFMA)  d = r^2 - m                      (1 DFMA)
+//   and "d < 0" (sign bit) is the test.  thr' = thr (1 + 1e-9) and
+//   kappa_h = 4e-20 (1 + thr) |E_h|_F^2 A^2 B^2  (A, B = max |(x, y, 1)| over each image)
+//   bound every rounding difference between this evaluation order and the reference's:
+//   |r_screen - r_ref| <= 32 u |E| A B =: eps and 2 |r| eps <= 1e-9 r^2 + 1e9 eps^2 (AM-GM), the
+//   same for the absolute errors of lb0, lb1 inside nb — so an inlier of the exact scorer
+//   can never be screened out, at any threshold.  The screen is written
+//   hypothesis-innermost so that consecutive DFMAs share the correspondence operand (a DFMA
+//   with three fresh 64-bit register operands issues at 2/3 rate on sm_100, measured by
+//   tools/fp64_micro.cu).
+//   FULL: the 21-slot two-sided division-free decision on the unscaled data (survivors ~
+//   inliers); identical results, kept as the like-for-like arithmetic baseline.
 //
 // Exact accumulation.  An inlier's sed (and sed^2) is split into five 14-bit chunks of a
 // fixed-point number scaled so that thr < 2^e maps below 2^70; chunks are added with native
@@ -85,18 +101,23 @@ constexpr int kScoreThreads = 128;
 constexpr int kScoreWarps = kScoreThreads / 32;
 constexpr int kTile = 128;    // correspondences per stage (4 KB)
 constexpr int kStages = 4;
+constexpr int kRing = 64;     // survivor ring per warp: < 32 pending + <= 32 new
 constexpr unsigned kMaxPoints = 1u << 25;
 constexpr int kChunks = 5;             // 14-bit chunks per exact sum
 constexpr int kAccWords = 1 + 2 * kChunks;  // count, sum(sed), sum(sed^2)
 constexpr long long kMaxItemPoints = 1ll << 17;  // 2^17 adds of <= 2^14 cannot overflow a 32-bit word
+constexpr double kKappaCoef = 4e-20;
 
 struct ScoreArgs {
-    const Corr* pts;
+    const Corr* pts;           // K-normalised correspondences (exact scorer)
+    const Corr* spts;          // screening copy: (xa/s, ya/s, xb, yb); == pts for the FULL variant
+    const double* bounds;      // [2]: max (xa^2+ya^2+1), max (xb^2+yb^2+1) over all correspondences
     long long n;
     const long long* offsets;  // [npairs+1] or null (single pair of n records)
     const double* E;           // [npairs][h][9]
     long long h;
-    double thr, thr_pre;
+    double thr, thr_pre, s;    // s = sqrt(thr_pre) (SCREEN)
+    double kappa_coef;         // kKappaCoef * (1 + thr)
     double scale1, scale2;     // 2^(14-e), 2^(14-2e) with thr < 2^e
     long long chunk;           // correspondences per split (multiple of kTile)
     int hblocks, nsplit;
@@ -111,6 +132,11 @@ __device__ __forceinline__ unsigned atom_add_acq_rel_shared(unsigned* p, unsigne
     asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
     return old;
 }
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
 
 // five 14-bit chunks of floor(x * 2^56), x in [0, 2^14): c[4] is the most significant
 __device__ __forceinline__ void chunks14(double x, unsigned (&c)[kChunks]) {
@@ -122,35 +148,63 @@ __device__ __forceinline__ void chunks14(double x, unsigned (&c)[kChunks]) {
     c[0] = __double2uint_rn(x);
 }
 
+// Screening copy of the correspondences + the coordinate bounds used by kappa (one pass
+// over N; thr-dependent, so it runs at the head of every scoring call).
+__global__ void __launch_bounds__(256) k_screen_pts(const Corr* __restrict__ pts, long long n, double inv_s,
+                                                    Corr* __restrict__ spts, unsigned long long* __restrict__ bounds) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    double a2 = 0.0, b2 = 0.0;
+    if (i < n) {
+        Corr c = pts[i];
+        a2 = fma(c.xa, c.xa, fma(c.ya, c.ya, 1.0));
+        b2 = fma(c.xb, c.xb, fma(c.yb, c.yb, 1.0));
+        if (spts) {
+            c.xa *= inv_s;
+            c.ya *= inv_s;
+            spts[i] = c;
+        }
+    }
+    // non-negative doubles order like their bit patterns; NaN coordinates poison the bound (kappa = NaN
+    // => d = NaN, sign clear) exactly like they poison the reference's score (NaN <= thr is False)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        a2 = fmax(a2, __shfl_xor_sync(0xffffffffu, a2, d));
+        b2 = fmax(b2, __shfl_xor_sync(0xffffffffu, b2, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(bounds, (unsigned long long)__double_as_longlong(a2));
+        atomicMax(bounds + 1, (unsigned long long)__double_as_longlong(b2));
+    }
+}
+
 template <int HPT, int G, bool SCREEN>
 __global__ void __launch_bounds__(kScoreThreads) k_score(const ScoreArgs a) {
-    constexpr int NB = HPT * G;  // survivor bits per step
-    static_assert(NB <= 16, "at most 16 evaluations per lane and step");
-    constexpr int RING = 64 * NB;  // >= 32*NB new + 31 pending
+    constexpr int NB = HPT * G;  // tests per lane and batch = survivor bits per vote
+    static_assert(NB <= 32 && (kTile % G) == 0, "a batch is at most 32 tests and divides a tile");
     __shared__ __align__(128) Corr tile[kStages][kTile];
     __shared__ __align__(8) unsigned long long full_bar[kStages];
     __shared__ unsigned done[kStages];
-    __shared__ unsigned ring[kScoreWarps][RING];
-    __shared__ unsigned ring_tail[kScoreWarps];
+    __shared__ unsigned ring[kScoreWarps][kRing];
     __shared__ unsigned sacc[kScoreWarps][HPT][kAccWords][32];
     __shared__ unsigned s_item;
 
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = lanemask_lt();
 
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); done[s] = 0; }
         mbar_fence_init();
     }
-    if (lane == 0) ring_tail[warp] = 0;
 #pragma unroll
     for (int j = 0; j < HPT; ++j)
 #pragma unroll
         for (int k = 0; k < kAccWords; ++k) sacc[warp][j][k][lane] = 0;
     unsigned* q = ring[warp];
-    unsigned head = 0;        // entries consumed so far (warp-uniform, monotone)
-    unsigned gt = 0;          // tiles consumed so far by this block (drives stage + parity)
+    unsigned head = 0, tail = 0;  // ring positions: warp-uniform, monotone, tail - head < 64
+    unsigned gt = 0;              // tiles consumed so far by this block (drives stage + parity)
+    const double ab2 = SCREEN ? a.bounds[0] * a.bounds[1] * a.kappa_coef : 0.0;
 
     for (;;) {
         __syncthreads();  // previous item completely finished; s_item free
@@ -173,6 +227,7 @@ __global__ void __launch_bounds__(kScoreThreads) k_score(const ScoreArgs a) {
         // this warp's hypotheses: lane l, slot j  ->  hyp_w + 32*j + l
         const long long hyp_w = (long long)hb * (kScoreThreads * HPT) + (long long)warp * (32 * HPT);
         const double* Ep = a.E + 9 * (long long)pair * a.h;
+        const Corr* src = SCREEN ? a.spts : a.pts;
 
         auto issue = [&](int t) {
             const int s = (int)((gt + (unsigned)t) % kStages);
@@ -180,23 +235,32 @@ __global__ void __launch_bounds__(kScoreThreads) k_score(const ScoreArgs a) {
             const long long rem = end - first;
             const uint32_t bytes = (uint32_t)((rem < kTile ? rem : kTile) * sizeof(Corr));
             mbar_expect_tx(&full_bar[s], bytes);
-            bulk_g2s(&tile[s][0], a.pts + first, bytes, &full_bar[s]);
+            bulk_g2s(&tile[s][0], src + first, bytes, &full_bar[s]);
         };
         if (threadIdx.x == 0)
             for (int t = 0; t < kStages && t < ntiles; ++t) issue(t);
 
-        double e[HPT][9];
+        // register-resident models; SCREEN: columns 0 and 1 scaled by s, kappa per hypothesis
+        double e[HPT][9], kap[HPT];
 #pragma unroll
         for (int j = 0; j < HPT; ++j) {
             const long long hyp = hyp_w + 32 * j + lane;
+            const bool real = hyp < a.h;
+            double f2 = 0.0;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) e[j][k] = (hyp < a.h) ? Ep[9 * hyp + k] : 0.0;
+            for (int k = 0; k < 9; ++k) {
+                const double v = real ? Ep[9 * hyp + k] : 0.0;
+                f2 = fma(v, v, f2);
+                e[j][k] = (SCREEN && (k % 3) != 2) ? v * a.s : v;
+            }
+            // padding lanes can never produce a survivor: m = -1, d = r^2 + 1 > 0
+            kap[j] = real ? f2 * ab2 : -1.0;
         }
 
         // exact evaluation of m (<= 32) queued candidates by all 32 lanes; the candidate's E
         // comes from global memory (L1/L2 hits), its correspondence by index
         auto drain = [&](unsigned m) {
-            const unsigned ent = (lane < (int)m) ? q[(head + lane) & (RING - 1)] : 0u;
+            const unsigned ent = (lane < (int)m) ? q[(head + lane) & (kRing - 1)] : 0u;
             const int owner = (int)(ent >> 27);
             const int slot = (int)((ent >> 25) & 3u);
             const unsigned gi = ent & (kMaxPoints - 1u);
@@ -219,61 +283,25 @@ __global__ void __launch_bounds__(kScoreThreads) k_score(const ScoreArgs a) {
                 for (int k = 0; k < kChunks; ++k) atomicAdd(dst + 32 * (1 + kChunks + k), ch[k]);
             }
             head += m;
+            __syncwarp();
         };
 
-        // one step: GG correspondences x HPT hypotheses per lane
-        auto step = [&](const Corr* tp, int p, unsigned gi0, auto gtag) {
-            constexpr int GG = decltype(gtag)::value;
-            unsigned pm = 0;  // survivor bits; evaluation i = g*HPT + j ends up at bit GG*HPT-1-i
-#pragma unroll
-            for (int g = 0; g < GG; ++g) {
-                const Corr c = tp[p + g];
-                double d[HPT];
-                if (SCREEN) {
-                    // hypothesis-innermost: consecutive DFMAs share c.yb / c.xb / c.ya / c.xa
-                    double t0[HPT], t1[HPT], t2[HPT];
-#pragma unroll
-                    for (int j = 0; j < HPT; ++j) {
-                        t0[j] = fma(c.yb, e[j][3], e[j][6]);
-                        t1[j] = fma(c.yb, e[j][4], e[j][7]);
-                        t2[j] = fma(c.yb, e[j][5], e[j][8]);
-                    }
-#pragma unroll
-                    for (int j = 0; j < HPT; ++j) {
-                        t0[j] = fma(c.xb, e[j][0], t0[j]);  // lb0
-                        t1[j] = fma(c.xb, e[j][1], t1[j]);  // lb1
-                        t2[j] = fma(c.xb, e[j][2], t2[j]);  // lb2
-                    }
-#pragma unroll
-                    for (int j = 0; j < HPT; ++j) t2[j] = fma(c.ya, t1[j], t2[j]);
-#pragma unroll
-                    for (int j = 0; j < HPT; ++j) t2[j] = fma(c.xa, t0[j], t2[j]);  // r
-#pragma unroll
-                    for (int j = 0; j < HPT; ++j) t1[j] = t1[j] * t1[j];
-#pragma unroll
-                    for (int j = 0; j < HPT; ++j) t1[j] = fma(t0[j], t0[j], t1[j]);  // nb
-#pragma unroll
-                    for (int j = 0; j < HPT; ++j) t1[j] = t1[j] * a.thr_pre;
-#pragma unroll
-                    for (int j = 0; j < HPT; ++j) d[j] = fma(t2[j], t2[j], -t1[j]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < HPT; ++j) d[j] = sed_full_decision(e[j], c.xa, c.ya, c.xb, c.yb, a.thr_pre);
+        // queue the set bits of pm (bit NB-1-i <-> test i = g*HPT + j of the batch starting at
+        // correspondence gi0): one ballot-compacted entry per lane and round
+        auto push = [&](unsigned pm, unsigned gi0) {
+            unsigned any = __ballot_sync(full, pm != 0u);
+            while (any) {
+                if (pm) {
+                    const int b = 31 - __clz(pm);
+                    pm ^= 1u << b;
+                    const int i = NB - 1 - b;
+                    const unsigned pos = tail + __popc(any & lt);
+                    q[pos & (kRing - 1)] = ((unsigned)lane << 27) | ((unsigned)(i % HPT) << 25) | (gi0 + (unsigned)(i / HPT));
                 }
-#pragma unroll
-                for (int j = 0; j < HPT; ++j) pm = __funnelshift_l((unsigned)__double2hiint(d[j]), pm, 1);
-            }
-            if (__any_sync(full, pm != 0u)) {
-                while (pm) {  // usually one bit in a few lanes
-                    const int b = __ffs(pm) - 1;
-                    pm &= pm - 1;
-                    const int i = GG * HPT - 1 - b;
-                    const unsigned pos = atomicAdd(&ring_tail[warp], 1u);
-                    q[pos & (RING - 1)] = ((unsigned)lane << 27) | ((unsigned)(i % HPT) << 25) | (gi0 + (unsigned)(i / HPT));
-                }
+                tail += __popc(any);
                 __syncwarp();
-                const unsigned tail = *(volatile unsigned*)&ring_tail[warp];
-                while (tail - head >= 32u) drain(32u);
+                if (tail - head >= 32u) drain(32u);
+                any = __ballot_sync(full, pm != 0u);
             }
         };
 
@@ -284,9 +312,48 @@ __global__ void __launch_bounds__(kScoreThreads) k_score(const ScoreArgs a) {
             const long long first = begin + (long long)t * kTile;
             const int np = (int)((end - first < kTile) ? (end - first) : kTile);
             const Corr* tp = tile[s];
-            int p = 0;
-            for (; p + G <= np; p += G) step(tp, p, (unsigned)(first + p), std::integral_constant<int, G>{});
-            for (; p < np; ++p) step(tp, p, (unsigned)(first + p), std::integral_constant<int, 1>{});
+            for (int p = 0; p < np; p += G) {
+                unsigned pm = 0;
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const Corr c = tp[p + g];
+                    double d[HPT];
+                    if (SCREEN) {
+                        // hypothesis-innermost: consecutive DFMAs share c.yb / c.xb / c.ya / c.xa
+                        double t0[HPT], t1[HPT], t2[HPT];
+#pragma unroll
+                        for (int j = 0; j < HPT; ++j) {
+                            t0[j] = fma(c.yb, e[j][3], e[j][6]);
+                            t1[j] = fma(c.yb, e[j][4], e[j][7]);
+                            t2[j] = fma(c.yb, e[j][5], e[j][8]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < HPT; ++j) {
+                            t0[j] = fma(c.xb, e[j][0], t0[j]);  // s lb0
+                            t1[j] = fma(c.xb, e[j][1], t1[j]);  // s lb1
+                            t2[j] = fma(c.xb, e[j][2], t2[j]);  // lb2
+                        }
+#pragma unroll
+                        for (int j = 0; j < HPT; ++j) t2[j] = fma(c.ya, t1[j], t2[j]);
+#pragma unroll
+                        for (int j = 0; j < HPT; ++j) t2[j] = fma(c.xa, t0[j], t2[j]);  // r
+#pragma unroll
+                        for (int j = 0; j < HPT; ++j) t1[j] = fma(t1[j], t1[j], kap[j]);
+#pragma unroll
+                        for (int j = 0; j < HPT; ++j) t1[j] = fma(t0[j], t0[j], t1[j]);  // thr' nb + kappa
+#pragma unroll
+                        for (int j = 0; j < HPT; ++j) d[j] = fma(t2[j], t2[j], -t1[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < HPT; ++j) d[j] = sed_full_decision(e[j], c.xa, c.ya, c.xb, c.yb, a.thr_pre);
+                    }
+#pragma unroll
+                    for (int j = 0; j < HPT; ++j) pm = __funnelshift_l((unsigned)__double2hiint(d[j]), pm, 1);
+                }
+                const int v = np - p;  // a partial last batch evaluated stale records: drop their bits
+                if (v < G) pm &= 0xffffffffu << (NB - v * HPT);
+                if (__any_sync(full, pm != 0u)) push(pm, (unsigned)(first + p));
+            }
             // release the stage: the last warp to finish it refills it (nobody waits)
             __syncwarp();
             if (lane == 0) {
@@ -300,12 +367,7 @@ __global__ void __launch_bounds__(kScoreThreads) k_score(const ScoreArgs a) {
         gt += (unsigned)ntiles;
 
         // tail of the queue, then publish this item's exact sums
-        {
-            __syncwarp();
-            const unsigned tail = *(volatile unsigned*)&ring_tail[warp];
-            while (tail != head) drain(tail - head < 32u ? tail - head : 32u);
-            __syncwarp();
-        }
+        if (tail != head) drain(tail - head);
 #pragma unroll
         for (int j = 0; j < HPT; ++j) {
             const long long hyp = hyp_w + 32 * j + lane;

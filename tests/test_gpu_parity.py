@@ -58,12 +58,12 @@ def test_sampler_table_roundtrip(engine):
     assert counts.min() > 20 and counts.max() < 130
 
 
-@pytest.mark.parametrize("variant,hpt,group", [("screen", 4, 1), ("screen", 4, 2), ("screen", 2, 4), ("screen", 2, 2),
-                                               ("screen", 1, 8), ("screen", 1, 1), ("full", 4, 1), ("full", 2, 2),
-                                               ("full", 1, 4), ("screen", 2, 1), ("screen", 1, 2)])
+@pytest.mark.parametrize("variant,hpt,group", [("screen", 2, 16), ("screen", 4, 8), ("screen", 1, 32), ("screen", 2, 8),
+                                               ("screen", 4, 4), ("screen", 4, 2), ("screen", 2, 4), ("screen", 1, 16),
+                                               ("full", 4, 8), ("full", 2, 16), ("full", 1, 32)])
 def test_scorer_bit_exact_against_oracle(engine, variant, hpt, group):
     """K2+K3 with oracle-supplied E's: counts equal, sums within 1e-12 (different summation order)."""
-    n, h = 3000, 700
+    n, h = 3003, 700  # 3003 = 23 tiles + 59: partial last tile, partial last batch for every group size
     K, x1, x2, *_ = make_scene(n, 0.4, seed=2)
     nxa, nya, nxb, nyb = _norm(K, x1, x2)
     rng = np.random.default_rng(5)
@@ -79,7 +79,7 @@ def test_scorer_bit_exact_against_oracle(engine, variant, hpt, group):
         engine.set_models(E)
         cnt, s1, s2, err = engine.score(THR, min_extra=10, aggregation="rms")
     finally:
-        engine.set_score_variant("screen", 4, 1)
+        engine.set_score_variant("screen", 2, 16)
     assert np.array_equal(cnt, cnt_o)
     np.testing.assert_allclose(s1, s1_o, rtol=1e-12, atol=0)
     np.testing.assert_allclose(s2, s2_o, rtol=1e-12, atol=0)
@@ -93,6 +93,29 @@ def test_scorer_bit_exact_against_oracle(engine, variant, hpt, group):
     sed_o = csed.sed_exact_many(E[best.index], nxa, nya, nxb, nyb)
     assert np.array_equal(sed, sed_o)
     assert np.array_equal(mask, sed_o <= THR)
+
+
+@pytest.mark.parametrize("thr", [0.0, 1e-30, 1e-18, 1e-12, 1e-9, 1.5e-6, 1e-3, 0.5, 40.0])
+@pytest.mark.parametrize("escale", [1.0, 1e6, 1e-7])
+def test_screen_never_drops_an_inlier(engine, thr, escale):
+    """The 11-slot screen is a necessary condition at EVERY threshold and model scale: counts and
+    masks equal the exact oracle scorer's (sed.py is scale-invariant in E; the screen's guard
+    kappa_h scales with |E_h|^2)."""
+    n, h = 1500, 256
+    K, x1, x2, *_ = make_scene(n, 0.3, seed=11)
+    nxa, nya, nxb, nyb = _norm(K, x1, x2)
+    rng = np.random.default_rng(9)
+    table = np.stack([rng.choice(n, 8, replace=False) for _ in range(h)]).astype(np.int32)
+    ca, cb = np.stack([nxa, nya], 1), np.stack([nxb, nyb], 1)
+    E = np.stack([o.eight_point(ca[s], cb[s]) for s in table]) * escale
+    cnt_o, s1_o, s2_o = csed.score_batch(E, nxa, nya, nxb, nyb, thr, table=table, nthreads=8)
+    engine.upload_pairs(x1, x2, K)
+    engine.set_table(table)
+    engine.set_models(E)
+    cnt, s1, s2, err = engine.score(thr, min_extra=0, aggregation="sum")
+    assert np.array_equal(cnt, cnt_o)
+    np.testing.assert_allclose(s1, s1_o, rtol=1e-12, atol=0)
+    np.testing.assert_allclose(s2, s2_o, rtol=1e-12, atol=0)
 
 
 @pytest.mark.parametrize("agg", ["sum", "square", "mean", "rms"])

@@ -1,0 +1,150 @@
+// Prototype of the K2 screening inner loop under different operand-delivery schemes.
+// Question: how close to the FP64 pipe rate (2 cycles per warp-DFMA per SMSP) can the
+// 11-DFMA test run, and what delivers the warp-uniform correspondence operand best?
+//   MODE 0  shared memory (LDS.128 broadcast) + compiler scheduling           (what K2 v5 does)
+//   MODE 1  shared memory + order pinned with volatile asm (hypothesis-innermost => .reuse)
+//   MODE 2  constant memory (LDCU -> uniform registers) + compiler scheduling
+//   MODE 3  constant memory + pinned order
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/bin/screen_proto tools/screen_proto.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+
+struct __align__(32) Corr { double xa, ya, xb, yb; };
+constexpr int NPTS = 512;
+__constant__ Corr c_pts[NPTS];
+
+#define VFMA(d, a, b, c) asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(d) : "d"(a), "d"(b), "d"(c))
+
+template <int HPT, int G, int MODE, int UNR = G>
+__global__ void __launch_bounds__(128) k(const double* __restrict__ E, const Corr* __restrict__ pts, int reps,
+                                         unsigned* __restrict__ out) {
+    __shared__ __align__(128) Corr tile[NPTS];
+    if (MODE < 2) {
+        for (int i = threadIdx.x; i < NPTS; i += blockDim.x) tile[i] = pts[i];
+        __syncthreads();
+    }
+    double e[HPT][9], kap[HPT];
+#pragma unroll
+    for (int j = 0; j < HPT; ++j) {
+#pragma unroll
+        for (int q = 0; q < 9; ++q) e[j][q] = E[((blockIdx.x * HPT + j) * 128 + threadIdx.x) * 9 + q];
+        kap[j] = 1e-30 * e[j][0];
+    }
+    unsigned acc = 0;
+    for (int r = 0; r < reps; ++r) {
+        for (int p = 0; p < NPTS; p += G) {
+            unsigned pm = 0;
+#pragma unroll UNR
+            for (int g = 0; g < G; ++g) {
+                const Corr c = (MODE < 2) ? tile[p + g] : c_pts[p + g];
+                double t0[HPT], t1[HPT], t2[HPT], d[HPT];
+                if (MODE & 1) {
+#pragma unroll
+                    for (int j = 0; j < HPT; ++j) { VFMA(t0[j], c.yb, e[j][3], e[j][6]); VFMA(t1[j], c.yb, e[j][4], e[j][7]); VFMA(t2[j], c.yb, e[j][5], e[j][8]); }
+#pragma unroll
+                    for (int j = 0; j < HPT; ++j) { VFMA(t0[j], c.xb, e[j][0], t0[j]); VFMA(t1[j], c.xb, e[j][1], t1[j]); VFMA(t2[j], c.xb, e[j][2], t2[j]); }
+#pragma unroll
+                    for (int j = 0; j < HPT; ++j) VFMA(t2[j], c.ya, t1[j], t2[j]);
+#pragma unroll
+                    for (int j = 0; j < HPT; ++j) VFMA(t2[j], c.xa, t0[j], t2[j]);
+#pragma unroll
+                    for (int j = 0; j < HPT; ++j) VFMA(t1[j], t1[j], t1[j], kap[j]);
+#pragma unroll
+                    for (int j = 0; j < HPT; ++j) VFMA(t1[j], t0[j], t0[j], t1[j]);
+#pragma unroll
+                    for (int j = 0; j < HPT; ++j) { double nt = -t1[j]; VFMA(d[j], t2[j], t2[j], nt); }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < HPT; ++j) { t0[j] = fma(c.yb, e[j][3], e[j][6]); t1[j] = fma(c.yb, e[j][4], e[j][7]); t2[j] = fma(c.yb, e[j][5], e[j][8]); }
+#pragma unroll
+                    for (int j = 0; j < HPT; ++j) { t0[j] = fma(c.xb, e[j][0], t0[j]); t1[j] = fma(c.xb, e[j][1], t1[j]); t2[j] = fma(c.xb, e[j][2], t2[j]); }
+#pragma unroll
+                    for (int j = 0; j < HPT; ++j) t2[j] = fma(c.ya, t1[j], t2[j]);
+#pragma unroll
+                    for (int j = 0; j < HPT; ++j) t2[j] = fma(c.xa, t0[j], t2[j]);
+#pragma unroll
+                    for (int j = 0; j < HPT; ++j) t1[j] = fma(t1[j], t1[j], kap[j]);
+#pragma unroll
+                    for (int j = 0; j < HPT; ++j) t1[j] = fma(t0[j], t0[j], t1[j]);
+#pragma unroll
+                    for (int j = 0; j < HPT; ++j) d[j] = fma(t2[j], t2[j], -t1[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < HPT; ++j) pm = __funnelshift_l((unsigned)__double2hiint(d[j]), pm, 1);
+            }
+            if (__any_sync(0xffffffffu, pm != 0u)) acc += pm;
+        }
+    }
+    out[blockIdx.x * 128 + threadIdx.x] = acc;
+}
+
+template <int HPT, int G, int MODE, int UNR = G>
+void run(const char* name, const double* E, const Corr* pts, unsigned* out, int sms) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k<HPT, G, MODE, UNR>, 128, 0);
+    for (int bps : {2, occ}) {
+        if (bps > occ) continue;
+        const int blocks = sms * bps, reps = 64;
+        k<HPT, G, MODE, UNR><<<blocks, 128>>>(E, pts, 2, out);
+        float best = 1e30f;
+        for (int r = 0; r < 3; ++r) {
+            cudaEventRecord(e0);
+            k<HPT, G, MODE, UNR><<<blocks, 128>>>(E, pts, reps, out);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (ms < best) best = ms;
+        }
+        const double evals = (double)blocks * 128 * HPT * NPTS * reps;
+        const double warp_dfma_per_smsp = evals * 11 / 32 / (sms * 4);
+        printf("%-40s blocks/SM %d (occ %d): %7.3f ms  %.3e evals/s  %.2f cycles/warp-DFMA/SMSP @1965MHz\n", name, bps, occ,
+               best, evals / (best * 1e-3), best * 1e-3 * 1.965e9 / warp_dfma_per_smsp);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) printf("  CUDA error: %s\n", cudaGetErrorString(e));
+    }
+}
+
+int main() {
+    cudaDeviceProp p;
+    cudaGetDeviceProperties(&p, 0);
+    const int sms = p.multiProcessorCount;
+    printf("%s, %d SMs\n", p.name, sms);
+    const size_t nE = (size_t)sms * 8 * 8 * 128 * 9;
+    double* E;
+    Corr* pts;
+    unsigned* out;
+    cudaMalloc(&E, nE * 8);
+    cudaMalloc(&pts, NPTS * sizeof(Corr));
+    cudaMalloc(&out, (size_t)sms * 8 * 128 * 4);
+    double* hE = new double[nE];
+    for (size_t i = 0; i < nE; ++i) hE[i] = 0.1 + 1e-3 * (double)(i % 977);
+    cudaMemcpy(E, hE, nE * 8, cudaMemcpyHostToDevice);
+    Corr h[NPTS];
+    for (int i = 0; i < NPTS; ++i) h[i] = {0.01 * i, 0.3 - 0.002 * i, 0.5 + 0.001 * i, -0.2 + 0.003 * i};
+    cudaMemcpy(pts, h, sizeof h, cudaMemcpyHostToDevice);
+    cudaMemcpyToSymbol(c_pts, h, sizeof h);
+    run<2, 16, 0>("smem  compiler order   HPT2 G16", E, pts, out, sms);
+    run<4, 8, 0>("smem  compiler order   HPT4 G8", E, pts, out, sms);
+    run<2, 16, 1>("smem  pinned order     HPT2 G16", E, pts, out, sms);
+    run<4, 8, 1>("smem  pinned order     HPT4 G8", E, pts, out, sms);
+    run<2, 16, 2>("const compiler order   HPT2 G16", E, pts, out, sms);
+    run<4, 8, 2>("const compiler order   HPT4 G8", E, pts, out, sms);
+    run<2, 16, 3>("const pinned order     HPT2 G16", E, pts, out, sms);
+    run<4, 8, 3>("const pinned order     HPT4 G8", E, pts, out, sms);
+    run<4, 8, 0, 1>("smem  unroll 1         HPT4 G8", E, pts, out, sms);
+    run<4, 8, 0, 2>("smem  unroll 2         HPT4 G8", E, pts, out, sms);
+    run<4, 8, 0, 4>("smem  unroll 4         HPT4 G8", E, pts, out, sms);
+    run<2, 16, 0, 1>("smem  unroll 1         HPT2 G16", E, pts, out, sms);
+    run<2, 16, 0, 2>("smem  unroll 2         HPT2 G16", E, pts, out, sms);
+    run<2, 16, 0, 4>("smem  unroll 4         HPT2 G16", E, pts, out, sms);
+    run<6, 4, 0, 1>("smem  unroll 1         HPT6 G4", E, pts, out, sms);
+    run<6, 4, 0, 2>("smem  unroll 2         HPT6 G4", E, pts, out, sms);
+    run<8, 4, 0, 1>("smem  unroll 1         HPT8 G4", E, pts, out, sms);
+    run<4, 8, 2, 1>("const unroll 1         HPT4 G8", E, pts, out, sms);
+    run<4, 8, 2, 2>("const unroll 2         HPT4 G8", E, pts, out, sms);
+    return 0;
+}

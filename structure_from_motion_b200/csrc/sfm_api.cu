@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -127,6 +128,14 @@ int check_launch(sfm_ctx* c, const char* what) {
     if (e != cudaSuccess) return fail(SFM_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
     c->launches += 1;
     return 0;
+}
+
+size_t score_warp_smem(int hpt) {
+    switch (hpt) {
+        case 1: return sizeof(ScoreWarpSmem<1>);
+        case 2: return sizeof(ScoreWarpSmem<2>);
+        default: return sizeof(ScoreWarpSmem<4>);
+    }
 }
 
 const void* score_kernel(int variant, int hpt, int group) {
@@ -493,7 +502,9 @@ int sfm_set_models(sfm_ctx* c, const double* E, const uint8_t* valid, int64_t h)
 
 // ---- score + select ---------------------------------------------------------------------
 static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int mode, bool use_table,
-                        long long idx_offset, long long max_len) {
+                        long long idx_offset, long long max_len, bool both_sums = false) {
+    // K2 accumulates only the sum the aggregation needs (ransac.py:96-108) unless the caller wants both
+    const int sums = both_sums ? (SUM_S1 | SUM_S2) : ((agg == AGG_SUM || agg == AGG_MEAN) ? SUM_S1 : SUM_S2);
     if (!c->has_pts || !c->has_models) return fail(SFM_ERR_STATE, "score needs correspondences and fitted models");
     if (use_table && !c->has_table) return fail(SFM_ERR_STATE, "sample rule requested but no table is loaded");
     if (agg < 0 || agg > 3) return fail(SFM_ERR_ARG, "bad aggregation %d", agg);
@@ -502,7 +513,7 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
     if (thr > 1e100) return fail(SFM_ERR_ARG, "threshold too large for the fixed-point accumulators");
     const long long h = c->h, P = c->npairs;
     const int hpt = c->hpt, G = c->group;
-    const long long hblocks = (h + (long long)kScoreThreads * hpt - 1) / ((long long)kScoreThreads * hpt);
+    const long long hblocks = (h + 32ll * hpt - 1) / (32ll * hpt);  // groups of 32*hpt hypotheses (one per warp item)
     const size_t H = (size_t)h * P;
     if (int r = c->count_extra.reserve(H * 4)) return r;
     if (int r = c->S1.reserve(H * 8)) return r;
@@ -523,20 +534,23 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
     double thr_pre = screen ? thr * (1.0 + 1e-9) : thr * (1.0 + 1e-9) + 1e-22;
     if (screen && thr_pre < 1e-280) thr_pre = 1e-280;  // keeps s = sqrt(thr') and 1/s normal; only widens the screen
     const double s_scale = sqrt(thr_pre);
-    const double scale1 = ldexp(1.0, 14 - e2), scale2 = ldexp(1.0, 14 - 2 * e2);
+    const double scale1 = ldexp(1.0, 63 - e2), scale2 = ldexp(1.0, 63 - 2 * e2);
     unsigned long long* acc_dev = nullptr;
     {
         // persistent blocks over (pair, split, hypothesis block) items
         const void* fn = score_kernel(c->variant, hpt, G);
         if (!fn) return fail(SFM_ERR_ARG, "unsupported scoring configuration (variant %d, hpt %d, group %d)", c->variant, hpt, G);
+        const size_t smem = (size_t)kScoreWarps * score_warp_smem(hpt);
+        CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kScoreThreads, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kScoreThreads, smem));
         if (occ < 1) occ = 1;
         const long long grid_blocks = (long long)c->sm_count * occ;
         const long long tiles = (max_len + kTile - 1) / kTile;
-        const long long target_items = grid_blocks * 12;
+        static const int items_per_warp = getenv("SFM_ITEMS_PER_WARP") ? atoi(getenv("SFM_ITEMS_PER_WARP")) : 12;  // tuning knob
+        const long long target_items = grid_blocks * kScoreWarps * items_per_warp;
         long long nsplit = (target_items + hblocks * P - 1) / (hblocks * P);
-        const long long max_split = tiles / 8 > 0 ? tiles / 8 : 1;  // keep >= 8 tiles per item
+        const long long max_split = tiles / 8 > 0 ? tiles / 8 : 1;  // keep >= 8 tiles (512 correspondences) per item
         if (nsplit > max_split) nsplit = max_split;
         const long long min_split = (max_len + kMaxItemPoints - 1) / kMaxItemPoints;  // 32-bit chunk sums cannot overflow
         if (nsplit < min_split) nsplit = min_split;
@@ -555,6 +569,7 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         a.bounds = c->bounds.as<double>();
         a.s = s_scale;
         a.kappa_coef = kKappaCoef * (1.0 + thr);
+        a.debug_flags = getenv("SFM_DEBUG_FLAGS") ? atoi(getenv("SFM_DEBUG_FLAGS")) : 0;
         a.n = c->n;
         a.offsets = c->batched ? c->offsets.as<long long>() : nullptr;
         a.E = c->E.as<double>();
@@ -563,6 +578,7 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         a.thr_pre = thr_pre;
         a.scale1 = scale1;
         a.scale2 = scale2;
+        a.sums = sums;
         a.chunk = chunk;
         a.hblocks = (int)hblocks;
         a.nsplit = (int)nsplit;
@@ -579,9 +595,10 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
                 c->pts.as<Corr>(), npts, 1.0 / s_scale, c->spts.as<Corr>(), c->bounds.as<unsigned long long>());
             if (int r = check_launch(c, "k_screen_pts")) return r;
         }
-        const long long launch_blocks = grid_blocks < total_items ? grid_blocks : total_items;
+        const long long want_blocks = (total_items + kScoreWarps - 1) / kScoreWarps;
+        const long long launch_blocks = grid_blocks < want_blocks ? grid_blocks : want_blocks;
         void* kargs[] = {(void*)&a};
-        CU(cudaLaunchKernel(fn, dim3((unsigned)launch_blocks), dim3(kScoreThreads), kargs, 0, c->stream));
+        CU(cudaLaunchKernel(fn, dim3((unsigned)launch_blocks), dim3(kScoreThreads), kargs, smem, c->stream));
         if (int r = check_launch(c, "k_score")) return r;
         c->toc(T_SCORE);
     }
@@ -597,8 +614,9 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
     f.idx_offset = idx_offset;
     f.htotal = (long long)H;
     f.acc = acc_dev;
-    f.inv_scale1 = ldexp(1.0, e2 - 70);
-    f.inv_scale2 = ldexp(1.0, 2 * e2 - 70);
+    f.inv_scale1 = ldexp(1.0, e2 - 63);
+    f.sums = sums;
+    f.inv_scale2 = ldexp(1.0, 2 * e2 - 63);
     f.thr = thr;
     f.min_extra = min_extra;
     f.agg = agg;
@@ -624,7 +642,7 @@ int sfm_score(sfm_ctx* c, double thr, double min_extra, int agg, int mode, int u
               int32_t* count_extra, double* S1, double* S2, double* err) {
     if (int r = use(c)) return r;
     if (c->batched) return fail(SFM_ERR_STATE, "sfm_score is a single-pair call; use sfm_batch_ransac");
-    if (int r = score_launch(c, thr, min_extra, agg, mode, use_table != 0, idx_offset, c->n)) return r;
+    if (int r = score_launch(c, thr, min_extra, agg, mode, use_table != 0, idx_offset, c->n, S1 || S2)) return r;
     const size_t H = (size_t)c->h;
     if (count_extra) CU(cudaMemcpyAsync(count_extra, c->count_extra.p, H * 4, cudaMemcpyDeviceToHost, c->stream));
     if (S1) CU(cudaMemcpyAsync(S1, c->S1.p, H * 8, cudaMemcpyDeviceToHost, c->stream));

@@ -55,18 +55,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 //
 // Mapping: lane = hypothesis.  Each thread keeps HPT essential matrices in registers and
 // streams correspondences from shared-memory tiles (every lane reads the same 32-byte record:
-// two broadcast LDS.128).  Tiles are filled by 1-D bulk async copies (TMA) into a
-// kStages-deep ring signalled through mbarriers; a stage is refilled by whichever warp
-// finishes it last, so no warp ever waits for a slower one (warps may drift kStages-1 tiles
-// apart) and there is no block barrier in the loop.
-//
-// Persistent blocks: the grid is one wave (SMs x resident blocks); work items
-// (pair, correspondence split, hypothesis block) are claimed from an atomic counter.
+// two broadcast LDS.128).  Every WARP is an autonomous worker: it claims work items
+// (pair, correspondence split, group of 32*HPT hypotheses) from an atomic counter and streams
+// its correspondences through its own kStages-deep ring of tiles filled by 1-D bulk async
+// copies (TMA, issued by lane 0, completion on the warp's own mbarriers).  There is no
+// block-level barrier anywhere: a warp that meets many survivors delays nobody.
+// Persistent: the grid is one wave (SMs x resident blocks).
 //
 // Two-level evaluation.  Every (hypothesis, correspondence) gets a cheap division-free
 // test; the sign bits of a BATCH of HPT*G (<= 32) tests are collected in one register per
 // lane and the warp votes once per batch.  Survivors (~1 %) are compacted with
-// ballot/popc into a 64-entry per-warp ring (positions are warp-uniform registers: no
+// a prefix sum into a 64-entry per-warp ring (positions are warp-uniform registers: no
 // atomics) and processed 32 at a time by all lanes (dense, no divergence): the exact
 // reference-order SED is evaluated and compared with thr.
 //
@@ -88,24 +87,26 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 //   FULL: the 21-slot two-sided division-free decision on the unscaled data (survivors ~
 //   inliers); identical results, kept as the like-for-like arithmetic baseline.
 //
-// Exact accumulation.  An inlier's sed (and sed^2) is split into five 14-bit chunks of a
-// fixed-point number scaled so that thr < 2^e maps below 2^70; chunks are added with native
-// 32-bit shared-memory atomics (a word cannot overflow within an item of <= 2^17
-// correspondences) and folded into 64-bit global accumulators at the end of the item.
-// Integer addition is associative, so the sums are EXACT (every double s >= thr*2^-17 is
-// represented without rounding) and independent of warp scheduling, split count and GPU
-// count — run-to-run deterministic by construction, and closer to the true sum than any
-// floating-point summation order (numpy's included).
+// Order-independent accumulation.  An inlier's sed (or sed^2 — only the sum the aggregation
+// method needs is accumulated unless both are requested) is converted to a 63-bit fixed-point
+// integer scaled so that thr < 2^e maps below 2^63, split into three 21-bit chunks and added with
+// native 32-bit shared-memory atomics (a word cannot overflow within an item of <= 2^11
+// correspondences); chunks are folded into 64-bit global accumulators at the end of the item.
+// Integer addition is associative, so the sums are independent of warp scheduling, split count
+// and GPU count — run-to-run deterministic by construction; every term >= thr * 2^-10 enters
+// without rounding, smaller ones are rounded at 2^-63 of the scale (<= 1e-19 thr per term).
 // ------------------------------------------------------------------------------------
 constexpr int kScoreThreads = 128;
 constexpr int kScoreWarps = kScoreThreads / 32;
-constexpr int kTile = 128;    // correspondences per stage (4 KB)
-constexpr int kStages = 4;
+constexpr int kTile = 64;     // correspondences per stage (2 KB)
+constexpr int kStages = 3;
 constexpr int kRing = 64;     // survivor ring per warp: < 32 pending + <= 32 new
 constexpr unsigned kMaxPoints = 1u << 25;
-constexpr int kChunks = 5;             // 14-bit chunks per exact sum
+constexpr int kChunks = 3;             // 21-bit chunks of a 63-bit fixed-point term
+constexpr int kChunkBits = 21;
 constexpr int kAccWords = 1 + 2 * kChunks;  // count, sum(sed), sum(sed^2)
-constexpr long long kMaxItemPoints = 1ll << 17;  // 2^17 adds of <= 2^14 cannot overflow a 32-bit word
+constexpr long long kMaxItemPoints = 1ll << 11;  // 2^11 adds of < 2^21 cannot overflow a 32-bit word
+enum { SUM_S1 = 1, SUM_S2 = 2 };       // which sums a launch accumulates
 constexpr double kKappaCoef = 4e-20;
 
 struct ScoreArgs {
@@ -118,13 +119,15 @@ struct ScoreArgs {
     long long h;
     double thr, thr_pre, s;    // s = sqrt(thr_pre) (SCREEN)
     double kappa_coef;         // kKappaCoef * (1 + thr)
-    double scale1, scale2;     // 2^(14-e), 2^(14-2e) with thr < 2^e
+    double scale1, scale2;     // 2^(63-e), 2^(63-2e) with thr < 2^e
+    int sums;                  // SUM_S1 | SUM_S2
     long long chunk;           // correspondences per split (multiple of kTile)
     int hblocks, nsplit;
     long long total_items;
     long long htotal;          // npairs * h
     unsigned* work_counter;
     unsigned long long* acc;   // [kAccWords][htotal] exact integer accumulators (pre-zeroed)
+    int debug_flags;           // experiments only: 1 = discard survivors instead of scoring them
 };
 
 __device__ __forceinline__ unsigned atom_add_acq_rel_shared(unsigned* p, unsigned v) {
@@ -138,14 +141,13 @@ __device__ __forceinline__ unsigned lanemask_lt() {
     return m;
 }
 
-// five 14-bit chunks of floor(x * 2^56), x in [0, 2^14): c[4] is the most significant
-__device__ __forceinline__ void chunks14(double x, unsigned (&c)[kChunks]) {
-#pragma unroll
-    for (int k = kChunks - 1; k > 0; --k) {
-        c[k] = __double2uint_rz(x);
-        x = (x - (double)c[k]) * 16384.0;
-    }
-    c[0] = __double2uint_rn(x);
+// three 21-bit chunks of V = rn(x * scale) < 2^63 (x <= thr < 2^e, scale = 2^(63-e)): c[2] is the most
+// significant.  One multiply, one conversion, five integer instructions.
+__device__ __forceinline__ void chunks21(double x, double scale, unsigned (&c)[kChunks]) {
+    const unsigned long long v = __double2ull_rn(x * scale);
+    c[0] = (unsigned)v & 0x1fffffu;
+    c[1] = (unsigned)(v >> kChunkBits) & 0x1fffffu;
+    c[2] = (unsigned)(v >> (2 * kChunkBits));
 }
 
 // Screening copy of the correspondences + the coordinate bounds used by kappa (one pass
@@ -177,42 +179,51 @@ __global__ void __launch_bounds__(256) k_screen_pts(const Corr* __restrict__ pts
     }
 }
 
+// Per-warp shared-memory state: every warp is an autonomous worker (own tile ring, own
+// mbarriers, own survivor ring and accumulators); there is no block-level barrier anywhere.
+template <int HPT>
+struct alignas(128) ScoreWarpSmem {
+    Corr tile[kStages][kTile];
+    unsigned sacc[HPT][kAccWords][32];
+    unsigned ring[kRing];
+    unsigned long long full_bar[kStages];
+};
+
+// resident blocks per SM the register budget is shaped for: 16 / 24 / 32 warps
+constexpr int score_min_blocks(int hpt) { return hpt >= 4 ? 4 : (hpt == 2 ? 6 : 8); }
+
 template <int HPT, int G, bool SCREEN>
-__global__ void __launch_bounds__(kScoreThreads) k_score(const ScoreArgs a) {
+__global__ void __launch_bounds__(kScoreThreads, score_min_blocks(HPT)) k_score(const ScoreArgs a) {
     constexpr int NB = HPT * G;  // tests per lane and batch = survivor bits per vote
     static_assert(NB <= 32 && (kTile % G) == 0, "a batch is at most 32 tests and divides a tile");
-    __shared__ __align__(128) Corr tile[kStages][kTile];
-    __shared__ __align__(8) unsigned long long full_bar[kStages];
-    __shared__ unsigned done[kStages];
-    __shared__ unsigned ring[kScoreWarps][kRing];
-    __shared__ unsigned sacc[kScoreWarps][HPT][kAccWords][32];
-    __shared__ unsigned s_item;
-
+    extern __shared__ __align__(128) unsigned char score_smem[];
     const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(full, (int)(threadIdx.x >> 5), 0);  // tells the compiler it is warp-uniform
     const unsigned lt = lanemask_lt();
+    ScoreWarpSmem<HPT>& ws = reinterpret_cast<ScoreWarpSmem<HPT>*>(score_smem)[warp];
 
-    if (threadIdx.x == 0) {
+    if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); done[s] = 0; }
+        for (int s = 0; s < kStages; ++s) mbar_init(&ws.full_bar[s], 1);
         mbar_fence_init();
     }
 #pragma unroll
     for (int j = 0; j < HPT; ++j)
 #pragma unroll
-        for (int k = 0; k < kAccWords; ++k) sacc[warp][j][k][lane] = 0;
-    unsigned* q = ring[warp];
+        for (int k = 0; k < kAccWords; ++k) ws.sacc[j][k][lane] = 0;
+    __syncwarp();
+    unsigned* q = ws.ring;
     unsigned head = 0, tail = 0;  // ring positions: warp-uniform, monotone, tail - head < 64
-    unsigned gt = 0;              // tiles consumed so far by this block (drives stage + parity)
+    unsigned gt = 0;              // tiles consumed so far by this warp (drives stage + parity)
     const double ab2 = SCREEN ? a.bounds[0] * a.bounds[1] * a.kappa_coef : 0.0;
 
     for (;;) {
-        __syncthreads();  // previous item completely finished; s_item free
-        if (threadIdx.x == 0) s_item = atomicAdd(a.work_counter, 1u);
-        __syncthreads();
-        const unsigned item = s_item;
+        unsigned item = 0;
+        if (lane == 0) item = atomicAdd(a.work_counter, 1u);
+        item = __shfl_sync(full, item, 0);
         if (item >= a.total_items) break;
-        const int hb = (int)(item % (unsigned)a.hblocks);
+        const int hw = (int)(item % (unsigned)a.hblocks);  // group of 32*HPT hypotheses
         const unsigned rest = item / (unsigned)a.hblocks;
         const int split = (int)(rest % (unsigned)a.nsplit);
         const int pair = (int)(rest / (unsigned)a.nsplit);
@@ -225,19 +236,19 @@ __global__ void __launch_bounds__(kScoreThreads) k_score(const ScoreArgs a) {
         begin += pbase;
         const int ntiles = (int)((end - begin + kTile - 1) / kTile);
         // this warp's hypotheses: lane l, slot j  ->  hyp_w + 32*j + l
-        const long long hyp_w = (long long)hb * (kScoreThreads * HPT) + (long long)warp * (32 * HPT);
+        const long long hyp_w = (long long)hw * (32 * HPT);
         const double* Ep = a.E + 9 * (long long)pair * a.h;
         const Corr* src = SCREEN ? a.spts : a.pts;
 
-        auto issue = [&](int t) {
+        auto issue = [&](int t) {  // lane 0 only
             const int s = (int)((gt + (unsigned)t) % kStages);
             const long long first = begin + (long long)t * kTile;
             const long long rem = end - first;
             const uint32_t bytes = (uint32_t)((rem < kTile ? rem : kTile) * sizeof(Corr));
-            mbar_expect_tx(&full_bar[s], bytes);
-            bulk_g2s(&tile[s][0], src + first, bytes, &full_bar[s]);
+            mbar_expect_tx(&ws.full_bar[s], bytes);
+            bulk_g2s(&ws.tile[s][0], src + first, bytes, &ws.full_bar[s]);
         };
-        if (threadIdx.x == 0)
+        if (lane == 0)
             for (int t = 0; t < kStages && t < ntiles; ++t) issue(t);
 
         // register-resident models; SCREEN: columns 0 and 1 scaled by s, kappa per hypothesis
@@ -260,58 +271,83 @@ __global__ void __launch_bounds__(kScoreThreads) k_score(const ScoreArgs a) {
         // exact evaluation of m (<= 32) queued candidates by all 32 lanes; the candidate's E
         // comes from global memory (L1/L2 hits), its correspondence by index
         auto drain = [&](unsigned m) {
+            if (a.debug_flags & 1) { head += m; return; }
             const unsigned ent = (lane < (int)m) ? q[(head + lane) & (kRing - 1)] : 0u;
+            // entry = owner lane | bit of its batch mask | first correspondence of the batch (item-relative)
             const int owner = (int)(ent >> 27);
-            const int slot = (int)((ent >> 25) & 3u);
-            const unsigned gi = ent & (kMaxPoints - 1u);
+            const int i = NB - 1 - (int)((ent >> 22) & 31u);  // test index in the batch: g * HPT + j
+            const int slot = i % HPT;
+            const long long gi = begin + (long long)((ent & 0x3fffffu) + (unsigned)(i / HPT));
             long long hyp = hyp_w + 32 * slot + owner;
             hyp = (hyp < a.h) ? hyp : 0;
             double eo[9];
 #pragma unroll
             for (int k = 0; k < 9; ++k) eo[k] = __ldg(Ep + 9 * hyp + k);
-            const Corr c = a.pts[(lane < (int)m) ? gi : (unsigned)begin];
+            const Corr c = a.pts[gi];
             const double sv = sed_exact(eo, c.xa, c.ya, c.xb, c.yb);
             if ((lane < (int)m) && (sv <= a.thr)) {  // ransac.py:73  score <= threshold
                 unsigned ch[kChunks];
-                unsigned* dst = &sacc[warp][slot][0][owner];
+                unsigned* dst = &ws.sacc[slot][0][owner];
                 atomicAdd(dst, 1u);
-                chunks14(sv * a.scale1, ch);
+                if (a.sums & SUM_S1) {
+                    chunks21(sv, a.scale1, ch);
 #pragma unroll
-                for (int k = 0; k < kChunks; ++k) atomicAdd(dst + 32 * (1 + k), ch[k]);
-                chunks14(__dmul_rn(sv, sv) * a.scale2, ch);
+                    for (int k = 0; k < kChunks; ++k) atomicAdd(dst + 32 * (1 + k), ch[k]);
+                }
+                if (a.sums & SUM_S2) {
+                    chunks21(__dmul_rn(sv, sv), a.scale2, ch);
 #pragma unroll
-                for (int k = 0; k < kChunks; ++k) atomicAdd(dst + 32 * (1 + kChunks + k), ch[k]);
+                    for (int k = 0; k < kChunks; ++k) atomicAdd(dst + 32 * (1 + kChunks + k), ch[k]);
+                }
             }
             head += m;
             __syncwarp();
         };
 
-        // queue the set bits of pm (bit NB-1-i <-> test i = g*HPT + j of the batch starting at
-        // correspondence gi0): one ballot-compacted entry per lane and round
-        auto push = [&](unsigned pm, unsigned gi0) {
-            unsigned any = __ballot_sync(full, pm != 0u);
-            while (any) {
-                if (pm) {
+        // queue the set bits of pm (bit NB-1-i <-> test i = g*HPT + j of the batch whose first
+        // correspondence is rel0, item-relative).  Usual case (<= 32 survivors in the warp, < 8 per
+        // lane): a prefix sum of the per-lane counts from three ballots, then every lane stores its
+        // own entries; otherwise one ballot-compacted entry per lane and round with drains in between.
+        auto push = [&](unsigned pm, unsigned rel0) {
+            if (a.debug_flags & 4) { tail += 1; head += 1; return; }
+            const unsigned base = ((unsigned)lane << 27) | rel0;
+            const int cnt = __popc(pm);
+            const unsigned b0 = __ballot_sync(full, cnt & 1), b1 = __ballot_sync(full, cnt & 2),
+                           b2 = __ballot_sync(full, cnt & 4), b3 = __ballot_sync(full, cnt >= 8);
+            const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+            if (b3 == 0u && total <= 32) {  // < 32 pending + <= 32 new fit the ring
+                unsigned pos = tail + (unsigned)(__popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt));
+                while (pm) {
                     const int b = 31 - __clz(pm);
                     pm ^= 1u << b;
-                    const int i = NB - 1 - b;
-                    const unsigned pos = tail + __popc(any & lt);
-                    q[pos & (kRing - 1)] = ((unsigned)lane << 27) | ((unsigned)(i % HPT) << 25) | (gi0 + (unsigned)(i / HPT));
+                    q[pos++ & (kRing - 1)] = base | ((unsigned)b << 22);
                 }
-                tail += __popc(any);
+                tail += (unsigned)total;
                 __syncwarp();
                 if (tail - head >= 32u) drain(32u);
-                any = __ballot_sync(full, pm != 0u);
+            } else {
+                unsigned any = __ballot_sync(full, pm != 0u);
+                while (any) {
+                    if (pm) {
+                        const int b = 31 - __clz(pm);
+                        pm ^= 1u << b;
+                        q[(tail + __popc(any & lt)) & (kRing - 1)] = base | ((unsigned)b << 22);
+                    }
+                    tail += __popc(any);
+                    __syncwarp();
+                    if (tail - head >= 32u) drain(32u);
+                    any = __ballot_sync(full, pm != 0u);
+                }
             }
         };
 
         for (int t = 0; t < ntiles; ++t) {
             const unsigned gti = gt + (unsigned)t;
             const int s = (int)(gti % kStages);
-            mbar_wait(&full_bar[s], (gti / kStages) & 1u);
+            mbar_wait(&ws.full_bar[s], (gti / kStages) & 1u);
             const long long first = begin + (long long)t * kTile;
             const int np = (int)((end - first < kTile) ? (end - first) : kTile);
-            const Corr* tp = tile[s];
+            const Corr* tp = ws.tile[s];
             for (int p = 0; p < np; p += G) {
                 unsigned pm = 0;
 #pragma unroll
@@ -352,17 +388,11 @@ __global__ void __launch_bounds__(kScoreThreads) k_score(const ScoreArgs a) {
                 }
                 const int v = np - p;  // a partial last batch evaluated stale records: drop their bits
                 if (v < G) pm &= 0xffffffffu << (NB - v * HPT);
-                if (__any_sync(full, pm != 0u)) push(pm, (unsigned)(first + p));
+                if (__any_sync(full, pm != 0u)) push(pm, (unsigned)(first - begin) + (unsigned)p);
             }
-            // release the stage: the last warp to finish it refills it (nobody waits)
+            // every lane is done with the stage: refill it with the tile kStages ahead
             __syncwarp();
-            if (lane == 0) {
-                const unsigned old = atom_add_acq_rel_shared(&done[s], 1u);
-                if (old == kScoreWarps - 1) {
-                    done[s] = 0;
-                    if (t + kStages < ntiles) issue(t + kStages);
-                }
-            }
+            if (lane == 0 && t + kStages < ntiles) issue(t + kStages);
         }
         gt += (unsigned)ntiles;
 
@@ -371,21 +401,22 @@ __global__ void __launch_bounds__(kScoreThreads) k_score(const ScoreArgs a) {
 #pragma unroll
         for (int j = 0; j < HPT; ++j) {
             const long long hyp = hyp_w + 32 * j + lane;
-            const unsigned cnt = sacc[warp][j][0][lane];
+            const unsigned cnt = ws.sacc[j][0][lane];
             if (cnt) {  // only real hypotheses can have inliers
                 unsigned long long* dst = a.acc + (long long)pair * a.h + hyp;
                 atomicAdd(dst, (unsigned long long)cnt);
-                sacc[warp][j][0][lane] = 0;
+                ws.sacc[j][0][lane] = 0;
 #pragma unroll
                 for (int k = 1; k < kAccWords; ++k) {
-                    const unsigned v = sacc[warp][j][k][lane];
+                    const unsigned v = ws.sacc[j][k][lane];
                     if (v) {
                         atomicAdd(dst + (long long)k * a.htotal, (unsigned long long)v);
-                        sacc[warp][j][k][lane] = 0;
+                        ws.sacc[j][k][lane] = 0;
                     }
                 }
             }
         }
+        __syncwarp();
     }
 }
 
@@ -455,11 +486,11 @@ __device__ __forceinline__ Best block_best(Best b, int mode, Best* sm /* 32 */) 
     return b;  // valid in thread 0
 }
 
-// sum_k plane[k] * 2^(14k) as a double; plane sums are < 2^40 each, the total < 2^96.
-__device__ __forceinline__ double fixed70_to_double(const unsigned long long* acc, long long stride) {
+// sum_k plane[k] * 2^(21k) as a double; plane sums are < 2^21 * N each, the total < 2^63 * N.
+__device__ __forceinline__ double fixed_to_double(const unsigned long long* acc, long long stride) {
     unsigned __int128 v = 0;
 #pragma unroll
-    for (int k = kChunks - 1; k >= 0; --k) v = (v << 14) + acc[(long long)k * stride];
+    for (int k = kChunks - 1; k >= 0; --k) v = (v << kChunkBits) + acc[(long long)k * stride];
     const unsigned long long hi = (unsigned long long)(v >> 64), lo = (unsigned long long)v;
     return fma((double)hi, 18446744073709551616.0, (double)lo);
 }
@@ -474,7 +505,8 @@ struct FinalArgs {
     long long idx_offset;  // global index of hypothesis 0 (hypothesis-sharded runs)
     long long htotal;                 // npairs * h (stride of the accumulator planes)
     const unsigned long long* acc;    // [kAccWords][htotal] exact sums from K2
-    double inv_scale1, inv_scale2;    // 2^(e-70), 2^(2e-70)
+    double inv_scale1, inv_scale2;    // 2^(e-63), 2^(2e-63)
+    int sums;                         // which sums K2 accumulated (the other one is reported as NaN)
     double thr, min_extra;
     int agg, mode;
     int32_t* count_extra;
@@ -494,8 +526,9 @@ __global__ void __launch_bounds__(256) k_finalise(const FinalArgs a) {
     if (li < a.h) {
         // exact integer sums -> one rounding each
         long long cnt = (long long)a.acc[i];
-        double s1 = fixed70_to_double(a.acc + 1 * a.htotal + i, a.htotal) * a.inv_scale1;
-        double s2 = fixed70_to_double(a.acc + (1 + kChunks) * a.htotal + i, a.htotal) * a.inv_scale2;
+        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+        double s1 = (a.sums & SUM_S1) ? fixed_to_double(a.acc + 1 * a.htotal + i, a.htotal) * a.inv_scale1 : qnan;
+        double s2 = (a.sums & SUM_S2) ? fixed_to_double(a.acc + (1 + kChunks) * a.htotal + i, a.htotal) * a.inv_scale2 : qnan;
         const bool valid = a.valid ? (a.valid[i] != 0) : true;
         if (a.table && valid) {
             double e[9];

@@ -77,7 +77,7 @@ struct sfm_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     // data
     Buf raw, pts, offsets, Ks, table, E, valid, eig;
-    Buf acc, count_extra, S1, S2, err, blocks, best, invalid, winnerE, spts, bounds;
+    Buf acc, count_extra, S1, S2, err, blocks, best, invalid, winnerE, spts, bounds, fitflag;
     Buf mask, sed, poses, pass, X, idx, scan, tmp;
     long long n = 0, h = 0, npairs = 1;
     long long raw_stride = 1;
@@ -235,7 +235,7 @@ int sfm_destroy(sfm_ctx* c) {
     Buf* bufs[] = {&c->raw, &c->pts, &c->offsets, &c->Ks, &c->table, &c->E, &c->valid, &c->eig, &c->acc,
                    &c->count_extra, &c->S1, &c->S2, &c->err, &c->blocks, &c->best,
                    &c->invalid, &c->winnerE, &c->mask, &c->sed, &c->poses, &c->pass, &c->X, &c->idx,
-                   &c->scan, &c->tmp, &c->spts, &c->bounds};
+                   &c->scan, &c->tmp, &c->spts, &c->bounds, &c->fitflag};
     for (Buf* b : bufs) b->release();
     for (int i = 0; i < T_COUNT; ++i) {
         cudaEventDestroy(c->ev0[i]);
@@ -460,11 +460,25 @@ static int fit_launch(sfm_ctx* c, bool want_eig) {
     if (int r = c->valid.reserve(H)) return r;
     if (want_eig)
         if (int r = c->eig.reserve(H * 9 * sizeof(double))) return r;
+    if (int r = c->fitflag.reserve(16)) return r;
     c->tic(T_FIT);
+    const long long* off = c->batched ? c->offsets.as<long long>() : nullptr;
     dim3 grid((unsigned)((c->h + kFitThreads - 1) / kFitThreads), (unsigned)c->npairs);
+    const unsigned* only = nullptr;
+    if (!want_eig) {
+        // fast path: Householder null vector in registers; flags the (rare) samples whose validity
+        // test is too close to call, which the Y^T Y Jacobi kernel then redoes
+        CU(cudaMemsetAsync(c->fitflag.p, 0, 16, c->stream));
+        dim3 gq((unsigned)((c->h + kFitQrThreads - 1) / kFitQrThreads), (unsigned)c->npairs);
+        k_fit_qr<<<gq, kFitQrThreads, 0, c->stream>>>(c->pts.as<Corr>(), off, c->table.as<int32_t>(), c->h,
+                                                      c->E.as<double>(), c->valid.as<uint8_t>(),
+                                                      c->fitflag.as<unsigned>());
+        if (int r = check_launch(c, "k_fit_qr")) return r;
+        only = c->fitflag.as<unsigned>();
+    }
     k_fit<<<grid, kFitThreads, kFitThreads * kFitSmemDoubles * sizeof(double), c->stream>>>(
-        c->pts.as<Corr>(), c->batched ? c->offsets.as<long long>() : nullptr, c->table.as<int32_t>(), c->h,
-        c->E.as<double>(), c->valid.as<uint8_t>(), want_eig ? c->eig.as<double>() : nullptr);
+        c->pts.as<Corr>(), off, c->table.as<int32_t>(), c->h, c->E.as<double>(), c->valid.as<uint8_t>(),
+        want_eig ? c->eig.as<double>() : nullptr, only);
     if (int r = check_launch(c, "k_fit")) return r;
     c->toc(T_FIT);
     c->has_models = true;

@@ -57,7 +57,9 @@ __global__ void k_sample(unsigned long long seed, unsigned long long stream0,
 }
 
 // ------------------------------------------------------------------------------------
-// K1 — eight-point fit, one thread per hypothesis.
+// K1 reference-arithmetic path — eight-point fit through Y^T Y, one thread per hypothesis.
+// Runs for the hypotheses the fast path (k_fit_qr above) flags as ambiguous, and for every
+// hypothesis when the eigenvalues are requested (sfm_fit with eig_out).
 //
 // Restates estimate_fundamental_mat (lib/epipolar/eight_point.py:136-170):
 //   Hartley normalisation (:308-338) -> Y^T Y (:363-393) -> eigenvector of the smallest
@@ -101,6 +103,184 @@ __device__ __forceinline__ void hartley(const double (&x)[8], const double (&y)[
         nx[i] = __dmul_rn(nx[i], scale);
         ny[i] = __dmul_rn(ny[i], scale);
     }
+}
+
+// Rank-2 projection (:430-446), E = T2^T F T1 (:163), E /= E[2,2] (:166) — shared by both fitters.
+__device__ __forceinline__ void finish_fit(double (&F)[9], double s1, double c1x, double c1y, double s2,
+                                           double c2x, double c2y, double (&E)[9]) {
+    // one-sided Jacobi SVD of F; the column of F V with the
+    // smallest norm is sigma_3 u_3, so F' = F - (sigma_3 u_3) v_3^T zeroes the smallest
+    // singular value without ever dividing by it.
+    {
+        double G[9], W[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) G[i] = F[i];
+        jacobi_svd_onesided<3, 3>(G, W, 30);
+        double nrm[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) nrm[j] = fma(G[6 + j], G[6 + j], fma(G[3 + j], G[3 + j], G[j] * G[j]));
+        int k3 = 0;
+        if (nrm[1] < nrm[0]) k3 = 1;
+        if (nrm[2] < (k3 == 0 ? nrm[0] : nrm[1])) k3 = 2;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double g = (k3 == 0) ? G[i * 3] : ((k3 == 1) ? G[i * 3 + 1] : G[i * 3 + 2]);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const double w = (k3 == 0) ? W[j * 3] : ((k3 == 1) ? W[j * 3 + 1] : W[j * 3 + 2]);
+                F[i * 3 + j] = fma(-g, w, F[i * 3 + j]);
+            }
+        }
+    }
+    // E = T2^T F T1 (:163), T = [[s,0,-s cx],[0,s,-s cy],[0,0,1]] (:329-336)
+    const double T1[9] = {s1, 0.0, -s1 * c1x, 0.0, s1, -s1 * c1y, 0.0, 0.0, 1.0};
+    const double T2t[9] = {s2, 0.0, 0.0, 0.0, s2, 0.0, -s2 * c2x, -s2 * c2y, 1.0};
+    double tmp[9];
+    mat3_mul(T2t, F, tmp);
+    mat3_mul(tmp, T1, E);
+    const double e22 = E[8];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) E[i] = E[i] / e22;  // (:166)
+}
+
+// ------------------------------------------------------------------------------------
+// K1 fast path — the same fit without forming Y^T Y.
+//
+// The 8x9 design matrix Y (:363-393) has rank 8 for a non-degenerate sample, and the
+// eigenvector the reference takes (smallest |eigenvalue| of Y^T Y, :423-425) is Y's null
+// vector.  Householder QR of Y^T (9x8, one reflector per correspondence) gives it as
+// Q e_9 = H_1 ... H_8 e_9 with a backward error of order eps * kappa(Y) — the reference's
+// own route through Y^T Y costs eps * kappa(Y)^2, so this path is the more accurate of the
+// two.  Everything is statically indexed and lives in registers (no shared memory, no
+// local memory): ~1.3k FP64 instructions per hypothesis instead of ~30k for the 9x9 Jacobi.
+//
+// Validity (:414-421) needs lambda_2(Y^T Y) = sigma_min(R)^2 against 1e-10.  R is the 8x8
+// triangular factor:  1/|R^-1|_F <= sigma_min(R) <= min |r_ii|,  so
+//     1/|R^-1|_F^2 > 1.001e-10   => valid,       min r_ii^2 < 0.999e-10  => degenerate,
+// and the (very rare: P ~ 1e-7 per sample) in-between case is flagged 2 and re-done by the
+// Jacobi kernel below, which follows the reference's Y^T Y arithmetic.
+// ------------------------------------------------------------------------------------
+enum { FIT_INVALID = 0, FIT_VALID = 1, FIT_AMBIGUOUS = 2 };
+
+__device__ __forceinline__ int eight_point_fit_qr(const Corr (&c)[8], double (&E)[9]) {
+    double s1, c1x, c1y, s2, c2x, c2y;
+    double M[9][8];  // M[i][k] = y_k[i]: column k is the design row of correspondence k
+    {
+        double xa[8], ya[8], xb[8], yb[8], nxa[8], nya[8], nxb[8], nyb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            xa[i] = c[i].xa; ya[i] = c[i].ya; xb[i] = c[i].xb; yb[i] = c[i].yb;
+        }
+        hartley(xa, ya, nxa, nya, s1, c1x, c1y);
+        hartley(xb, yb, nxb, nyb, s2, c2x, c2y);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // eight_point.py:376-393
+            M[0][k] = __dmul_rn(nxb[k], nxa[k]); M[1][k] = __dmul_rn(nxb[k], nya[k]); M[2][k] = nxb[k];
+            M[3][k] = __dmul_rn(nyb[k], nxa[k]); M[4][k] = __dmul_rn(nyb[k], nya[k]); M[5][k] = nyb[k];
+            M[6][k] = nxa[k]; M[7][k] = nya[k]; M[8][k] = 1.0;
+        }
+    }
+    double beta[8], rdiag[8];
+    bool rank_ok = true;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        // reflector for x = M[k..8][k]:  v = x - alpha e_1, alpha = -sign(x_0) |x|, H = I - beta v v^T
+        double n2 = 0.0;
+#pragma unroll
+        for (int i = k; i < 9; ++i) n2 = fma(M[i][k], M[i][k], n2);
+        const double nrm = sqrt(n2);
+        const double x0 = M[k][k];
+        const double alpha = (x0 > 0.0) ? -nrm : nrm;
+        const double v0 = x0 - alpha;                       // |v0| = |x0| + |x|: no cancellation
+        const double vtv = 2.0 * fma(nrm, fabs(x0), n2);     // v^T v = 2 |x| (|x| + |x0|)
+        rank_ok = rank_ok && (n2 > 0.0);
+        beta[k] = (n2 > 0.0) ? 2.0 / vtv : 0.0;
+        rdiag[k] = alpha;
+        M[k][k] = v0;  // column k below the diagonal now holds v_k
+#pragma unroll
+        for (int j = k + 1; j < 8; ++j) {
+            double w = 0.0;
+#pragma unroll
+            for (int i = k; i < 9; ++i) w = fma(M[i][k], M[i][j], w);
+            w *= beta[k];
+#pragma unroll
+            for (int i = k; i < 9; ++i) M[i][j] = fma(-w, M[i][k], M[i][j]);
+        }
+    }
+    // sigma_min(R)^2 bounds; R = rdiag on the diagonal, M[i][j] (i < j) above it
+    double min_r2 = rdiag[0] * rdiag[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) min_r2 = fmin(min_r2, rdiag[k] * rdiag[k]);
+    int status;
+    if (!rank_ok || !(min_r2 >= 0.999 * kVerySmall)) {
+        status = FIT_INVALID;
+    } else {
+        // X = R^-1 (upper triangular), column by column; only its Frobenius norm is needed
+        double rinv[8], f2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) rinv[k] = 1.0 / rdiag[k];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            double x[8];
+            x[j] = rinv[j];
+            f2 = fma(x[j], x[j], f2);
+#pragma unroll
+            for (int i = j - 1; i >= 0; --i) {
+                double acc = 0.0;
+#pragma unroll
+                for (int k = i + 1; k <= j; ++k) acc = fma(M[i][k], x[k], acc);
+                x[i] = -acc * rinv[i];
+                f2 = fma(x[i], x[i], f2);
+            }
+        }
+        status = (1.0 / f2 > 1.001 * kVerySmall) ? FIT_VALID : FIT_AMBIGUOUS;
+    }
+    // null vector z = H_1 ... H_8 e_9
+    double z[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) z[i] = (i == 8) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 7; k >= 0; --k) {
+        double w = 0.0;
+#pragma unroll
+        for (int i = k; i < 9; ++i) w = fma(M[i][k], z[i], w);
+        w *= beta[k];
+#pragma unroll
+        for (int i = k; i < 9; ++i) z[i] = fma(-w, M[i][k], z[i]);
+    }
+    finish_fit(z, s1, c1x, c1y, s2, c2x, c2y, E);  // v_min.reshape((3,3)) (:424-425)
+    return status;
+}
+
+constexpr int kFitQrThreads = 64;
+
+__global__ void __launch_bounds__(kFitQrThreads)
+k_fit_qr(const Corr* __restrict__ pts, const long long* __restrict__ offsets, const int32_t* __restrict__ table,
+         long long h, double* __restrict__ E_out, uint8_t* __restrict__ valid_out,
+         unsigned* __restrict__ ambiguous_count) {
+    const long long li = blockIdx.x * (long long)kFitQrThreads + threadIdx.x;
+    if (li >= h) return;
+    const long long i = (long long)blockIdx.y * h + li;  // blockIdx.y = image pair
+    if (offsets) {
+        if (offsets[blockIdx.y + 1] - offsets[blockIdx.y] < 8) {
+            for (int k = 0; k < 9; ++k) E_out[9 * i + k] = 0.0;
+            valid_out[i] = FIT_INVALID;
+            return;
+        }
+        pts += offsets[blockIdx.y];
+    }
+    Corr c[8];
+    const int4 t0 = reinterpret_cast<const int4*>(table + 8 * i)[0];
+    const int4 t1 = reinterpret_cast<const int4*>(table + 8 * i)[1];
+    const int idx[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) c[k] = pts[idx[k]];
+    double E[9];
+    const int status = eight_point_fit_qr(c, E);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) E_out[9 * i + k] = (status == FIT_VALID) ? E[k] : 0.0;
+    valid_out[i] = (uint8_t)status;
+    if (status == FIT_AMBIGUOUS) atomicAdd(ambiguous_count, 1u);
 }
 
 // Fit one hypothesis from 8 correspondences.  sm points at this thread's column of the
@@ -197,50 +377,21 @@ __device__ inline bool eight_point_fit(const Corr (&c)[8], double* sm, double (&
     for (int i = 0; i < 9; ++i) F[i] = V_(i, imin);  // v_min.reshape((3,3)) (:424-425)
 #undef A_
 #undef V_
-    // rank-2 projection (:430-446): one-sided Jacobi SVD of F; the column of F V with the
-    // smallest norm is sigma_3 u_3, so F' = F - (sigma_3 u_3) v_3^T zeroes the smallest
-    // singular value without ever dividing by it.
-    {
-        double G[9], W[9];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) G[i] = F[i];
-        jacobi_svd_onesided<3, 3>(G, W, 30);
-        double nrm[3];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) nrm[j] = fma(G[6 + j], G[6 + j], fma(G[3 + j], G[3 + j], G[j] * G[j]));
-        int k3 = 0;
-        if (nrm[1] < nrm[0]) k3 = 1;
-        if (nrm[2] < (k3 == 0 ? nrm[0] : nrm[1])) k3 = 2;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const double g = (k3 == 0) ? G[i * 3] : ((k3 == 1) ? G[i * 3 + 1] : G[i * 3 + 2]);
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const double w = (k3 == 0) ? W[j * 3] : ((k3 == 1) ? W[j * 3 + 1] : W[j * 3 + 2]);
-                F[i * 3 + j] = fma(-g, w, F[i * 3 + j]);
-            }
-        }
-    }
-    // E = T2^T F T1 (:163), T = [[s,0,-s cx],[0,s,-s cy],[0,0,1]] (:329-336)
-    const double T1[9] = {s1, 0.0, -s1 * c1x, 0.0, s1, -s1 * c1y, 0.0, 0.0, 1.0};
-    const double T2t[9] = {s2, 0.0, 0.0, 0.0, s2, 0.0, -s2 * c2x, -s2 * c2y, 1.0};
-    double tmp[9];
-    mat3_mul(T2t, F, tmp);
-    mat3_mul(tmp, T1, E);
-    const double e22 = E[8];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) E[i] = E[i] / e22;  // (:166)
+    finish_fit(F, s1, c1x, c1y, s2, c2x, c2y, E);
     return valid;
 }
 
 __global__ void __launch_bounds__(kFitThreads)
 k_fit(const Corr* __restrict__ pts, const long long* __restrict__ offsets,
       const int32_t* __restrict__ table, long long h, double* __restrict__ E_out,
-      uint8_t* __restrict__ valid_out, double* __restrict__ eig_out) {
+      uint8_t* __restrict__ valid_out, double* __restrict__ eig_out,
+      const unsigned* __restrict__ only_ambiguous /* null = fit everything */) {
     extern __shared__ double fit_smem[];
+    if (only_ambiguous && *only_ambiguous == 0u) return;  // the usual case: nothing was flagged
     const long long li = blockIdx.x * (long long)kFitThreads + threadIdx.x;
     if (li >= h) return;
     const long long i = (long long)blockIdx.y * h + li;  // blockIdx.y = image pair
+    if (only_ambiguous && valid_out[i] != FIT_AMBIGUOUS) return;
     bool enough = true;
     if (offsets) {
         enough = offsets[blockIdx.y + 1] - offsets[blockIdx.y] >= 8;

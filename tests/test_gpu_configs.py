@@ -1,0 +1,199 @@
+"""GPU parity at the BASELINE.json configuration sizes.
+
+config 2 (10k correspondences x 16k hypotheses): full-size comparison with the oracle on the
+  reference-RNG sample table.
+config 3 (100k x 64k): size-independent properties — run-to-run determinism, invariance under
+  hypothesis sharding and under the scoring variant, K2's count of the winner against K4's mask.
+config 4 (batch of image pairs): the batched call against per-pair calls, ragged and empty pairs.
+"""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import csed
+from oracle import restatement as o
+from structure_from_motion_b200 import _native, two_view
+from structure_from_motion_b200.scenes import make_scene
+
+pytestmark = pytest.mark.gpu
+
+THR = 1.5e-6  # apps/config/config.yaml:7
+BAND = 1e-9
+
+
+def _norm(K, x1, x2):
+    nxa, nya = o.k_normalise(x1[:, 0], x1[:, 1], K)
+    nxb, nyb = o.k_normalise(x2[:, 0], x2[:, 1], K)
+    return nxa, nya, nxb, nyb
+
+
+def _e_close(a, b, tol=1e-6):
+    a = a.reshape(-1) / np.linalg.norm(a)
+    b = b.reshape(-1) / np.linalg.norm(b)
+    return min(np.abs(a - b).max(), np.abs(a + b).max()) <= tol
+
+
+def test_config2_full_size_against_oracle(engine):
+    """10 000 correspondences x 16 384 hypotheses, 40 % outliers, sample table drawn by the
+    CPython-exact sampler from random.seed(5) (what ransac.py:62 would draw)."""
+    n, h = 10_000, 16_384
+    K, x1, x2, *_ = make_scene(n, 0.4, seed=0)
+    nxa, nya, nxb, nyb = _norm(K, x1, x2)
+    random.seed(5)
+    state = random.getstate()
+    st = np.array(state[1], dtype=np.uint32)
+    table, _ = _native.mt_shuffle_table(st, n, h)
+    # spot-check the table against CPython itself on a prefix
+    random.setstate(state)
+    perm = list(range(n))
+    for it in range(3):
+        random.shuffle(perm)
+        assert perm[:8] == table[it].tolist()
+
+    # (1) the scorer alone, with the oracle's models: counts bit-exact, sums to 1e-12
+    ca, cb = np.stack([nxa, nya], 1), np.stack([nxb, nyb], 1)
+    E_o = np.stack([o.eight_point(ca[s], cb[s]) for s in table])
+    cnt_o, s1_o, s2_o = csed.score_batch(E_o, nxa, nya, nxb, nyb, THR, table=table, nthreads=16)
+    engine.upload_pairs(x1, x2, K)
+    engine.set_table(table)
+    engine.set_models(E_o)
+    cnt, s1, s2, err = engine.score(THR, min_extra=10, aggregation="rms")
+    assert np.array_equal(cnt, cnt_o)
+    np.testing.assert_allclose(s1, s1_o, rtol=1e-12, atol=0)
+    np.testing.assert_allclose(s2, s2_o, rtol=1e-12, atol=0)
+    err_o = np.where(cnt_o >= 10, np.sqrt(s2_o / (8 + cnt_o)), np.inf)
+    win_o = int(np.argmin(err_o))
+    assert engine.get_best().index == win_o
+
+    # (2) the whole GPU pipeline (own fitter) from the same global RNG state
+    random.setstate(state)
+    res = two_view.ransac_essential_arrays(K, x1, x2, THR, 10, "rms", h, engine=engine)
+    assert res.best_index == win_o
+    assert _e_close(res.E, E_o[win_o])
+    assert abs(res.error - err_o[win_o]) <= 1e-9 * err_o[win_o]
+    sed_o = csed.sed_exact_many(E_o[win_o], nxa, nya, nxb, nyb)
+    in_band = np.abs(sed_o - THR) <= BAND * THR
+    mask_o = sed_o <= THR
+    mask_o[table[win_o]] = True  # samples are always part of the model's inliers (ransac.py:76)
+    got = np.zeros(n, dtype=bool)
+    got[res.inlier_indices] = True
+    assert not ((got != mask_o) & ~in_band).any()
+    assert res.inlier_indices[:8].tolist() == table[win_o].tolist()
+    # per-hypothesis fitted models against the oracle's, on a subsample (conditioning-scaled)
+    engine.set_table(table)
+    E_g, valid, _ = engine.fit()
+    assert valid.all()
+    worst = 0.0
+    for i in range(0, h, 37):
+        d = np.linalg.norm(E_g[i] / np.linalg.norm(E_g[i]) - E_o[i] / np.linalg.norm(E_o[i]))
+        worst = max(worst, d)
+    assert worst <= 1e-6, worst
+
+
+@pytest.fixture(scope="module")
+def config3(engine):
+    n, h = 100_000, 65_536
+    K, x1, x2, *_ = make_scene(n, 0.4, seed=0)
+    engine.upload_pairs(x1, x2, K)
+    engine.sample_device(seed=3, h=h)
+    engine.fit(want_E=False)
+    cnt, s1, s2, err = engine.score(THR, min_extra=10, aggregation="rms")
+    best = engine.get_best()
+    return dict(n=n, h=h, K=K, x1=x1, x2=x2, cnt=cnt, s1=s1, s2=s2, err=err, best=best)
+
+
+def test_config3_deterministic_and_variant_invariant(engine, config3):
+    c = config3
+    for variant, hpt, group in [("screen", 2, 16), ("screen", 4, 8), ("full", 2, 16)]:
+        engine.set_score_variant(variant, hpt, group)
+        try:
+            cnt, s1, s2, err = engine.score(THR, min_extra=10, aggregation="rms")
+        finally:
+            engine.set_score_variant("screen", 2, 16)
+        assert np.array_equal(cnt, c["cnt"]), variant
+        # integer accumulation: the sums are bit-identical whatever the schedule or the variant
+        assert np.array_equal(s1, c["s1"]) and np.array_equal(s2, c["s2"]), variant
+        assert np.array_equal(err, c["err"]), variant
+        assert engine.get_best().index == c["best"].index
+
+
+def test_config3_hypothesis_sharding_invariant(engine, config3):
+    """Scoring the hypothesis range in four shards (what bench.py --gpus 4 does per rank) gives
+    the same per-hypothesis results and, merged by the reference's rule, the same winner."""
+    c = config3
+    h, parts = c["h"], 4
+    rows = []
+    for r in range(parts):
+        lo = r * h // parts
+        engine.sample_device(seed=3, h=h // parts, hyp_offset=lo)
+        engine.fit(want_E=False)
+        cnt, s1, s2, err = engine.score(THR, min_extra=10, aggregation="rms", idx_offset=lo)
+        assert np.array_equal(cnt, c["cnt"][lo:lo + h // parts])
+        assert np.array_equal(err, c["err"][lo:lo + h // parts])
+        b = engine.get_best()
+        rows.append((b.err, b.index))
+    # strict <, earliest index on ties (ransac.py:83)
+    win = min(rows, key=lambda t: (t[0], t[1]))
+    assert win[1] == c["best"].index
+    engine.sample_device(seed=3, h=h)
+    engine.fit(want_E=False)
+    engine.score(THR, min_extra=10, aggregation="rms", want_arrays=False)
+
+
+def test_config3_winner_count_equals_mask(engine, config3):
+    c = config3
+    best = engine.get_best()
+    assert best.index == c["best"].index
+    mask, sed = engine.inlier_mask(THR)
+    table = engine.get_table()
+    samples = table[best.index]
+    assert np.array_equal(mask, sed <= THR)
+    # ransac.py:63-64,70-76: samples are not thresholded but always part of the model's inliers
+    n_extra = int(mask.sum()) - int(mask[samples].sum())
+    assert n_extra == best.count_extra == c["cnt"][best.index]
+    s2 = float(np.sum(sed[mask] ** 2) + np.sum(sed[samples][~mask[samples]] ** 2))
+    assert abs(np.sqrt(s2 / (8 + n_extra)) - best.err) <= 1e-12 * best.err
+    # and the exact C scorer agrees bit for bit with K4 on every correspondence
+    nxa, nya, nxb, nyb = _norm(c["K"], c["x1"], c["x2"])
+    E = np.array(best.E, dtype=np.float64).reshape(3, 3)
+    assert np.array_equal(sed, csed.sed_exact_many(E, nxa, nya, nxb, nyb))
+
+
+def test_config4_batch_matches_single_pairs(engine):
+    """Ragged batch (a pair with too few correspondences and an empty pair included): every pair's
+    winner equals the single-pair pipeline on the same (seed, pair id) sample table."""
+    sizes = [2000, 1500, 5, 0, 2000, 700, 8, 33]
+    h, seed, pair0 = 2000, 9, 40
+    scenes = [make_scene(max(s, 8), 0.4, seed=100 + p) for p, s in enumerate(sizes)]
+    K = scenes[0][0]
+    xa = np.concatenate([sc[1][:s] for sc, s in zip(scenes, sizes)])
+    xb = np.concatenate([sc[2][:s] for sc, s in zip(scenes, sizes)])
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    Ks = np.stack([K] * len(sizes))
+    out = engine.batch_ransac(xa, xb, offsets, Ks, h, seed, THR, 10, "rms", pair_id0=pair0)
+    for p, s in enumerate(sizes):
+        if s < 8 + 10:  # cannot have 10 extra inliers
+            assert out["best_index"][p] == -1, (p, s)
+            continue
+        a, b = xa[offsets[p]:offsets[p + 1]], xb[offsets[p]:offsets[p + 1]]
+        engine.upload_pairs(a, b, K)
+        engine.sample_device(seed=seed, h=h, stream=pair0 + p)
+        best, _, _ = engine.ransac_essential(THR, 10, "rms", want_mask=False, want_sed=False)
+        assert best.index == out["best_index"][p], p
+        if best.index < 0:  # no model with enough inliers (ransac.py:88-91)
+            assert np.isinf(out["best_err"][p])
+            continue
+        assert best.count_extra == out["count_extra"][p]
+        assert best.err == out["best_err"][p]
+        assert np.array_equal(np.array(best.E).reshape(3, 3), out["E"][p])
+        # and against the oracle on that table
+        table = engine.get_table()
+        try:
+            ref = o.ransac_essential(K, a[:, 0], a[:, 1], b[:, 0], b[:, 1], THR, 10, "rms", h, table=table,
+                                     on_degenerate="skip")
+        except ValueError:  # ransac.py:88-91: no model with enough inliers
+            assert best.index == -1
+            continue
+        assert ref["best_index"] == best.index
+        assert _e_close(out["E"][p], ref["E"])

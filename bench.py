@@ -60,8 +60,8 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="config3", choices=list(WORKLOADS) + ["config4"])
     ap.add_argument("--variant", default=os.environ.get("SFM_SCORE_VARIANT", "screen"), choices=["screen", "full"])
-    ap.add_argument("--hpt", type=int, default=int(os.environ.get("SFM_SCORE_HPT", "0")))
-    ap.add_argument("--group", type=int, default=int(os.environ.get("SFM_SCORE_GROUP", "0")))
+    ap.add_argument("--hpt", type=int, default=int(os.environ.get("SFM_SCORE_HPT", "2")))
+    ap.add_argument("--group", type=int, default=int(os.environ.get("SFM_SCORE_GROUP", "16")))
     ap.add_argument("--pairs", type=int, default=512, help="config4: image pairs per GPU per step")
     ap.add_argument("--cpu-sample-hyps", type=int, default=0, help="reference arm: hypotheses per step (0 = auto)")
     ap.add_argument("--cpu-step-seconds", type=float, default=2.0, help="reference arm: target seconds per step")
@@ -409,7 +409,7 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        algo_bytes = BYTES_PER_CORR * n * ((h_rank + 127) // 128) + 72.0 * h_rank
+        algo_bytes = BYTES_PER_CORR * n * ((h_rank + 32 * args.hpt - 1) // (32 * args.hpt)) + 72.0 * h_rank  # one pass per hypothesis group
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -431,8 +431,8 @@ def main():
                 "traffic": traffic,
                 "peak_source": "DFMA microbenchmark in this run (sfm_measure_fp64_peak); MEASURED_PEAKS.json has no fp64 entry",
                 "algorithmic_flop_per_eval": FLOP_PER_EVAL,
-                "executed_fp64_slots_per_eval": 12.0 if args.variant.startswith("screen") else 21.0,
-                "fp64_pipe_busy_frac_est": kern_evals * (12.0 if args.variant.startswith("screen") else 21.0) / fp64_peak_dfma,
+                "executed_fp64_slots_per_eval": 11.0 if args.variant.startswith("screen") else 21.0,
+                "fp64_pipe_busy_frac_est": kern_evals * (11.0 if args.variant.startswith("screen") else 21.0) / fp64_peak_dfma,
                 "hbm_achieved_gbs": algo_bytes / (score_ms_per_launch * 1e-3) / 1e9,
                 "hbm_peak_gbs": peaks.get("hbm_gbs"),
             },

@@ -12,7 +12,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsfm_b200.so")
+LIB_PATH = os.environ.get("SFM_B200_LIB") or os.path.join(_HERE, "libsfm_b200.so")  # override: A/B experiments only
 
 AGG = {"sum": 0, "square": 1, "mean": 2, "rms": 3}
 SELECT = {"min_error": 0, "max_inliers": 1}

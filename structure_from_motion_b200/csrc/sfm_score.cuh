@@ -64,10 +64,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 //
 // Two-level evaluation.  Every (hypothesis, correspondence) gets a cheap division-free
 // test; the sign bits of a BATCH of HPT*G (<= 32) tests are collected in one register per
-// lane and the warp votes once per batch.  Survivors (~1 %) are compacted with
-// a prefix sum into a 64-entry per-warp ring (positions are warp-uniform registers: no
-// atomics) and processed 32 at a time by all lanes (dense, no divergence): the exact
-// reference-order SED is evaluated and compared with thr.
+// lane and the warp votes once per batch.  Lanes with survivors (~1 % of the tests survive)
+// append one {mask, origin} record to a 64-record per-warp ring (ballot-compacted, positions
+// are warp-uniform registers: no atomics); whenever 32 survivors are queued all lanes expand
+// the records and process them 32 at a time (dense, no divergence): the exact reference-order
+// SED is evaluated and compared with thr.
 //
 //   SCREEN (default), 11 FP64 issue slots per evaluation.  sed <= thr implies
 //   r^2 <= thr * nb  (drop the image-A term), nb = lb0^2 + lb1^2, lb = E^T b, r = lb . a.
@@ -100,7 +101,7 @@ constexpr int kScoreThreads = 128;
 constexpr int kScoreWarps = kScoreThreads / 32;
 constexpr int kTile = 64;     // correspondences per stage (2 KB)
 constexpr int kStages = 3;
-constexpr int kRing = 64;     // survivor ring per warp: < 32 pending + <= 32 new
+constexpr int kRing = 64;     // survivor records per warp: < 32 pending + <= 32 new
 constexpr unsigned kMaxPoints = 1u << 25;
 constexpr int kChunks = 3;             // 21-bit chunks of a 63-bit fixed-point term
 constexpr int kChunkBits = 21;
@@ -185,12 +186,20 @@ template <int HPT>
 struct alignas(128) ScoreWarpSmem {
     Corr tile[kStages][kTile];
     unsigned sacc[HPT][kAccWords][32];
-    unsigned ring[kRing];
+    uint2 ring[kRing];
     unsigned long long full_bar[kStages];
 };
 
-// resident blocks per SM the register budget is shaped for: 16 / 24 / 32 warps
-constexpr int score_min_blocks(int hpt) { return hpt >= 4 ? 4 : (hpt == 2 ? 6 : 8); }
+// resident blocks per SM the register budget is shaped for (HPT 4 / 2 / 1): 16 / 20 / 32 warps.  Measured on
+// config 3: HPT 2 at 96 registers (5 blocks) beats 80 registers (6 blocks) by ~1.5 %: the extra registers let
+// ptxas keep more independent DFMA chains in flight, which is what the FP64 pipe's ~25-cycle latency needs.
+#ifndef SFM_SCORE_MINB4
+#define SFM_SCORE_MINB4 4
+#endif
+#ifndef SFM_SCORE_MINB2
+#define SFM_SCORE_MINB2 5
+#endif
+constexpr int score_min_blocks(int hpt) { return hpt >= 4 ? SFM_SCORE_MINB4 : (hpt == 2 ? SFM_SCORE_MINB2 : 8); }
 
 template <int HPT, int G, bool SCREEN>
 __global__ void __launch_bounds__(kScoreThreads, score_min_blocks(HPT)) k_score(const ScoreArgs a) {
@@ -213,8 +222,9 @@ __global__ void __launch_bounds__(kScoreThreads, score_min_blocks(HPT)) k_score(
 #pragma unroll
         for (int k = 0; k < kAccWords; ++k) ws.sacc[j][k][lane] = 0;
     __syncwarp();
-    unsigned* q = ws.ring;
-    unsigned head = 0, tail = 0;  // ring positions: warp-uniform, monotone, tail - head < 64
+    uint2* q = ws.ring;
+    unsigned head = 0, tail = 0;  // ring positions (records): warp-uniform, monotone, tail - head < 64
+    unsigned pending = 0;         // queued survivors (set bits of the queued records)
     unsigned gt = 0;              // tiles consumed so far by this warp (drives stage + parity)
     const double ab2 = SCREEN ? a.bounds[0] * a.bounds[1] * a.kappa_coef : 0.0;
 
@@ -268,77 +278,92 @@ __global__ void __launch_bounds__(kScoreThreads, score_min_blocks(HPT)) k_score(
             kap[j] = real ? f2 * ab2 : -1.0;
         }
 
-        // exact evaluation of m (<= 32) queued candidates by all 32 lanes; the candidate's E
-        // comes from global memory (L1/L2 hits), its correspondence by index
-        auto drain = [&](unsigned m) {
-            if (a.debug_flags & 1) { head += m; return; }
-            const unsigned ent = (lane < (int)m) ? q[(head + lane) & (kRing - 1)] : 0u;
-            // entry = owner lane | bit of its batch mask | first correspondence of the batch (item-relative)
-            const int owner = (int)(ent >> 27);
-            const int i = NB - 1 - (int)((ent >> 22) & 31u);  // test index in the batch: g * HPT + j
-            const int slot = i % HPT;
-            const long long gi = begin + (long long)((ent & 0x3fffffu) + (unsigned)(i / HPT));
-            long long hyp = hyp_w + 32 * slot + owner;
-            hyp = (hyp < a.h) ? hyp : 0;
-            double eo[9];
+        // The survivor ring holds one RECORD per (lane, batch) with survivors: {batch mask pm, owner
+        // lane | first correspondence of the batch (item-relative)}; bit NB-1-i of pm <-> test
+        // i = g*HPT + j.  `pending` counts queued survivors (bits).  drain() expands the first <= 32
+        // records into <= 32 survivors, one per lane (prefix sum of the popcounts, binary search of
+        // the owning record by shuffles, n-th set bit), and evaluates them with the exact scorer: the
+        // candidate's E comes from global memory (L1/L2 hits), its correspondence by index.
+        auto drain = [&]() {
+            const unsigned nrec = tail - head;  // 1..63
+            uint2 rec = make_uint2(0u, 0u);
+            if ((unsigned)lane < nrec) rec = q[(head + lane) & (kRing - 1)];
+            const int cnt = __popc(rec.x);
+            int incl = cnt;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) eo[k] = __ldg(Ep + 9 * hyp + k);
-            const Corr c = a.pts[gi];
-            const double sv = sed_exact(eo, c.xa, c.ya, c.xb, c.yb);
-            if ((lane < (int)m) && (sv <= a.thr)) {  // ransac.py:73  score <= threshold
-                unsigned ch[kChunks];
-                unsigned* dst = &ws.sacc[slot][0][owner];
-                atomicAdd(dst, 1u);
-                if (a.sums & SUM_S1) {
-                    chunks21(sv, a.scale1, ch);
+            for (int d = 1; d < 32; d <<= 1) {
+                const int up = __shfl_up_sync(full, incl, d);
+                if (lane >= d) incl += up;
+            }
+            const int total = __shfl_sync(full, incl, 31);
+            const int m = total < 32 ? total : 32;  // survivors handled now
+            // record owning survivor #lane: the first j with incl_j > lane
+            int j = 0;
 #pragma unroll
-                    for (int k = 0; k < kChunks; ++k) atomicAdd(dst + 32 * (1 + k), ch[k]);
-                }
-                if (a.sums & SUM_S2) {
-                    chunks21(__dmul_rn(sv, sv), a.scale2, ch);
+            for (int step = 16; step > 0; step >>= 1) {
+                const int v = __shfl_sync(full, incl, j + step - 1);
+                if (v <= lane) j += step;
+            }
+            j &= 31;
+            unsigned pmj = __shfl_sync(full, rec.x, j);
+            const unsigned basej = __shfl_sync(full, rec.y, j);
+            int k = lane - (__shfl_sync(full, incl, j) - __shfl_sync(full, cnt, j));  // rank inside the record
+            // ring bookkeeping: records entirely inside the first 32 survivors are retired; the one
+            // straddling the boundary keeps its remaining (higher) bits
+            const unsigned done_mask = __ballot_sync(full, (unsigned)lane < nrec && incl <= 32);
+            const int ndone = __popc(done_mask);
+            if (lane == ndone && (unsigned)lane < nrec) {  // first record not retired
+                int take = 32 - (incl - cnt);              // its survivors consumed now (may be 0)
+                unsigned pm = rec.x;
+                for (; take > 0; --take) pm &= pm - 1u;
+                q[(head + lane) & (kRing - 1)].x = pm;
+            }
+            if (!(a.debug_flags & 1)) {
+                const bool act = lane < m;
+                if (!act) k = 0;
+                for (; k > 0; --k) pmj &= pmj - 1u;           // drop the k lowest set bits
+                const int bit = act ? (__ffs(pmj) - 1) : 0;
+                const int owner = (int)(basej >> 27);
+                const int i = NB - 1 - bit;                    // test index in the batch: g * HPT + j
+                const int slot = i % HPT;
+                const long long gi = begin + (long long)((basej & 0x3fffffu) + (unsigned)(i / HPT));
+                long long hyp = hyp_w + 32 * slot + owner;
+                hyp = (act && hyp < a.h) ? hyp : 0;
+                double eo[9];
 #pragma unroll
-                    for (int k = 0; k < kChunks; ++k) atomicAdd(dst + 32 * (1 + kChunks + k), ch[k]);
+                for (int kk = 0; kk < 9; ++kk) eo[kk] = __ldg(Ep + 9 * hyp + kk);
+                const Corr c = a.pts[act ? gi : begin];
+                const double sv = sed_exact(eo, c.xa, c.ya, c.xb, c.yb);
+                if (act && (sv <= a.thr)) {  // ransac.py:73  score <= threshold
+                    unsigned ch[kChunks];
+                    unsigned* dst = &ws.sacc[slot][0][owner];
+                    atomicAdd(dst, 1u);
+                    if (a.sums & SUM_S1) {
+                        chunks21(sv, a.scale1, ch);
+#pragma unroll
+                        for (int kk = 0; kk < kChunks; ++kk) atomicAdd(dst + 32 * (1 + kk), ch[kk]);
+                    }
+                    if (a.sums & SUM_S2) {
+                        chunks21(__dmul_rn(sv, sv), a.scale2, ch);
+#pragma unroll
+                        for (int kk = 0; kk < kChunks; ++kk) atomicAdd(dst + 32 * (1 + kChunks + kk), ch[kk]);
+                    }
                 }
             }
-            head += m;
+            head += (unsigned)ndone;
+            pending -= (unsigned)m;
             __syncwarp();
         };
 
-        // queue the set bits of pm (bit NB-1-i <-> test i = g*HPT + j of the batch whose first
-        // correspondence is rel0, item-relative).  Usual case (<= 32 survivors in the warp, < 8 per
-        // lane): a prefix sum of the per-lane counts from three ballots, then every lane stores its
-        // own entries; otherwise one ballot-compacted entry per lane and round with drains in between.
+        // one record per lane with survivors in this batch (ballot-compacted: no atomics, no loop)
         auto push = [&](unsigned pm, unsigned rel0) {
-            if (a.debug_flags & 4) { tail += 1; head += 1; return; }
-            const unsigned base = ((unsigned)lane << 27) | rel0;
-            const int cnt = __popc(pm);
-            const unsigned b0 = __ballot_sync(full, cnt & 1), b1 = __ballot_sync(full, cnt & 2),
-                           b2 = __ballot_sync(full, cnt & 4), b3 = __ballot_sync(full, cnt >= 8);
-            const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
-            if (b3 == 0u && total <= 32) {  // < 32 pending + <= 32 new fit the ring
-                unsigned pos = tail + (unsigned)(__popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt));
-                while (pm) {
-                    const int b = 31 - __clz(pm);
-                    pm ^= 1u << b;
-                    q[pos++ & (kRing - 1)] = base | ((unsigned)b << 22);
-                }
-                tail += (unsigned)total;
-                __syncwarp();
-                if (tail - head >= 32u) drain(32u);
-            } else {
-                unsigned any = __ballot_sync(full, pm != 0u);
-                while (any) {
-                    if (pm) {
-                        const int b = 31 - __clz(pm);
-                        pm ^= 1u << b;
-                        q[(tail + __popc(any & lt)) & (kRing - 1)] = base | ((unsigned)b << 22);
-                    }
-                    tail += __popc(any);
-                    __syncwarp();
-                    if (tail - head >= 32u) drain(32u);
-                    any = __ballot_sync(full, pm != 0u);
-                }
-            }
+            if (a.debug_flags & 4) return;
+            const unsigned vote = __ballot_sync(full, pm != 0u);
+            if (pm) q[(tail + __popc(vote & lt)) & (kRing - 1)] = make_uint2(pm, ((unsigned)lane << 27) | rel0);
+            tail += __popc(vote);
+            pending += __reduce_add_sync(full, (unsigned)__popc(pm));
+            __syncwarp();
+            while (pending >= 32u) drain();
         };
 
         for (int t = 0; t < ntiles; ++t) {
@@ -397,7 +422,7 @@ __global__ void __launch_bounds__(kScoreThreads, score_min_blocks(HPT)) k_score(
         gt += (unsigned)ntiles;
 
         // tail of the queue, then publish this item's exact sums
-        if (tail != head) drain(tail - head);
+        while (pending) drain();
 #pragma unroll
         for (int j = 0; j < HPT; ++j) {
             const long long hyp = hyp_w + 32 * j + lane;

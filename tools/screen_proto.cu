@@ -10,17 +10,22 @@
 #include <cuda_runtime.h>
 
 struct __align__(32) Corr { double xa, ya, xb, yb; };
-constexpr int NPTS = 512;
+#ifndef NPTS
+#define NPTS 512
+#endif
+#ifndef ROTATE
+#define ROTATE 0
+#endif
 __constant__ Corr c_pts[NPTS];
 
 #define VFMA(d, a, b, c) asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(d) : "d"(a), "d"(b), "d"(c))
 
-template <int HPT, int G, int MODE, int UNR = G>
+template <int HPT, int G, int MODE, int UNR = G, int XTRA = 0>
 __global__ void __launch_bounds__(128) k(const double* __restrict__ E, const Corr* __restrict__ pts, int reps,
                                          unsigned* __restrict__ out) {
-    __shared__ __align__(128) Corr tile[NPTS];
+    __shared__ __align__(128) Corr tile[MODE < 2 ? (NPTS > 1024 ? 1024 : NPTS) : 1];
     if (MODE < 2) {
-        for (int i = threadIdx.x; i < NPTS; i += blockDim.x) tile[i] = pts[i];
+        for (int i = threadIdx.x; i < (NPTS > 1024 ? 1024 : NPTS); i += blockDim.x) tile[i] = pts[i];
         __syncthreads();
     }
     double e[HPT][9], kap[HPT];
@@ -30,13 +35,16 @@ __global__ void __launch_bounds__(128) k(const double* __restrict__ E, const Cor
         for (int q = 0; q < 9; ++q) e[j][q] = E[((blockIdx.x * HPT + j) * 128 + threadIdx.x) * 9 + q];
         kap[j] = 1e-30 * e[j][0];
     }
-    unsigned acc = 0;
+    unsigned acc = 0, dummy = 0;
+    // ROTATE: every warp starts at its own offset, so the warps of an SM stream different parts of the buffer
+    const int rot = ROTATE ? (int)(((blockIdx.x * 4 + (threadIdx.x >> 5)) * 7919u) % (NPTS / G)) * G : 0;
     for (int r = 0; r < reps; ++r) {
-        for (int p = 0; p < NPTS; p += G) {
+        for (int p0 = 0; p0 < NPTS; p0 += G) {
+            const int p = __shfl_sync(0xffffffffu, (p0 + rot) % NPTS, 0);
             unsigned pm = 0;
 #pragma unroll UNR
             for (int g = 0; g < G; ++g) {
-                const Corr c = (MODE < 2) ? tile[p + g] : c_pts[p + g];
+                const Corr c = (MODE < 2) ? tile[(p + g) & 1023] : c_pts[p + g];
                 double t0[HPT], t1[HPT], t2[HPT], d[HPT];
                 if (MODE & 1) {
 #pragma unroll
@@ -70,29 +78,34 @@ __global__ void __launch_bounds__(128) k(const double* __restrict__ E, const Cor
                     for (int j = 0; j < HPT; ++j) d[j] = fma(t2[j], t2[j], -t1[j]);
                 }
 #pragma unroll
-                for (int j = 0; j < HPT; ++j) pm = __funnelshift_l((unsigned)__double2hiint(d[j]), pm, 1);
+                for (int j = 0; j < HPT; ++j) {
+                    if (XTRA < 0) pm |= (unsigned)__double2hiint(d[j]);  // sensitivity test: OR only (LOP3 merges three)
+                    else pm = __funnelshift_l((unsigned)__double2hiint(d[j]), pm, 1);
+                    if (XTRA > 0) dummy = __funnelshift_l(dummy ^ (unsigned)__double2loint(d[j]), pm, 3);  // one more SHF
+                }
             }
+            if (XTRA < 0) pm &= 0x80000000u;
             if (__any_sync(0xffffffffu, pm != 0u)) acc += pm;
         }
     }
-    out[blockIdx.x * 128 + threadIdx.x] = acc;
+    out[blockIdx.x * 128 + threadIdx.x] = acc + dummy;
 }
 
-template <int HPT, int G, int MODE, int UNR = G>
+template <int HPT, int G, int MODE, int UNR = G, int XTRA = 0>
 void run(const char* name, const double* E, const Corr* pts, unsigned* out, int sms) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k<HPT, G, MODE, UNR>, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k<HPT, G, MODE, UNR, XTRA>, 128, 0);
     for (int bps : {2, occ}) {
         if (bps > occ) continue;
-        const int blocks = sms * bps, reps = 64;
-        k<HPT, G, MODE, UNR><<<blocks, 128>>>(E, pts, 2, out);
+        const int blocks = sms * bps, reps = 64 * 512 / NPTS;
+        k<HPT, G, MODE, UNR, XTRA><<<blocks, 128>>>(E, pts, 2, out);
         float best = 1e30f;
         for (int r = 0; r < 3; ++r) {
             cudaEventRecord(e0);
-            k<HPT, G, MODE, UNR><<<blocks, 128>>>(E, pts, reps, out);
+            k<HPT, G, MODE, UNR, XTRA><<<blocks, 128>>>(E, pts, reps, out);
             cudaEventRecord(e1);
             cudaEventSynchronize(e1);
             float ms;
@@ -127,24 +140,14 @@ int main() {
     for (int i = 0; i < NPTS; ++i) h[i] = {0.01 * i, 0.3 - 0.002 * i, 0.5 + 0.001 * i, -0.2 + 0.003 * i};
     cudaMemcpy(pts, h, sizeof h, cudaMemcpyHostToDevice);
     cudaMemcpyToSymbol(c_pts, h, sizeof h);
-    run<2, 16, 0>("smem  compiler order   HPT2 G16", E, pts, out, sms);
-    run<4, 8, 0>("smem  compiler order   HPT4 G8", E, pts, out, sms);
-    run<2, 16, 1>("smem  pinned order     HPT2 G16", E, pts, out, sms);
-    run<4, 8, 1>("smem  pinned order     HPT4 G8", E, pts, out, sms);
-    run<2, 16, 2>("const compiler order   HPT2 G16", E, pts, out, sms);
-    run<4, 8, 2>("const compiler order   HPT4 G8", E, pts, out, sms);
-    run<2, 16, 3>("const pinned order     HPT2 G16", E, pts, out, sms);
-    run<4, 8, 3>("const pinned order     HPT4 G8", E, pts, out, sms);
-    run<4, 8, 0, 1>("smem  unroll 1         HPT4 G8", E, pts, out, sms);
-    run<4, 8, 0, 2>("smem  unroll 2         HPT4 G8", E, pts, out, sms);
-    run<4, 8, 0, 4>("smem  unroll 4         HPT4 G8", E, pts, out, sms);
-    run<2, 16, 0, 1>("smem  unroll 1         HPT2 G16", E, pts, out, sms);
-    run<2, 16, 0, 2>("smem  unroll 2         HPT2 G16", E, pts, out, sms);
-    run<2, 16, 0, 4>("smem  unroll 4         HPT2 G16", E, pts, out, sms);
-    run<6, 4, 0, 1>("smem  unroll 1         HPT6 G4", E, pts, out, sms);
-    run<6, 4, 0, 2>("smem  unroll 2         HPT6 G4", E, pts, out, sms);
-    run<8, 4, 0, 1>("smem  unroll 1         HPT8 G4", E, pts, out, sms);
-    run<4, 8, 2, 1>("const unroll 1         HPT4 G8", E, pts, out, sms);
-    run<4, 8, 2, 2>("const unroll 2         HPT4 G8", E, pts, out, sms);
+    run<2, 16, 0>("smem  HPT2 G16  32 SHF", E, pts, out, sms);
+    run<2, 16, 0, 16, -1>("smem  HPT2 G16  OR only (~11 LOP3)", E, pts, out, sms);
+    run<2, 16, 0, 16, 1>("smem  HPT2 G16  64 SHF", E, pts, out, sms);
+    run<4, 8, 0>("smem  HPT4 G8   32 SHF", E, pts, out, sms);
+    run<4, 8, 0, 8, -1>("smem  HPT4 G8   OR only", E, pts, out, sms);
+    run<4, 8, 0, 8, 1>("smem  HPT4 G8   64 SHF", E, pts, out, sms);
+    run<4, 8, 2>("const HPT4 G8   32 SHF", E, pts, out, sms);
+    run<4, 8, 2, 8, -1>("const HPT4 G8   OR only", E, pts, out, sms);
+    run<4, 8, 2, 8, 1>("const HPT4 G8   64 SHF", E, pts, out, sms);
     return 0;
 }

@@ -41,9 +41,13 @@ enum sfm_status {
 enum sfm_aggregation { SFM_AGG_SUM = 0, SFM_AGG_SQUARE = 1, SFM_AGG_MEAN = 2, SFM_AGG_RMS = 3 };
 /* lib/ransac/ransac.py:83 selects by minimum aggregated error (default); max-inliers is an extra. */
 enum sfm_selection { SFM_SELECT_MIN_ERROR = 0, SFM_SELECT_MAX_INLIERS = 1 };
-/* scoring kernel variant: screened (12 FP64 slots per evaluation + exact re-check of
- * candidates) or full two-sided decision (21 slots + exact re-check).  Same results. */
-enum sfm_score_variant { SFM_SCORE_SCREEN = 0, SFM_SCORE_FULL = 1 };
+/* scoring kernel variant — all three give bit-identical results (every inlier decision and
+ * every summed value comes from the exact fp64 scorer):
+ *   SCREEN    fp64 one-sided screen (11 FP64 slots per evaluation) + exact re-check of survivors (default)
+ *   FULL      fp64 two-sided division-free decision (21 slots) + exact re-check
+ *   SCREEN32  the screen evaluated in fp32 as a pre-filter (rigorous guard band, ~2 % more
+ *             survivors) + exact fp64 re-check; reported separately from the fp64 headline */
+enum sfm_score_variant { SFM_SCORE_SCREEN = 0, SFM_SCORE_FULL = 1, SFM_SCORE_SCREEN32 = 2 };
 
 /* ---- context ------------------------------------------------------------------------ */
 int sfm_version(void);
@@ -55,8 +59,9 @@ int sfm_destroy(sfm_ctx *ctx);
  * context's own stream. */
 int sfm_set_stream(sfm_ctx *ctx, void *cuda_stream);
 int sfm_synchronize(sfm_ctx *ctx);
-/* hyps_per_thread: essential matrices per thread (1, 2 or 4); group: correspondences evaluated
- * per step (1, 2, 4; at most 8 evaluations per lane and step); 0 keeps the current value. */
+/* hyps_per_thread: essential matrices per thread (1, 2, 4; fp32 pre-filter: 2, 4, 8); group:
+ * correspondences per vote (hyps_per_thread * group <= 32 tests per lane and vote); 0 keeps the
+ * current shape, or selects the variant's default when switching to/from SCREEN32. */
 int sfm_set_score_variant(sfm_ctx *ctx, int variant, int hyps_per_thread, int group);
 /* Pinned host memory for the caller's buffers (so that H2D/D2H copies are true async DMA). */
 int sfm_host_alloc(uint64_t bytes, void **out);

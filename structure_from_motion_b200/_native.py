@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("SFM_B200_LIB") or os.path.join(_HERE, "libsfm_b200.so
 
 AGG = {"sum": 0, "square": 1, "mean": 2, "rms": 3}
 SELECT = {"min_error": 0, "max_inliers": 1}
-VARIANT = {"screen": 0, "full": 1}
+VARIANT = {"screen": 0, "full": 1, "screen32": 2}
 
 
 class NativeUnavailableError(RuntimeError):

@@ -134,13 +134,20 @@ size_t score_warp_smem(int hpt) {
     switch (hpt) {
         case 1: return sizeof(ScoreWarpSmem<1>);
         case 2: return sizeof(ScoreWarpSmem<2>);
-        default: return sizeof(ScoreWarpSmem<4>);
+        case 4: return sizeof(ScoreWarpSmem<4>);
+        default: return sizeof(ScoreWarpSmem<8>);
     }
 }
 
 const void* score_kernel(int variant, int hpt, int group) {
-#define SFM_K(H, G) if (hpt == H && group == G) return scr ? reinterpret_cast<const void*>(&k_score<H, G, true>) \
-                                                           : reinterpret_cast<const void*>(&k_score<H, G, false>)
+    if (variant == SFM_SCORE_SCREEN32) {
+#define SFM_K32(H, G) if (hpt == H && group == G) return reinterpret_cast<const void*>(&k_score<H, G, MODE_SCREEN32>)
+        SFM_K32(2, 16); SFM_K32(4, 8); SFM_K32(8, 4);
+#undef SFM_K32
+        return nullptr;
+    }
+#define SFM_K(H, G) if (hpt == H && group == G) return scr ? reinterpret_cast<const void*>(&k_score<H, G, MODE_SCREEN>) \
+                                                           : reinterpret_cast<const void*>(&k_score<H, G, MODE_FULL>)
     const bool scr = variant == SFM_SCORE_SCREEN;
     SFM_K(1, 16); SFM_K(1, 32);
     SFM_K(2, 4); SFM_K(2, 8); SFM_K(2, 16);
@@ -261,8 +268,14 @@ int sfm_synchronize(sfm_ctx* c) {
 
 int sfm_set_score_variant(sfm_ctx* c, int variant, int hpt, int group) {
     if (!c) return fail(SFM_ERR_ARG, "null context");
-    if (variant != SFM_SCORE_SCREEN && variant != SFM_SCORE_FULL) return fail(SFM_ERR_ARG, "bad variant %d", variant);
-    const int nh = hpt ? hpt : c->hpt, ng = group ? group : c->group;
+    if (variant != SFM_SCORE_SCREEN && variant != SFM_SCORE_FULL && variant != SFM_SCORE_SCREEN32)
+        return fail(SFM_ERR_ARG, "bad variant %d", variant);
+    // hyps_per_thread == 0: keep the current shape, or the variant's default when the arithmetic changes
+    int nh = hpt ? hpt : c->hpt, ng = group ? group : c->group;
+    if (!hpt && (variant == SFM_SCORE_SCREEN32) != (c->variant == SFM_SCORE_SCREEN32)) {
+        nh = variant == SFM_SCORE_SCREEN32 ? 4 : 2;
+        ng = variant == SFM_SCORE_SCREEN32 ? 8 : 16;
+    }
     if (!score_kernel(variant, nh, ng))
         return fail(SFM_ERR_ARG, "unsupported combination: hyps_per_thread %d, group %d", nh, ng);
     c->variant = variant;
@@ -526,7 +539,8 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
     if (!(thr >= 0.0)) return fail(SFM_ERR_ARG, "threshold must be >= 0");
     if (thr > 1e100) return fail(SFM_ERR_ARG, "threshold too large for the fixed-point accumulators");
     const long long h = c->h, P = c->npairs;
-    const int hpt = c->hpt, G = c->group;
+    const int hpt = (c->variant == SFM_SCORE_SCREEN32 && thr > 1e6) ? 2 : c->hpt;
+    const int G = (c->variant == SFM_SCORE_SCREEN32 && thr > 1e6) ? 16 : c->group;
     const long long hblocks = (h + 32ll * hpt - 1) / (32ll * hpt);  // groups of 32*hpt hypotheses (one per warp item)
     const size_t H = (size_t)h * P;
     if (int r = c->count_extra.reserve(H * 4)) return r;
@@ -542,18 +556,24 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
     if (e2 < -400) e2 = -400;
     // rounding guard of the screening tests: relative slack + an absolute term that covers a
     // cancelling residual r at the 1-ulp level (only matters for thr -> 0)
-    const bool screen = c->variant == SFM_SCORE_SCREEN;
+    // the fp32 pre-filter needs s = sqrt(thr32) and 1/s inside the fp32 range: huge thresholds use the fp64 screen
+    int variant = c->variant;
+    if (variant == SFM_SCORE_SCREEN32 && thr > 1e6) variant = SFM_SCORE_SCREEN;  // with hpt 2 / group 16, see above
+    const bool f32 = variant == SFM_SCORE_SCREEN32;
+    const bool screen = variant != SFM_SCORE_FULL;
     // SCREEN: relative guard here, absolute guard = kappa_h inside the kernel (see sfm_score.cuh);
-    // FULL: relative guard + an absolute term that covers a cancelling residual at the 1-ulp level
-    double thr_pre = screen ? thr * (1.0 + 1e-9) : thr * (1.0 + 1e-9) + 1e-22;
+    // SCREEN32: thr32 = 1.0316 thr, kappa32; FULL: relative guard + an absolute term that covers a
+    // cancelling residual at the 1-ulp level
+    double thr_pre = f32 ? thr * kThr32Factor : (screen ? thr * (1.0 + 1e-9) : thr * (1.0 + 1e-9) + 1e-22);
+    if (f32 && thr_pre < 1e-24) thr_pre = 1e-24;  // keeps s and 1/s comfortably inside fp32; only widens the screen
     if (screen && thr_pre < 1e-280) thr_pre = 1e-280;  // keeps s = sqrt(thr') and 1/s normal; only widens the screen
     const double s_scale = sqrt(thr_pre);
     const double scale1 = ldexp(1.0, 63 - e2), scale2 = ldexp(1.0, 63 - 2 * e2);
     unsigned long long* acc_dev = nullptr;
     {
         // persistent blocks over (pair, split, hypothesis block) items
-        const void* fn = score_kernel(c->variant, hpt, G);
-        if (!fn) return fail(SFM_ERR_ARG, "unsupported scoring configuration (variant %d, hpt %d, group %d)", c->variant, hpt, G);
+        const void* fn = score_kernel(variant, hpt, G);
+        if (!fn) return fail(SFM_ERR_ARG, "unsupported scoring configuration (variant %d, hpt %d, group %d)", variant, hpt, G);
         const size_t smem = (size_t)kScoreWarps * score_warp_smem(hpt);
         CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
@@ -576,13 +596,14 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         if (int r = c->acc.reserve(H * kAccWords * 8 + 64)) return r;
         const long long npts = c->n;  // total records (all pairs)
         if (int r = c->bounds.reserve(16)) return r;
-        if (screen) { if (int r = c->spts.reserve((size_t)npts * sizeof(Corr))) return r; }
+        if (screen) { if (int r = c->spts.reserve((size_t)npts * (f32 ? sizeof(Corr32) : sizeof(Corr)))) return r; }
         ScoreArgs a;
         a.pts = c->pts.as<Corr>();
-        a.spts = screen ? c->spts.as<Corr>() : c->pts.as<Corr>();
+        a.spts = screen ? c->spts.p : c->pts.p;
         a.bounds = c->bounds.as<double>();
         a.s = s_scale;
         a.kappa_coef = kKappaCoef * (1.0 + thr);
+        a.kappa32_coef = kKappa32Coef * (1.0 + thr);
         a.debug_flags = getenv("SFM_DEBUG_FLAGS") ? atoi(getenv("SFM_DEBUG_FLAGS")) : 0;
         a.n = c->n;
         a.offsets = c->batched ? c->offsets.as<long long>() : nullptr;
@@ -605,8 +626,12 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         CU(cudaMemsetAsync(c->acc.p, 0, H * kAccWords * 8 + 64, c->stream));
         if (screen) {
             CU(cudaMemsetAsync(c->bounds.p, 0, 16, c->stream));
-            k_screen_pts<<<(unsigned)((npts + 255) / 256), 256, 0, c->stream>>>(
-                c->pts.as<Corr>(), npts, 1.0 / s_scale, c->spts.as<Corr>(), c->bounds.as<unsigned long long>());
+            if (f32)
+                k_screen_pts<true><<<(unsigned)((npts + 255) / 256), 256, 0, c->stream>>>(
+                    c->pts.as<Corr>(), npts, 1.0 / s_scale, c->spts.p, c->bounds.as<unsigned long long>());
+            else
+                k_screen_pts<false><<<(unsigned)((npts + 255) / 256), 256, 0, c->stream>>>(
+                    c->pts.as<Corr>(), npts, 1.0 / s_scale, c->spts.p, c->bounds.as<unsigned long long>());
             if (int r = check_launch(c, "k_screen_pts")) return r;
         }
         const long long want_blocks = (total_items + kScoreWarps - 1) / kScoreWarps;

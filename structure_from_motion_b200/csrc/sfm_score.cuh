@@ -87,6 +87,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 //   tools/fp64_micro.cu).
 //   FULL: the 21-slot two-sided division-free decision on the unscaled data (survivors ~
 //   inliers); identical results, kept as the like-for-like arithmetic baseline.
+//   SCREEN32 (reported separately, never the fp64 headline): the same 11-slot test in fp32 on
+//   E/|E|_F and fp32 copies of the correspondences — a PRE-FILTER only: every survivor is still
+//   decided and summed by the exact fp64 scorer, so counts, sums and the winner are bit-identical
+//   to the fp64 variants.  With u = 2^-24: |r32 - r| <= eps = 16 u A B, |lb' - s lb| <= 4 u s B;
+//   (|r| + eps)^2 <= (1+l) r^2 + (1+1/l) eps^2 and the same for nb with l = 1/64 give the test
+//   r32^2 < thr32 nb32 + kappa32, thr32 = 1.0316 thr, kappa32 = 1.2e-10 (1+thr) A^2 B^2
+//   (>= u^2 [2113 thr B^2 + 16640 A^2 B^2]); ~2 % more survivors than the fp64 screen.
 //
 // Order-independent accumulation.  An inlier's sed (or sed^2 — only the sum the aggregation
 // method needs is accumulated unless both are requested) is converted to a 63-bit fixed-point
@@ -109,10 +116,12 @@ constexpr int kAccWords = 1 + 2 * kChunks;  // count, sum(sed), sum(sed^2)
 constexpr long long kMaxItemPoints = 1ll << 11;  // 2^11 adds of < 2^21 cannot overflow a 32-bit word
 enum { SUM_S1 = 1, SUM_S2 = 2 };       // which sums a launch accumulates
 constexpr double kKappaCoef = 4e-20;
+constexpr double kKappa32Coef = 1.2e-10;   // fp32 pre-filter, see the K2 header
+constexpr double kThr32Factor = 1.0316;   // (1 + 1/64)^2 (1 + 1e-4)
 
 struct ScoreArgs {
     const Corr* pts;           // K-normalised correspondences (exact scorer)
-    const Corr* spts;          // screening copy: (xa/s, ya/s, xb, yb); == pts for the FULL variant
+    const void* spts;          // screening copy: Corr (xa/s, ya/s, xb, yb), or Corr32 for the fp32 pre-filter
     const double* bounds;      // [2]: max (xa^2+ya^2+1), max (xb^2+yb^2+1) over all correspondences
     long long n;
     const long long* offsets;  // [npairs+1] or null (single pair of n records)
@@ -120,6 +129,7 @@ struct ScoreArgs {
     long long h;
     double thr, thr_pre, s;    // s = sqrt(thr_pre) (SCREEN)
     double kappa_coef;         // kKappaCoef * (1 + thr)
+    double kappa32_coef;       // kKappa32Coef * (1 + thr)
     double scale1, scale2;     // 2^(63-e), 2^(63-2e) with thr < 2^e
     int sums;                  // SUM_S1 | SUM_S2
     long long chunk;           // correspondences per split (multiple of kTile)
@@ -151,20 +161,31 @@ __device__ __forceinline__ void chunks21(double x, double scale, unsigned (&c)[k
     c[2] = (unsigned)(v >> (2 * kChunkBits));
 }
 
+// fp32 twin of the screening record
+struct __align__(16) Corr32 {
+    float xa, ya, xb, yb;
+};
+
 // Screening copy of the correspondences + the coordinate bounds used by kappa (one pass
-// over N; thr-dependent, so it runs at the head of every scoring call).
+// over N; thr-dependent, so it runs at the head of every scoring call).  F32: the copy is
+// rounded to fp32 (16-byte records) for the fp32 pre-filter.
+template <bool F32>
 __global__ void __launch_bounds__(256) k_screen_pts(const Corr* __restrict__ pts, long long n, double inv_s,
-                                                    Corr* __restrict__ spts, unsigned long long* __restrict__ bounds) {
+                                                    void* __restrict__ spts, unsigned long long* __restrict__ bounds) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     double a2 = 0.0, b2 = 0.0;
     if (i < n) {
         Corr c = pts[i];
         a2 = fma(c.xa, c.xa, fma(c.ya, c.ya, 1.0));
         b2 = fma(c.xb, c.xb, fma(c.yb, c.yb, 1.0));
-        if (spts) {
-            c.xa *= inv_s;
-            c.ya *= inv_s;
-            spts[i] = c;
+        c.xa *= inv_s;
+        c.ya *= inv_s;
+        if (F32) {
+            Corr32 f;
+            f.xa = (float)c.xa; f.ya = (float)c.ya; f.xb = (float)c.xb; f.yb = (float)c.yb;
+            reinterpret_cast<Corr32*>(spts)[i] = f;
+        } else {
+            reinterpret_cast<Corr*>(spts)[i] = c;
         }
     }
     // non-negative doubles order like their bit patterns; NaN coordinates poison the bound (kappa = NaN
@@ -201,8 +222,18 @@ struct alignas(128) ScoreWarpSmem {
 #endif
 constexpr int score_min_blocks(int hpt) { return hpt >= 4 ? SFM_SCORE_MINB4 : (hpt == 2 ? SFM_SCORE_MINB2 : 8); }
 
-template <int HPT, int G, bool SCREEN>
-__global__ void __launch_bounds__(kScoreThreads, score_min_blocks(HPT)) k_score(const ScoreArgs a) {
+enum { MODE_FULL = 0, MODE_SCREEN = 1, MODE_SCREEN32 = 2 };
+
+__device__ __forceinline__ int sign_word(double d) { return __double2hiint(d); }
+__device__ __forceinline__ int sign_word(float f) { return __float_as_int(f); }
+
+template <int HPT, int G, int MODE>
+__global__ void __launch_bounds__(kScoreThreads, score_min_blocks(MODE == MODE_SCREEN32 ? HPT / 2 : HPT))
+k_score(const ScoreArgs a) {
+    constexpr bool SCREEN = MODE != MODE_FULL;
+    constexpr bool F32 = MODE == MODE_SCREEN32;
+    using T = typename std::conditional<F32, float, double>::type;       // arithmetic of the per-test work
+    using P = typename std::conditional<F32, Corr32, Corr>::type;       // record streamed through shared memory
     constexpr int NB = HPT * G;  // tests per lane and batch = survivor bits per vote
     static_assert(NB <= 32 && (kTile % G) == 0, "a batch is at most 32 tests and divides a tile");
     extern __shared__ __align__(128) unsigned char score_smem[];
@@ -226,7 +257,7 @@ __global__ void __launch_bounds__(kScoreThreads, score_min_blocks(HPT)) k_score(
     unsigned head = 0, tail = 0;  // ring positions (records): warp-uniform, monotone, tail - head < 64
     unsigned pending = 0;         // queued survivors (set bits of the queued records)
     unsigned gt = 0;              // tiles consumed so far by this warp (drives stage + parity)
-    const double ab2 = SCREEN ? a.bounds[0] * a.bounds[1] * a.kappa_coef : 0.0;
+    const double ab2 = SCREEN ? a.bounds[0] * a.bounds[1] * (F32 ? a.kappa32_coef : a.kappa_coef) : 0.0;
 
     for (;;) {
         unsigned item = 0;
@@ -248,34 +279,39 @@ __global__ void __launch_bounds__(kScoreThreads, score_min_blocks(HPT)) k_score(
         // this warp's hypotheses: lane l, slot j  ->  hyp_w + 32*j + l
         const long long hyp_w = (long long)hw * (32 * HPT);
         const double* Ep = a.E + 9 * (long long)pair * a.h;
-        const Corr* src = SCREEN ? a.spts : a.pts;
+        const P* src = reinterpret_cast<const P*>(SCREEN ? a.spts : (const void*)a.pts);
 
         auto issue = [&](int t) {  // lane 0 only
             const int s = (int)((gt + (unsigned)t) % kStages);
             const long long first = begin + (long long)t * kTile;
             const long long rem = end - first;
-            const uint32_t bytes = (uint32_t)((rem < kTile ? rem : kTile) * sizeof(Corr));
+            const uint32_t bytes = (uint32_t)((rem < kTile ? rem : kTile) * sizeof(P));
             mbar_expect_tx(&ws.full_bar[s], bytes);
             bulk_g2s(&ws.tile[s][0], src + first, bytes, &ws.full_bar[s]);
         };
         if (lane == 0)
             for (int t = 0; t < kStages && t < ntiles; ++t) issue(t);
 
-        // register-resident models; SCREEN: columns 0 and 1 scaled by s, kappa per hypothesis
-        double e[HPT][9], kap[HPT];
+        // register-resident models; SCREEN: columns 0 and 1 scaled by s, kappa per hypothesis;
+        // SCREEN32: additionally normalised to |E|_F = 1 (sed is scale-invariant in E) and rounded to fp32
+        T e[HPT][9], kap[HPT];
 #pragma unroll
         for (int j = 0; j < HPT; ++j) {
             const long long hyp = hyp_w + 32 * j + lane;
             const bool real = hyp < a.h;
-            double f2 = 0.0;
+            double v[9], f2 = 0.0;
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
-                const double v = real ? Ep[9 * hyp + k] : 0.0;
-                f2 = fma(v, v, f2);
-                e[j][k] = (SCREEN && (k % 3) != 2) ? v * a.s : v;
+                v[k] = real ? Ep[9 * hyp + k] : 0.0;
+                f2 = fma(v[k], v[k], f2);
             }
-            // padding lanes can never produce a survivor: m = -1, d = r^2 + 1 > 0
-            kap[j] = real ? f2 * ab2 : -1.0;
+            const double nrm = F32 ? rsqrt(f2) : 1.0;  // inf/NaN models screen nothing out wrongly: see below
+#pragma unroll
+            for (int k = 0; k < 9; ++k) e[j][k] = (T)((SCREEN && (k % 3) != 2) ? v[k] * nrm * a.s : v[k] * nrm);
+            // padding lanes can never produce a survivor: m = -1, d = r^2 + 1 > 0.  A model whose norm
+            // is 0, inf or NaN gets kappa = +inf in fp32 mode: every test survives and the exact scorer decides.
+            if (F32) kap[j] = (T)(real ? ((f2 > 0.0 && f2 < 1e300) ? ab2 : __longlong_as_double(0x7ff0000000000000LL)) : -1.0);
+            else kap[j] = (T)(real ? f2 * ab2 : -1.0);
         }
 
         // The survivor ring holds one RECORD per (lane, batch) with survivors: {batch mask pm, owner
@@ -372,16 +408,16 @@ __global__ void __launch_bounds__(kScoreThreads, score_min_blocks(HPT)) k_score(
             mbar_wait(&ws.full_bar[s], (gti / kStages) & 1u);
             const long long first = begin + (long long)t * kTile;
             const int np = (int)((end - first < kTile) ? (end - first) : kTile);
-            const Corr* tp = ws.tile[s];
+            const P* tp = reinterpret_cast<const P*>(&ws.tile[s][0]);
             for (int p = 0; p < np; p += G) {
                 unsigned pm = 0;
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    const Corr c = tp[p + g];
-                    double d[HPT];
+                    const P c = tp[p + g];
+                    T d[HPT];
                     if (SCREEN) {
-                        // hypothesis-innermost: consecutive DFMAs share c.yb / c.xb / c.ya / c.xa
-                        double t0[HPT], t1[HPT], t2[HPT];
+                        // hypothesis-innermost: consecutive FMAs share c.yb / c.xb / c.ya / c.xa
+                        T t0[HPT], t1[HPT], t2[HPT];
 #pragma unroll
                         for (int j = 0; j < HPT; ++j) {
                             t0[j] = fma(c.yb, e[j][3], e[j][6]);
@@ -404,12 +440,12 @@ __global__ void __launch_bounds__(kScoreThreads, score_min_blocks(HPT)) k_score(
                         for (int j = 0; j < HPT; ++j) t1[j] = fma(t0[j], t0[j], t1[j]);  // thr' nb + kappa
 #pragma unroll
                         for (int j = 0; j < HPT; ++j) d[j] = fma(t2[j], t2[j], -t1[j]);
-                    } else {
+                    } else if constexpr (!SCREEN) {
 #pragma unroll
                         for (int j = 0; j < HPT; ++j) d[j] = sed_full_decision(e[j], c.xa, c.ya, c.xb, c.yb, a.thr_pre);
                     }
 #pragma unroll
-                    for (int j = 0; j < HPT; ++j) pm = __funnelshift_l((unsigned)__double2hiint(d[j]), pm, 1);
+                    for (int j = 0; j < HPT; ++j) pm = __funnelshift_l((unsigned)sign_word(d[j]), pm, 1);
                 }
                 const int v = np - p;  // a partial last batch evaluated stale records: drop their bits
                 if (v < G) pm &= 0xffffffffu << (NB - v * HPT);

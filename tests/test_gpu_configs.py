@@ -105,12 +105,12 @@ def config3(engine):
 
 def test_config3_deterministic_and_variant_invariant(engine, config3):
     c = config3
-    for variant, hpt, group in [("screen", 2, 16), ("screen", 4, 8), ("full", 2, 16)]:
+    for variant, hpt, group in [("screen", 2, 16), ("screen", 4, 8), ("full", 2, 16), ("screen32", 4, 8)]:
         engine.set_score_variant(variant, hpt, group)
         try:
             cnt, s1, s2, err = engine.score(THR, min_extra=10, aggregation="rms")
         finally:
-            engine.set_score_variant("screen", 2, 16)
+            engine.set_score_variant("screen")
         assert np.array_equal(cnt, c["cnt"]), variant
         # integer accumulation: the sums are bit-identical whatever the schedule or the variant
         assert np.array_equal(s1, c["s1"]) and np.array_equal(s2, c["s2"]), variant

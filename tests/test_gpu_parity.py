@@ -60,7 +60,8 @@ def test_sampler_table_roundtrip(engine):
 
 @pytest.mark.parametrize("variant,hpt,group", [("screen", 2, 16), ("screen", 4, 8), ("screen", 1, 32), ("screen", 2, 8),
                                                ("screen", 4, 4), ("screen", 4, 2), ("screen", 2, 4), ("screen", 1, 16),
-                                               ("full", 4, 8), ("full", 2, 16), ("full", 1, 32)])
+                                               ("full", 4, 8), ("full", 2, 16), ("full", 1, 32),
+                                               ("screen32", 4, 8), ("screen32", 8, 4), ("screen32", 2, 16)])
 def test_scorer_bit_exact_against_oracle(engine, variant, hpt, group):
     """K2+K3 with oracle-supplied E's: counts equal, sums within 1e-12 (different summation order)."""
     n, h = 3003, 700  # 3003 = 23 tiles + 59: partial last tile, partial last batch for every group size
@@ -79,7 +80,7 @@ def test_scorer_bit_exact_against_oracle(engine, variant, hpt, group):
         engine.set_models(E)
         cnt, s1, s2, err = engine.score(THR, min_extra=10, aggregation="rms")
     finally:
-        engine.set_score_variant("screen", 2, 16)
+        engine.set_score_variant("screen")
     assert np.array_equal(cnt, cnt_o)
     np.testing.assert_allclose(s1, s1_o, rtol=1e-12, atol=0)
     np.testing.assert_allclose(s2, s2_o, rtol=1e-12, atol=0)
@@ -97,7 +98,8 @@ def test_scorer_bit_exact_against_oracle(engine, variant, hpt, group):
 
 @pytest.mark.parametrize("thr", [0.0, 1e-30, 1e-18, 1e-12, 1e-9, 1.5e-6, 1e-3, 0.5, 40.0])
 @pytest.mark.parametrize("escale", [1.0, 1e6, 1e-7])
-def test_screen_never_drops_an_inlier(engine, thr, escale):
+@pytest.mark.parametrize("variant", ["screen", "screen32"])
+def test_screen_never_drops_an_inlier(engine, thr, escale, variant):
     """The 11-slot screen is a necessary condition at EVERY threshold and model scale: counts and
     masks equal the exact oracle scorer's (sed.py is scale-invariant in E; the screen's guard
     kappa_h scales with |E_h|^2)."""
@@ -112,7 +114,11 @@ def test_screen_never_drops_an_inlier(engine, thr, escale):
     engine.upload_pairs(x1, x2, K)
     engine.set_table(table)
     engine.set_models(E)
-    cnt, s1, s2, err = engine.score(thr, min_extra=0, aggregation="sum")
+    engine.set_score_variant(variant)
+    try:
+        cnt, s1, s2, err = engine.score(thr, min_extra=0, aggregation="sum")
+    finally:
+        engine.set_score_variant("screen")
     assert np.array_equal(cnt, cnt_o)
     np.testing.assert_allclose(s1, s1_o, rtol=1e-12, atol=0)
     np.testing.assert_allclose(s2, s2_o, rtol=1e-12, atol=0)

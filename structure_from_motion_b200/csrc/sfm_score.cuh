@@ -146,6 +146,12 @@ __device__ __forceinline__ unsigned atom_add_acq_rel_shared(unsigned* p, unsigne
     asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
     return old;
 }
+// one step of a warp inclusive scan: v += shfl_up(v, d) where the source lane exists
+__device__ __forceinline__ int scan_step(int v, int d) {
+    asm volatile("{ .reg .pred p; .reg .b32 t; shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff; @p add.s32 %0, %0, t; }"
+                 : "+r"(v) : "r"(d));
+    return v;
+}
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
@@ -208,6 +214,7 @@ struct alignas(128) ScoreWarpSmem {
     Corr tile[kStages][kTile];
     unsigned sacc[HPT][kAccWords][32];
     uint2 ring[kRing];
+    unsigned short own[32];
     unsigned long long full_bar[kStages];
 };
 
@@ -279,6 +286,8 @@ k_score(const ScoreArgs a) {
         // this warp's hypotheses: lane l, slot j  ->  hyp_w + 32*j + l
         const long long hyp_w = (long long)hw * (32 * HPT);
         const double* Ep = a.E + 9 * (long long)pair * a.h;
+        const double* Ew = Ep + 9 * hyp_w;   // this warp's models
+        const Corr* pbeg = a.pts + begin;    // this item's correspondences (exact copies)
         const P* src = reinterpret_cast<const P*>(SCREEN ? a.spts : (const void*)a.pts);
 
         auto issue = [&](int t) {  // lane 0 only
@@ -327,48 +336,42 @@ k_score(const ScoreArgs a) {
             const int cnt = __popc(rec.x);
             int incl = cnt;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int up = __shfl_up_sync(full, incl, d);
-                if (lane >= d) incl += up;
-            }
+            for (int d = 1; d < 32; d <<= 1) incl = scan_step(incl, d);
             const int total = __shfl_sync(full, incl, 31);
             const int m = total < 32 ? total : 32;  // survivors handled now
-            // record owning survivor #lane: the first j with incl_j > lane
-            int j = 0;
-#pragma unroll
-            for (int step = 16; step > 0; step >>= 1) {
-                const int v = __shfl_sync(full, incl, j + step - 1);
-                if (v <= lane) j += step;
-            }
-            j &= 31;
-            unsigned pmj = __shfl_sync(full, rec.x, j);
-            const unsigned basej = __shfl_sync(full, rec.y, j);
-            int k = lane - (__shfl_sync(full, incl, j) - __shfl_sync(full, cnt, j));  // rank inside the record
+            // survivor slot t in [excl, incl) of this lane's record -> owner table {record, rank in record}
+            const int excl = incl - cnt;
+            for (int t = excl; t < incl && t < 32; ++t) ws.own[t] = (unsigned short)(lane | ((t - excl) << 8));
             // ring bookkeeping: records entirely inside the first 32 survivors are retired; the one
             // straddling the boundary keeps its remaining (higher) bits
             const unsigned done_mask = __ballot_sync(full, (unsigned)lane < nrec && incl <= 32);
             const int ndone = __popc(done_mask);
+            __syncwarp();
+            const bool act = lane < m;
+            const unsigned o = act ? ws.own[lane] : 0u;
+            const uint2 rj = q[(head + (o & 255u)) & (kRing - 1)];
+            __syncwarp();
             if (lane == ndone && (unsigned)lane < nrec) {  // first record not retired
-                int take = 32 - (incl - cnt);              // its survivors consumed now (may be 0)
+                int take = 32 - excl;                      // its survivors consumed now (may be <= 0)
                 unsigned pm = rec.x;
                 for (; take > 0; --take) pm &= pm - 1u;
                 q[(head + lane) & (kRing - 1)].x = pm;
             }
             if (!(a.debug_flags & 1)) {
-                const bool act = lane < m;
-                if (!act) k = 0;
-                for (; k > 0; --k) pmj &= pmj - 1u;           // drop the k lowest set bits
+                unsigned pmj = rj.x;
+                for (int k = (int)(o >> 8); k > 0; --k) pmj &= pmj - 1u;  // drop the k lowest set bits
                 const int bit = act ? (__ffs(pmj) - 1) : 0;
-                const int owner = (int)(basej >> 27);
+                const int owner = (int)(rj.y >> 27);
                 const int i = NB - 1 - bit;                    // test index in the batch: g * HPT + j
                 const int slot = i % HPT;
-                const long long gi = begin + (long long)((basej & 0x3fffffu) + (unsigned)(i / HPT));
-                long long hyp = hyp_w + 32 * slot + owner;
-                hyp = (act && hyp < a.h) ? hyp : 0;
+                const unsigned rel = act ? (rj.y & 0x3fffffu) + (unsigned)(i / HPT) : 0u;
+                // padding hypotheses never survive the screen, so an active entry is a real hypothesis
+                const unsigned hl = act ? (unsigned)(32 * slot + owner) : 0u;
+                const double* er = Ew + 9u * hl;
                 double eo[9];
 #pragma unroll
-                for (int kk = 0; kk < 9; ++kk) eo[kk] = __ldg(Ep + 9 * hyp + kk);
-                const Corr c = a.pts[act ? gi : begin];
+                for (int kk = 0; kk < 9; ++kk) eo[kk] = __ldg(er + kk);
+                const Corr c = pbeg[rel];
                 const double sv = sed_exact(eo, c.xa, c.ya, c.xb, c.yb);
                 if (act && (sv <= a.thr)) {  // ransac.py:73  score <= threshold
                     unsigned ch[kChunks];

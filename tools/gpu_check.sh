@@ -15,7 +15,7 @@ python bench.py > $O/bench_$tag.json 2> $O/bench_$tag.err; echo "bench rc=$?"
 cat $O/bench_$tag.json; tail -5 $O/bench_$tag.err
 python tools/time_score.py config3 > $O/time_score_$tag.log 2>&1; cat $O/time_score_$tag.log
 if [ "$2" != "noncu" ]; then
-  BCMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
+  BCMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-fp32-variant"
   $BCMD > $O/plain_bench_$tag.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_$tag.csv $BCMD > $O/ncu_launch_$tag.log 2>&1
   echo "ncu launches rc=$?"

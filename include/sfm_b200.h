@@ -183,6 +183,44 @@ int sfm_batch_ransac(sfm_ctx *ctx, const double *xa, const double *ya, const dou
                      double min_extra, int aggregation, int selection, double *E, int64_t *best_index,
                      double *best_err, int32_t *count_extra, int64_t *num_invalid);
 
+/* ---- the stage in front of the hot path: brute-force matcher ------ */
+/* lib/feature_matching/matching.py:36-118 match_brute_force with ncc.py:7-54 (score_kind 0, score
+ * in [0,2], 2.0 when a window leaves the image) or ssd.py:7-36 (score_kind 1, +inf outside) as the
+ * score function.  Images: row-major rows x cols, image_dtype 0 = uint8 (numpy's uint8 arithmetic
+ * of ssd.py is reproduced), 1 = float64.  feats_*: double[n][2] = (x, y) (lib/common/feature.py).
+ * validation: bit 0 RATIO_TEST (heap[0]/heap[1] <= ratio_threshold, matching.py:84-97 - heap[1] of
+ * the reference's heapq, not the second smallest score), bit 1 CROSSCHECK (matching.py:100-118).
+ * Outputs per feature of image A: best_b int32[na], best_score double[na], keep uint8[na] (1 = the
+ * match survives the validations; the reference returns exactly those, in order); scores (optional)
+ * double[na][nb] = the full score matrix. */
+int sfm_match_brute_force(sfm_ctx *ctx, const void *image_a, const void *image_b, int image_dtype,
+                          int64_t rows, int64_t cols, const double *feats_a, int64_t na,
+                          const double *feats_b, int64_t nb, int score_kind, int window, int validation,
+                          double ratio_threshold, int32_t *best_b, double *best_score, uint8_t *keep,
+                          double *scores);
+
+/* The same selection + validations on a caller-supplied score matrix double[na][nb] (the scores of
+ * an arbitrary Python score_function, matching.py:55-65). */
+int sfm_match_from_scores(sfm_ctx *ctx, const double *scores, int64_t na, int64_t nb, int validation,
+                          double ratio_threshold, int32_t *best_b, double *best_score, uint8_t *keep);
+
+/* ---- the first stage of apps/sfm.py: Harris corners -------------------- */
+/* lib/common/correlate.py:4-39 cross_correlate: zero "same" border, odd square kernel double[ksize][ksize],
+ * out double[rows][cols].  image_dtype as above. */
+int sfm_cross_correlate(sfm_ctx *ctx, const void *image, int image_dtype, int64_t rows, int64_t cols,
+                        const double *kernel, int ksize, double *out);
+/* Shape of the cornerness image: rows/cols - int(np.around(block_size / 2)) (harris_detector.py:66-72). */
+int sfm_harris_output_shape(int64_t rows, int64_t cols, int block_size, int64_t *out_rows, int64_t *out_cols);
+/* lib/harris/harris_detector.py:11-55 detect_harris_corners: Sobel responses, block sums, det - k trace^2,
+ * negatives clamped to 0, the reference's in-place (scan-order dependent) 3x3 non-maximum suppression, the
+ * num_corners highest non-zero values in descending order (exact ties: descending flat index).
+ * xy double[num_corners][2] = (x, y) = (col, row) + block_size/2; score double[num_corners];
+ * *num_found <= num_corners; cornerness (optional) double[out_rows][out_cols] after suppression;
+ * nms_sweeps (optional) = parallel sweeps the suppression needed. */
+int sfm_harris_corners(sfm_ctx *ctx, const void *image, int image_dtype, int64_t rows, int64_t cols,
+                       int64_t num_corners, int block_size, double k, double *xy, double *score,
+                       int64_t *num_found, double *cornerness, int32_t *nms_sweeps);
+
 /* ---- measurement --------------------------------------------------------------------- */
 /* Per-stage device times (CUDA events on the context's stream) of the most recent
  * pipeline call: ms[0]=upload+normalise ms[1]=sample ms[2]=fit ms[3]=score ms[4]=finalise+select

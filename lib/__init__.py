@@ -9,8 +9,11 @@ import sys
 
 _IMPL = "structure_from_motion_b200"
 _MODULES = [
-    "common", "common.feature",
-    "feature_matching", "feature_matching.matching",
+    "common", "common.feature", "common.correlate",
+    "blur", "blur.gaussian",
+    "harris", "harris.harris_detector",
+    "feature_matching", "feature_matching.util", "feature_matching.ncc", "feature_matching.ssd",
+    "feature_matching.matching",
     "transforms", "transforms.transforms",
     "ransac", "ransac.ransac",
     "epipolar", "epipolar.triangulation", "epipolar.sed", "epipolar.eight_point",

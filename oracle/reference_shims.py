@@ -81,6 +81,12 @@ def load():
             ("eight_point", "lib.epipolar.eight_point"),
             ("ransac", "lib.ransac.ransac"),
             ("epipolar_ransac", "lib.epipolar.epipolar_ransac"),
+            ("ncc", "lib.feature_matching.ncc"),
+            ("ssd", "lib.feature_matching.ssd"),
+            ("fm_util", "lib.feature_matching.util"),
+            ("correlate", "lib.common.correlate"),
+            ("harris", "lib.harris.harris_detector"),
+            ("gaussian", "lib.blur.gaussian"),
         ]:
             mods[short] = importlib.import_module(name)
         for m in mods.values():
@@ -103,6 +109,14 @@ def load():
                 return it
 
         ns.ransac.tqdm = _Quiet
+        ns.matching.tqdm = _Quiet
+
+        class _QuietH(_Quiet):
+            @staticmethod
+            def trange(n, *a, **k):
+                return range(n)
+
+        ns.harris.tqdm = _QuietH
     except Exception:
         pass
     sys.modules[_PKG + ".loaded"] = ns

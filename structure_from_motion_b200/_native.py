@@ -71,6 +71,13 @@ _SIGNATURES = {
                                            C.POINTER(C.c_int64), _P, _P, _P]),
     "sfm_batch_ransac": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P, C.c_int64, _P, C.c_int64, C.c_uint64,
                                    C.c_uint64, C.c_double, C.c_double, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
+    "sfm_match_brute_force": (C.c_int, [_P, _P, _P, C.c_int, C.c_int64, C.c_int64, _P, C.c_int64, _P, C.c_int64, C.c_int,
+                                        C.c_int, C.c_int, C.c_double, _P, _P, _P, _P]),
+    "sfm_match_from_scores": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int, C.c_double, _P, _P, _P]),
+    "sfm_cross_correlate": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int64, _P, C.c_int, _P]),
+    "sfm_harris_output_shape": (C.c_int, [C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "sfm_harris_corners": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_double, _P, _P,
+                                     C.POINTER(C.c_int64), _P, C.POINTER(C.c_int32)]),
     "sfm_enable_timing": (C.c_int, [_P, C.c_int]),
     "sfm_get_timing": (C.c_int, [_P, _P, C.POINTER(C.c_int64)]),
     "sfm_measure_fp64_peak": (C.c_int, [_P, C.POINTER(C.c_double)]),
@@ -329,6 +336,86 @@ class Engine:
                                            AGG[aggregation], SELECT[selection], _ptr(E), _ptr(bi), _ptr(be), _ptr(ce),
                                            _ptr(ni)), "sfm_batch_ransac")
         return dict(E=E, best_index=bi, best_err=be, count_extra=ce, num_invalid=ni)
+
+    # -- front end: brute-force matcher (N1) ---------------------------------------------------
+    def match_brute_force(self, image_a, image_b, feats_a, feats_b, kind="ncc", window=None, ratio_test=False,
+                          crosscheck=False, ratio_threshold=0.5, want_scores=False):
+        """feats_*: [n,2] (x, y).  Returns (best_b int32[na], best_score[na], keep bool[na], scores|None)."""
+        image_a, image_b = np.asarray(image_a), np.asarray(image_b)
+        if image_a.shape != image_b.shape:
+            raise ValueError("the images must have the same shape")  # ncc.py:22-23
+        if image_a.ndim != 2:
+            raise ValueError("grayscale (2-D) images expected")
+        if image_a.dtype == np.uint8 and image_b.dtype == np.uint8:
+            dt, ia, ib = 0, np.ascontiguousarray(image_a), np.ascontiguousarray(image_b)
+        else:
+            dt, ia, ib = 1, _f64(image_a), _f64(image_b)
+        fa = _f64(np.asarray(feats_a, dtype=np.float64).reshape(-1, 2))
+        fb = _f64(np.asarray(feats_b, dtype=np.float64).reshape(-1, 2))
+        na, nb = fa.shape[0], fb.shape[0]
+        if window is None:
+            window = 3 if kind == "ncc" else 5
+        best_b = np.full(na, -1, dtype=np.int32)
+        best_s = np.full(na, np.inf, dtype=np.float64)
+        keep = np.zeros(na, dtype=np.uint8)
+        S = np.empty((na, nb), dtype=np.float64) if want_scores else None
+        self._ck(self.lib.sfm_match_brute_force(self.h, _ptr(ia), _ptr(ib), dt, ia.shape[0], ia.shape[1], _ptr(fa), na,
+                                                _ptr(fb), nb, {"ncc": 0, "ssd": 1}[kind], int(window),
+                                                (1 if ratio_test else 0) | (2 if crosscheck else 0),
+                                                float(ratio_threshold), _ptr(best_b), _ptr(best_s), _ptr(keep),
+                                                _ptr(S)), "sfm_match_brute_force")
+        return best_b, best_s, keep.astype(bool), S
+
+    def match_from_scores(self, scores, ratio_test=False, crosscheck=False, ratio_threshold=0.5):
+        """The selection + validations of match_brute_force on a caller-supplied score matrix [na, nb]."""
+        S = _f64(scores)
+        if S.ndim != 2:
+            raise ValueError("a [na, nb] score matrix is expected")
+        na, nb = S.shape
+        best_b = np.full(na, -1, dtype=np.int32)
+        best_s = np.full(na, np.inf, dtype=np.float64)
+        keep = np.zeros(na, dtype=np.uint8)
+        self._ck(self.lib.sfm_match_from_scores(self.h, _ptr(S), na, nb, (1 if ratio_test else 0) | (2 if crosscheck else 0),
+                                                float(ratio_threshold), _ptr(best_b), _ptr(best_s), _ptr(keep)),
+                 "sfm_match_from_scores")
+        return best_b, best_s, keep.astype(bool)
+
+    # -- front end: Harris corners (N2) ---------------------------------------------------------
+    @staticmethod
+    def _image(image):
+        image = np.asarray(image)
+        if image.ndim != 2:
+            raise ValueError("Only 2D single channel images are supported")
+        if image.dtype == np.uint8:
+            return 0, np.ascontiguousarray(image)
+        return 1, _f64(image)
+
+    def cross_correlate(self, image, kernel):
+        dt, img = self._image(image)
+        kernel = _f64(kernel)
+        out = np.empty(img.shape, dtype=np.float64)
+        self._ck(self.lib.sfm_cross_correlate(self.h, _ptr(img), dt, img.shape[0], img.shape[1], _ptr(kernel),
+                                              kernel.shape[0], _ptr(out)), "sfm_cross_correlate")
+        return out
+
+    def harris_corners(self, image, num_corners=50, block_size=2, k=0.04, want_cornerness=False):
+        """Returns (xy [m,2] = (x, y), cornerness score [m], dict(cornerness=..., nms_sweeps=...))."""
+        dt, img = self._image(image)
+        orows, ocols = C.c_int64(0), C.c_int64(0)
+        self._ck(self.lib.sfm_harris_output_shape(img.shape[0], img.shape[1], int(block_size), C.byref(orows),
+                                                  C.byref(ocols)), "sfm_harris_output_shape")
+        if orows.value <= 0 or ocols.value <= 0:
+            raise ValueError("negative dimensions are not allowed")  # np.zeros at harris_detector.py:66-72
+        cap = max(1, min(int(num_corners), orows.value * ocols.value))
+        xy = np.empty((cap, 2), dtype=np.float64)
+        score = np.empty(cap, dtype=np.float64)
+        found, sweeps = C.c_int64(0), C.c_int32(0)
+        cim = np.empty((orows.value, ocols.value), dtype=np.float64) if want_cornerness else None
+        self._ck(self.lib.sfm_harris_corners(self.h, _ptr(img), dt, img.shape[0], img.shape[1], int(num_corners),
+                                             int(block_size), float(k), _ptr(xy), _ptr(score), C.byref(found), _ptr(cim),
+                                             C.byref(sweeps)), "sfm_harris_corners")
+        m = int(found.value)
+        return xy[:m], score[:m], dict(cornerness=cim, nms_sweeps=int(sweeps.value))
 
     # -- measurement ------------------------------------------------------------------------
     def enable_timing(self, on=True):

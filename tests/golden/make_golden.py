@@ -238,7 +238,99 @@ def main():
                                             ref.ransac.ErrorAggregationMethod.RMS)
     dump("line_ransac_known_answer.json", dict(points=allp, model=list(model), inliers=np.array(inl),
                                                state_after=list(random.getstate()[1])))
+    front_end_golden()
+
+
+def synthetic_image_pair(seed, h=72, w=96):
+    """A textured uint8 image and a shifted, noisy second view of it (what cv.cvtColor would hand over)."""
+    rng = np.random.default_rng(seed)
+    base = rng.random((h + 16, w + 16))
+    # smooth a little so that windows carry structure, keep it integer-valued like a camera image
+    k = np.ones((3, 3)) / 9.0
+    sm = sum(base[i:i + h + 14, j:j + w + 14] * k[i, j] for i in range(3) for j in range(3))
+    img = np.clip(np.round(255 * (sm - sm.min()) / (sm.max() - sm.min())), 0, 255)
+    a = img[4:4 + h, 4:4 + w]
+    b = np.clip(img[6:6 + h, 7:7 + w] + np.round(rng.normal(0, 2.0, (h, w))), 0, 255)
+    return a.astype(np.uint8), b.astype(np.uint8)
+
+
+def front_end_golden():
+    """brute-force matcher + NCC / SSD on the unmodified reference."""
+    import functools
+
+    img_a, img_b = synthetic_image_pair(3)
+    rng = np.random.default_rng(11)
+    h, w = img_a.shape
+    na, nb = 40, 37
+    # Harris returns integer-valued float coordinates (+ block_size/2); include border cases and x.5 positions
+    fa = np.stack([rng.integers(0, w, na), rng.integers(0, h, na)], 1).astype(np.float64)
+    fb = np.stack([np.clip(fa[:nb, 0] - 3 + rng.integers(-1, 2, nb), 0, w - 1),
+                   np.clip(fa[:nb, 1] - 2 + rng.integers(-1, 2, nb), 0, h - 1)], 1).astype(np.float64)
+    fb = fb[rng.permutation(nb)]
+    fa[5] += 0.5
+    fb[7] += 0.5
+    fa[0] = [0.0, 0.0]
+    fb[1] = [w - 1.0, h - 1.0]
+    feats_a = [F(x=float(x), y=float(y)) for x, y in fa]
+    feats_b = [F(x=float(x), y=float(y)) for x, y in fb]
+    out = dict(image_a=img_a.astype(int), image_b=img_b.astype(int), feats_a=fa, feats_b=fb, cases=[])
+    VS = ref.matching.ValidationStrategy
+    for kind, window in [("ncc", 9), ("ncc", 3), ("ssd", 5)]:
+        base_fn = ref.ncc.calculate_ncc if kind == "ncc" else ref.ssd.calculate_ssd
+        score = functools.partial(base_fn, img_a, img_b, window_size=window)
+        S = np.array([[score(a, b) for b in feats_b] for a in feats_a])
+        for strategies, thr in [(None, 0.5), (VS.RATIO_TEST, 0.7), (VS.CROSSCHECK, 0.5),
+                                ({VS.RATIO_TEST, VS.CROSSCHECK}, 0.7), ({VS.RATIO_TEST, VS.CROSSCHECK}, 0.95)]:
+            m = ref.matching.match_brute_force(feats_a, feats_b, score, validation_strategies=strategies,
+                                               ratio_test_threshold=thr)
+            names = [] if strategies is None else sorted(x.name for x in (strategies if isinstance(strategies, set) else {strategies}))
+            out["cases"].append(dict(kind=kind, window=window, strategies=names, ratio=thr,
+                                     matches=[[x.a_index, x.b_index, x.match_score] for x in m],
+                                     scores=S if not names else None))
+    dump("matching_known_answer.json", out)
+    harris_golden()
+
+
+def harris_golden():
+    """Harris detector + cross-correlation + Gaussian kernel on the unmodified reference."""
+    img_a, _ = synthetic_image_pair(3)
+    img = img_a[:48, :64]
+    # a few bright rectangles so that there are real corners (and flat areas with zero cornerness)
+    img = img.copy()
+    img[10:22, 12:30] = 230
+    img[28:40, 36:58] = 20
+    out = dict(image=img.astype(int), cases=[])
+    for num, bs, k in [(50, 2, 0.04), (20, 3, 0.06), (100000, 2, 0.04)]:
+        cim = ref.harris._calculate_cornerness_image(img, bs, k)
+        raw = cim.copy()
+        cim[cim < 0] = 0.0
+        ref.harris._non_max_suppress(cim)
+        corners = ref.harris.detect_harris_corners(img, num_corners=num, block_size=bs, k=k)
+        out["cases"].append(dict(num_corners=num, block_size=bs, k=k, cornerness_raw=raw, cornerness=cim,
+                                 corners=[[float(c.x), float(c.y)] for c in corners]))
+    # the reference's own fixture (test_harris_detector.py:14-32): a white square on black
+    sq = np.zeros((20, 20), dtype=np.uint8)
+    sq[5:15, 5:15] = 255
+    corners = ref.harris.detect_harris_corners(sq, num_corners=4)
+    out["square"] = dict(image=sq.astype(int), corners=[[float(c.x), float(c.y)] for c in corners])
+    # test_harris_detector.py:14-32: cv.rectangle(zeros((100, 200)), (50, 25), (150, 75), 255, -1) fills both corners inclusively
+    rect = np.zeros((100, 200), dtype=float)
+    rect[25:76, 50:151] = 255.0
+    corners = ref.harris.detect_harris_corners(rect)
+    out["rectangle"] = dict(fill=[25, 76, 50, 151], shape=[100, 200],
+                            corners=[[float(c.x), float(c.y)] for c in corners],
+                            expected_yx=[[75, 50], [75, 150], [25, 50], [25, 150]])
+    fimg = img.astype(np.float64) / 255.0
+    kern = ref.gaussian.create_gaussian_kernel(5, 1.2)
+    out["correlate"] = dict(kernel=kern, result=ref.correlate.cross_correlate(fimg[:20, :24], kern),
+                            sobel_u8=ref.correlate.cross_correlate(img[:20, :24], ref.harris._sobel_x_kernel))
+    dump("harris_known_answer.json", out)
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "front_end":
+        front_end_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == "harris":
+        harris_golden()
+    else:
+        main()

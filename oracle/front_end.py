@@ -284,3 +284,30 @@ def harris_corners_vectorised(image, num_corners=50, block_size=2, k=0.04):
     ys, xs = np.unravel_index(order, cim.shape)
     xy = np.stack([xs.astype(float) + float(block_size) / 2.0, ys.astype(float) + float(block_size) / 2.0], 1)
     return xy, flat[order], cim, sweeps
+
+
+# --------------------------------------------------------------------------------------
+# N3: the whole of apps/sfm.py:34-186 without GUI / hydra / dataset (restated with the pieces above)
+# --------------------------------------------------------------------------------------
+def sfm_pipeline(image_1, image_2, K, num_harris_corners=600, ncc_window_size=9, ratio_test_threshold=0.7,
+                 match_score_threshold=0.3, sed_inlier_threshold=1.5e-6, min_num_extra_inliers=10, max_iterations=2000):
+    """apps/sfm.py: Harris corners (:64-71) -> brute-force NCC matching with ratio test + cross-check (:73-87) ->
+    score filter (:107, :280-296) -> RANSAC essential matrix (:110-119) -> pose (:133-138) -> triangulation of the
+    pairs passing the cheirality vote (:165-186).  Uses the global ``random`` state like the reference."""
+    from oracle import restatement as o
+
+    c1, _, _, _ = harris_corners_vectorised(image_1, num_harris_corners)
+    c2, _, _, _ = harris_corners_vectorised(image_2, num_harris_corners)
+    S = score_matrix(image_1, image_2, c1, c2, "ncc", ncc_window_size)
+    matches = match_from_scores(S, True, True, ratio_test_threshold)
+    matches = [m for m in matches if not (m[2] > match_score_threshold)]
+    ia, ib = np.array([m[0] for m in matches], dtype=int), np.array([m[1] for m in matches], dtype=int)
+    pa, pb = c1[ia], c2[ib]
+    r = o.ransac_essential(K, pa[:, 0], pa[:, 1], pb[:, 0], pb[:, 1], sed_inlier_threshold, min_num_extra_inliers, "rms",
+                           max_iterations)
+    inl = r["inlier_indices"]
+    R, t, mask, _ = o.recover_r_t_from_e(r["E"], K, pa[inl, 0], pa[inl, 1], pb[inl, 0], pb[inl, 1])
+    keep = inl[mask]
+    X = o.triangulate_points(pa[keep, 0], pa[keep, 1], pb[keep, 0], pb[keep, 1], K, o.tmat(R, t))
+    return dict(corners_1=c1, corners_2=c2, matches=matches, E=r["E"], best_index=r["best_index"], inlier_indices=inl,
+                R=R, t=t, pose_mask=mask, points=X)

@@ -40,3 +40,47 @@ def make_scene(n: int, outlier_frac: float, seed: int, noise_px: float = 0.5,
     idx = rng.choice(n, n_out, replace=False)
     x2[idx] = np.column_stack([rng.uniform(0, w, n_out), rng.uniform(0, h, n_out)])
     return K, np.ascontiguousarray(x1), np.ascontiguousarray(x2), R, t, idx
+
+
+def make_image_pair(seed: int = 0, h: int = 480, w: int = 640, f: float = 520.0, noise: float = 1.5):
+    """A synthetic grayscale image pair for the whole pipeline (detector -> matcher -> two-view geometry).
+
+    The scene is three textured fronto-parallel layers at depths 8, 6 and 4.5 in front of camera 1 (so the
+    correspondences are not coplanar); camera 2 = [R|t] with R = euler XYZ (1, -4, 0.5) deg, t = (-0.5, 0.02,
+    0.05).  Image 1 is the texture; image 2 is rendered by inverse mapping through the plane-induced homographies
+    ``H_d = K (R + t n^T / d) K^-1`` (front layer first), bilinear sampling, plus Gaussian noise.
+    Returns (image_1 uint8[h,w], image_2 uint8[h,w], K, R, t).  numpy only."""
+    rng = np.random.default_rng(seed)
+    tex = np.full((h, w), 110.0)
+    for _ in range(260):  # random rectangles: plenty of corners
+        y0, x0 = int(rng.integers(0, h - 8)), int(rng.integers(0, w - 8))
+        dy, dx = int(rng.integers(8, 60)), int(rng.integers(8, 60))
+        tex[y0:y0 + dy, x0:x0 + dx] = rng.integers(10, 246)
+    tex += rng.normal(0, 4.0, tex.shape)
+    pad = np.pad(tex, 1, mode="edge")
+    tex = sum(pad[i:i + h, j:j + w] for i in range(3) for j in range(3)) / 9.0  # a light blur
+    K = np.array([[f, 0.0, w / 2], [0.0, f, h / 2], [0.0, 0.0, 1.0]])
+    R = euler_xyz_intrinsic(1.0, -4.0, 0.5)
+    t = np.array([-0.5, 0.02, 0.05])
+    # (depth, region in image-1 pixels [y0, y1, x0, x1]), front to back
+    layers = [(4.5, (250, 440, 330, 600)), (6.0, (60, 300, 60, 320)), (8.0, (-10 ** 6, 10 ** 6, -10 ** 6, 10 ** 6))]
+    ys, xs = np.mgrid[0:h, 0:w]
+    p2 = np.stack([xs.ravel(), ys.ravel(), np.ones(h * w)]).astype(np.float64)
+    out = np.zeros(h * w)
+    done = np.zeros(h * w, dtype=bool)
+    Kinv = np.linalg.inv(K)
+    for depth, (y0, y1, x0, x1) in layers:
+        H = K @ (R + np.outer(t, [0.0, 0.0, 1.0]) / depth) @ Kinv
+        p1 = np.linalg.solve(H, p2)
+        u, v = p1[0] / p1[2], p1[1] / p1[2]
+        inside = (~done) & (u >= max(x0, 0)) & (u < min(x1, w - 1)) & (v >= max(y0, 0)) & (v < min(y1, h - 1))
+        ui, vi = np.floor(u[inside]).astype(int), np.floor(v[inside]).astype(int)
+        fu, fv = u[inside] - ui, v[inside] - vi
+        out[inside] = ((1 - fv) * ((1 - fu) * tex[vi, ui] + fu * tex[vi, ui + 1])
+                       + fv * ((1 - fu) * tex[vi + 1, ui] + fu * tex[vi + 1, ui + 1]))
+        done |= inside
+    out[~done] = 110.0
+    img2 = out.reshape(h, w) + rng.normal(0, noise, (h, w))
+    img1 = tex + rng.normal(0, noise, (h, w))
+    to_u8 = lambda a: np.clip(np.round(a), 0, 255).astype(np.uint8)  # noqa: E731
+    return to_u8(img1), to_u8(img2), K, R, t

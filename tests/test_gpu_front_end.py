@@ -332,3 +332,45 @@ def test_cross_correlate(engine, hg):
         correlate.cross_correlate(np.zeros((3, 3, 3)), np.ones((3, 3)))
     with pytest.raises(ValueError):
         gaussian.create_gaussian_kernel(4, 1.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# N3: the whole pipeline of apps/sfm.py on a rendered image pair
+# ------------------------------------------------------------------------------------------------
+def test_headless_sfm_app_against_oracle_pipeline():
+    import random
+
+    from apps import sfm as app
+    from structure_from_motion_b200.scenes import make_image_pair
+
+    img1, img2, K, R_true, t_true = make_image_pair(0)
+    cfg = app.load_config(num_harris_corners=400, sed_inlier_threshold=1e-5, min_num_extra_inliers=60, max_iterations=1000)
+    try:
+        import cv2  # noqa: F401
+
+        check = True
+    except ImportError:
+        check = False
+    random.seed(5)
+    res = app.run_sfm(img1, img2, K, cfg, check_opencv=check)  # raises if OpenCV's pose / points disagree (apps/sfm.py:140-202)
+    state_after = random.getstate()
+    random.seed(5)
+    ref = fe.sfm_pipeline(img1, img2, K, num_harris_corners=400, sed_inlier_threshold=1e-5, min_num_extra_inliers=60,
+                          max_iterations=1000)
+    assert random.getstate() == state_after  # the global RNG advanced exactly as in the reference
+    assert np.array_equal(np.array([[c.x, c.y] for c in res.corners_1]), ref["corners_1"])
+    assert np.array_equal(np.array([[c.x, c.y] for c in res.corners_2]), ref["corners_2"])
+    assert [(m.a_index, m.b_index) for m in res.matches] == [(a, b) for a, b, _ in ref["matches"]]
+    assert np.allclose([m.match_score for m in res.matches], [s for _, _, s in ref["matches"]], rtol=0, atol=NCC_ATOL)
+    assert np.allclose(res.e, ref["E"], rtol=1e-6, atol=1e-9)
+    pa, pb = ref["corners_1"], ref["corners_2"]
+    want_pairs = [(tuple(pa[ref["matches"][i][0]]), tuple(pb[ref["matches"][i][1]])) for i in ref["inlier_indices"]]
+    assert [((p[0].x, p[0].y), (p[1].x, p[1].y)) for p in res.inlier_feature_pairs] == want_pairs
+    assert np.allclose(res.r, ref["R"], atol=1e-6) and np.allclose(res.t, ref["t"], atol=1e-6)
+    assert np.array_equal(res.inlier_mask, ref["pose_mask"])
+    assert np.allclose(res.world_points, ref["points"], rtol=1e-6, atol=1e-9)
+    # and the answer is right: rotation within 0.5 deg, translation direction within 3 deg of the rendered truth
+    rot_err = np.degrees(np.arccos(np.clip((np.trace(res.r.T @ R_true) - 1) / 2, -1, 1)))
+    t_err = np.degrees(np.arccos(np.clip(res.t @ t_true / np.linalg.norm(t_true) / np.linalg.norm(res.t), -1, 1)))
+    assert rot_err < 0.5 and t_err < 3.0, (rot_err, t_err)
+    assert len(res.inlier_feature_pairs) >= 68 and (res.world_points[:, 2] > 0).all()

@@ -58,7 +58,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="config3", choices=list(WORKLOADS) + ["config4"])
+    ap.add_argument("--workload", default="config3", choices=list(WORKLOADS) + ["config4", "frontend"])
     ap.add_argument("--variant", default=os.environ.get("SFM_SCORE_VARIANT", "screen"), choices=["screen", "full", "screen32"])
     ap.add_argument("--hpt", type=int, default=int(os.environ.get("SFM_SCORE_HPT", "2")))
     ap.add_argument("--group", type=int, default=int(os.environ.get("SFM_SCORE_GROUP", "16")))
@@ -306,6 +306,8 @@ def main():
 
     if args.workload == "config4":
         return bench_pairs(args, eng, world, rank, barrier, flush_l2, torch, dist)
+    if args.workload == "frontend":
+        return bench_frontend(args, eng, world, rank, barrier, flush_l2, torch, dist)
 
     n, h_cfg, frac = WORKLOADS[args.workload]
     strong = args.workload == "config5"
@@ -549,6 +551,80 @@ def bench_pairs(args, eng, world, rank, barrier, flush_l2, torch, dist):
             "clocks": clk,
             "gpu_launches": l1 - l0,
         }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_frontend(args, eng, world, rank, barrier, flush_l2, torch, dist):
+    """--workload frontend (SURVEY.md §8(f) N1+N2, not the headline): the stages in front of the hot path at the
+    sizes of apps/config/config.yaml — Harris corners (600 per image, 640x480) on both images + brute-force 9x9 NCC
+    matching with ratio test and cross-check.  Host images in, host results out (the only API these stages have);
+    image pairs are independent, so ranks simply process their own pairs."""
+    from structure_from_motion_b200.scenes import make_image_pair
+
+    img1, img2, *_ = make_image_pair(rank)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        c1, _, _ = eng.harris_corners(img1, 600, 2, 0.04)
+        c2, _, _ = eng.harris_corners(img2, 600, 2, 0.04)
+        bb, bs, keep, _ = eng.match_brute_force(img1, img2, c1, c2, kind="ncc", window=9, ratio_test=True, crosscheck=True,
+                                                ratio_threshold=0.7)
+        return c1, c2, bb, keep
+
+    clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    clocks.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    _, l0 = eng.get_timing()
+    clocks.mark_begin()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms = 0.0
+    for _ in range(args.steps):
+        flush_l2()
+        ev0.record(stream)
+        c1, c2, bb, keep = step()
+        ev1.record(stream)
+        ev1.synchronize()
+        ms += ev0.elapsed_time(ev1)
+    barrier()
+    clocks.mark_end()
+    clk = clocks.stop()
+    _, l1 = eng.get_timing()
+    vals = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    ms = float(vals.cpu()[0])
+    if rank == 0:
+        line = {
+            "metric": "front-end image pairs/sec (2 x Harris 640x480 -> 600 corners, 600x600 9x9 NCC match)",
+            "value": world * args.steps / (ms * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "frontend: rendered 640x480 uint8 image pair, 600 Harris corners per image, "
+                                   f"9x9 NCC, ratio 0.7 + cross-check ({int(keep.sum())} matches kept), host buffers",
+                       "l2": "flushed between timed steps", "parallelism": f"pair-sharded x{world}, no collective"},
+            "clocks": clk, "gpu_launches": l1 - l0,
+            "e2e": {"value": world * args.steps / (ms * 1e-3), "unit": "pairs/s",
+                    "h2d_bytes_per_step": int(4 * img1.size + 2 * 16 * 600), "d2h_bytes_per_step": int(2 * 600 * 24 + 600 * 13)},
+        }
+        if not args.no_cpu_baseline:
+            from oracle import front_end as fe
+
+            t0 = time.perf_counter()
+            o1, _, _, _ = fe.harris_corners_vectorised(img1, 600)
+            o2, _, _, _ = fe.harris_corners_vectorised(img2, 600)
+            t_h = time.perf_counter() - t0
+            rows = 24  # a bounded sample of the 600 rows of the score matrix (Python loop, as the reference)
+            t0 = time.perf_counter()
+            fe.score_matrix(img1, img2, o1[:rows], o2, "ncc", 9)
+            t_m = (time.perf_counter() - t0) * len(o1) / rows
+            line["cpu_baseline"] = {"value": 1.0 / (t_h + t_m), "unit": "pairs/s", "cores": 1, "kind": "port",
+                                    "sample": f"vectorised-numpy Harris on both images ({t_h:.2f} s) + {rows} of {len(o1)} rows "
+                                              f"of the per-pair NCC loop, extrapolated ({t_m:.1f} s)"}
+            line["parity"] = bool(np.array_equal(o1, c1) and np.array_equal(o2, c2))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

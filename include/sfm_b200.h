@@ -39,8 +39,10 @@ enum sfm_status {
 
 /* lib/ransac/ransac.py:12-16  ErrorAggregationMethod */
 enum sfm_aggregation { SFM_AGG_SUM = 0, SFM_AGG_SQUARE = 1, SFM_AGG_MEAN = 2, SFM_AGG_RMS = 3 };
-/* lib/ransac/ransac.py:83 selects by minimum aggregated error (default); max-inliers is an extra. */
-enum sfm_selection { SFM_SELECT_MIN_ERROR = 0, SFM_SELECT_MAX_INLIERS = 1 };
+/* lib/ransac/ransac.py:83 selects by minimum aggregated error (default).  Extras behind non-default values
+ * (SURVEY.md 8(f) N4): max-inliers; MSAC = minimum of sum_i min(sed_i, threshold) over all correspondences
+ * (best.err / err[] then hold that cost). */
+enum sfm_selection { SFM_SELECT_MIN_ERROR = 0, SFM_SELECT_MAX_INLIERS = 1, SFM_SELECT_MSAC = 2 };
 /* scoring kernel variant — all three give bit-identical results (every inlier decision and
  * every summed value comes from the exact fp64 scorer):
  *   SCREEN    fp64 one-sided screen (11 FP64 slots per evaluation) + exact re-check of survivors (default)

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SFM_B200_LIB") or os.path.join(_HERE, "libsfm_b200.so")  # override: A/B experiments only
 
 AGG = {"sum": 0, "square": 1, "mean": 2, "rms": 3}
-SELECT = {"min_error": 0, "max_inliers": 1}
+SELECT = {"min_error": 0, "max_inliers": 1, "msac": 2}
 VARIANT = {"screen": 0, "full": 1, "screen32": 2}
 
 

@@ -537,11 +537,12 @@ int sfm_set_models(sfm_ctx* c, const double* E, const uint8_t* valid, int64_t h)
 static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int mode, bool use_table,
                         long long idx_offset, long long max_len, bool both_sums = false) {
     // K2 accumulates only the sum the aggregation needs (ransac.py:96-108) unless the caller wants both
-    const int sums = both_sums ? (SUM_S1 | SUM_S2) : ((agg == AGG_SUM || agg == AGG_MEAN) ? SUM_S1 : SUM_S2);
+    int sums = both_sums ? (SUM_S1 | SUM_S2) : ((agg == AGG_SUM || agg == AGG_MEAN) ? SUM_S1 : SUM_S2);
+    if (mode == SELECT_MSAC) sums |= SUM_S1;  // the MSAC cost is built from the sum of the inlier distances
     if (!c->has_pts || !c->has_models) return fail(SFM_ERR_STATE, "score needs correspondences and fitted models");
     if (use_table && !c->has_table) return fail(SFM_ERR_STATE, "sample rule requested but no table is loaded");
     if (agg < 0 || agg > 3) return fail(SFM_ERR_ARG, "bad aggregation %d", agg);
-    if (mode != 0 && mode != 1) return fail(SFM_ERR_ARG, "bad selection %d", mode);
+    if (mode < 0 || mode > 2) return fail(SFM_ERR_ARG, "bad selection %d", mode);
     if (!(thr >= 0.0)) return fail(SFM_ERR_ARG, "threshold must be >= 0");
     if (thr > 1e100) return fail(SFM_ERR_ARG, "threshold too large for the fixed-point accumulators");
     const long long h = c->h, P = c->npairs;
@@ -656,6 +657,7 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
     f.valid = c->valid.as<uint8_t>();
     f.table = use_table ? c->table.as<int32_t>() : nullptr;
     f.h = h;
+    f.n = c->n;
     f.idx_offset = idx_offset;
     f.htotal = (long long)H;
     f.acc = acc_dev;

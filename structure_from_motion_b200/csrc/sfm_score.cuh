@@ -493,10 +493,11 @@ k_score(const ScoreArgs a) {
 // (SUM / SQUARE / MEAN / RMS); candidate iff valid and min_extra <= count_extra
 // (ransac.py:75; min_extra may be fractional).  Then argmin of the error with the lowest
 // index winning ties (ransac.py:83: strict <, earliest iteration kept).  mode 1 selects by
-// maximum inlier count instead (lowest index on ties; non-default).
+// maximum inlier count instead (lowest index on ties; non-default); mode 2 by the MSAC cost
+// sum_i min(sed_i, thr) over ALL correspondences of the pair (non-default; err then holds that cost).
 // ------------------------------------------------------------------------------------
 enum { AGG_SUM = 0, AGG_SQUARE = 1, AGG_MEAN = 2, AGG_RMS = 3 };
-enum { SELECT_MIN_ERROR = 0, SELECT_MAX_INLIERS = 1 };
+enum { SELECT_MIN_ERROR = 0, SELECT_MAX_INLIERS = 1, SELECT_MSAC = 2 };
 
 struct Best {
     double err;
@@ -566,6 +567,7 @@ struct FinalArgs {
     const uint8_t* valid;
     const int32_t* table;  // may be null: no sample rule
     long long h;
+    long long n;           // correspondences of the pair when offsets is null
     long long idx_offset;  // global index of hypothesis 0 (hypothesis-sharded runs)
     long long htotal;                 // npairs * h (stride of the accumulator planes)
     const unsigned long long* acc;    // [kAccWords][htotal] exact sums from K2
@@ -594,6 +596,8 @@ __global__ void __launch_bounds__(256) k_finalise(const FinalArgs a) {
         double s1 = (a.sums & SUM_S1) ? fixed_to_double(a.acc + 1 * a.htotal + i, a.htotal) * a.inv_scale1 : qnan;
         double s2 = (a.sums & SUM_S2) ? fixed_to_double(a.acc + (1 + kChunks) * a.htotal + i, a.htotal) * a.inv_scale2 : qnan;
         const bool valid = a.valid ? (a.valid[i] != 0) : true;
+        const long long npts = a.offsets ? a.offsets[blockIdx.y + 1] - a.offsets[blockIdx.y] : a.n;
+        const double msac = __dadd_rn(s1, __dmul_rn(a.thr, (double)(npts - cnt)));  // K2 saw every correspondence
         if (a.table && valid) {
             double e[9];
 #pragma unroll
@@ -617,6 +621,7 @@ __global__ void __launch_bounds__(256) k_finalise(const FinalArgs a) {
             case AGG_MEAN: err = s1 / n; break;
             default: err = sqrt(s2 / n); break;
         }
+        if (a.mode == SELECT_MSAC) err = msac;
         const bool cand = valid && (a.min_extra <= (double)cnt) && (err == err);
         a.count_extra[i] = valid ? (int32_t)cnt : -1;
         a.S1[i] = s1;

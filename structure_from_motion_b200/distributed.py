@@ -38,7 +38,8 @@ def merge_best(rows: np.ndarray, selection: str = "min_error"):
     """Pick the global winner from per-rank rows (see pack_local_best).
 
     min_error: smallest error, lowest global index on ties (ransac.py:83 keeps the earliest
-    iteration).  max_inliers: largest count, lowest index on ties.  Returns
+    iteration; "msac" merges the same way, the error being the MSAC cost).  max_inliers: largest count,
+    lowest index on ties.  Returns
     (owner_rank, err, index, count, E) or (-1, inf, -1, -1, None) when no rank has a candidate.
     """
     rows = np.asarray(rows, dtype=np.float64).reshape(-1, 12)

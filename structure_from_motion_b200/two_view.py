@@ -152,6 +152,45 @@ def ransac_essential_arrays(
     )
 
 
+def ransac_essential_adaptive(camera_matrix, pts_a, pts_b, threshold, min_num_extra_inliers=None,
+                              error_aggregation_method=None, max_iterations: int = 65536, *, confidence: float = 0.99,
+                              chunk: int = 4096, seed: int = 0, selection: str = "max_inliers",
+                              engine: Optional[_native.Engine] = None):
+    """Early termination (the reference always runs ``max_iterations``): hypotheses are drawn
+    by the device sampler and evaluated ``chunk`` at a time; after each chunk the standard RANSAC bound
+    ``log(1 - confidence) / log(1 - w^8)`` is recomputed from the inlier ratio ``w`` of the best model so far and the
+    run stops once that many hypotheses have been evaluated.  Because the sampler is keyed by the global hypothesis
+    index, the result equals ``ransac_essential_arrays(..., sampler="device")`` over the same number of hypotheses.
+    Returns (RansacResult, hypotheses evaluated)."""
+    from .distributed import merge_best, pack_local_best
+
+    eng = engine or _native.get_engine()
+    n = np.asarray(pts_a).reshape(-1, 2).shape[0]
+    best_row, best_res, done = None, None, 0
+    needed = float(max_iterations)
+    while done < max_iterations and done < needed:
+        h = int(min(chunk, max_iterations - done))
+        try:
+            res = ransac_essential_arrays(camera_matrix, pts_a, pts_b, threshold, min_num_extra_inliers,
+                                          error_aggregation_method, h, sampler="device", seed=seed, hyp_offset=done,
+                                          on_degenerate="skip", selection=selection, engine=eng)
+            row = pack_local_best(res.error, res.best_index, res.count_extra, res.E)
+            rows = row[None] if best_row is None else np.stack([best_row, row])
+            owner, *_ = merge_best(rows, selection)
+            if best_row is None or owner == 1:
+                best_row, best_res = row, res
+        except ValueError:
+            pass  # no candidate in this chunk
+        done += h
+        if best_res is not None:
+            w = min(1.0, (8 + best_res.count_extra) / max(n, 1))
+            miss = 1.0 - w ** 8
+            needed = 0.0 if miss <= 0.0 else (np.log(1.0 - confidence) / np.log(miss) if miss < 1.0 else float(max_iterations))
+    if best_res is None:
+        raise ValueError(f"No model could be found with at least {(min_num_extra_inliers or 0) + 8} inliers.")
+    return best_res, done
+
+
 def eight_point_arrays(pts_a, pts_b, camera_matrix=None, engine=None) -> np.ndarray:
     """estimate_essential_mat / estimate_fundamental_mat on 8 gathered pairs ([8,2] arrays).
 

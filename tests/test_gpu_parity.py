@@ -294,3 +294,51 @@ def test_two_view_pipeline(engine):
     rel = np.linalg.norm(res.points[ok] - X_o[ok], axis=1) / np.linalg.norm(X_o[ok], axis=1)
     assert rel.max() <= 1e-6
     assert np.isnan(res.points[~ok]).all()
+
+
+# ---- robustness extras behind non-default flags -----------------------------
+@pytest.mark.parametrize("agg", ["rms", "sum"])
+def test_msac_selection_against_oracle(engine, agg):
+    """selection="msac": minimum of sum_i min(sed_i, thr) over ALL correspondences, candidates as in ransac.py:76."""
+    n, h = 1200, 400
+    K, x1, x2, *_ = make_scene(n, 0.35, seed=9)
+    nxa, nya, nxb, nyb = _norm(K, x1, x2)
+    rng = np.random.default_rng(2)
+    table = np.stack([rng.choice(n, 8, replace=False) for _ in range(h)]).astype(np.int32)
+    engine.upload_pairs(x1, x2, K)
+    engine.set_table(table)
+    E, valid, _ = engine.fit()
+    assert valid.all()
+    cnt, _, _, err = engine.score(THR, min_extra=10, aggregation=agg, selection="msac")
+    best = engine.get_best()
+    cost = np.empty(h)
+    for i in range(h):
+        sed = csed.sed_exact_many(E[i], nxa, nya, nxb, nyb)
+        cost[i] = np.minimum(sed, THR).sum()
+    cnt_o, _, _ = csed.score_batch(E, nxa, nya, nxb, nyb, THR, table=table, nthreads=4)
+    assert np.array_equal(cnt, cnt_o)
+    want = np.where(cnt_o >= 10, cost, np.inf)
+    np.testing.assert_allclose(err, want, rtol=1e-10)
+    assert best.index == int(np.argmin(want)) and abs(best.err - want.min()) <= 1e-10 * want.min()
+    # the default selection is untouched by the extra
+    _, _, _, err_default = engine.score(THR, min_extra=10, aggregation=agg)
+    assert engine.get_best().index == int(np.argmin(err_default))
+
+
+def test_adaptive_early_termination(engine):
+    n = 5000
+    K, x1, x2, *_ = make_scene(n, 0.3, seed=12)
+    res, done = two_view.ransac_essential_adaptive(K, x1, x2, THR, 10, "rms", max_iterations=65536, chunk=2048, seed=7,
+                                                   engine=engine)
+    assert done < 65536 and done % 2048 == 0  # 30 % outliers: a few hundred hypotheses suffice at 99 %
+    w = (8 + res.count_extra) / n
+    assert done >= np.log(0.01) / np.log(1 - w ** 8)
+    full = two_view.ransac_essential_arrays(K, x1, x2, THR, 10, "rms", done, sampler="device", seed=7, on_degenerate="skip",
+                                            selection="max_inliers", engine=engine)
+    assert full.best_index == res.best_index and np.array_equal(full.E, res.E)
+    assert np.array_equal(full.inlier_indices, res.inlier_indices)
+    # a hopeless scene runs to the cap and reports the reference's error
+    rng = np.random.default_rng(0)
+    with pytest.raises(ValueError, match="No model could be found"):
+        two_view.ransac_essential_adaptive(K, rng.uniform(0, 1000, (300, 2)), rng.uniform(0, 1000, (300, 2)), 1e-12, 50,
+                                           "rms", max_iterations=4096, chunk=1024, engine=engine)

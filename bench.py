@@ -58,7 +58,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="config3", choices=list(WORKLOADS) + ["config4", "frontend"])
+    ap.add_argument("--workload", default="config3", choices=list(WORKLOADS) + ["config1", "config4", "frontend"])
     ap.add_argument("--variant", default=os.environ.get("SFM_SCORE_VARIANT", "screen"), choices=["screen", "full", "screen32"])
     ap.add_argument("--hpt", type=int, default=int(os.environ.get("SFM_SCORE_HPT", "2")))
     ap.add_argument("--group", type=int, default=int(os.environ.get("SFM_SCORE_GROUP", "16")))
@@ -308,6 +308,8 @@ def main():
         return bench_pairs(args, eng, world, rank, barrier, flush_l2, torch, dist)
     if args.workload == "frontend":
         return bench_frontend(args, eng, world, rank, barrier, flush_l2, torch, dist)
+    if args.workload == "config1":
+        return bench_config1(args, eng, world, rank, barrier, flush_l2, torch, dist)
 
     n, h_cfg, frac = WORKLOADS[args.workload]
     strong = args.workload == "config5"
@@ -551,6 +553,79 @@ def bench_pairs(args, eng, world, rank, barrier, flush_l2, torch, dist):
             "clocks": clk,
             "gpu_launches": l1 - l0,
         }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_config1(args, eng, world, rank, barrier, flush_l2, torch, dist):
+    """--workload config1 (BASELINE.json configs[0], the reference's own CPU-runnable case): 500 correspondences, 30 %
+    outliers, 1000 iterations through the REFERENCE SIGNATURE — lists of Feature / Match objects in, (E, list of
+    inlier pairs) out, the CPython-exact sampler on the global ``random`` state.  Everything (marshalling, sampler, H2D,
+    kernels, D2H, rebuilding the inlier list) is inside the timed region.  Ranks run independent replicas."""
+    import random
+
+    from lib.common.feature import Feature
+    from lib.epipolar.epipolar_ransac import estimate_essential_mat_with_ransac
+    from lib.feature_matching.matching import Match
+    from lib.ransac.ransac import ErrorAggregationMethod
+    from structure_from_motion_b200.scenes import make_scene
+
+    n, h = 500, 1000
+    K, x1, x2, *_ = make_scene(n, 0.3, seed=0)
+    fa = [Feature(x=float(p[0]), y=float(p[1])) for p in x1]
+    fb = [Feature(x=float(p[0]), y=float(p[1])) for p in x2]
+    ms = [Match(a_index=i, b_index=i) for i in range(n)]
+
+    def step():
+        random.seed(5)
+        return estimate_essential_mat_with_ransac(K, fa, fb, ms, THR, min_num_extra_inliers=MIN_EXTRA,
+                                                  error_aggregation_method=ErrorAggregationMethod.RMS, max_iterations=h)
+
+    clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    clocks.start()
+    for _ in range(max(args.warmup, 3)):
+        e, pairs = step()
+    barrier()
+    _, l0 = eng.get_timing()
+    clocks.mark_begin()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush_l2()
+        e, pairs = step()
+    barrier()
+    ms_total = (time.perf_counter() - t0) * 1e3
+    clocks.mark_end()
+    clk = clocks.stop()
+    _, l1 = eng.get_timing()
+    vals = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    ms_total = float(vals.cpu()[0])
+    if rank == 0:
+        evals = float(n - 8) * h * world * args.steps
+        golden = json.load(open(os.path.join(ROOT, "tests", "golden", "config1_known_answer.json")))
+        line = {
+            "metric": METRIC, "value": evals / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"config1: {n} correspondences x {h} iterations, 30% outliers, thr 1.5e-6, RMS, min_extra 10, "
+                                   "through estimate_essential_mat_with_ransac(list[Feature], list[Match]) with the CPython-exact "
+                                   "sampler; wall clock incl. marshalling (this workload is host-bound: ~5e5 evaluations)",
+                       "l2": "flushed between timed steps", "parallelism": f"{world} independent replicas"},
+            "clocks": clk, "gpu_launches": l1 - l0,
+            "parity": {"inliers": len(pairs), "E_matches_reference_1e-6": bool(np.allclose(e, np.array(golden["E"]), rtol=1e-6, atol=1e-9)),
+                       "golden": "tests/golden/config1_known_answer.json (unmodified reference: iteration 87, 23 inliers)"},
+        }
+        line["e2e"] = {"value": line["value"], "unit": UNIT, "ms_per_step": line["ms_per_step"],
+                       "h2d_bytes_per_step": n * 32 + h * 32 + 72, "d2h_bytes_per_step": n * 9 + 136}
+        tp = os.path.join(ROOT, "profiles", "r1_true_reference_config1.json")
+        if os.path.exists(tp):
+            t = json.load(open(tp))
+            line["cpu_baseline"] = {"value": t["evals_per_s"], "unit": UNIT, "cores": 1, "kind": "reference",
+                                    "sample": f"the UNMODIFIED reference on this exact workload: {t['seconds']:.1f} s per estimate, "
+                                              "recorded in the build container by tools/time_true_reference.py (the reference "
+                                              "cannot travel to the GPU box)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -1196,24 +1196,25 @@ int sfm_harris_corners(sfm_ctx* c, const void* image, int image_dtype, int64_t r
     k_cornerness<<<gopx, 256, 0, c->stream>>>(c->h_gx.as<double>(), c->h_gy.as<double>(), (int)rows, (int)cols, block_size,
                                               k, (int)orows, (int)ocols, corner);
     if (int r = check_launch(c, "k_cornerness")) return r;
-    // non-maximum suppression: sweeps in batches of 8 until a whole batch changes nothing
+    // non-maximum suppression: sweeps in batches of 8, one "changed" flag per sweep; a sweep that changes
+    // nothing has reached the fixed point, so only the last flag of a batch needs to be looked at
     uint8_t* alive[2] = {c->h_alive.as<uint8_t>(), c->h_alive.as<uint8_t>() + opx};
-    int* d_changed = c->h_small.as<int>();
-    unsigned* d_count = reinterpret_cast<unsigned*>(d_changed + 1);
+    int* d_changed = c->h_small.as<int>();            // [8]
+    unsigned* d_count = reinterpret_cast<unsigned*>(d_changed + 8);
     CU(cudaMemsetAsync(alive[0], 1, opx, c->stream));
     int cur = 0, sweeps = 0;
     for (;;) {
-        CU(cudaMemsetAsync(d_changed, 0, 4, c->stream));
+        CU(cudaMemsetAsync(d_changed, 0, 32, c->stream));
         for (int it = 0; it < 8; ++it) {
-            k_nms_sweep<<<gopx, 256, 0, c->stream>>>(corner, (int)orows, (int)ocols, alive[cur], alive[cur ^ 1], d_changed);
+            k_nms_sweep<<<gopx, 256, 0, c->stream>>>(corner, (int)orows, (int)ocols, alive[cur], alive[cur ^ 1], d_changed + it);
             if (int r = check_launch(c, "k_nms_sweep")) return r;
             cur ^= 1;
         }
         sweeps += 8;
-        int changed = 0;
-        CU(cudaMemcpyAsync(&changed, d_changed, 4, cudaMemcpyDeviceToHost, c->stream));
+        int changed[8] = {0};
+        CU(cudaMemcpyAsync(changed, d_changed, 32, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
-        if (!changed) break;
+        if (!changed[7]) break;
         if ((size_t)sweeps > opx + 16) return fail(SFM_ERR_CUDA, "non-maximum suppression did not converge");
     }
     k_nms_apply<<<gopx, 256, 0, c->stream>>>(corner, (long long)opx, alive[cur]);

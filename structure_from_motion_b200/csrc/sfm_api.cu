@@ -165,27 +165,44 @@ const void* score_kernel(int variant, int hpt, int group) {
 // ---------------------------------------------------------------------------------------
 struct PyMT {
     uint32_t mt[624];
+    uint32_t out[624];  // tempered outputs of the current block (filled per twist: straight-line, vectorisable)
     int pos;
-    uint32_t next() {
-        if (pos >= 624) {
-            for (int k = 0; k < 624; ++k) {
-                uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
-                mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-            }
-            pos = 0;
+    static inline uint32_t twist(uint32_t u, uint32_t v, uint32_t m) {
+        const uint32_t y = (u & 0x80000000u) | (v & 0x7fffffffu);
+        return m ^ (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu);
+    }
+    void temper_block() {
+        for (int k = 0; k < 624; ++k) {
+            uint32_t y = mt[k];
+            y ^= y >> 11;
+            y ^= (y << 7) & 0x9d2c5680u;
+            y ^= (y << 15) & 0xefc60000u;
+            y ^= y >> 18;
+            out[k] = y;
         }
-        uint32_t y = mt[pos++];
-        y ^= y >> 11;
-        y ^= (y << 7) & 0x9d2c5680u;
-        y ^= (y << 15) & 0xefc60000u;
-        y ^= y >> 18;
-        return y;
+    }
+    void regenerate() {
+        int k = 0;
+        for (; k < 624 - 397; ++k) mt[k] = twist(mt[k], mt[k + 1], mt[k + 397]);
+        for (; k < 623; ++k) mt[k] = twist(mt[k], mt[k + 1], mt[k - (624 - 397)]);
+        mt[623] = twist(mt[623], mt[0], mt[396]);
+        temper_block();
+        pos = 0;
+    }
+    void load(const uint32_t* state625) {
+        memcpy(mt, state625, 624 * sizeof(uint32_t));
+        pos = (int)state625[624];
+        temper_block();
+    }
+    inline uint32_t next() {
+        if (pos >= 624) regenerate();
+        return out[pos++];
     }
     // Random._randbelow_with_getrandbits(n): k = n.bit_length(); r = getrandbits(k) until r < n
-    uint32_t below(uint32_t n) {
-        int k = 32 - __builtin_clz(n);
-        uint32_t r = next() >> (32 - k);
-        while (r >= n) r = next() >> (32 - k);
+    inline uint32_t below(uint32_t n) {
+        const int sh = __builtin_clz(n);  // 32 - k
+        uint32_t r = next() >> sh;
+        while (r >= n) r = next() >> sh;
         return r;
     }
 };
@@ -306,19 +323,24 @@ int sfm_mt_shuffle_table(uint32_t* state625, int64_t n, int64_t h, int32_t* tabl
     if (!state625 || !table) return fail(SFM_ERR_ARG, "null argument");
     if (n < 8 || n > 0x7fffffff) return fail(SFM_ERR_ARG, "need 8 <= n < 2^31 correspondences, got %lld", (long long)n);
     if (h < 0) return fail(SFM_ERR_ARG, "negative hypothesis count");
+    if ((int)state625[624] < 0 || (int)state625[624] > 624) return fail(SFM_ERR_ARG, "bad MT position %d", (int)state625[624]);
     PyMT g;
-    memcpy(g.mt, state625, 624 * sizeof(uint32_t));
-    g.pos = (int)state625[624];
-    if (g.pos < 0 || g.pos > 624) return fail(SFM_ERR_ARG, "bad MT position %d", g.pos);
+    g.load(state625);
     std::vector<int32_t> perm((size_t)n);
     for (int64_t i = 0; i < n; ++i) perm[(size_t)i] = (int32_t)i;
     for (int64_t it = 0; it < h; ++it) {
         // random.shuffle: for i in reversed(range(1, len(x))): j = randbelow(i + 1); swap
-        for (int64_t i = n - 1; i >= 1; --i) {
-            const uint32_t j = g.below((uint32_t)(i + 1));
-            const int32_t t = perm[(size_t)i];
-            perm[(size_t)i] = perm[j];
-            perm[j] = t;
+        // j = _randbelow(i + 1) = the first getrandbits(bit_length(i + 1)) that is <= i.  Branch-free form: every
+        // stream word is consumed; a rejected one swaps position i with itself and leaves i where it is.
+        int32_t* pp = perm.data();
+        for (uint32_t i = (uint32_t)n - 1; i >= 1;) {
+            const uint32_t r = g.next() >> __builtin_clz(i + 1);
+            const uint32_t acc = r <= i ? 1u : 0u;
+            const uint32_t j = acc ? r : i;
+            const int32_t t = pp[i];
+            pp[i] = pp[j];
+            pp[j] = t;
+            i -= acc;
         }
         memcpy(table + 8 * it, perm.data(), 8 * sizeof(int32_t));
         if (perm_out && it == perm_at) memcpy(perm_out, perm.data(), (size_t)n * sizeof(int32_t));

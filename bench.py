@@ -69,6 +69,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fp32-variant", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="config4: one context instead of the two-context pipeline")
     return ap.parse_args()
 
 
@@ -509,7 +510,13 @@ def bench_pairs(args, eng, world, rank, barrier, flush_l2, torch, dist):
     Ks = np.stack(Ks)
     stream = torch.cuda.current_stream()
 
+    from structure_from_motion_b200.distributed import PairPipeline
+
+    pipe = None if args.no_pipeline else PairPipeline(depth=2)
+
     def step(seed):
+        if pipe is not None:  # H2D of one chunk of pairs overlaps the kernels of another (two contexts, two streams)
+            return pipe.batch_ransac(pa, pb, offsets, Ks, h, seed, THR, MIN_EXTRA, AGG, pair_id0=rank * P)
         return eng.batch_ransac(pa, pb, offsets, Ks, h, seed, THR, MIN_EXTRA, AGG, pair_id0=rank * P)
 
     clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
@@ -517,23 +524,28 @@ def bench_pairs(args, eng, world, rank, barrier, flush_l2, torch, dist):
     for w in range(max(args.warmup, 3)):
         step(100 + w)
     barrier()
-    eng.enable_timing(True)
-    _, l0 = eng.get_timing()
+    if pipe is None:
+        eng.enable_timing(True)
+    count_launches = (lambda: pipe.launches()) if pipe is not None else (lambda: eng.get_timing()[1])
+    l0 = count_launches()
     clocks.mark_begin()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     stage = {}
     for s in range(args.steps):
         flush_l2()
+        if pipe is not None:
+            stream.synchronize()  # the pipeline's own streams do not wait for the flush on torch's stream
         ev[s][0].record(stream)
-        out = step(s)
+        out = step(s)             # returns when every result is back on the host
         ev[s][1].record(stream)
-        t, _ = eng.get_timing()
-        for k, v in t.items():
-            stage[k] = stage.get(k, 0.0) + v
+        if pipe is None:
+            t, _ = eng.get_timing()
+            for k, v in t.items():
+                stage[k] = stage.get(k, 0.0) + v
     barrier()
     clocks.mark_end()
     clk = clocks.stop()
-    _, l1 = eng.get_timing()
+    l1 = count_launches()
     ms = sum(a.elapsed_time(b) for a, b in ev)
     vals = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -548,6 +560,7 @@ def bench_pairs(args, eng, world, rank, barrier, flush_l2, torch, dist):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"config4: {P} image pairs per GPU x {n} correspondences x {h} hypotheses, "
                                    f"pair-sharded, host buffers (H2D inside the timed region), models found {found}/{P}",
+                       "pipeline": "one context" if pipe is None else "2 contexts x 4 chunks of pairs: H2D of a chunk overlaps the kernels of another",
                        "l2": "flushed between timed steps", "parallelism": f"pair-sharded x{world}, no collective"},
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
             "clocks": clk,

@@ -114,3 +114,57 @@ def shard_pairs(offsets: Sequence[int], rank: int, world: int):
     offsets = np.asarray(offsets, dtype=np.int64)
     p0, p1 = shard_range(len(offsets) - 1, rank, world)
     return p0, p1, offsets[p0:p1 + 1] - offsets[p0]
+
+
+class PairPipeline:
+    """Pair-sharded batches from HOST buffers with the H2D copy of one chunk hidden behind the kernels of another:
+    the pairs are cut into chunks that alternate between ``depth`` contexts on the same GPU (each with its own
+    non-blocking stream), driven by one thread per context (ctypes releases the GIL during the C call).  Results are
+    identical to one ``Engine.batch_ransac`` call over all pairs: the device sampler is keyed by (seed, global pair
+    id, hypothesis), not by the chunking."""
+
+    def __init__(self, device: Optional[int] = None, depth: int = 2):
+        from concurrent.futures import ThreadPoolExecutor
+
+        from . import _native
+
+        dev = _native.default_device() if device is None else int(device)
+        self.engines = [_native.Engine(dev) for _ in range(depth)]
+        self.pool = ThreadPoolExecutor(max_workers=depth)
+
+    def set_score_variant(self, *a, **k):
+        for e in self.engines:
+            e.set_score_variant(*a, **k)
+
+    def launches(self) -> int:
+        return sum(e.get_timing()[1] for e in self.engines)
+
+    def batch_ransac(self, pts_a, pts_b, offsets, Ks, h, seed, threshold, min_extra=0.0, aggregation="rms",
+                     selection="min_error", pair_id0=0, chunk_pairs: Optional[int] = None):
+        offsets = np.asarray(offsets, dtype=np.int64)
+        P = len(offsets) - 1
+        Ks = np.asarray(Ks, dtype=np.float64).reshape(P, 3, 3)
+        depth = len(self.engines)
+        if chunk_pairs is None:
+            chunk_pairs = max(1, -(-P // (2 * depth)))
+        bounds = list(range(0, P, chunk_pairs)) + [P]
+
+        def run(k):
+            p0, p1 = bounds[k], bounds[k + 1]
+            lo, hi = int(offsets[p0]), int(offsets[p1])
+            return self.engines[k % depth].batch_ransac(pts_a[lo:hi], pts_b[lo:hi], offsets[p0:p1 + 1] - lo, Ks[p0:p1], h,
+                                                        seed, threshold, min_extra, aggregation, selection,
+                                                        pair_id0=pair_id0 + p0)
+
+        # chunk k runs on engine k % depth; a worker thread keeps one engine busy with its chunks in order
+        def worker(e):
+            return [(k, run(k)) for k in range(e, len(bounds) - 1, depth)]
+
+        parts = dict(kv for res in self.pool.map(worker, range(depth)) for kv in res)
+        keys = parts[0].keys()
+        return {key: np.concatenate([parts[k][key] for k in range(len(bounds) - 1)]) for key in keys}
+
+    def close(self):
+        self.pool.shutdown()
+        for e in self.engines:
+            e.close()

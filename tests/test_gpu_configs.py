@@ -197,3 +197,25 @@ def test_config4_batch_matches_single_pairs(engine):
             continue
         assert ref["best_index"] == best.index
         assert _e_close(out["E"][p], ref["E"])
+
+
+def test_pair_pipeline_equals_single_call(engine):
+    """distributed.PairPipeline (two contexts, chunks of pairs, H2D overlapped with compute) returns exactly what one
+    batch_ransac call over all pairs returns, for ragged pairs and any chunking."""
+    from structure_from_motion_b200.distributed import PairPipeline
+
+    sizes = [700, 64, 333, 9, 1200, 500, 8, 410, 77]
+    scenes = [make_scene(max(s, 8), 0.35, seed=40 + p) for p, s in enumerate(sizes)]
+    xa = np.concatenate([sc[1][:s] for sc, s in zip(scenes, sizes)])
+    xb = np.concatenate([sc[2][:s] for sc, s in zip(scenes, sizes)])
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    Ks = np.stack([sc[0] for sc in scenes])
+    want = engine.batch_ransac(xa, xb, off, Ks, 300, 11, 1.5e-6, 5, "rms", pair_id0=1000)
+    pipe = PairPipeline(depth=2)
+    try:
+        for chunk in (None, 1, 4, 100):
+            got = pipe.batch_ransac(xa, xb, off, Ks, 300, 11, 1.5e-6, 5, "rms", pair_id0=1000, chunk_pairs=chunk)
+            for k in want:
+                assert np.array_equal(got[k], want[k], equal_nan=True) if got[k].dtype.kind == "f" else np.array_equal(got[k], want[k]), (chunk, k)
+    finally:
+        pipe.close()

@@ -188,7 +188,8 @@ int sfm_batch_ransac(sfm_ctx *ctx, const double *xa, const double *ya, const dou
 /* ---- the stage in front of the hot path: brute-force matcher ------ */
 /* lib/feature_matching/matching.py:36-118 match_brute_force with ncc.py:7-54 (score_kind 0, score
  * in [0,2], 2.0 when a window leaves the image) or ssd.py:7-36 (score_kind 1, +inf outside) as the
- * score function.  Images: row-major rows x cols, image_dtype 0 = uint8 (numpy's uint8 arithmetic
+ * score function.  window <= 15; like util.py:21-27 the patch spans center +- int(window/2), so an even
+ * window covers window + 1 pixels.  Images: row-major rows x cols, image_dtype 0 = uint8 (numpy's uint8 arithmetic
  * of ssd.py is reproduced), 1 = float64.  feats_*: double[n][2] = (x, y) (lib/common/feature.py).
  * validation: bit 0 RATIO_TEST (heap[0]/heap[1] <= ratio_threshold, matching.py:84-97 - heap[1] of
  * the reference's heapq, not the second smallest score), bit 1 CROSSCHECK (matching.py:100-118).

@@ -198,13 +198,6 @@ struct PyMT {
         if (pos >= 624) regenerate();
         return out[pos++];
     }
-    // Random._randbelow_with_getrandbits(n): k = n.bit_length(); r = getrandbits(k) until r < n
-    inline uint32_t below(uint32_t n) {
-        const int sh = __builtin_clz(n);  // 32 - k
-        uint32_t r = next() >> sh;
-        while (r >= n) r = next() >> sh;
-        return r;
-    }
 };
 
 }  // namespace
@@ -1093,6 +1086,7 @@ int sfm_match_brute_force(sfm_ctx* c, const void* image_a, const void* image_b, 
     if (image_dtype != IMG_U8 && image_dtype != IMG_F64) return fail(SFM_ERR_ARG, "image dtype must be 0 (uint8) or 1 (float64)");
     if (score_kind != SCORE_NCC && score_kind != SCORE_SSD) return fail(SFM_ERR_ARG, "score kind must be 0 (ncc) or 1 (ssd)");
     if (window < 1 || window > kMaxWindow) return fail(SFM_ERR_ARG, "window size must be in [1, %d]", kMaxWindow);
+    window = 2 * (window / 2) + 1;  // util.py:21-27 cuts [c - int(w/2), c + int(w/2)]: an even w yields w + 1 pixels
     if (int r = match_check_counts(na, nb, best_b, best_score, keep)) return r;
     if ((na > 0 && !feats_a) || (nb > 0 && !feats_b)) return fail(SFM_ERR_ARG, "bad feature arrays");
     if (na == 0) return 0;

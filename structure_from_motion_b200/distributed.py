@@ -146,8 +146,12 @@ class PairPipeline:
         Ks = np.asarray(Ks, dtype=np.float64).reshape(P, 3, 3)
         depth = len(self.engines)
         if chunk_pairs is None:
-            chunk_pairs = max(1, -(-P // (2 * depth)))
-        bounds = list(range(0, P, chunk_pairs)) + [P]
+            # uneven chunks de-phase the contexts: equal chunks would copy at the same time and compute at the same
+            # time; a short first chunk lets context 0 compute while context 1 still copies, and so on
+            fr = np.cumsum([0.0, 1 / 8, 3 / 8, 3 / 8, 1 / 8]) if depth == 2 else np.linspace(0.0, 1.0, 2 * depth + 1)
+            bounds = sorted(set(int(round(f * P)) for f in fr))
+        else:
+            bounds = list(range(0, P, chunk_pairs)) + [P]
 
         def run(k):
             p0, p1 = bounds[k], bounds[k + 1]

@@ -62,6 +62,17 @@ def test_score_matrix_against_reference(engine, mg):
             assert np.allclose(Sf[ok], ref_f[ok], rtol=1e-14, atol=0)  # integer-valued: exact up to the final division
 
 
+def test_even_window_sizes_follow_the_reference_slicing(engine, mg):
+    """util.py:21-27 cuts center +- int(w/2): w = 4 is a 5x5 patch, w = 1 a single pixel."""
+    for kind, w in [("ncc", 4), ("ssd", 2), ("ssd", 1), ("ncc", 8)]:
+        ref = fe.score_matrix(mg["image_a"], mg["image_b"], mg["feats_a"][:20], mg["feats_b"][:19], kind, w)
+        _, _, _, S = engine.match_brute_force(mg["image_a"], mg["image_b"], mg["feats_a"][:20], mg["feats_b"][:19], kind=kind,
+                                              window=w, want_scores=True)
+        assert np.array_equal(np.isfinite(S), np.isfinite(ref))
+        ok = np.isfinite(ref)
+        assert np.abs(S[ok] - ref[ok]).max() <= (NCC_ATOL if kind == "ncc" else 0.0)
+
+
 def test_matches_against_reference_all_validation_modes(engine, mg):
     for case in mg["cases"]:
         ratio, cross = "RATIO_TEST" in case["strategies"], "CROSSCHECK" in case["strategies"]

@@ -9,6 +9,7 @@ Every numeric stage runs in libsfm_b200.so on the GPU (no CPU fallback).
 
     python apps/sfm.py --synthetic 0                      # rendered image pair with known pose
     python apps/sfm.py --image1 a.npy --image2 b.npy --camera-matrix K.npy [--config apps/config/config.yaml]
+    python apps/sfm.py --dataset-dir data/temple --index1 170 --index2 172      # Middlebury layout, as the reference
 """
 from __future__ import annotations
 
@@ -29,6 +30,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from lib.common import feature  # noqa: E402
+from lib.data_utils.middlebury_utils import load_camera_k_r_t  # noqa: E402
 from lib.epipolar.eight_point import recover_r_t_from_e  # noqa: E402
 from lib.epipolar.epipolar_ransac import estimate_essential_mat_with_ransac  # noqa: E402
 from lib.epipolar.triangulation import triangulate_points  # noqa: E402
@@ -166,10 +168,39 @@ def run_sfm(image_1_gray: np.ndarray, image_2_gray: np.ndarray, camera_matrix: n
                      cam2_T_cam1, world_points, secs)
 
 
+def load_middlebury_pair(dataset_dir, index_1, index_2, downscale_factor=1.0):
+    """apps/sfm.py:44-62, 218-234 of the reference: <name>_par.txt + <name><index>.png, OpenCV decode, Lanczos
+    downscale, RGB2GRAY; both images must share the intrinsics."""
+    import glob
+
+    import cv2 as cv
+
+    pars = glob.glob(os.path.join(dataset_dir, "*_par.txt"))
+    if len(pars) != 1:
+        raise FileNotFoundError(f"expected exactly one *_par.txt in {dataset_dir}")
+    from pathlib import Path
+
+    stem = os.path.basename(pars[0])[:-len("_par.txt")]
+    out = []
+    for idx in (index_1, index_2):
+        k, _ = load_camera_k_r_t(Path(pars[0]), int(idx))
+        image = cv.imread(os.path.join(dataset_dir, f"{stem}{int(idx):04d}.png"))
+        if image is None:
+            raise FileNotFoundError(os.path.join(dataset_dir, f"{stem}{int(idx):04d}.png"))
+        size = (int(image.shape[1] / downscale_factor), int(image.shape[0] / downscale_factor))
+        image = cv.resize(image, size, interpolation=cv.INTER_LANCZOS4)
+        out.append((cv.cvtColor(image, cv.COLOR_RGB2GRAY), k))
+    if not np.allclose(out[0][1], out[1][1]):
+        raise ValueError("Camera intrinsics params are different for the images, which is currently not supported.")
+    return out[0][0], out[1][0], out[0][1]
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("--synthetic", type=int, default=None, metavar="SEED", help="render a synthetic image pair")
     ap.add_argument("--image1"), ap.add_argument("--image2"), ap.add_argument("--camera-matrix")
+    ap.add_argument("--dataset-dir", help="Middlebury multi-view layout (<name>_par.txt, <name>NNNN.png)")
+    ap.add_argument("--index1", type=int, default=170), ap.add_argument("--index2", type=int, default=172)
     ap.add_argument("--config", default=os.path.join(ROOT, "apps", "config", "config.yaml"))
     ap.add_argument("--seed", type=int, default=None, help="random.seed() for the RANSAC sampler")
     ap.add_argument("--check-opencv", action="store_true")
@@ -183,9 +214,11 @@ def main(argv=None):
         img1, img2, K, R, t = make_image_pair(args.synthetic)
         truth = (R, t)
         cfg["ransac"].update(sed_inlier_threshold=1e-5, min_num_extra_inliers=60)  # integer-pixel corners at f = 520
+    elif args.dataset_dir:
+        img1, img2, K = load_middlebury_pair(args.dataset_dir, args.index1, args.index2, cfg["image_downscale_factor"])
     else:
         if not (args.image1 and args.image2 and args.camera_matrix):
-            ap.error("--synthetic SEED or --image1/--image2/--camera-matrix (.npy files) are required")
+            ap.error("--synthetic SEED, --dataset-dir DIR or --image1/--image2/--camera-matrix (.npy files) are required")
         img1, img2, K = np.load(args.image1), np.load(args.image2), np.load(args.camera_matrix)
     if args.seed is not None:
         import random

@@ -15,6 +15,7 @@ _MODULES = [
     "feature_matching", "feature_matching.util", "feature_matching.ncc", "feature_matching.ssd",
     "feature_matching.matching",
     "transforms", "transforms.transforms",
+    "data_utils", "data_utils.middlebury_utils",
     "ransac", "ransac.ransac",
     "epipolar", "epipolar.triangulation", "epipolar.sed", "epipolar.eight_point",
     "epipolar.epipolar_ransac",

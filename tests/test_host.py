@@ -235,3 +235,76 @@ def test_scene_generator_is_deterministic():
     assert len(idx) == 40 and np.allclose(R @ R.T, np.eye(3)) and abs(np.linalg.det(R) - 1) < 1e-12
     assert x1.shape == (100, 2) and np.isfinite(x2).all()
     assert np.allclose(euler_xyz_intrinsic(0, 0, 90), [[0, -1, 0], [1, 0, 0], [0, 0, 1]])
+
+
+def test_middlebury_parameter_file(tmp_path):
+    """lib/data_utils/tests/test_middlebury_utils.py with the same two-entry file."""
+    from lib.data_utils.middlebury_utils import load_camera_k_r_t
+    from lib.transforms.transforms import Transform3D
+
+    par = tmp_path / "test_par.txt"
+    par.write_text("2\nfile01.png 1 2 3 4 5 6 7 8 9 1 2 3 4 5 6 7 8 9 1 2 3\n"
+                   "file02.png 9 8 7 6 5 4 3 2 1 9 8 7 6 5 4 3 2 1 3 2 1\n")
+    k, transform = load_camera_k_r_t(par, 1)
+    np.testing.assert_almost_equal(np.arange(1, 10).reshape(3, 3), k)
+    expected = Transform3D.from_rmat_t(np.arange(1.0, 10.0).reshape(3, 3), np.arange(1.0, 4.0).reshape(3, 1))
+    np.testing.assert_almost_equal(expected.Tmat, transform.Tmat)
+    k2, t2 = load_camera_k_r_t(par, 2)
+    assert k2[0, 0] == 9 and t2.t.tolist() == [3, 2, 1]
+    with pytest.raises(ValueError, match="There are 2 entries"):
+        load_camera_k_r_t(par, 3)
+    par.write_text("5\nfile01.png 1 2 3 4 5 6 7 8 9 1 2 3 4 5 6 7 8 9 1 2 3\n")
+    with pytest.raises(ValueError, match="Could not find"):
+        load_camera_k_r_t(par, 4)
+    par.write_text("1\nnonsense 1 2 3\n")
+    with pytest.raises(RuntimeError, match="Could not decode"):
+        load_camera_k_r_t(par, 1)
+
+
+def test_front_end_host_logic():
+    """What the front-end mirrors decide on the host: window bookkeeping, the Gaussian table, which score functions
+    the GPU may evaluate itself, validation-strategy normalisation, errors raised before any GPU work."""
+    from lib.blur import gaussian
+    from lib.common.feature import Feature
+    from lib.feature_matching import matching, ncc, ssd, util
+    from lib.harris import harris_detector as harris
+
+    # util.py:8-27 (test_util.py): float comparison for the bounds, int() for the slice
+    assert util.is_within_bounds(Feature(1, 1), (3, 3), 3) and not util.is_within_bounds(Feature(0, 1), (3, 3), 3)
+    assert not util.is_within_bounds(Feature(1, 2), (3, 3), 3) and util.is_within_bounds(Feature(1.9, 1.0), (3, 3), 3)
+    img = np.arange(25).reshape(5, 5)
+    assert util.select_window(img, Feature(2.7, 1.2), 3).tolist() == [[1, 2, 3], [6, 7, 8], [11, 12, 13]]
+    # gaussian.py:4-26 (test_gaussian.py)
+    g = gaussian.create_gaussian_kernel(3, 1.0)
+    assert g.shape == (3, 3) and abs(g.sum() - 1.0) < 1e-15 and g[1, 1] == g.max() and np.allclose(g, g.T)
+    for bad in (2, 4, 1):
+        with pytest.raises(ValueError):
+            gaussian.create_gaussian_kernel(bad, 1.0)
+    # score-function recognition
+    a, b = np.zeros((8, 8), dtype=np.uint8), np.ones((8, 8), dtype=np.uint8)
+    p = matching._recognise(functools.partial(ncc.calculate_ncc, a, b, window_size=5))
+    assert p is not None and (p.kind, p.window_size) == ("ncc", 5) and p.image_a is a and p.image_b is b
+    p = matching._recognise(functools.partial(ssd.calculate_ssd, image_a=a, image_b=b))
+    assert p is not None and (p.kind, p.window_size) == ("ssd", 5)
+
+    def create(image_a, image_b, full):  # apps/sfm.py:266-277
+        def score(fa, fb):
+            return full(image_a, image_b, fa, fb)
+        return score
+
+    p = matching._recognise(create(a, b, functools.partial(ncc.calculate_ncc, window_size=9)))
+    assert p is not None and (p.kind, p.window_size) == ("ncc", 9) and p.image_a is a
+    assert matching._recognise(create(a, b, ncc.calculate_ncc)).window_size == 3
+    assert matching._recognise(lambda fa, fb: 0.0) is None
+    assert matching._recognise(functools.partial(ncc.calculate_ncc, a)) is None            # one image only
+    assert matching._recognise(functools.partial(ncc.calculate_ncc, a, b[:4])) is None     # shapes differ: the call raises later
+    assert matching._recognise(create(a, b, lambda *x: 0.0)) is None
+    # enum values and the trivial outcomes that need no GPU
+    assert matching.ValidationStrategy.CROSSCHECK.value == 1 and matching.ValidationStrategy.RATIO_TEST.value == 2
+    assert matching.match_brute_force([], [Feature(1, 1)], lambda fa, fb: 0.0) == []
+    with pytest.raises(IndexError):
+        matching.match_brute_force([Feature(1, 1)], [], lambda fa, fb: 0.0)
+    assert matching.match_brute_force([Feature(1, 1)], [], lambda fa, fb: 0.0,
+                                      validation_strategies=matching.ValidationStrategy.RATIO_TEST) == []
+    with pytest.raises(ValueError, match="at least 1"):
+        harris.detect_harris_corners(np.zeros((8, 8)), num_corners=0)

@@ -860,7 +860,7 @@ int sfm_recover_pose(sfm_ctx* c, const double* E, const double* xa, const double
         }
         k_normalise<<<dim3((unsigned)((m + 255) / 256), 1), 256, 0, c->stream>>>(sxa, sya, sxb, syb, stride, m, nullptr, dK, dpts);
         if (int r = check_launch(c, "k_normalise")) return r;
-        k_cheirality<<<(unsigned)((m + 127) / 128), 128, 0, c->stream>>>(dpts, m, nullptr, nullptr, c->poses.as<PoseSet>(),
+        k_cheirality<<<(unsigned)((4 * m + 127) / 128), 128, 0, c->stream>>>(dpts, m, nullptr, nullptr, c->poses.as<PoseSet>(),
                                                                         dist_thr, c->pass.as<uint8_t>(), nullptr);
         if (int r = check_launch(c, "k_cheirality")) return r;
     }
@@ -939,7 +939,7 @@ int sfm_pose_and_triangulate(sfm_ctx* c, double thr, double dist_thr, sfm_poses*
     if (int r = check_launch(c, "k_decompose")) return r;
     // the number of inliers stays on the device: launch over n and let threads beyond it exit
     const long long* cnt_dev = c->scan.as<long long>() + cblocks;
-    k_cheirality<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(
+    k_cheirality<<<(unsigned)((4 * n + 127) / 128), 128, 0, c->stream>>>(
         c->pts.as<Corr>(), -1, c->idx.as<long long>(), cnt_dev, c->poses.as<PoseSet>(), dist_thr, c->pass.as<uint8_t>(),
         have_row ? c->table.as<int32_t>() + 8 * c->winner_local : nullptr);
     if (int r = check_launch(c, "k_cheirality")) return r;

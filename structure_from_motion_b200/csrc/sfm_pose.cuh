@@ -134,51 +134,52 @@ __device__ __forceinline__ void dlt_triangulate(double xa, double ya, double xb,
 }
 
 // _cheirality_check for the 4 candidates of one pair (lib/epipolar/eight_point.py:449-488,
-// looped as in :210-230).  One thread per correspondence (K-normalised coordinates).
-// pass[i] bit p = correspondence i passes pose p.  counts follow the reference's
-// np.count_nonzero(passing_indices) (:228-230): correspondence 0 never counts.
+// looped as in :210-230).  One thread per (correspondence, candidate pose): the four poses of a
+// correspondence sit in four consecutive lanes (the 4x4 Jacobi SVDs are latency-bound, so the pose loop
+// is spread over lanes instead of running in sequence).  pass[i] bit p = correspondence i passes pose p.
+// counts follow the reference's np.count_nonzero(passing_indices) (:228-230): correspondence 0 never counts.
 __global__ void __launch_bounds__(128)
 k_cheirality(const Corr* __restrict__ pts, long long m, const long long* __restrict__ gather,
              const long long* __restrict__ m_dev, PoseSet* __restrict__ poses, double dist_thr,
              uint8_t* __restrict__ pass, const int32_t* __restrict__ quirk_row) {
     // gather != null: correspondence i is pts[gather[i]] and the count lives on the device
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long i = t >> 2;
+    const int p = (int)(t & 3);
     if (m_dev) m = *m_dev;
     __shared__ int s_cnt[4];
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
     __syncthreads();
-    unsigned bits = 0;
+    bool ok = false, counts = false;
     if (i < m) {
         const long long gi = gather ? gather[i] : i;
         const Corr c = pts[gi];
         const double P1[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};  // Transform3D.identity() (:473)
-        for (int p = 0; p < 4; ++p) {
-            double P2[12];
+        double P2[12];
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                P2[4 * r + 0] = poses->R[p][3 * r + 0];
-                P2[4 * r + 1] = poses->R[p][3 * r + 1];
-                P2[4 * r + 2] = poses->R[p][3 * r + 2];
-                P2[4 * r + 3] = poses->t[p][r];
-            }
-            double X1[3];
-            dlt_triangulate(c.xa, c.ya, c.xb, c.yb, P1, P2, X1);
-            const double z2 = fma(P2[8], X1[0], fma(P2[9], X1[1], fma(P2[10], X1[2], P2[11])));  // :476
-            const double nrm = sqrt(fma(X1[2], X1[2], fma(X1[1], X1[1], X1[0] * X1[0])));
-            const bool ok = (X1[2] >= -kCheiralityTolerance) && (z2 >= -kCheiralityTolerance) &&
-                            (nrm <= dist_thr);  // :478-487
-            bits |= ok ? (1u << p) : 0u;
+        for (int r = 0; r < 3; ++r) {
+            P2[4 * r + 0] = poses->R[p][3 * r + 0];
+            P2[4 * r + 1] = poses->R[p][3 * r + 1];
+            P2[4 * r + 2] = poses->R[p][3 * r + 2];
+            P2[4 * r + 3] = poses->t[p][r];
         }
-        pass[i] = (uint8_t)bits;
+        double X1[3];
+        dlt_triangulate(c.xa, c.ya, c.xb, c.yb, P1, P2, X1);
+        const double z2 = fma(P2[8], X1[0], fma(P2[9], X1[1], fma(P2[10], X1[2], P2[11])));  // :476
+        const double nrm = sqrt(fma(X1[2], X1[2], fma(X1[1], X1[1], X1[0] * X1[0])));
+        ok = (X1[2] >= -kCheiralityTolerance) && (z2 >= -kCheiralityTolerance) && (nrm <= dist_thr);  // :478-487
         // the count_nonzero-of-indices quirk (:228-230): the correspondence at list position 0
         // never counts.  In the fused pipeline position 0 is the winner's first sample point
         // (lib/ransac/ransac.py:76 returns the samples first).
-        if (quirk_row ? (gi == quirk_row[0]) : (i == 0)) bits = 0;
+        counts = ok && !(quirk_row ? (gi == quirk_row[0]) : (i == 0));
     }
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        const unsigned b = __ballot_sync(0xffffffffu, (bits >> p) & 1u);
-        if ((threadIdx.x & 31) == 0 && b) atomicAdd(&s_cnt[p], __popc(b));
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned okb = __ballot_sync(0xffffffffu, ok);
+    if (i < m && p == 0) pass[i] = (uint8_t)((okb >> (lane & ~3u)) & 0xfu);
+    const unsigned cb = __ballot_sync(0xffffffffu, counts);
+    if (lane < 4) {
+        const int n = __popc(cb & (0x11111111u << lane));  // lanes with pose == lane
+        if (n) atomicAdd(&s_cnt[lane], n);
     }
     __syncthreads();
     if (threadIdx.x < 4 && s_cnt[threadIdx.x])

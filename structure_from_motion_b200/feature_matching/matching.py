@@ -161,10 +161,12 @@ def match_brute_force(
     patch = _recognise(score_function)
     if patch is not None:
         fa, fb = _patch.feature_array(features_a), _patch.feature_array(features_b)
+        # a forwarding closure is only trusted after probing a few pairs against the score matrix (see _agrees)
+        probe = not isinstance(score_function, (PatchScore, functools.partial))
         best_b, best_s, keep, S = eng.match_brute_force(
             patch.image_a, patch.image_b, fa, fb, kind=patch.kind, window=patch.window_size, ratio_test=ratio,
-            crosscheck=cross, ratio_threshold=ratio_test_threshold, want_scores=True)
-        if not _agrees(patch, score_function, features_a, features_b, S):
+            crosscheck=cross, ratio_threshold=ratio_test_threshold, want_scores=probe)
+        if probe and not _agrees(patch, score_function, features_a, features_b, S):
             best_b = None
     if best_b is None:
         S = np.empty((na, nb), dtype=np.float64)

@@ -219,3 +219,54 @@ def test_pair_pipeline_equals_single_call(engine):
                 assert np.array_equal(got[k], want[k], equal_nan=True) if got[k].dtype.kind == "f" else np.array_equal(got[k], want[k]), (chunk, k)
     finally:
         pipe.close()
+
+
+def test_config5_scale_invariants(engine):
+    """BASELINE.json configs[4] sizes on one GPU: 1 048 576 correspondences and one rank's share (1/64 here) of the
+    1 048 576 hypotheses.  Size-independent properties: shard invariance, count == mask, the error from the mask, the
+    exact C scorer on a sample of hypotheses, and the whole tail (pose vote + triangulation of ~400k inliers)."""
+    n, h_total, shard = 1_048_576, 1_048_576, 16_384
+    K, x1, x2, R_true, t_true, _ = make_scene(n, 0.4, seed=5)
+    engine.upload_pairs(x1, x2, K)
+    lo = 37 * shard  # rank 37 of 64
+    engine.sample_device(seed=9, h=shard, hyp_offset=lo)
+    E, valid, _ = engine.fit()
+    cnt, s1, s2, err = engine.score(THR, min_extra=10, aggregation="rms", idx_offset=lo)
+    best = engine.get_best()
+    assert lo <= best.index < lo + shard and best.index - lo == int(np.argmin(err))
+    # the same hypotheses scored as two half shards
+    for part in range(2):
+        plo = lo + part * shard // 2
+        engine.sample_device(seed=9, h=shard // 2, hyp_offset=plo)
+        engine.fit(want_E=False)
+        c2, _, _, e2 = engine.score(THR, min_extra=10, aggregation="rms", idx_offset=plo)
+        sl = slice(part * shard // 2, (part + 1) * shard // 2)
+        assert np.array_equal(c2, cnt[sl]) and np.array_equal(e2, err[sl])
+    engine.sample_device(seed=9, h=shard, hyp_offset=lo)
+    engine.fit(want_E=False)
+    engine.score(THR, min_extra=10, aggregation="rms", idx_offset=lo, want_arrays=False)
+    best = engine.get_best()
+    mask, sed = engine.inlier_mask(THR)
+    samples = engine.get_table()[best.index - lo]
+    n_extra = int(mask.sum()) - int(mask[samples].sum())
+    assert n_extra == best.count_extra == cnt[best.index - lo]
+    ssum = float(np.sum(sed[mask] ** 2) + np.sum(sed[samples][~mask[samples]] ** 2))
+    assert abs(np.sqrt(ssum / (8 + n_extra)) - best.err) <= 1e-11 * best.err
+    # exact C scorer on a few hypotheses of the shard, all 1M correspondences
+    nxa, nya, nxb, nyb = _norm(K, x1, x2)
+    pick = np.array([0, 1, 4097, shard - 1, best.index - lo])
+    table = engine.get_table()
+    cnt_o, s1_o, s2_o = csed.score_batch(E[pick].reshape(-1, 9), nxa, nya, nxb, nyb, THR, table=table[pick], nthreads=8)
+    assert np.array_equal(cnt[pick], cnt_o)
+    np.testing.assert_allclose(s2[pick], s2_o, rtol=1e-11)
+    # tail: cheirality vote + triangulation of the winner's inliers; the pose is the scene's (to the accuracy of an
+    # eight-point fit on one minimal sample selected by min-RMS, which is what the reference computes)
+    poses, num, idx, ok, X = engine.pose_and_triangulate(THR, 50.0)
+    assert num == int(mask.sum() + (~mask[samples]).sum()) and num > 300_000
+    b = poses.best
+    Rg = np.array(poses.R, dtype=np.float64).reshape(4, 3, 3)[b]
+    tg = np.array(poses.t, dtype=np.float64).reshape(4, 3)[b]
+    assert np.degrees(np.arccos(np.clip((np.trace(Rg.T @ R_true) - 1) / 2, -1, 1))) < 2.5
+    assert np.degrees(np.arccos(np.clip(tg @ t_true / np.linalg.norm(t_true), -1, 1))) < 10.0
+    passing = ((ok >> b) & 1).astype(bool)
+    assert passing.mean() > 0.95 and np.isfinite(X[passing]).all() and (X[passing][:, 2] > 0).all()

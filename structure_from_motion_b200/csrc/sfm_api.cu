@@ -79,13 +79,15 @@ struct sfm_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     // data
     Buf raw, pts, offsets, Ks, table, E, valid, eig;
-    Buf acc, count_extra, S1, S2, err, blocks, best, invalid, winnerE, spts, bounds, fitflag;
+    Buf acc, count_extra, S1, S2, err, blocks, best, invalid, winnerE, spts, bounds, fitflag, record;
     Buf m_img, m_feat, m_W, m_ss, m_ok, m_S, m_out;
     Buf h_img, h_gx, h_gy, h_corner, h_alive, h_key, h_idx, h_small, h_xy;
     Buf mask, sed, poses, pass, X, idx, scan, tmp;
     long long n = 0, h = 0, npairs = 1;
     long long raw_stride = 1;
     bool batched = false, has_pts = false, has_table = false, has_models = false, has_score = false;
+    const void* occ_fn = nullptr;  // scoring kernel whose launch configuration is cached
+    int occ_blocks = 0;
     long long winner_local = -1;  // index into E of the current winner, -1 = use winnerE
     bool winner_set = false;
     long long last_idx_offset = 0;
@@ -255,7 +257,7 @@ int sfm_destroy(sfm_ctx* c) {
     cudaStreamSynchronize(c->stream);
     Buf* bufs[] = {&c->raw, &c->pts, &c->offsets, &c->Ks, &c->table, &c->E, &c->valid, &c->eig, &c->acc,
                    &c->count_extra, &c->S1, &c->S2, &c->err, &c->blocks, &c->best,
-                   &c->invalid, &c->winnerE, &c->mask, &c->sed, &c->poses, &c->pass, &c->X, &c->idx,
+                   &c->invalid, &c->winnerE, &c->record, &c->mask, &c->sed, &c->poses, &c->pass, &c->X, &c->idx,
                    &c->scan, &c->tmp, &c->spts, &c->bounds, &c->fitflag,
                    &c->m_img, &c->m_feat, &c->m_W, &c->m_ss, &c->m_ok, &c->m_S, &c->m_out,
                    &c->h_img, &c->h_gx, &c->h_gy, &c->h_corner, &c->h_alive, &c->h_key, &c->h_idx, &c->h_small, &c->h_xy};
@@ -597,10 +599,16 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         const void* fn = score_kernel(variant, hpt, G);
         if (!fn) return fail(SFM_ERR_ARG, "unsupported scoring configuration (variant %d, hpt %d, group %d)", variant, hpt, G);
         const size_t smem = (size_t)kScoreWarps * score_warp_smem(hpt);
-        CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kScoreThreads, smem));
-        if (occ < 1) occ = 1;
+        if (c->occ_fn == fn) {
+            occ = c->occ_blocks;  // attribute set and occupancy queried once per kernel instantiation
+        } else {
+            CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kScoreThreads, smem));
+            if (occ < 1) occ = 1;
+            c->occ_fn = fn;
+            c->occ_blocks = occ;
+        }
         const long long grid_blocks = (long long)c->sm_count * occ;
         const long long tiles = (max_len + kTile - 1) / kTile;
         static const int items_per_warp = getenv("SFM_ITEMS_PER_WARP") ? atoi(getenv("SFM_ITEMS_PER_WARP")) : 12;  // tuning knob
@@ -690,8 +698,10 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
     f.block_out = c->blocks.as<Best>();
     k_finalise<<<dim3((unsigned)fblocks, (unsigned)P), 256, 0, c->stream>>>(f);
     if (int r = check_launch(c, "k_finalise")) return r;
+    if (int r = c->record.reserve((size_t)P * sizeof(SelectRecord))) return r;
     k_select<<<(unsigned)P, 256, 0, c->stream>>>(c->blocks.as<Best>(), fblocks, mode, c->valid.as<uint8_t>(), h,
-                                                  idx_offset, c->best.as<Best>(), c->invalid.as<long long>());
+                                                  idx_offset, c->best.as<Best>(), c->invalid.as<long long>(),
+                                                  c->E.as<double>(), c->record.as<SelectRecord>());
     if (int r = check_launch(c, "k_select")) return r;
     c->toc(T_SELECT);
     c->has_score = true;
@@ -715,28 +725,21 @@ int sfm_score(sfm_ctx* c, double thr, double min_extra, int agg, int mode, int u
 }
 
 static int fetch_best(sfm_ctx* c, sfm_best* out) {
-    if (int r = ensure_pinned(c, sizeof(Best) + 16 + 72)) return r;
-    char* hp = (char*)c->hpin;
-    CU(cudaMemcpyAsync(hp, c->best.p, sizeof(Best), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(hp + sizeof(Best), c->invalid.p, 16, cudaMemcpyDeviceToHost, c->stream));
+    // k_select left {best, invalid counters, winning E} in one record: one copy, one synchronisation
+    if (int r = ensure_pinned(c, sizeof(SelectRecord))) return r;
+    CU(cudaMemcpyAsync(c->hpin, c->record.p, sizeof(SelectRecord), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    Best b;
-    memcpy(&b, hp, sizeof b);
-    long long inv[2];
-    memcpy(inv, hp + sizeof(Best), 16);
-    out->err = b.err;
-    out->index = b.idx;
-    out->count_extra = b.count;
+    SelectRecord r;
+    memcpy(&r, c->hpin, sizeof r);
+    out->err = r.best.err;
+    out->index = r.best.idx;
+    out->count_extra = r.best.count;
     out->reserved = 0;
-    out->num_invalid = inv[0];
-    out->first_invalid = inv[1];
-    for (int k = 0; k < 9; ++k) out->E[k] = 0.0;
-    if (b.idx >= 0) {
-        const long long local = b.idx - c->last_idx_offset;
-        CU(cudaMemcpyAsync(hp, c->E.as<double>() + 9 * local, 72, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        memcpy(out->E, hp, 72);
-        c->winner_local = local;
+    out->num_invalid = r.num_invalid;
+    out->first_invalid = r.first_invalid;
+    memcpy(out->E, r.E, 72);
+    if (r.best.idx >= 0) {
+        c->winner_local = r.best.idx - c->last_idx_offset;
         c->winner_set = true;
     } else {
         out->err = __builtin_inf();

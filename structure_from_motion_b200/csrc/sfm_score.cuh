@@ -506,6 +506,12 @@ struct Best {
     int pad;
 };
 
+struct SelectRecord {
+    Best best;
+    long long num_invalid, first_invalid;
+    double E[9];
+};
+
 __device__ __forceinline__ bool better(const Best& x, const Best& y, int mode) {
     // is x better than y ?
     if (y.idx < 0) return x.idx >= 0;
@@ -637,7 +643,8 @@ __global__ void __launch_bounds__(256) k_finalise(const FinalArgs a) {
 // try/except around the fitter, so one degenerate sample aborts the reference run).
 __global__ void __launch_bounds__(256)
 k_select(const Best* __restrict__ blocks, int nblocks, int mode, const uint8_t* __restrict__ valid,
-         long long h, long long idx_offset, Best* __restrict__ out, long long* __restrict__ invalid_out) {
+         long long h, long long idx_offset, Best* __restrict__ out, long long* __restrict__ invalid_out,
+         const double* __restrict__ E, SelectRecord* __restrict__ record) {
     __shared__ Best sm[32];
     __shared__ long long s_ninv, s_first;
     if (threadIdx.x == 0) { s_ninv = 0; s_first = 0x7fffffffffffffffLL; }
@@ -669,6 +676,13 @@ k_select(const Best* __restrict__ blocks, int nblocks, int mode, const uint8_t* 
         *out = b;
         invalid_out[0] = s_ninv;
         invalid_out[1] = s_ninv ? s_first : -1;
+        // everything the host wants about this pair in one 120-byte record (one D2H copy, one synchronisation)
+        SelectRecord& r = record[blockIdx.x];
+        r.best = b;
+        r.num_invalid = s_ninv;
+        r.first_invalid = s_ninv ? s_first : -1;
+        const double* e = E + 9 * ((long long)blockIdx.x * h + (b.idx >= 0 ? b.idx - idx_offset : 0));
+        for (int k = 0; k < 9; ++k) r.E[k] = b.idx >= 0 ? e[k] : 0.0;
     }
 }
 

@@ -334,3 +334,37 @@ def two_view_arrays(camera_matrix, pts_a, pts_b, threshold, min_num_extra_inlier
     t = np.array(p.t, dtype=np.float64).reshape(4, 3)[b].copy()
     return TwoViewResult(ransac=res, R=R, t=t, inlier_indices=idx, passing=((ok >> b) & 1).astype(bool),
                          points=X, counts=counts)
+
+
+@dataclasses.dataclass
+class ImagePairResult:
+    corners_a: np.ndarray        # [na,2] (x, y), descending cornerness
+    corners_b: np.ndarray
+    match_a: np.ndarray          # int64 indices into corners_a of the matches handed to RANSAC
+    match_b: np.ndarray
+    match_score: np.ndarray
+    two_view: TwoViewResult      # indices inside it refer to the match arrays
+
+
+def image_pair_arrays(image_a, image_b, camera_matrix, *, num_harris_corners: int = 600, ncc_window_size: int = 9,
+                      ratio_test_threshold: float = 0.7, match_score_threshold: float = 0.3,
+                      sed_inlier_threshold: float = 1.5e-6, min_num_extra_inliers=10, max_iterations: int = 2000,
+                      error_aggregation_method="rms", sampler: str = "reference", seed: int = 0,
+                      engine: Optional[_native.Engine] = None) -> ImagePairResult:
+    """The whole of apps/sfm.py:64-186 on arrays, with the defaults of apps/config/config.yaml: Harris corners on
+    both images -> brute-force NCC matching with ratio test + cross-check -> score filter (apps/sfm.py:280-296) ->
+    RANSAC essential matrix -> cheirality vote -> triangulation.  No ``Feature`` / ``Match`` objects are built; with
+    ``sampler="reference"`` the results equal those of the list-based pipeline (same global ``random`` stream)."""
+    eng = engine or _native.get_engine()
+    ca, _, _ = eng.harris_corners(image_a, num_harris_corners)
+    cb, _, _ = eng.harris_corners(image_b, num_harris_corners)
+    if len(ca) == 0 or len(cb) == 0:
+        raise ValueError("Eight feature pairs are expected.")
+    best_b, best_s, keep, _ = eng.match_brute_force(image_a, image_b, ca, cb, kind="ncc", window=ncc_window_size,
+                                                    ratio_test=True, crosscheck=True, ratio_threshold=ratio_test_threshold)
+    keep &= ~(best_s > match_score_threshold)
+    ia = np.flatnonzero(keep)
+    ib = best_b[ia].astype(np.int64)
+    tv = two_view_arrays(camera_matrix, ca[ia], cb[ib], sed_inlier_threshold, min_num_extra_inliers,
+                         error_aggregation_method, max_iterations, sampler=sampler, seed=seed, engine=eng)
+    return ImagePairResult(corners_a=ca, corners_b=cb, match_a=ia, match_b=ib, match_score=best_s[ia], two_view=tv)

@@ -385,3 +385,31 @@ def test_headless_sfm_app_against_oracle_pipeline():
     t_err = np.degrees(np.arccos(np.clip(res.t @ t_true / np.linalg.norm(t_true) / np.linalg.norm(res.t), -1, 1)))
     assert rot_err < 0.5 and t_err < 3.0, (rot_err, t_err)
     assert len(res.inlier_feature_pairs) >= 68 and (res.world_points[:, 2] > 0).all()
+
+
+def test_array_native_image_pair_pipeline_equals_the_list_based_app(engine):
+    """two_view.image_pair_arrays (no Feature / Match objects) against apps/sfm.run_sfm on the same image pair."""
+    import random
+
+    from apps import sfm as app
+    from structure_from_motion_b200 import two_view
+    from structure_from_motion_b200.scenes import make_image_pair
+
+    img1, img2, K, *_ = make_image_pair(4, h=240, w=320)
+    kw = dict(num_harris_corners=300, sed_inlier_threshold=2e-5, min_num_extra_inliers=30, max_iterations=500)
+    random.seed(11)
+    res = app.run_sfm(img1, img2, K, app.load_config(**kw))
+    state = random.getstate()
+    random.seed(11)
+    arr = two_view.image_pair_arrays(img1, img2, K, engine=engine, **kw)
+    assert random.getstate() == state
+    assert np.array_equal(arr.corners_a, np.array([[c.x, c.y] for c in res.corners_1]))
+    assert [(int(a), int(b)) for a, b in zip(arr.match_a, arr.match_b)] == [(m.a_index, m.b_index) for m in res.matches]
+    assert np.array_equal(arr.two_view.ransac.E, res.e)
+    assert np.array_equal(arr.two_view.R, res.r) and np.array_equal(arr.two_view.t, res.t)
+    # the list pipeline triangulates the pairs that pass the vote, in the reference's inlier order; the array pipeline
+    # reports every inlier in ascending index order with NaN for the ones that fail: same set of points
+    got = arr.two_view.points[arr.two_view.passing]
+    assert len(got) == len(res.world_points)
+    key = lambda X: X[np.lexsort(X.T[::-1])]  # noqa: E731
+    assert np.allclose(key(got), key(res.world_points), rtol=1e-9, atol=1e-12)

@@ -1,8 +1,9 @@
-"""Mirror of lib/common/feature.py:4-7 (boundary value type)."""
-import dataclasses
+"""The image-feature value type that crosses the hot-path boundary (lib/common/feature.py:4-7): a position in
+pixel (or K-normalised) coordinates.  Field order, equality and repr are what callers of the reference rely on."""
+from dataclasses import dataclass
 
 
-@dataclasses.dataclass
+@dataclass
 class Feature:
-    x: float
-    y: float
+    x: float  # column
+    y: float  # row

@@ -18,23 +18,21 @@ FeaturePair = Tuple[Feature, Feature]
 
 
 def calculate_sed_inlier_score(e, matching_features: FeaturePair, camera_matrix) -> float:
-    """epipolar_ransac.py:18-25."""
-    feature_a = to_normalized_image_coords(matching_features[0], camera_matrix)
-    feature_b = to_normalized_image_coords(matching_features[1], camera_matrix)
-    return calculate_symmetric_epipolar_distance(feature_a=feature_a, feature_b=feature_b, e=e)
+    """Symmetric epipolar distance of one pixel-coordinate pair under E (epipolar_ransac.py:18-25): both features are
+    K-normalised first.  ``fit_with_ransac`` recognises ``partial(calculate_sed_inlier_score, camera_matrix=K)``."""
+    normalised = [to_normalized_image_coords(f, camera_matrix) for f in matching_features[:2]]
+    return calculate_symmetric_epipolar_distance(feature_a=normalised[0], feature_b=normalised[1], e=e)
 
 
 def eight_point_model_fitter(matching_features: list, camera_matrix):
-    """epipolar_ransac.py:28-42."""
-    if 8 != len(matching_features):
+    """E from exactly eight pixel-coordinate pairs (epipolar_ransac.py:28-42); ValueError for any other count."""
+    count = len(matching_features)
+    if count != 8:
         raise ValueError("Eight feature pairs are expected.")
-    matches = [Match(a_index=i, b_index=i) for i in range(len(matching_features))]
-    return estimate_essential_mat(
-        camera_matrix=camera_matrix,
-        features_a=[p[0] for p in matching_features],
-        features_b=[p[1] for p in matching_features],
-        matches=matches,
-    )
+    first, second = zip(*matching_features)
+    identity_matches = [Match(a_index=k, b_index=k) for k in range(count)]
+    return estimate_essential_mat(camera_matrix=camera_matrix, features_a=list(first), features_b=list(second),
+                                  matches=identity_matches)
 
 
 def estimate_essential_mat_with_ransac(

@@ -1,4 +1,5 @@
-"""Mirror of lib/feature_matching/util.py:8-27 (window bookkeeping, no arithmetic)."""
+"""Window bookkeeping of the patch scores — the two helpers of lib/feature_matching/util.py:8-27, re-implemented.
+No arithmetic happens here; the CUDA kernel ``k_patch_prepare`` applies the same two rules on the device."""
 from typing import Tuple
 
 import numpy as np
@@ -6,20 +7,21 @@ import numpy as np
 from ..common import feature as feat
 
 
+def _reach(window_size: int) -> int:
+    """Pixels covered on each side of the centre: int(window_size / 2), so an even size w spans w + 1 pixels."""
+    return int(window_size / 2)
+
+
 def is_within_bounds(feature: feat.Feature, image_shape: Tuple[int, int], window_size: int) -> bool:
-    """util.py:8-18: the float coordinates are compared, the window itself is cut with int()."""
-    half_window_size = int(window_size / 2)
-    if not half_window_size <= feature.y < (image_shape[0] - half_window_size):
-        return False
-    if not half_window_size <= feature.x < (image_shape[1] - half_window_size):
-        return False
-    return True
+    """True iff the window around the feature stays inside the image.  The FLOAT coordinates are compared
+    (util.py:12-16), while the window itself is cut at the truncated coordinates."""
+    reach = _reach(window_size)
+    rows, cols = image_shape[0], image_shape[1]
+    return bool(reach <= feature.y < rows - reach and reach <= feature.x < cols - reach)
 
 
 def select_window(image: np.ndarray, feature: feat.Feature, window_size: int) -> np.ndarray:
-    """util.py:21-27 (a view, as in the reference)."""
-    half_window_size = int(window_size / 2)
-    return image[
-        int(feature.y) - half_window_size: int(feature.y) + half_window_size + 1,
-        int(feature.x) - half_window_size: int(feature.x) + half_window_size + 1,
-    ]
+    """The (2 reach + 1)^2 view centred on (int(y), int(x)) (util.py:21-27)."""
+    reach = _reach(window_size)
+    row, col = int(feature.y), int(feature.x)
+    return image[row - reach: row + reach + 1, col - reach: col + reach + 1]

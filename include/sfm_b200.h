@@ -160,6 +160,11 @@ int sfm_decompose_essential(sfm_ctx *ctx, const double *E, sfm_poses *out);
 int sfm_recover_pose(sfm_ctx *ctx, const double *E, const double *xa, const double *ya,
                      const double *xb, const double *yb, int64_t stride, int64_t m,
                      double distance_threshold, sfm_poses *out, uint8_t *pass4);
+/* The same with PIXEL coordinates: to_normalized_image_coords (eight_point.py:127-133) is applied on the device with
+ * K (double[9], row-major) first — recover_r_t_from_e (eight_point.py:65-96). */
+int sfm_recover_pose_pixels(sfm_ctx *ctx, const double *E, const double *K, const double *xa, const double *ya,
+                            const double *xb, const double *yb, int64_t stride, int64_t m,
+                            double distance_threshold, sfm_poses *out, uint8_t *pass4);
 /* lib/epipolar/triangulation.py:9-62: DLT triangulation of m correspondences (pixel
  * coordinates) with 3x4 row-major camera matrices P1, P2.  X: double[m][3]. */
 int sfm_triangulate(sfm_ctx *ctx, const double *P1, const double *P2, const double *xa,

@@ -66,6 +66,8 @@ _SIGNATURES = {
     "sfm_ransac_essential": (C.c_int, [_P, C.c_double, C.c_double, C.c_int, C.c_int, C.POINTER(Best), _P, _P]),
     "sfm_decompose_essential": (C.c_int, [_P, _P, C.POINTER(Poses)]),
     "sfm_recover_pose": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_double, C.POINTER(Poses), _P]),
+    "sfm_recover_pose_pixels": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_double,
+                                          C.POINTER(Poses), _P]),
     "sfm_triangulate": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P]),
     "sfm_pose_and_triangulate": (C.c_int, [_P, C.c_double, C.c_double, C.POINTER(Poses), C.c_int64,
                                            C.POINTER(C.c_int64), _P, _P, _P]),
@@ -282,16 +284,23 @@ class Engine:
         self._ck(self.lib.sfm_decompose_essential(self.h, _ptr(E), C.byref(p)), "sfm_decompose_essential")
         return p
 
-    def recover_pose(self, E, norm_a, norm_b, distance_threshold=50.0):
-        """norm_a, norm_b: [m,2] K-normalised coordinates."""
+    def recover_pose(self, E, norm_a, norm_b, distance_threshold=50.0, camera_matrix=None):
+        """norm_a, norm_b: [m,2] K-normalised coordinates — or pixel coordinates when ``camera_matrix`` is given
+        (they are then normalised on the device)."""
         E = _f64(E).reshape(9)
         na, nb = _split_xy(norm_a), _split_xy(norm_b)
         m = na.shape[0]
         p = Poses()
         pass4 = np.zeros(m, dtype=np.uint8)
         a, b = na.ctypes.data, nb.ctypes.data
-        self._ck(self.lib.sfm_recover_pose(self.h, _ptr(E), _P(a), _P(a + 8), _P(b), _P(b + 8), 2, m,
-                                           float(distance_threshold), C.byref(p), _ptr(pass4)), "sfm_recover_pose")
+        if camera_matrix is None:
+            self._ck(self.lib.sfm_recover_pose(self.h, _ptr(E), _P(a), _P(a + 8), _P(b), _P(b + 8), 2, m,
+                                               float(distance_threshold), C.byref(p), _ptr(pass4)), "sfm_recover_pose")
+        else:
+            K = _f64(camera_matrix).reshape(9)
+            self._ck(self.lib.sfm_recover_pose_pixels(self.h, _ptr(E), _ptr(K), _P(a), _P(a + 8), _P(b), _P(b + 8), 2, m,
+                                                      float(distance_threshold), C.byref(p), _ptr(pass4)),
+                     "sfm_recover_pose_pixels")
         return p, pass4
 
     def triangulate(self, P1, P2, pts_a, pts_b):

@@ -86,6 +86,7 @@ struct sfm_ctx {
     long long n = 0, h = 0, npairs = 1;
     long long raw_stride = 1;
     bool batched = false, has_pts = false, has_table = false, has_models = false, has_score = false;
+    double Kstage[9] = {0};
     const void* occ_fn = nullptr;  // scoring kernel whose launch configuration is cached
     int occ_blocks = 0;
     long long winner_local = -1;  // index into E of the current winner, -1 = use winnerE
@@ -826,9 +827,26 @@ int sfm_decompose_essential(sfm_ctx* c, const double* E, sfm_poses* out) {
     return 0;
 }
 
+static int recover_pose_impl(sfm_ctx* c, const double* E, const double* K9, const double* xa, const double* ya,
+                             const double* xb, const double* yb, int64_t stride, int64_t m, double dist_thr,
+                             sfm_poses* out, uint8_t* pass4);
+
 int sfm_recover_pose(sfm_ctx* c, const double* E, const double* xa, const double* ya, const double* xb,
                      const double* yb, int64_t stride, int64_t m, double dist_thr, sfm_poses* out,
                      uint8_t* pass4) {
+    return recover_pose_impl(c, E, nullptr, xa, ya, xb, yb, stride, m, dist_thr, out, pass4);
+}
+
+int sfm_recover_pose_pixels(sfm_ctx* c, const double* E, const double* K, const double* xa, const double* ya,
+                            const double* xb, const double* yb, int64_t stride, int64_t m, double dist_thr,
+                            sfm_poses* out, uint8_t* pass4) {
+    if (!K) return fail(SFM_ERR_ARG, "null camera matrix");
+    return recover_pose_impl(c, E, K, xa, ya, xb, yb, stride, m, dist_thr, out, pass4);
+}
+
+static int recover_pose_impl(sfm_ctx* c, const double* E, const double* K9, const double* xa, const double* ya,
+                             const double* xb, const double* yb, int64_t stride, int64_t m, double dist_thr,
+                             sfm_poses* out, uint8_t* pass4) {
     if (int r = use(c)) return r;
     if (!E || !out) return fail(SFM_ERR_ARG, "null argument");
     if (m < 0) return fail(SFM_ERR_ARG, "negative count");
@@ -845,9 +863,11 @@ int sfm_recover_pose(sfm_ctx* c, const double* E, const double* xa, const double
     if (int r = check_launch(c, "k_decompose")) return r;
     if (m > 0) {
         if (!xa || !ya || !xb || !yb) return fail(SFM_ERR_ARG, "null coordinates");
-        // inputs are already K-normalised: pack them into Corr records with an identity K
+        // K9 == null: the inputs are already K-normalised and are packed into Corr records with an identity K;
+        // otherwise k_normalise applies eight_point.py:127-133 on the device (bit-identical IEEE operations)
         const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-        CU(cudaMemcpyAsync(dK, I, 72, cudaMemcpyHostToDevice, c->stream));
+        memcpy(c->Kstage, K9 ? K9 : I, 72);  // staged in the context: the async copy must not read caller memory later
+        CU(cudaMemcpyAsync(dK, c->Kstage, 72, cudaMemcpyHostToDevice, c->stream));
         const double *sxa, *sya, *sxb, *syb;
         if (stride == 1) {
             const double* src[4] = {xa, ya, xb, yb};

@@ -35,10 +35,9 @@ def estimate_r_t(camera_matrix, features_a: List[Feature], features_b: List[Feat
 
 def recover_r_t_from_e(e, camera_matrix, features_a: list, features_b: list, distance_threshold=None):
     """eight_point.py:65-96 — (cam2_R_cam1, cam2_t_cam2_cam1, mask); mask is an int64 index array."""
-    na = two_view.k_normalise_arrays(_coords(features_a), camera_matrix)
-    nb = two_view.k_normalise_arrays(_coords(features_b), camera_matrix)
-    n = min(len(na), len(nb))
-    res = two_view.recover_pose_arrays(e, na[:n], nb[:n], distance_threshold)
+    pa, pb = _coords(features_a), _coords(features_b)
+    n = min(len(pa), len(pb))
+    res = two_view.recover_pose_arrays(e, pa[:n], pb[:n], distance_threshold, camera_matrix=camera_matrix)
     return res.R, res.t, res.passing_indices
 
 

@@ -250,14 +250,16 @@ def recover_all_r_t_arrays(e, engine=None):
     return R[0], R[2], t[0]
 
 
-def recover_pose_arrays(e, norm_a, norm_b, distance_threshold=None, engine=None) -> PoseResult:
-    """_recover_r_t (lib/epipolar/eight_point.py:181-242) on [m,2] K-normalised arrays."""
+def recover_pose_arrays(e, pts_a, pts_b, distance_threshold=None, engine=None, camera_matrix=None) -> PoseResult:
+    """_recover_r_t (lib/epipolar/eight_point.py:181-242) on [m,2] arrays of K-normalised coordinates; with
+    ``camera_matrix`` the arrays hold pixel coordinates and to_normalized_image_coords (eight_point.py:127-133) runs
+    on the device first — recover_r_t_from_e (eight_point.py:65-96)."""
     if distance_threshold is None:
         distance_threshold = 50.0  # eight_point.py:469-470
     eng = engine or _native.get_engine()
-    na = np.ascontiguousarray(norm_a, dtype=np.float64).reshape(-1, 2)
-    nb = np.ascontiguousarray(norm_b, dtype=np.float64).reshape(-1, 2)
-    p, pass4 = eng.recover_pose(e, na, nb, distance_threshold)
+    na = np.ascontiguousarray(pts_a, dtype=np.float64).reshape(-1, 2)
+    nb = np.ascontiguousarray(pts_b, dtype=np.float64).reshape(-1, 2)
+    p, pass4 = eng.recover_pose(e, na, nb, distance_threshold, camera_matrix=camera_matrix)
     _check_decomposition(p)
     counts = np.array(p.counts, dtype=np.int64)
     if 0 == np.count_nonzero(counts):
@@ -268,20 +270,6 @@ def recover_pose_arrays(e, norm_a, norm_b, distance_threshold=None, engine=None)
     idx = np.nonzero((pass4 >> b) & 1)[0].astype(np.int64)
     return PoseResult(R=R[b].copy(), t=t[b].copy(), passing_indices=idx, counts=counts,
                       candidates=[(R[i], t[i]) for i in range(4)], singular_values=np.array(p.sv))
-
-
-def k_normalise_arrays(pts, camera_matrix):
-    """to_normalized_image_coords (lib/epipolar/eight_point.py:127-133) for an [n,2] array.
-
-    Host arithmetic on purpose: two IEEE operations per coordinate, used only to prepare the
-    arguments of the list-based pose API; the RANSAC path normalises on the device (K0).
-    """
-    K = np.asarray(camera_matrix, dtype=np.float64)
-    pts = np.asarray(pts, dtype=np.float64).reshape(-1, 2)
-    out = np.empty_like(pts)
-    out[:, 0] = (pts[:, 0] - K[0][2]) / K[0][0]
-    out[:, 1] = (pts[:, 1] - K[1][2]) / K[1][1]
-    return out
 
 
 def triangulate_arrays(pts_a, pts_b, P1, P2, engine=None) -> np.ndarray:

@@ -612,7 +612,7 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         }
         const long long grid_blocks = (long long)c->sm_count * occ;
         const long long tiles = (max_len + kTile - 1) / kTile;
-        static const int items_per_warp = getenv("SFM_ITEMS_PER_WARP") ? atoi(getenv("SFM_ITEMS_PER_WARP")) : 12;  // tuning knob
+        static const int items_per_warp = getenv("SFM_ITEMS_PER_WARP") ? atoi(getenv("SFM_ITEMS_PER_WARP")) : 32;  // tuning knob: 12 -> 32 shortens the end-of-launch tail (+1 % on config 3)
         const long long target_items = grid_blocks * kScoreWarps * items_per_warp;
         long long nsplit = (target_items + hblocks * P - 1) / (hblocks * P);
         const long long max_split = tiles / 8 > 0 ? tiles / 8 : 1;  // keep >= 8 tiles (512 correspondences) per item

@@ -106,8 +106,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 // ------------------------------------------------------------------------------------
 constexpr int kScoreThreads = 128;
 constexpr int kScoreWarps = kScoreThreads / 32;
-constexpr int kTile = 64;     // correspondences per stage (2 KB)
-constexpr int kStages = 3;
+#ifndef SFM_SCORE_TILE
+#define SFM_SCORE_TILE 64
+#endif
+#ifndef SFM_SCORE_STAGES
+#define SFM_SCORE_STAGES 3
+#endif
+constexpr int kTile = SFM_SCORE_TILE;     // correspondences per stage (2 KB)
+constexpr int kStages = SFM_SCORE_STAGES;
 constexpr int kRing = 64;     // survivor records per warp: < 32 pending + <= 32 new
 constexpr unsigned kMaxPoints = 1u << 25;
 constexpr int kChunks = 3;             // 21-bit chunks of a 63-bit fixed-point term

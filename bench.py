@@ -326,6 +326,13 @@ def main():
     fp64_peak_dfma = eng.measure_fp64_peak()
 
     def step_resident(seed):
+        if world == 1:  # one GPU: no merge step, so selection -> mask -> pose vote -> triangulation is one C call
+            eng.sample_device(seed, h_rank)
+            best, _, _, poses, num, idx, ok, X = eng.two_view(THR, MIN_EXTRA, AGG, "min_error", 50.0, want_mask=False,
+                                                              want_sed=False)
+            if best.index < 0:
+                raise RuntimeError("no model found")
+            return {"index": int(best.index)}, num
         r = distributed.ransac_essential_sharded(K, None, None, THR, MIN_EXTRA, AGG, h_rank, seed, engine=eng,
                                                  rank=rank, world=world, resident=True)
         if r["owner"] < 0:

@@ -178,6 +178,12 @@ int sfm_triangulate(sfm_ctx *ctx, const double *P1, const double *P2, const doub
 int sfm_pose_and_triangulate(sfm_ctx *ctx, double threshold, double distance_threshold,
                              sfm_poses *poses, int64_t cap, int64_t *num_inliers,
                              int64_t *inlier_idx, uint8_t *pass, double *X);
+/* sfm_ransac_essential + sfm_pose_and_triangulate in one call (apps/sfm.py:110-186): the winner never leaves the
+ * device between selection and the tail, the host synchronises once for the fixed-size results.  mask / sed
+ * (optional) are "sed <= threshold" / the distances under the winner, as sfm_ransac_essential returns them. */
+int sfm_two_view(sfm_ctx *ctx, double threshold, double min_extra, int aggregation, int selection,
+                 double distance_threshold, sfm_best *best, sfm_poses *poses, int64_t cap, int64_t *num_inliers,
+                 int64_t *inlier_idx, uint8_t *pass, double *X, uint8_t *mask, double *sed);
 
 /* ---- batched image pairs (pair-sharded workloads) ------------------------------------ */
 /* P independent pairs; pair p owns correspondences [offsets[p], offsets[p+1]) of the

@@ -71,6 +71,8 @@ _SIGNATURES = {
     "sfm_triangulate": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P]),
     "sfm_pose_and_triangulate": (C.c_int, [_P, C.c_double, C.c_double, C.POINTER(Poses), C.c_int64,
                                            C.POINTER(C.c_int64), _P, _P, _P]),
+    "sfm_two_view": (C.c_int, [_P, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.POINTER(Best), C.POINTER(Poses),
+                               C.c_int64, C.POINTER(C.c_int64), _P, _P, _P, _P, _P]),
     "sfm_batch_ransac": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P, C.c_int64, _P, C.c_int64, C.c_uint64,
                                    C.c_uint64, C.c_double, C.c_double, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "sfm_match_brute_force": (C.c_int, [_P, _P, _P, C.c_int, C.c_int64, C.c_int64, _P, C.c_int64, _P, C.c_int64, C.c_int,
@@ -326,6 +328,24 @@ class Engine:
                  "sfm_pose_and_triangulate")
         m = min(int(num.value), cap)
         return p, int(num.value), idx[:m], ok[:m], X[:m]
+
+    def two_view(self, threshold, min_extra=0.0, aggregation="rms", selection="min_error", distance_threshold=50.0,
+                 cap=None, want_mask=True, want_sed=True):
+        """ransac_essential + pose_and_triangulate in one C call (one synchronisation for the fixed-size results).
+        Returns (best, mask, sed, poses, num_inliers, inlier_idx, pass_bits, X)."""
+        cap = self.n if cap is None else int(cap)
+        b, p = Best(), Poses()
+        num = C.c_int64(0)
+        idx = np.empty(cap, dtype=np.int64)
+        ok = np.empty(cap, dtype=np.uint8)
+        X = np.empty((cap, 3), dtype=np.float64)
+        mask = np.empty(self.n, dtype=np.uint8) if want_mask else None
+        sed = np.empty(self.n, dtype=np.float64) if want_sed else None
+        self._ck(self.lib.sfm_two_view(self.h, float(threshold), float(min_extra), AGG[aggregation], SELECT[selection],
+                                       float(distance_threshold), C.byref(b), C.byref(p), cap, C.byref(num), _ptr(idx),
+                                       _ptr(ok), _ptr(X), _ptr(mask), _ptr(sed)), "sfm_two_view")
+        m = min(int(num.value), cap)
+        return b, mask, sed, p, int(num.value), idx[:m], ok[:m], X[:m]
 
     # -- batches ----------------------------------------------------------------------------
     def batch_ransac(self, pts_a, pts_b, offsets, Ks, h, seed, threshold, min_extra=0.0, aggregation="rms",

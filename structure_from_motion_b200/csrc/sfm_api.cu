@@ -931,17 +931,22 @@ int sfm_triangulate(sfm_ctx* c, const double* P1, const double* P2, const double
     return 0;
 }
 
-int sfm_pose_and_triangulate(sfm_ctx* c, double thr, double dist_thr, sfm_poses* poses, int64_t cap,
-                             int64_t* num_inliers, int64_t* inlier_idx, uint8_t* pass, double* X) {
-    if (int r = use(c)) return r;
-    if (!poses || !num_inliers) return fail(SFM_ERR_ARG, "null argument");
-    if (!c->has_pts || c->batched) return fail(SFM_ERR_STATE, "no single-pair correspondences loaded");
-    if (!c->winner_set) return fail(SFM_ERR_STATE, "no winner: run sfm_ransac_essential / sfm_get_best first");
+// The tail of apps/sfm.py:133-186 for the current winner: inlier mask -> compaction -> decomposition -> 4-pose
+// cheirality vote -> triangulation of the passing inliers.  best_dev != null: the winner is read from K3's device
+// output, so everything is enqueued without waiting for the selection to reach the host.
+static int pose_tail_launch(sfm_ctx* c, double thr, double dist_thr, const Best* best_dev, uint8_t* mask_host = nullptr,
+                            double* sed_host = nullptr) {
     const long long n = c->n;
-    if (int r = mask_launch(c, thr, nullptr)) return r;
-    const bool have_row = c->has_table && c->winner_local >= 0;
+    if (int r = mask_launch(c, thr, best_dev)) return r;
+    // the caller's mask is "sed <= thr" (copied before the sample points are forced in below)
+    if (mask_host) CU(cudaMemcpyAsync(mask_host, c->mask.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    if (sed_host) CU(cudaMemcpyAsync(sed_host, c->sed.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    const bool have_row = c->has_table && (best_dev || c->winner_local >= 0);
     if (have_row) {
-        k_mark_samples<<<1, 32, 0, c->stream>>>(c->table.as<int32_t>() + 8 * c->winner_local, c->mask.as<uint8_t>());
+        if (best_dev)
+            k_mark_samples_dev<<<1, 32, 0, c->stream>>>(c->table.as<int32_t>(), best_dev, c->last_idx_offset, c->mask.as<uint8_t>());
+        else
+            k_mark_samples<<<1, 32, 0, c->stream>>>(c->table.as<int32_t>() + 8 * c->winner_local, c->mask.as<uint8_t>());
         if (int r = check_launch(c, "k_mark_samples")) return r;
     }
     // compact the winner's inliers (ascending index): block counts -> scan -> scatter
@@ -958,13 +963,17 @@ int sfm_pose_and_triangulate(sfm_ctx* c, double thr, double dist_thr, sfm_poses*
     if (int r = check_launch(c, "k_compact_scan")) return r;
     k_compact_scatter<<<cblocks, 256, 0, c->stream>>>(c->mask.as<uint8_t>(), n, c->scan.as<long long>(), c->idx.as<long long>());
     if (int r = check_launch(c, "k_compact_scatter")) return r;
-    k_decompose<<<1, 32, 0, c->stream>>>(winner_E_dev(c), nullptr, 0, c->poses.as<PoseSet>(), 1);
+    if (best_dev)
+        k_decompose<<<1, 32, 0, c->stream>>>(c->E.as<double>(), best_dev, c->last_idx_offset, c->poses.as<PoseSet>(), 1);
+    else
+        k_decompose<<<1, 32, 0, c->stream>>>(winner_E_dev(c), nullptr, 0, c->poses.as<PoseSet>(), 1);
     if (int r = check_launch(c, "k_decompose")) return r;
     // the number of inliers stays on the device: launch over n and let threads beyond it exit
     const long long* cnt_dev = c->scan.as<long long>() + cblocks;
+    const int32_t* quirk = !have_row ? nullptr : (best_dev ? c->table.as<int32_t>() : c->table.as<int32_t>() + 8 * c->winner_local);
     k_cheirality<<<(unsigned)((4 * n + 127) / 128), 128, 0, c->stream>>>(
         c->pts.as<Corr>(), -1, c->idx.as<long long>(), cnt_dev, c->poses.as<PoseSet>(), dist_thr, c->pass.as<uint8_t>(),
-        have_row ? c->table.as<int32_t>() + 8 * c->winner_local : nullptr);
+        quirk, have_row ? best_dev : nullptr, c->last_idx_offset);
     if (int r = check_launch(c, "k_cheirality")) return r;
     k_vote<<<1, 32, 0, c->stream>>>(c->poses.as<PoseSet>());
     if (int r = check_launch(c, "k_vote")) return r;
@@ -980,12 +989,38 @@ int sfm_pose_and_triangulate(sfm_ctx* c, double thr, double dist_thr, sfm_poses*
                                                                       c->X.as<double>(), c->idx.as<long long>());
     if (int r = check_launch(c, "k_triangulate")) return r;
     c->toc(T_TRI);
-    if (int r = ensure_pinned(c, 64)) return r;
+    return 0;
+}
+
+// results of pose_tail_launch to the host: fixed-size part first (one synchronisation), then the per-inlier arrays
+static int pose_tail_fetch(sfm_ctx* c, sfm_poses* poses, int64_t cap, int64_t* num_inliers, int64_t* inlier_idx,
+                           uint8_t* pass, double* X, sfm_best* best /* may be null */) {
+    const int cblocks = (int)((c->n + 1023) / 1024);
+    const long long* cnt_dev = c->scan.as<long long>() + cblocks;
+    if (int r = ensure_pinned(c, 64 + sizeof(SelectRecord))) return r;
     CU(cudaMemcpyAsync(c->hpin, cnt_dev, 8, cudaMemcpyDeviceToHost, c->stream));
+    if (best) CU(cudaMemcpyAsync((char*)c->hpin + 64, c->record.p, sizeof(SelectRecord), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(poses, c->poses.p, sizeof(PoseSet), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     long long m;
     memcpy(&m, c->hpin, 8);
+    if (best) {
+        SelectRecord r;
+        memcpy(&r, (char*)c->hpin + 64, sizeof r);
+        best->err = r.best.idx >= 0 ? r.best.err : __builtin_inf();
+        best->index = r.best.idx;
+        best->count_extra = r.best.count;
+        best->reserved = 0;
+        best->num_invalid = r.num_invalid;
+        best->first_invalid = r.first_invalid;
+        memcpy(best->E, r.E, 72);
+        if (r.best.idx >= 0) {
+            c->winner_local = r.best.idx - c->last_idx_offset;
+            c->winner_set = true;
+        } else {
+            m = 0;  // no model: the tail ran on an empty mask
+        }
+    }
     *num_inliers = m;
     const long long take = m < cap ? m : cap;
     if (take > 0) {
@@ -995,6 +1030,30 @@ int sfm_pose_and_triangulate(sfm_ctx* c, double thr, double dist_thr, sfm_poses*
         CU(cudaStreamSynchronize(c->stream));
     }
     return 0;
+}
+
+int sfm_pose_and_triangulate(sfm_ctx* c, double thr, double dist_thr, sfm_poses* poses, int64_t cap,
+                             int64_t* num_inliers, int64_t* inlier_idx, uint8_t* pass, double* X) {
+    if (int r = use(c)) return r;
+    if (!poses || !num_inliers) return fail(SFM_ERR_ARG, "null argument");
+    if (!c->has_pts || c->batched) return fail(SFM_ERR_STATE, "no single-pair correspondences loaded");
+    if (!c->winner_set) return fail(SFM_ERR_STATE, "no winner: run sfm_ransac_essential / sfm_get_best first");
+    if (int r = pose_tail_launch(c, thr, dist_thr, nullptr)) return r;
+    return pose_tail_fetch(c, poses, cap, num_inliers, inlier_idx, pass, X, nullptr);
+}
+
+int sfm_two_view(sfm_ctx* c, double thr, double min_extra, int agg, int mode, double dist_thr, sfm_best* best,
+                 sfm_poses* poses, int64_t cap, int64_t* num_inliers, int64_t* inlier_idx, uint8_t* pass, double* X,
+                 uint8_t* mask, double* sed) {
+    if (int r = use(c)) return r;
+    if (!best || !poses || !num_inliers) return fail(SFM_ERR_ARG, "null argument");
+    if (c->batched) return fail(SFM_ERR_STATE, "single-pair call on a batched context");
+    if (int r = fit_launch(c, false)) return r;
+    if (int r = score_launch(c, thr, min_extra, agg, mode, true, 0, c->n)) return r;
+    // the winner stays on the device: mask, compaction, decomposition, vote and triangulation are enqueued right
+    // behind the selection, and the host synchronises once for all fixed-size results
+    if (int r = pose_tail_launch(c, thr, dist_thr, c->best.as<Best>(), mask, sed)) return r;
+    return pose_tail_fetch(c, poses, cap, num_inliers, inlier_idx, pass, X, best);
 }
 
 // ---- batched pairs ------------------------------------------------------------------------

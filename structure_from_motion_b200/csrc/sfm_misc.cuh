@@ -10,6 +10,13 @@ namespace sfm {
 __global__ void k_mark_samples(const int32_t* __restrict__ row, uint8_t* __restrict__ mask) {
     if (threadIdx.x < 8 && blockIdx.x == 0) mask[row[threadIdx.x]] = 1;
 }
+// the same with the winner taken from K3's device output (no host round trip between selection and the tail)
+__global__ void k_mark_samples_dev(const int32_t* __restrict__ table, const Best* __restrict__ best,
+                                   long long idx_offset, uint8_t* __restrict__ mask) {
+    const long long local = best->idx - idx_offset;
+    if (best->idx < 0 || threadIdx.x >= 8 || blockIdx.x != 0) return;
+    mask[table[8 * local + threadIdx.x]] = 1;
+}
 
 // Stream compaction of a byte mask into ascending indices: per-1024-element block counts,
 // single-block exclusive scan, ordered scatter.  scan[nblocks] receives the total.

@@ -141,7 +141,10 @@ __device__ __forceinline__ void dlt_triangulate(double xa, double ya, double xb,
 __global__ void __launch_bounds__(128)
 k_cheirality(const Corr* __restrict__ pts, long long m, const long long* __restrict__ gather,
              const long long* __restrict__ m_dev, PoseSet* __restrict__ poses, double dist_thr,
-             uint8_t* __restrict__ pass, const int32_t* __restrict__ quirk_row) {
+             uint8_t* __restrict__ pass, const int32_t* __restrict__ quirk_row,
+             const Best* __restrict__ quirk_best = nullptr, long long quirk_offset = 0) {
+    // quirk_best != null: quirk_row is the BASE of the sample table and the winner's row is looked up on the device
+    if (quirk_best) quirk_row = quirk_best->idx >= 0 ? quirk_row + 8 * (quirk_best->idx - quirk_offset) : nullptr;
     // gather != null: correspondence i is pts[gather[i]] and the count lives on the device
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long i = t >> 2;

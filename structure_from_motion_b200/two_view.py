@@ -65,6 +65,7 @@ def ransac_essential_arrays(
     selection: str = "min_error",
     engine: Optional[_native.Engine] = None,
     table: Optional[np.ndarray] = None,
+    _tail: Optional[dict] = None,
 ) -> RansacResult:
     """estimate_essential_mat_with_ransac (lib/epipolar/epipolar_ransac.py:45-70) on arrays.
 
@@ -109,7 +110,12 @@ def ransac_essential_arrays(
         eng.sample_device(seed, H, hyp_offset=hyp_offset)
     else:
         eng.set_table(table)
-    best, mask, sed = eng.ransac_essential(threshold, float(min_num_extra_inliers), agg, selection)
+    if _tail is None:
+        best, mask, sed = eng.ransac_essential(threshold, float(min_num_extra_inliers), agg, selection)
+    else:  # two_view_arrays: selection, inlier mask, pose vote and triangulation in one C call
+        best, mask, sed, *rest = eng.two_view(threshold, float(min_num_extra_inliers), agg, selection,
+                                              _tail["distance_threshold"])
+        _tail["out"] = rest
 
     if sampler == "reference":
         if best.num_invalid > 0 and on_degenerate == "raise":
@@ -310,9 +316,10 @@ def two_view_arrays(camera_matrix, pts_a, pts_b, threshold, min_num_extra_inlier
         distance_threshold = 50.0
     eng = kw.get("engine") or _native.get_engine()
     kw["engine"] = eng
+    tail = {"distance_threshold": float(distance_threshold)}
     res = ransac_essential_arrays(camera_matrix, pts_a, pts_b, threshold, min_num_extra_inliers,
-                                  error_aggregation_method, max_iterations, **kw)
-    p, num, idx, ok, X = eng.pose_and_triangulate(threshold, distance_threshold)
+                                  error_aggregation_method, max_iterations, _tail=tail, **kw)
+    p, num, idx, ok, X = tail["out"]
     _check_decomposition(p)
     counts = np.array(p.counts, dtype=np.int64)
     if 0 == np.count_nonzero(counts):

@@ -342,3 +342,28 @@ def test_adaptive_early_termination(engine):
     with pytest.raises(ValueError, match="No model could be found"):
         two_view.ransac_essential_adaptive(K, rng.uniform(0, 1000, (300, 2)), rng.uniform(0, 1000, (300, 2)), 1e-12, 50,
                                            "rms", max_iterations=4096, chunk=1024, engine=engine)
+
+
+@pytest.mark.parametrize("min_extra", [10, 10 ** 9])
+def test_fused_two_view_call_equals_the_two_step_sequence(engine, min_extra):
+    """sfm_two_view (winner handed to the tail on the device) against sfm_ransac_essential + sfm_pose_and_triangulate,
+    including the no-model case (min_extra that no hypothesis reaches)."""
+    K, x1, x2, *_ = make_scene(3000, 0.35, seed=21)
+    engine.upload_pairs(x1, x2, K)
+    engine.sample_device(5, 700)
+    best_a, mask_a, sed_a = engine.ransac_essential(THR, min_extra, "rms")
+    engine.sample_device(5, 700)
+    best_b, mask_b, sed_b, poses_b, num_b, idx_b, ok_b, X_b = engine.two_view(THR, min_extra, "rms", "min_error", 50.0)
+    assert best_a.index == best_b.index and best_a.count_extra == best_b.count_extra
+    assert (best_a.err == best_b.err) and list(best_a.E) == list(best_b.E)
+    if min_extra > 10 ** 6:
+        assert best_b.index == -1 and num_b == 0 and len(idx_b) == 0
+        return
+    assert np.array_equal(mask_a, mask_b) and np.array_equal(sed_a, sed_b)
+    engine.sample_device(5, 700)
+    engine.ransac_essential(THR, min_extra, "rms", want_mask=False, want_sed=False)
+    poses_a, num_a, idx_a, ok_a, X_a = engine.pose_and_triangulate(THR, 50.0)
+    assert num_a == num_b and np.array_equal(idx_a, idx_b) and np.array_equal(ok_a, ok_b)
+    assert np.array_equal(X_a, X_b, equal_nan=True)
+    assert poses_a.best == poses_b.best and list(poses_a.counts) == list(poses_b.counts)
+    assert np.array_equal(np.array(poses_a.R), np.array(poses_b.R))

@@ -19,7 +19,8 @@ winner -> decomposition + cheirality vote -> triangulation of the passing inlier
 * ``cpu_baseline`` the oracle port (numpy eight-point + threaded C scorer) on the host cores, on a
                 bounded sample of the same workload.
 N > 1 (torchrun): hypotheses are sharded — every rank scores its own 64k hypotheses of the same
-pair (weak scaling), winners merged by one 96-byte-per-rank NCCL all-gather.
+pair (weak scaling); the 112-byte selection records are all-gathered device-to-device by NCCL (the one collective),
+merged by a kernel, and the tail runs behind it without a host round trip.
 """
 from __future__ import annotations
 
@@ -333,23 +334,22 @@ def main():
             if best.index < 0:
                 raise RuntimeError("no model found")
             return {"index": int(best.index)}, num
-        r = distributed.ransac_essential_sharded(K, None, None, THR, MIN_EXTRA, AGG, h_rank, seed, engine=eng,
-                                                 rank=rank, world=world, resident=True)
+        # several GPUs: records all-gathered device-to-device (the one collective), merged by a kernel, tail enqueued
+        # behind it - the host synchronises once per estimate
+        r = distributed.two_view_sharded(THR, MIN_EXTRA, AGG, h_rank, seed, engine=eng, rank=rank, world=world)
         if r["owner"] < 0:
             raise RuntimeError("no model found")
-        poses, num, idx, ok, X = eng.pose_and_triangulate(THR, 50.0)
-        return r, num
+        return r, r["num_inliers"]
 
     def step_e2e(seed):
         if world == 1:
             res = two_view.two_view_arrays(K, pa, pb, THR, MIN_EXTRA, AGG, h_rank, sampler="device", seed=seed,
                                            on_degenerate="skip", engine=eng)
             return res.points.shape[0]
-        r = distributed.ransac_essential_sharded(K, pa, pb, THR, MIN_EXTRA, AGG, h_rank, seed, engine=eng,
-                                                 rank=rank, world=world, resident=False)
+        eng.upload_pairs(pa, pb, K)  # every rank uploads the (replicated) correspondences from its host buffers
+        r = distributed.two_view_sharded(THR, MIN_EXTRA, AGG, h_rank, seed, engine=eng, rank=rank, world=world)
         mask, sed = eng.inlier_mask(THR)
-        poses, num, idx, ok, X = eng.pose_and_triangulate(THR, 50.0)
-        return num
+        return r["num_inliers"]
 
     # ---- warm-up -------------------------------------------------------------------------------
     clocks = ClockSampler(local_rank)
@@ -457,7 +457,7 @@ def main():
                             f"vote + triangulation of the {num_inl} inliers",
                 "sampler": "device (Philox)", "score_variant": args.variant, "hyps_per_thread": args.hpt, "group": args.group,
                 "l2": "flushed (256 MiB memset) between timed steps",
-                "parallelism": f"hypothesis-sharded x{world}, one 96 B/rank all-gather" if world > 1 else "single GPU",
+                "parallelism": f"hypothesis-sharded x{world}, one 112 B/rank device-to-device all-gather + merge kernel" if world > 1 else "single GPU",
             },
             "ms_per_estimate": ms_total / args.steps,
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},

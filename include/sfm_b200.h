@@ -196,6 +196,25 @@ int sfm_batch_ransac(sfm_ctx *ctx, const double *xa, const double *ya, const dou
                      double min_extra, int aggregation, int selection, double *E, int64_t *best_index,
                      double *best_err, int32_t *count_extra, int64_t *num_invalid);
 
+/* ---- hypothesis-sharded estimates without a host round trip ---------- */
+/* One rank of a run whose hypotheses are split over `world` GPUs (correspondences replicated):
+ *   1. sfm_score_async  : fit + score + select of this rank's hypotheses, nothing synchronised; *record_dev is the
+ *                         DEVICE address of this rank's SFM_RECORD_BYTES-byte selection record;
+ *   2. the caller all-gathers the records of all ranks into one device buffer on the context's stream
+ *      (ncclAllGather / torch.distributed.all_gather_into_tensor - the path's only collective, 112 bytes per rank);
+ *   3. sfm_sharded_tail : merges the records on the device with the reference's rule (ransac.py:83: smallest error,
+ *                         earliest GLOBAL iteration = rank * hyps_per_rank + local index on ties) and enqueues the
+ *                         inlier mask, pose vote and triangulation of the global winner;
+ *   4. sfm_sharded_fetch: the single synchronisation; best->index is the global index, *owner the rank that fitted
+ *                         the winner (-1: no model anywhere). */
+#define SFM_RECORD_BYTES 112
+int sfm_score_async(sfm_ctx *ctx, double threshold, double min_extra, int aggregation, int selection,
+                    void **record_dev);
+int sfm_sharded_tail(sfm_ctx *ctx, const void *gathered_records_dev, int world, int rank, int64_t hyps_per_rank,
+                     int selection, double threshold, double distance_threshold);
+int sfm_sharded_fetch(sfm_ctx *ctx, sfm_best *best, int32_t *owner, sfm_poses *poses, int64_t cap,
+                      int64_t *num_inliers, int64_t *inlier_idx, uint8_t *pass, double *X);
+
 /* ---- the stage in front of the hot path: brute-force matcher ------ */
 /* lib/feature_matching/matching.py:36-118 match_brute_force with ncc.py:7-54 (score_kind 0, score
  * in [0,2], 2.0 when a window leaves the image) or ssd.py:7-36 (score_kind 1, +inf outside) as the

@@ -73,6 +73,10 @@ _SIGNATURES = {
                                            C.POINTER(C.c_int64), _P, _P, _P]),
     "sfm_two_view": (C.c_int, [_P, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.POINTER(Best), C.POINTER(Poses),
                                C.c_int64, C.POINTER(C.c_int64), _P, _P, _P, _P, _P]),
+    "sfm_score_async": (C.c_int, [_P, C.c_double, C.c_double, C.c_int, C.c_int, C.POINTER(_P)]),
+    "sfm_sharded_tail": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_double, C.c_double]),
+    "sfm_sharded_fetch": (C.c_int, [_P, C.POINTER(Best), C.POINTER(C.c_int32), C.POINTER(Poses), C.c_int64,
+                                    C.POINTER(C.c_int64), _P, _P, _P]),
     "sfm_batch_ransac": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P, C.c_int64, _P, C.c_int64, C.c_uint64,
                                    C.c_uint64, C.c_double, C.c_double, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "sfm_match_brute_force": (C.c_int, [_P, _P, _P, C.c_int, C.c_int64, C.c_int64, _P, C.c_int64, _P, C.c_int64, C.c_int,
@@ -346,6 +350,34 @@ class Engine:
                                        _ptr(ok), _ptr(X), _ptr(mask), _ptr(sed)), "sfm_two_view")
         m = min(int(num.value), cap)
         return b, mask, sed, p, int(num.value), idx[:m], ok[:m], X[:m]
+
+    # -- hypothesis-sharded runs: nothing synchronises between scoring and the final fetch ----
+    RECORD_BYTES = 112  # include/sfm_b200.h SFM_RECORD_BYTES
+
+    def score_async(self, threshold, min_extra=0.0, aggregation="rms", selection="min_error") -> int:
+        """fit + score + select, enqueued only.  Returns the DEVICE address of this rank's selection record."""
+        ptr = _P()
+        self._ck(self.lib.sfm_score_async(self.h, float(threshold), float(min_extra), AGG[aggregation], SELECT[selection],
+                                          C.byref(ptr)), "sfm_score_async")
+        return int(ptr.value)
+
+    def sharded_tail(self, gathered_dev_ptr: int, world: int, rank: int, hyps_per_rank: int, threshold,
+                     distance_threshold=50.0, selection="min_error"):
+        self._ck(self.lib.sfm_sharded_tail(self.h, _P(gathered_dev_ptr), int(world), int(rank), int(hyps_per_rank),
+                                           SELECT[selection], float(threshold), float(distance_threshold)),
+                 "sfm_sharded_tail")
+
+    def sharded_fetch(self, cap=None):
+        cap = self.n if cap is None else int(cap)
+        b, p = Best(), Poses()
+        owner, num = C.c_int32(-1), C.c_int64(0)
+        idx = np.empty(cap, dtype=np.int64)
+        ok = np.empty(cap, dtype=np.uint8)
+        X = np.empty((cap, 3), dtype=np.float64)
+        self._ck(self.lib.sfm_sharded_fetch(self.h, C.byref(b), C.byref(owner), C.byref(p), cap, C.byref(num), _ptr(idx),
+                                            _ptr(ok), _ptr(X)), "sfm_sharded_fetch")
+        m = min(int(num.value), cap)
+        return b, int(owner.value), p, int(num.value), idx[:m], ok[:m], X[:m]
 
     # -- batches ----------------------------------------------------------------------------
     def batch_ransac(self, pts_a, pts_b, offsets, Ks, h, seed, threshold, min_extra=0.0, aggregation="rms",

@@ -23,6 +23,7 @@ using namespace sfm;
 
 static_assert(sizeof(Corr) == 32, "Corr must be 32 bytes");
 static_assert(sizeof(PoseSet) == sizeof(sfm_poses), "PoseSet/sfm_poses layout mismatch");
+static_assert(sizeof(SelectRecord) == SFM_RECORD_BYTES, "SelectRecord / SFM_RECORD_BYTES mismatch");
 
 namespace {
 
@@ -79,7 +80,7 @@ struct sfm_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     // data
     Buf raw, pts, offsets, Ks, table, E, valid, eig;
-    Buf acc, count_extra, S1, S2, err, blocks, best, invalid, winnerE, spts, bounds, fitflag, record;
+    Buf acc, count_extra, S1, S2, err, blocks, best, invalid, winnerE, spts, bounds, fitflag, record, merged;
     Buf m_img, m_feat, m_W, m_ss, m_ok, m_S, m_out;
     Buf h_img, h_gx, h_gy, h_corner, h_alive, h_key, h_idx, h_small, h_xy;
     Buf mask, sed, poses, pass, X, idx, scan, tmp;
@@ -258,7 +259,7 @@ int sfm_destroy(sfm_ctx* c) {
     cudaStreamSynchronize(c->stream);
     Buf* bufs[] = {&c->raw, &c->pts, &c->offsets, &c->Ks, &c->table, &c->E, &c->valid, &c->eig, &c->acc,
                    &c->count_extra, &c->S1, &c->S2, &c->err, &c->blocks, &c->best,
-                   &c->invalid, &c->winnerE, &c->record, &c->mask, &c->sed, &c->poses, &c->pass, &c->X, &c->idx,
+                   &c->invalid, &c->winnerE, &c->record, &c->merged, &c->mask, &c->sed, &c->poses, &c->pass, &c->X, &c->idx,
                    &c->scan, &c->tmp, &c->spts, &c->bounds, &c->fitflag,
                    &c->m_img, &c->m_feat, &c->m_W, &c->m_ss, &c->m_ok, &c->m_S, &c->m_out,
                    &c->h_img, &c->h_gx, &c->h_gy, &c->h_corner, &c->h_alive, &c->h_key, &c->h_idx, &c->h_small, &c->h_xy};
@@ -775,13 +776,15 @@ static const double* winner_E_dev(sfm_ctx* c) {
     return c->winner_local >= 0 ? c->E.as<double>() + 9 * c->winner_local : c->winnerE.as<double>();
 }
 
-static int mask_launch(sfm_ctx* c, double thr, const Best* best_dev) {
+static int mask_launch(sfm_ctx* c, double thr, const Best* best_dev, const double* E_override = nullptr) {
     if (int r = c->mask.reserve((size_t)c->n)) return r;
     if (int r = c->sed.reserve((size_t)c->n * 8)) return r;
     c->tic(T_MASK);
-    const double* E = best_dev ? c->E.as<double>() : winner_E_dev(c);
+    // E_override: one model on the device (the merged winner of a sharded run), used as is
+    const double* E = E_override ? E_override : (best_dev ? c->E.as<double>() : winner_E_dev(c));
     k_inlier_mask<<<(unsigned)((c->n + 255) / 256), 256, 0, c->stream>>>(
-        c->pts.as<Corr>(), c->n, E, best_dev, c->last_idx_offset, 0, thr, c->mask.as<uint8_t>(), c->sed.as<double>());
+        c->pts.as<Corr>(), c->n, E, E_override ? nullptr : best_dev, c->last_idx_offset, 0, thr, c->mask.as<uint8_t>(),
+        c->sed.as<double>());
     if (int r = check_launch(c, "k_inlier_mask")) return r;
     c->toc(T_MASK);
     return 0;
@@ -935,9 +938,9 @@ int sfm_triangulate(sfm_ctx* c, const double* P1, const double* P2, const double
 // cheirality vote -> triangulation of the passing inliers.  best_dev != null: the winner is read from K3's device
 // output, so everything is enqueued without waiting for the selection to reach the host.
 static int pose_tail_launch(sfm_ctx* c, double thr, double dist_thr, const Best* best_dev, uint8_t* mask_host = nullptr,
-                            double* sed_host = nullptr) {
+                            double* sed_host = nullptr, const double* E_override = nullptr) {
     const long long n = c->n;
-    if (int r = mask_launch(c, thr, best_dev)) return r;
+    if (int r = mask_launch(c, thr, best_dev, E_override)) return r;
     // the caller's mask is "sed <= thr" (copied before the sample points are forced in below)
     if (mask_host) CU(cudaMemcpyAsync(mask_host, c->mask.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     if (sed_host) CU(cudaMemcpyAsync(sed_host, c->sed.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -963,7 +966,9 @@ static int pose_tail_launch(sfm_ctx* c, double thr, double dist_thr, const Best*
     if (int r = check_launch(c, "k_compact_scan")) return r;
     k_compact_scatter<<<cblocks, 256, 0, c->stream>>>(c->mask.as<uint8_t>(), n, c->scan.as<long long>(), c->idx.as<long long>());
     if (int r = check_launch(c, "k_compact_scatter")) return r;
-    if (best_dev)
+    if (E_override)
+        k_decompose<<<1, 32, 0, c->stream>>>(E_override, nullptr, 0, c->poses.as<PoseSet>(), 1);
+    else if (best_dev)
         k_decompose<<<1, 32, 0, c->stream>>>(c->E.as<double>(), best_dev, c->last_idx_offset, c->poses.as<PoseSet>(), 1);
     else
         k_decompose<<<1, 32, 0, c->stream>>>(winner_E_dev(c), nullptr, 0, c->poses.as<PoseSet>(), 1);
@@ -1054,6 +1059,76 @@ int sfm_two_view(sfm_ctx* c, double thr, double min_extra, int agg, int mode, do
     // behind the selection, and the host synchronises once for all fixed-size results
     if (int r = pose_tail_launch(c, thr, dist_thr, c->best.as<Best>(), mask, sed)) return r;
     return pose_tail_fetch(c, poses, cap, num_inliers, inlier_idx, pass, X, best);
+}
+
+// ---- hypothesis-sharded runs without a host round trip -----------------------
+int sfm_score_async(sfm_ctx* c, double thr, double min_extra, int agg, int mode, void** record_dev) {
+    if (int r = use(c)) return r;
+    if (c->batched) return fail(SFM_ERR_STATE, "single-pair call on a batched context");
+    if (int r = fit_launch(c, false)) return r;
+    if (int r = score_launch(c, thr, min_extra, agg, mode, true, 0, c->n)) return r;
+    if (record_dev) *record_dev = c->record.p;  // SFM_RECORD_BYTES bytes, valid once the stream reaches this point
+    return 0;
+}
+
+int sfm_sharded_tail(sfm_ctx* c, const void* gathered_records_dev, int world, int rank, int64_t hyps_per_rank, int mode,
+                     double thr, double dist_thr) {
+    if (int r = use(c)) return r;
+    if (!gathered_records_dev || world < 1 || rank < 0 || rank >= world) return fail(SFM_ERR_ARG, "bad gather arguments");
+    if (!c->has_score) return fail(SFM_ERR_STATE, "sfm_score_async first");
+    if (mode < 0 || mode > 2) return fail(SFM_ERR_ARG, "bad selection %d", mode);
+    if (int r = c->winnerE.reserve(72)) return r;
+    if (int r = c->merged.reserve(sizeof(SelectRecord) + sizeof(Best) + 16)) return r;
+    SelectRecord* merged = c->merged.as<SelectRecord>();
+    Best* local_best = reinterpret_cast<Best*>(merged + 1);
+    int* owner = reinterpret_cast<int*>(local_best + 1);
+    k_merge_records<<<1, 32, 0, c->stream>>>(reinterpret_cast<const SelectRecord*>(gathered_records_dev), world, rank,
+                                             (long long)hyps_per_rank, mode, merged, owner, c->winnerE.as<double>(), local_best);
+    if (int r = check_launch(c, "k_merge_records")) return r;
+    return pose_tail_launch(c, thr, dist_thr, local_best, nullptr, nullptr, c->winnerE.as<double>());
+}
+
+int sfm_sharded_fetch(sfm_ctx* c, sfm_best* best, int32_t* owner, sfm_poses* poses, int64_t cap, int64_t* num_inliers,
+                      int64_t* inlier_idx, uint8_t* pass, double* X) {
+    if (int r = use(c)) return r;
+    if (!best || !owner || !poses || !num_inliers) return fail(SFM_ERR_ARG, "null argument");
+    if (!c->merged.p) return fail(SFM_ERR_STATE, "sfm_sharded_tail first");
+    const int cblocks = (int)((c->n + 1023) / 1024);
+    const long long* cnt_dev = c->scan.as<long long>() + cblocks;
+    const size_t mbytes = sizeof(SelectRecord) + sizeof(Best) + 16;
+    if (int r = ensure_pinned(c, 64 + mbytes)) return r;
+    CU(cudaMemcpyAsync(c->hpin, cnt_dev, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync((char*)c->hpin + 64, c->merged.p, mbytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(poses, c->poses.p, sizeof(PoseSet), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    long long m;
+    memcpy(&m, c->hpin, 8);
+    SelectRecord r;
+    Best lb;
+    int own;
+    memcpy(&r, (char*)c->hpin + 64, sizeof r);
+    memcpy(&lb, (char*)c->hpin + 64 + sizeof r, sizeof lb);
+    memcpy(&own, (char*)c->hpin + 64 + sizeof r + sizeof lb, sizeof own);
+    best->err = r.best.idx >= 0 ? r.best.err : __builtin_inf();
+    best->index = r.best.idx;  // GLOBAL hypothesis index
+    best->count_extra = r.best.count;
+    best->reserved = 0;
+    best->num_invalid = r.num_invalid;
+    best->first_invalid = r.first_invalid;
+    memcpy(best->E, r.E, 72);
+    *owner = own;
+    c->winner_local = lb.idx >= 0 ? lb.idx : -1;  // -1: the model lives in winnerE
+    c->winner_set = r.best.idx >= 0;
+    if (r.best.idx < 0) m = 0;
+    *num_inliers = m;
+    const long long take = m < cap ? m : cap;
+    if (take > 0) {
+        if (inlier_idx) CU(cudaMemcpyAsync(inlier_idx, c->idx.p, (size_t)take * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (pass) CU(cudaMemcpyAsync(pass, c->pass.p, (size_t)take, cudaMemcpyDeviceToHost, c->stream));
+        if (X) CU(cudaMemcpyAsync(X, c->X.p, (size_t)take * 24, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
 }
 
 // ---- batched pairs ------------------------------------------------------------------------

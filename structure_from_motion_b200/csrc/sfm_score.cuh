@@ -682,7 +682,7 @@ k_select(const Best* __restrict__ blocks, int nblocks, int mode, const uint8_t* 
         *out = b;
         invalid_out[0] = s_ninv;
         invalid_out[1] = s_ninv ? s_first : -1;
-        // everything the host wants about this pair in one 120-byte record (one D2H copy, one synchronisation)
+        // everything the host wants about this pair in one 112-byte record (one D2H copy, one synchronisation)
         SelectRecord& r = record[blockIdx.x];
         r.best = b;
         r.num_invalid = s_ninv;
@@ -690,6 +690,38 @@ k_select(const Best* __restrict__ blocks, int nblocks, int mode, const uint8_t* 
         const double* e = E + 9 * ((long long)blockIdx.x * h + (b.idx >= 0 ? b.idx - idx_offset : 0));
         for (int k = 0; k < 9; ++k) r.E[k] = b.idx >= 0 ? e[k] : 0.0;
     }
+}
+
+// Hypothesis-sharded runs: every rank's SelectRecord, gathered by one NCCL all-gather, is merged on
+// the device with the reference's rule (smallest error, earliest GLOBAL iteration on ties, ransac.py:83; or the
+// non-default modes) so that the tail can be enqueued without a host round trip.  One thread.
+//   merged      : winner with its global index (idx = owner * hyps_per_rank + local idx), this rank's invalid counters
+//   winner_E    : the winning model (the tail reads it from here whichever rank fitted it)
+//   local_best  : Best whose idx is this rank's local index if it owns the winner, else -1 (sample-row lookups)
+__global__ void k_merge_records(const SelectRecord* __restrict__ gathered, int world, int rank, long long hyps_per_rank,
+                                int mode, SelectRecord* __restrict__ merged, int* __restrict__ owner_out,
+                                double* __restrict__ winner_E, Best* __restrict__ local_best) {
+    if (threadIdx.x || blockIdx.x) return;
+    Best b;
+    b.err = 0.0; b.idx = -1; b.count = 0; b.pad = 0;
+    int owner = -1;
+    for (int r = 0; r < world; ++r) {
+        Best o = gathered[r].best;
+        if (o.idx >= 0) o.idx += (long long)r * hyps_per_rank;
+        if (better(o, b, mode)) { b = o; owner = r; }
+    }
+    merged->best = b;
+    merged->num_invalid = gathered[rank].num_invalid;
+    merged->first_invalid = gathered[rank].first_invalid;
+    for (int k = 0; k < 9; ++k) {
+        const double v = owner >= 0 ? gathered[owner].E[k] : 0.0;
+        merged->E[k] = v;
+        winner_E[k] = v;
+    }
+    *owner_out = owner;
+    Best lb = b;
+    lb.idx = (owner == rank) ? gathered[rank].best.idx : -1;
+    *local_best = lb;
 }
 
 // ------------------------------------------------------------------------------------

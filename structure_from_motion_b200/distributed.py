@@ -109,6 +109,42 @@ def ransac_essential_sharded(camera_matrix, pts_a, pts_b, threshold, min_num_ext
                 num_invalid=int(best.num_invalid))
 
 
+class _DeviceBuffer:
+    """Zero-copy view of library-owned device memory for torch (``torch.as_tensor`` reads __cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, n_doubles: int):
+        self.__cuda_array_interface__ = {"shape": (n_doubles,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+
+def two_view_sharded(threshold, min_num_extra_inliers, aggregation, hyps_per_rank: int, seed: int, *, engine, rank: int,
+                     world: int, selection: str = "min_error", distance_threshold: float = 50.0, group=None):
+    """One complete estimate (RANSAC E -> cheirality vote -> triangulation) with the hypotheses sharded over ``world``
+    GPUs and NO host round trip between scoring and the final results: every rank scores its hypotheses
+    (``sfm_score_async``), the 112-byte selection records are all-gathered device-to-device by NCCL on the engine's
+    stream — the path's only collective — and merged by a kernel with the reference's rule (``sfm_sharded_tail``),
+    which also enqueues the inlier mask, pose vote and triangulation of the global winner.  The correspondences must
+    already be resident (``engine.upload_pairs``) and the engine must run on torch's current stream.
+    Returns dict(err, index (global), count, E, owner, num_invalid, poses, num_inliers, inlier_idx, pass_bits, points)."""
+    import torch
+    import torch.distributed as dist
+
+    n_doubles = engine.RECORD_BYTES // 8
+    engine.sample_device(seed, hyps_per_rank, hyp_offset=rank * hyps_per_rank)
+    rec_ptr = engine.score_async(threshold, float(min_num_extra_inliers or 0), aggregation, selection)
+    dev = torch.device("cuda", engine.device)
+    mine = torch.as_tensor(_DeviceBuffer(rec_ptr, n_doubles), device=dev)
+    if world > 1:
+        gathered = torch.empty(world * n_doubles, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(gathered, mine, group=group)
+    else:
+        gathered = mine
+    engine.sharded_tail(gathered.data_ptr(), world, rank, hyps_per_rank, threshold, distance_threshold, selection)
+    best, owner, poses, num, idx, ok, X = engine.sharded_fetch()
+    return dict(err=float(best.err), index=int(best.index), count=int(best.count_extra),
+                E=np.array(best.E, dtype=np.float64).reshape(3, 3), owner=owner, num_invalid=int(best.num_invalid),
+                poses=poses, num_inliers=num, inlier_idx=idx, pass_bits=ok, points=X, _keep=gathered)
+
+
 def shard_pairs(offsets: Sequence[int], rank: int, world: int):
     """Pair-sharded mode: the pairs [p0, p1) this rank owns and their re-based offsets."""
     offsets = np.asarray(offsets, dtype=np.int64)

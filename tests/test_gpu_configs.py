@@ -270,3 +270,59 @@ def test_config5_scale_invariants(engine):
     assert np.degrees(np.arccos(np.clip(tg @ t_true / np.linalg.norm(t_true), -1, 1))) < 10.0
     passing = ((ok >> b) & 1).astype(bool)
     assert passing.mean() > 0.95 and np.isfinite(X[passing]).all() and (X[passing][:, 2] > 0).all()
+
+
+def test_device_side_merge_of_sharded_records(engine):
+    """sfm_sharded_tail's merge kernel against distributed.merge_best (the host rule the gloo tests pin) on crafted
+    records, and the fused sharded path with world = 1 against the plain fused call."""
+    import torch
+
+    from structure_from_motion_b200 import distributed
+
+    K, x1, x2, *_ = make_scene(4000, 0.35, seed=31)
+    engine.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        engine.upload_pairs(x1, x2, K)
+        r = distributed.two_view_sharded(THR, 10, "rms", 600, 4, engine=engine, rank=0, world=1)
+        engine.sample_device(4, 600)
+        best, _, _, poses, num, idx, ok, X = engine.two_view(THR, 10, "rms", "min_error", 50.0)
+        assert r["index"] == best.index and r["owner"] == 0 and r["err"] == best.err
+        assert r["num_inliers"] == num and np.array_equal(r["inlier_idx"], idx) and np.array_equal(r["pass_bits"], ok)
+        assert np.array_equal(r["points"], X, equal_nan=True)
+        # crafted gather: rank 2 of 4 holds the winner (a tie on the error with rank 3: the earlier global index wins),
+        # rank 0 has no candidate
+        H = 600
+        engine.sample_device(4, H, hyp_offset=1 * H)
+        ptr = engine.score_async(THR, 10, "rms")
+        mine = torch.as_tensor(distributed._DeviceBuffer(ptr, 14), device="cuda").clone()
+        torch.cuda.synchronize()
+        rec = mine.cpu().numpy().copy()  # [err, idx(bits), count|pad(bits), ninv, first, E[9]]
+        as_i64 = rec.view(np.int64)
+        rows = []
+        for rank_r, (err_scale, idx_local) in enumerate([(None, -1), (1.0, int(as_i64[1])), (0.5, 7), (0.5, 3)]):
+            row = rec.copy()
+            ri = row.view(np.int64)
+            if err_scale is None:
+                ri[1] = -1
+            else:
+                row[0] = rec[0] * err_scale
+                ri[1] = idx_local
+                row[5:] = rec[5:] * (1.0 + rank_r)  # a recognisable E per rank
+            rows.append(row)
+        gathered = torch.from_numpy(np.concatenate(rows)).cuda()
+        engine.sharded_tail(gathered.data_ptr(), 4, 1, H, THR, 50.0)
+        b, owner, poses, num, idx, ok, X = engine.sharded_fetch()
+        want = distributed.merge_best(np.array([distributed.pack_local_best(
+            rows[k][0], (k * H + int(rows[k].view(np.int64)[1])) if rows[k].view(np.int64)[1] >= 0 else -1,
+            int(rows[k].view(np.int32)[4]), rows[k][5:]) for k in range(4)]))
+        assert owner == want[0] == 2 and b.index == want[2] == 2 * H + 7 and b.err == want[1]
+        assert np.array_equal(np.array(b.E), rows[2][5:])
+        # all ranks empty
+        for row in rows:
+            row.view(np.int64)[1] = -1
+        gathered = torch.from_numpy(np.concatenate(rows)).cuda()
+        engine.sharded_tail(gathered.data_ptr(), 4, 1, H, THR, 50.0)
+        b, owner, poses, num, idx, ok, X = engine.sharded_fetch()
+        assert owner == -1 and b.index == -1 and num == 0 and np.isinf(b.err)
+    finally:
+        engine.set_stream(0)

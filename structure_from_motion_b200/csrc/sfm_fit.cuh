@@ -254,7 +254,10 @@ __device__ __forceinline__ int eight_point_fit_qr(const Corr (&c)[8], double (&E
 
 constexpr int kFitQrThreads = 64;
 
-__global__ void __launch_bounds__(kFitQrThreads)
+#ifndef SFM_FIT_MINB
+#define SFM_FIT_MINB 6  // 168 registers + 0.7 KB of L1-resident spills: 12 warps/SM instead of 8 hide the sqrt/div latency chains (config 4: 0.54 -> 0.44 ms)
+#endif
+__global__ void __launch_bounds__(kFitQrThreads, SFM_FIT_MINB)
 k_fit_qr(const Corr* __restrict__ pts, const long long* __restrict__ offsets, const int32_t* __restrict__ table,
          long long h, double* __restrict__ E_out, uint8_t* __restrict__ valid_out,
          unsigned* __restrict__ ambiguous_count) {

@@ -88,7 +88,6 @@ struct sfm_ctx {
     long long raw_stride = 1;
     bool batched = false, has_pts = false, has_table = false, has_models = false, has_score = false;
     double Kstage[9] = {0};
-    int nms_blocks = 0;  // co-resident blocks of the cooperative suppression kernel
     const void* occ_fn = nullptr;  // scoring kernel whose launch configuration is cached
     int occ_blocks = 0;
     long long winner_local = -1;  // index into E of the current winner, -1 = use winnerE
@@ -1370,31 +1369,28 @@ int sfm_harris_corners(sfm_ctx* c, const void* image, int image_dtype, int64_t r
     k_cornerness<<<gopx, 256, 0, c->stream>>>(c->h_gx.as<double>(), c->h_gy.as<double>(), (int)rows, (int)cols, block_size,
                                               k, (int)orows, (int)ocols, corner);
     if (int r = check_launch(c, "k_cornerness")) return r;
-    // non-maximum suppression: the reference's scan-order dependent result as the fixed point of parallel sweeps,
-    // iterated inside one cooperative launch (grid-wide barriers, convergence detected on the device)
-    uint8_t* alive0 = c->h_alive.as<uint8_t>();
-    uint8_t* alive1 = alive0 + opx;
-    int* d_flags = c->h_small.as<int>();             // [3] changed flags | [3] sweeps | [4] candidate count
-    int* d_sweeps = d_flags + 3;
-    unsigned* d_count = reinterpret_cast<unsigned*>(d_flags + 4);
-    CU(cudaMemsetAsync(alive0, 1, opx, c->stream));
-    CU(cudaMemsetAsync(d_flags, 0, 32, c->stream));
-    {
-        if (c->nms_blocks == 0) {
-            int occ = 0;
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_nms_fixed_point, 256, 0));
-            c->nms_blocks = (occ < 1 ? 1 : occ) * c->sm_count;
+    // non-maximum suppression: sweeps in batches of 8, one "changed" flag per sweep; a sweep that changes
+    // nothing has reached the fixed point, so only the last flag of a batch needs to be looked at
+    uint8_t* alive[2] = {c->h_alive.as<uint8_t>(), c->h_alive.as<uint8_t>() + opx};
+    int* d_changed = c->h_small.as<int>();            // [8]
+    unsigned* d_count = reinterpret_cast<unsigned*>(d_changed + 8);
+    CU(cudaMemsetAsync(alive[0], 1, opx, c->stream));
+    int cur = 0, sweeps = 0;
+    for (;;) {
+        CU(cudaMemsetAsync(d_changed, 0, 32, c->stream));
+        for (int it = 0; it < 8; ++it) {
+            k_nms_sweep<<<gopx, 256, 0, c->stream>>>(corner, (int)orows, (int)ocols, alive[cur], alive[cur ^ 1], d_changed + it);
+            if (int r = check_launch(c, "k_nms_sweep")) return r;
+            cur ^= 1;
         }
-        long long want = ((long long)opx + 255) / 256;
-        int blocks = (int)(want < c->nms_blocks ? want : c->nms_blocks);
-        const double* a_v = corner;
-        int a_rows = (int)orows, a_cols = (int)ocols, a_max = (int)((opx + 16 < 0x7fffffff) ? opx + 16 : 0x7fffffff);
-        void* kargs[] = {(void*)&a_v, (void*)&a_rows, (void*)&a_cols, (void*)&alive0, (void*)&alive1, (void*)&d_flags,
-                         (void*)&d_sweeps, (void*)&a_max};
-        CU(cudaLaunchCooperativeKernel((const void*)k_nms_fixed_point, dim3((unsigned)blocks), dim3(256), kargs, 0, c->stream));
-        if (int r = check_launch(c, "k_nms_fixed_point")) return r;
+        sweeps += 8;
+        int changed[8] = {0};
+        CU(cudaMemcpyAsync(changed, d_changed, 32, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (!changed[7]) break;
+        if ((size_t)sweeps > opx + 16) return fail(SFM_ERR_CUDA, "non-maximum suppression did not converge");
     }
-    k_nms_apply<<<gopx, 256, 0, c->stream>>>(corner, (long long)opx, alive0);
+    k_nms_apply<<<gopx, 256, 0, c->stream>>>(corner, (long long)opx, alive[cur]);
     if (int r = check_launch(c, "k_nms_apply")) return r;
     // candidates -> sort -> first num_corners
     CU(cudaMemsetAsync(d_count, 0, 4, c->stream));
@@ -1434,8 +1430,6 @@ int sfm_harris_corners(sfm_ctx* c, const void* image, int image_dtype, int64_t r
         CU(cudaMemcpyAsync(score, d_score, (size_t)found * 8, cudaMemcpyDeviceToHost, c->stream));
     }
     if (cornerness) CU(cudaMemcpyAsync(cornerness, corner, opx * 8, cudaMemcpyDeviceToHost, c->stream));
-    int sweeps = 0;
-    CU(cudaMemcpyAsync(&sweeps, d_sweeps, 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (nms_sweeps) *nms_sweeps = sweeps;
     return 0;

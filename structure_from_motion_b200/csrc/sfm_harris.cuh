@@ -21,8 +21,6 @@
 // uint8 images make every Sobel response, product and block sum an exact integer in fp64, so the
 // cornerness differs from the reference only through its LAPACK/log/exp determinant (1e-13 relative).
 #pragma once
-#include <cooperative_groups.h>
-
 #include "sfm_device.cuh"
 #include "sfm_match.cuh"
 
@@ -96,54 +94,26 @@ __global__ void k_cornerness(const double* __restrict__ gx, const double* __rest
     out[i] = v;
 }
 
-// C4.  One pixel of one sweep: alive given the previous sweep's flags.
-// The flags are rewritten by other blocks between sweeps of the same launch: they are read with ld.global.cg (L2),
-// never through the non-coherent path.
-__device__ __forceinline__ uint8_t nms_pixel(const double* __restrict__ v, int rows, int cols, long long i,
-                                             const uint8_t* alive_in) {
+// C4.  alive0: every pixel starts alive; each sweep recomputes alive from the previous sweep.
+__global__ void k_nms_sweep(const double* __restrict__ v, int rows, int cols, const uint8_t* __restrict__ alive_in,
+                            uint8_t* __restrict__ alive_out, int* __restrict__ changed) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)rows * cols) return;
     const int r = (int)(i / cols), c = (int)(i % cols);
     const double p = v[i];
-    for (int dr = -1; dr <= 1; ++dr)
+    bool alive = true;
+    for (int dr = -1; dr <= 1 && alive; ++dr)
         for (int dc = -1; dc <= 1; ++dc) {
             const int rr = r + dr, cc = c + dc;
             if ((dr == 0 && dc == 0) || rr < 0 || rr >= rows || cc < 0 || cc >= cols) continue;
             const long long j = (long long)rr * cols + cc;
             if (!(p < v[j])) continue;
             const bool earlier = dr < 0 || (dr == 0 && dc < 0);  // already visited by the row-major scan
-            if (!earlier || __ldcg(alive_in + j)) return 0;
+            if (!earlier || alive_in[j]) { alive = false; break; }
         }
-    return 1;
-}
-
-// The whole fixed point in ONE cooperative launch: grid-wide barrier between sweeps, convergence detected on the
-// device (three rotating "changed" flags: written in sweep s, read after its barrier, cleared two sweeps later).
-// alive0 starts all ones; on return alive0 holds the fixed point (the last sweep changes nothing, so both buffers
-// agree) and *sweeps_out the number of sweeps executed.
-__global__ void __launch_bounds__(256)
-k_nms_fixed_point(const double* __restrict__ v, int rows, int cols, uint8_t* alive0, uint8_t* alive1,
-                  int* flags /* [3], zeroed */, int* __restrict__ sweeps_out, int max_sweeps) {
-    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
-    const long long n = (long long)rows * cols;
-    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
-    uint8_t* in = alive0;
-    uint8_t* out = alive1;
-    int sweep = 0;
-    for (;;) {
-        bool changed = false;
-        for (long long i = tid; i < n; i += stride) {
-            const uint8_t a = nms_pixel(v, rows, cols, i, in);
-            changed |= (a != __ldcg(in + i));
-            out[i] = a;
-        }
-        if (changed) flags[sweep % 3] = 1;
-        grid.sync();
-        const int any = *reinterpret_cast<volatile int*>(flags + sweep % 3);
-        if (tid == 0) flags[(sweep + 2) % 3] = 0;
-        ++sweep;
-        if (!any || sweep >= max_sweeps) break;
-        uint8_t* t = in; in = out; out = t;
-    }
-    if (tid == 0) *sweeps_out = sweep;
+    const uint8_t a = alive ? 1 : 0;
+    if (a != alive_in[i]) *changed = 1;
+    alive_out[i] = a;
 }
 
 __global__ void k_nms_apply(double* __restrict__ v, long long n, const uint8_t* __restrict__ alive) {

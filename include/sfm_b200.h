@@ -78,6 +78,10 @@ int sfm_host_free(void *p);
  * the inliers in that order, ransac.py:70-76).  Host-only; needs no context. */
 int sfm_mt_shuffle_table(uint32_t *state625, int64_t n, int64_t h, int32_t *table, int64_t perm_at,
                          int32_t *perm_out);
+/* The same iterations continued from a caller-held permutation (perm_inout[n], updated in place; table may be NULL):
+ * lets the caller keep (state, permutation) snapshots every few iterations and replay only a short stretch to
+ * recover the permutation of the winning iteration. */
+int sfm_mt_shuffle_resume(uint32_t *state625, int64_t n, int64_t h, int32_t *table, int32_t *perm_inout);
 /* Upload a sample table (h x 8 indices into the correspondences). */
 int sfm_set_table(sfm_ctx *ctx, const int32_t *table, int64_t h);
 /* Device sampler (Philox4x32-10 keyed by seed/stream/global hypothesis index): 8 distinct

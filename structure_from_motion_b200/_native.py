@@ -51,6 +51,7 @@ _SIGNATURES = {
     "sfm_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(_P)]),
     "sfm_host_free": (C.c_int, [_P]),
     "sfm_mt_shuffle_table": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int64, _P]),
+    "sfm_mt_shuffle_resume": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
     "sfm_set_table": (C.c_int, [_P, _P, C.c_int64]),
     "sfm_sample_device": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64]),
     "sfm_get_table": (C.c_int, [_P, _P, C.c_int64, C.c_int64]),
@@ -508,6 +509,42 @@ def mt_shuffle_table(state625: np.ndarray, n: int, h: int, perm_at: int = -1):
     if st is not state625:
         state625[...] = st
     return table, perm
+
+
+class ReferenceSampler:
+    """The reference's sampling (cumulative ``random.shuffle`` + first 8, lib/ransac/ransac.py:62-63) for H iterations
+    over n items, with (state, permutation) snapshots every ``stride`` iterations so that the permutation — or the RNG
+    state — after any given iteration is recovered by replaying at most ``stride`` iterations instead of the whole run."""
+
+    SNAPSHOT_BYTES = 64 << 20
+
+    def __init__(self, state625: np.ndarray, n: int, h: int):
+        lib = load_library()
+        self.n, self.h = int(n), int(h)
+        self.stride = max(1, -(-(self.h * self.n * 4) // self.SNAPSHOT_BYTES))
+        self.table = np.empty((self.h, 8), dtype=np.int32)
+        st = np.ascontiguousarray(state625, dtype=np.uint32).copy()
+        assert st.shape == (625,)
+        perm = np.arange(self.n, dtype=np.int32)
+        self._snap = []
+        for first in range(0, self.h, self.stride):
+            self._snap.append((st.copy(), perm.copy()))
+            count = min(self.stride, self.h - first)
+            rc = lib.sfm_mt_shuffle_resume(_ptr(st), self.n, count, _ptr(self.table[first:first + count]), _ptr(perm))
+            if rc != 0:
+                raise NativeError(f"sfm_mt_shuffle_resume -> {rc}: {lib.sfm_last_error().decode()}")
+        self.final_state = st
+
+    def after(self, iteration: int):
+        """(state625, permutation) right after 0-based ``iteration``."""
+        lib = load_library()
+        k = int(iteration) // self.stride
+        st, perm = self._snap[k][0].copy(), self._snap[k][1].copy()
+        count = int(iteration) - k * self.stride + 1
+        rc = lib.sfm_mt_shuffle_resume(_ptr(st), self.n, count, None, _ptr(perm))
+        if rc != 0:
+            raise NativeError(f"sfm_mt_shuffle_resume -> {rc}: {lib.sfm_last_error().decode()}")
+        return st, perm
 
 
 def pinned_empty(shape, dtype=np.float64):

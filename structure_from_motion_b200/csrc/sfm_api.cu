@@ -315,21 +315,12 @@ int sfm_host_free(void* p) {
 }
 
 // ---- sampling ---------------------------------------------------------------------------
-int sfm_mt_shuffle_table(uint32_t* state625, int64_t n, int64_t h, int32_t* table, int64_t perm_at,
-                         int32_t* perm_out) {
-    if (!state625 || !table) return fail(SFM_ERR_ARG, "null argument");
-    if (n < 8 || n > 0x7fffffff) return fail(SFM_ERR_ARG, "need 8 <= n < 2^31 correspondences, got %lld", (long long)n);
-    if (h < 0) return fail(SFM_ERR_ARG, "negative hypothesis count");
-    if ((int)state625[624] < 0 || (int)state625[624] > 624) return fail(SFM_ERR_ARG, "bad MT position %d", (int)state625[624]);
-    PyMT g;
-    g.load(state625);
-    std::vector<int32_t> perm((size_t)n);
-    for (int64_t i = 0; i < n; ++i) perm[(size_t)i] = (int32_t)i;
+// cumulative Fisher-Yates iterations on `perm` (random.shuffle, CPython semantics); row `it` of `table` receives the
+// first 8 entries after iteration `it`
+static void mt_shuffle_rounds(PyMT& g, int32_t* pp, int64_t n, int64_t h, int32_t* table, int64_t perm_at, int32_t* perm_out) {
     for (int64_t it = 0; it < h; ++it) {
-        // random.shuffle: for i in reversed(range(1, len(x))): j = randbelow(i + 1); swap
         // j = _randbelow(i + 1) = the first getrandbits(bit_length(i + 1)) that is <= i.  Branch-free form: every
         // stream word is consumed; a rejected one swaps position i with itself and leaves i where it is.
-        int32_t* pp = perm.data();
         for (uint32_t i = (uint32_t)n - 1; i >= 1;) {
             const uint32_t r = g.next() >> __builtin_clz(i + 1);
             const uint32_t acc = r <= i ? 1u : 0u;
@@ -339,9 +330,39 @@ int sfm_mt_shuffle_table(uint32_t* state625, int64_t n, int64_t h, int32_t* tabl
             pp[j] = t;
             i -= acc;
         }
-        memcpy(table + 8 * it, perm.data(), 8 * sizeof(int32_t));
-        if (perm_out && it == perm_at) memcpy(perm_out, perm.data(), (size_t)n * sizeof(int32_t));
+        if (table) memcpy(table + 8 * it, pp, 8 * sizeof(int32_t));
+        if (perm_out && it == perm_at) memcpy(perm_out, pp, (size_t)n * sizeof(int32_t));
     }
+}
+
+static int mt_check(const uint32_t* state625, int64_t n, int64_t h) {
+    if (!state625) return fail(SFM_ERR_ARG, "null argument");
+    if (n < 8 || n > 0x7fffffff) return fail(SFM_ERR_ARG, "need 8 <= n < 2^31 correspondences, got %lld", (long long)n);
+    if (h < 0) return fail(SFM_ERR_ARG, "negative hypothesis count");
+    if ((int)state625[624] < 0 || (int)state625[624] > 624) return fail(SFM_ERR_ARG, "bad MT position %d", (int)state625[624]);
+    return 0;
+}
+
+int sfm_mt_shuffle_table(uint32_t* state625, int64_t n, int64_t h, int32_t* table, int64_t perm_at,
+                         int32_t* perm_out) {
+    if (!table) return fail(SFM_ERR_ARG, "null argument");
+    if (int r = mt_check(state625, n, h)) return r;
+    PyMT g;
+    g.load(state625);
+    std::vector<int32_t> perm((size_t)n);
+    for (int64_t i = 0; i < n; ++i) perm[(size_t)i] = (int32_t)i;
+    mt_shuffle_rounds(g, perm.data(), n, h, table, perm_at, perm_out);
+    memcpy(state625, g.mt, 624 * sizeof(uint32_t));
+    state625[624] = (uint32_t)g.pos;
+    return 0;
+}
+
+int sfm_mt_shuffle_resume(uint32_t* state625, int64_t n, int64_t h, int32_t* table, int32_t* perm_inout) {
+    if (!perm_inout) return fail(SFM_ERR_ARG, "null permutation");
+    if (int r = mt_check(state625, n, h)) return r;
+    PyMT g;
+    g.load(state625);
+    mt_shuffle_rounds(g, perm_inout, n, h, table, -1, nullptr);
     memcpy(state625, g.mt, 624 * sizeof(uint32_t));
     state625[624] = (uint32_t)g.pos;
     return 0;

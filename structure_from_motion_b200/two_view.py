@@ -96,11 +96,10 @@ def ransac_essential_arrays(
         raise ValueError("Eight feature pairs are expected.")  # epipolar_ransac.py:31-32
     eng = engine or _native.get_engine()
 
-    state0 = None
     if sampler == "reference":
         version, words, gauss = _get_state_words()
-        state0 = words.copy()
-        table, _ = _native.mt_shuffle_table(words, n, H)
+        ref_sampler = _native.ReferenceSampler(words, n, H)
+        table, words = ref_sampler.table, ref_sampler.final_state
     elif sampler == "table":
         table = np.ascontiguousarray(table, dtype=np.int32).reshape(-1, 8)
         H = table.shape[0]
@@ -120,8 +119,7 @@ def ransac_essential_arrays(
     if sampler == "reference":
         if best.num_invalid > 0 and on_degenerate == "raise":
             # the reference aborts inside iteration first_invalid: only that many shuffles happened
-            w = state0.copy()
-            _native.mt_shuffle_table(w, n, int(best.first_invalid) + 1)
+            w, _ = ref_sampler.after(int(best.first_invalid))
             _set_state_words(version, w, gauss)
         else:
             _set_state_words(version, words, gauss)
@@ -137,8 +135,7 @@ def ransac_essential_arrays(
     is_sample[sample] = True
     if sampler == "reference":
         # inliers in the reference's order: samples, then the rest of that iteration's permutation
-        w = state0.copy()
-        _, perm = _native.mt_shuffle_table(w, n, int(best.index) + 1, perm_at=int(best.index))
+        _, perm = ref_sampler.after(int(best.index))  # replayed from the nearest snapshot
         rest = perm[8:].astype(np.int64)
         extra = rest[mask[rest]]
     else:

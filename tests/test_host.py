@@ -308,3 +308,23 @@ def test_front_end_host_logic():
                                       validation_strategies=matching.ValidationStrategy.RATIO_TEST) == []
     with pytest.raises(ValueError, match="at least 1"):
         harris.detect_harris_corners(np.zeros((8, 8)), num_corners=0)
+
+
+@pytest.mark.parametrize("n,h,budget", [(500, 300, 64 << 20), (40, 1000, 4096), (1000, 77, 100_000)])
+def test_reference_sampler_snapshots(n, h, budget, monkeypatch):
+    """_native.ReferenceSampler (chunked, snapshot + short replay) against the one-shot sampler and CPython itself."""
+    monkeypatch.setattr(_native.ReferenceSampler, "SNAPSHOT_BYTES", budget)
+    random.seed(17)
+    st0 = np.array(random.getstate()[1], dtype=np.uint32)
+    rs = _native.ReferenceSampler(st0, n, h)
+    assert rs.stride == max(1, -(-(h * n * 4) // budget))
+    w = st0.copy()
+    table, _ = _native.mt_shuffle_table(w, n, h)
+    assert np.array_equal(rs.table, table) and np.array_equal(rs.final_state, w)
+    assert np.array_equal(st0, np.array(random.getstate()[1], dtype=np.uint32))  # the caller's state is not touched
+    data = list(range(n))
+    for it in range(h):
+        random.shuffle(data)
+        if it in (0, 1, h // 3, h - 2, h - 1):
+            st, perm = rs.after(it)
+            assert perm.tolist() == data and st.tolist() == list(random.getstate()[1])

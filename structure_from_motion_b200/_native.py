@@ -517,11 +517,13 @@ class ReferenceSampler:
     state — after any given iteration is recovered by replaying at most ``stride`` iterations instead of the whole run."""
 
     SNAPSHOT_BYTES = 64 << 20
+    MAX_SNAPSHOTS = 64
 
     def __init__(self, state625: np.ndarray, n: int, h: int):
         lib = load_library()
         self.n, self.h = int(n), int(h)
-        self.stride = max(1, -(-(self.h * self.n * 4) // self.SNAPSHOT_BYTES))
+        # at most MAX_SNAPSHOTS snapshots (each costs a call and two copies) and at most SNAPSHOT_BYTES of them
+        self.stride = max(1, -(-self.h // self.MAX_SNAPSHOTS), -(-(self.h * self.n * 4) // self.SNAPSHOT_BYTES))
         self.table = np.empty((self.h, 8), dtype=np.int32)
         st = np.ascontiguousarray(state625, dtype=np.uint32).copy()
         assert st.shape == (625,)

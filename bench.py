@@ -53,6 +53,29 @@ WORKLOADS = {
 }
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything libraries print to stdout during the run (NCCL's version banner, for one) goes to stderr; the
+    one JSON line is written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -251,7 +274,7 @@ def run_reference_arm(args):
                                    f"{args.steps} steps, {secs:.1f} s"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return line
 
 
@@ -277,6 +300,7 @@ def main():
         run_reference_arm(args)
         return
 
+    quiet_stdout()
     import torch
     import torch.distributed as dist
 
@@ -490,7 +514,7 @@ def main():
                            "h2d_bytes_per_step": int(n * 32 + 72), "d2h_bytes_per_step": int(d2h)}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_subprocess(args, args.workload)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -573,7 +597,7 @@ def bench_pairs(args, eng, world, rank, barrier, flush_l2, torch, dist):
             "clocks": clk,
             "gpu_launches": l1 - l0,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -646,7 +670,7 @@ def bench_config1(args, eng, world, rank, barrier, flush_l2, torch, dist):
                                     "sample": f"the UNMODIFIED reference on this exact workload: {t['seconds']:.1f} s per estimate, "
                                               "recorded in the build container by tools/time_true_reference.py (the reference "
                                               "cannot travel to the GPU box)"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -720,7 +744,7 @@ def bench_frontend(args, eng, world, rank, barrier, flush_l2, torch, dist):
                                     "sample": f"vectorised-numpy Harris on both images ({t_h:.2f} s) + {rows} of {len(o1)} rows "
                                               f"of the per-pair NCC loop, extrapolated ({t_m:.1f} s)"}
             line["parity"] = bool(np.array_equal(o1, c1) and np.array_equal(o2, c2))
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

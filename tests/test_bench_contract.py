@@ -1,0 +1,44 @@
+"""bench.py's output contract: exactly one JSON line on stdout with the keys the driver reads."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline"}
+
+
+def _run(*flags, timeout=600):
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *flags], capture_output=True, text=True,
+                         timeout=timeout, env=env, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    return json.loads(lines[0])
+
+
+def test_reference_arm_line():
+    d = _run("--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-step-seconds", "0.5")
+    assert d["impl"] == "reference" and BASE_KEYS <= set(d)
+    assert d["metric"] == "hyp x point evals/sec (fp64)" and d["unit"] == "evals/s" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and d["vs_baseline"] is None and d["dtype"] == "f64"
+
+
+@pytest.mark.gpu
+def test_native_arm_line():
+    d = _run("--steps", "2", "--warmup", "3", "--cpu-baseline-seconds", "1")
+    assert BASE_KEYS | {"roofline", "clocks", "gpu_launches"} <= set(d)
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3 and d["scaling"] == "weak" and d["data"] == "synthetic"
+    assert d["value"] > 5e11 and d["e2e"]["value"] > 5e11 and d["e2e"]["h2d_bytes_per_step"] >= 3_200_000
+    r = d["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and 0.5 < r["frac"] < 1.2
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["unit"] == "TFLOP/s"
+    assert d["gpu_launches"] >= 2 * 10 and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["kind"] == "port"
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    assert "workload" in d["config"] and "config3" in d["config"]["workload"]

@@ -637,7 +637,8 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         static const int items_per_warp = getenv("SFM_ITEMS_PER_WARP") ? atoi(getenv("SFM_ITEMS_PER_WARP")) : 32;  // tuning knob: 12 -> 32 shortens the end-of-launch tail (+1 % on config 3)
         const long long target_items = grid_blocks * kScoreWarps * items_per_warp;
         long long nsplit = (target_items + hblocks * P - 1) / (hblocks * P);
-        const long long max_split = tiles / 8 > 0 ? tiles / 8 : 1;  // keep >= 8 tiles (512 correspondences) per item
+        static const int min_tiles = getenv("SFM_MIN_TILES_PER_ITEM") ? atoi(getenv("SFM_MIN_TILES_PER_ITEM")) : 2;  // 8 -> 2: mid-size pairs (config 2) get enough items to balance the warps (+6 %)
+        const long long max_split = tiles / min_tiles > 0 ? tiles / min_tiles : 1;  // keep >= min_tiles x 64 correspondences per item
         if (nsplit > max_split) nsplit = max_split;
         const long long min_split = (max_len + kMaxItemPoints - 1) / kMaxItemPoints;  // 32-bit chunk sums cannot overflow
         if (nsplit < min_split) nsplit = min_split;

@@ -158,19 +158,6 @@ __device__ __forceinline__ int scan_step(int v, int d) {
                  : "+r"(v) : "r"(d));
     return v;
 }
-// position of the n-th (0-based) lowest set bit of m (popc(m) > n): branch-free binary search on popcounts
-__device__ __forceinline__ int nth_set_bit(unsigned m, int n) {
-    int pos = 0;
-#pragma unroll
-    for (int w = 16; w >= 1; w >>= 1) {
-        const int c = __popc(m & ((1u << w) - 1u));
-        const bool up = n >= c;
-        n -= up ? c : 0;
-        m = up ? (m >> w) : m;
-        pos += up ? w : 0;
-    }
-    return pos;
-}
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
@@ -371,30 +358,15 @@ k_score(const ScoreArgs a) {
             const uint2 rj = q[(head + (o & 255u)) & (kRing - 1)];
             __syncwarp();
             if (lane == ndone && (unsigned)lane < nrec) {  // first record not retired
-                const int take = 32 - excl;                // its survivors consumed now (may be <= 0)
+                int take = 32 - excl;                      // its survivors consumed now (may be <= 0)
                 unsigned pm = rec.x;
-                // drop the `take` lowest set bits (take < popc(pm): the record straddles the boundary)
-                if (take > 2) {
-                    pm &= ~((2u << nth_set_bit(pm, take - 1)) - 1u);
-                } else {
-                    if (take >= 1) pm &= pm - 1u;
-                    if (take == 2) pm &= pm - 1u;
-                }
+                for (; take > 0; --take) pm &= pm - 1u;
                 q[(head + lane) & (kRing - 1)].x = pm;
             }
             if (!(a.debug_flags & 1)) {
-                // this lane's survivor is the (o >> 8)-th set bit of its record.  Records mostly carry one or two
-                // survivors (a short loop); when some record in the drain carries many (high inlier rates) the whole
-                // warp takes the branch-free select instead of a long divergent loop
-                const int kth = (int)(o >> 8);
-                int bit;
-                if (__any_sync(full, kth > 2)) {
-                    bit = act ? nth_set_bit(rj.x, kth) : 0;
-                } else {
-                    unsigned pmj = rj.x;
-                    for (int k = kth; k > 0; --k) pmj &= pmj - 1u;  // drop the k lowest set bits
-                    bit = act ? (__ffs(pmj) - 1) : 0;
-                }
+                unsigned pmj = rj.x;
+                for (int k = (int)(o >> 8); k > 0; --k) pmj &= pmj - 1u;  // drop the k lowest set bits
+                const int bit = act ? (__ffs(pmj) - 1) : 0;
                 const int owner = (int)(rj.y >> 27);
                 const int i = NB - 1 - bit;                    // test index in the batch: g * HPT + j
                 const int slot = i % HPT;

@@ -17,5 +17,5 @@ eng.set_score_variant(variant, hpt, group)
 eng.upload_pairs(x1, x2, K)
 for r in range(reps):
     eng.sample_device(r, h)
-    b, _, _ = eng.ransac_essential(1.5e-6, 10, "rms", want_mask=False, want_sed=False)
+    b, _, _ = eng.ransac_essential(float(os.environ.get("SFM_THR", "1.5e-6")), 10, "rms", want_mask=False, want_sed=False)
     print("best", b.index, b.err, b.count_extra, "invalid", b.num_invalid)

@@ -80,7 +80,7 @@ struct sfm_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     // data
     Buf raw, pts, offsets, Ks, table, E, valid, eig;
-    Buf acc, count_extra, S1, S2, err, blocks, best, invalid, winnerE, spts, bounds, fitflag, record, merged;
+    Buf acc, count_extra, S1, S2, err, blocks, best, invalid, winnerE, spts, bounds, fitflag, record, merged, rows;
     Buf m_img, m_feat, m_W, m_ss, m_ok, m_S, m_out;
     Buf h_img, h_gx, h_gy, h_corner, h_alive, h_key, h_idx, h_small, h_xy;
     Buf mask, sed, poses, pass, X, idx, scan, tmp;
@@ -259,7 +259,7 @@ int sfm_destroy(sfm_ctx* c) {
     cudaStreamSynchronize(c->stream);
     Buf* bufs[] = {&c->raw, &c->pts, &c->offsets, &c->Ks, &c->table, &c->E, &c->valid, &c->eig, &c->acc,
                    &c->count_extra, &c->S1, &c->S2, &c->err, &c->blocks, &c->best,
-                   &c->invalid, &c->winnerE, &c->record, &c->merged, &c->mask, &c->sed, &c->poses, &c->pass, &c->X, &c->idx,
+                   &c->invalid, &c->winnerE, &c->record, &c->merged, &c->rows, &c->mask, &c->sed, &c->poses, &c->pass, &c->X, &c->idx,
                    &c->scan, &c->tmp, &c->spts, &c->bounds, &c->fitflag,
                    &c->m_img, &c->m_feat, &c->m_W, &c->m_ss, &c->m_ok, &c->m_S, &c->m_out,
                    &c->h_img, &c->h_gx, &c->h_gy, &c->h_corner, &c->h_alive, &c->h_key, &c->h_idx, &c->h_small, &c->h_xy};
@@ -662,6 +662,8 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         a.n = c->n;
         a.offsets = c->batched ? c->offsets.as<long long>() : nullptr;
         a.E = c->E.as<double>();
+        if (int r = c->rows.reserve(H * sizeof(ModelRow))) return r;
+        a.rows = c->rows.as<ModelRow>();
         a.h = h;
         a.thr = thr;
         a.thr_pre = thr_pre;
@@ -678,6 +680,8 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         acc_dev = a.acc;
         c->tic(T_SCORE);
         CU(cudaMemsetAsync(c->acc.p, 0, H * kAccWords * 8 + 64, c->stream));
+        k_pad_models<<<(unsigned)((H + 255) / 256), 256, 0, c->stream>>>(c->E.as<double>(), (long long)H, c->rows.as<ModelRow>());
+        if (int r = check_launch(c, "k_pad_models")) return r;
         if (screen) {
             CU(cudaMemsetAsync(c->bounds.p, 0, 16, c->stream));
             if (f32)

@@ -125,6 +125,25 @@ constexpr double kKappaCoef = 4e-20;
 constexpr double kKappa32Coef = 1.2e-10;   // fp32 pre-filter, see the K2 header
 constexpr double kThr32Factor = 1.0316;   // (1 + 1/64)^2 (1 + 1e-4)
 
+// One model padded to 96 bytes = three 32-byte sectors: the survivor path gathers a candidate's row with three
+// 256-bit loads (one sector each) instead of nine 8-byte loads that straddle 3-4 sectors - the gather was the
+// L1TEX-bound part of the drain (ncu at a 7 % inlier rate: l1tex 76 % busy).
+struct __align__(32) ModelRow {
+    double4 a, b, c;  // e0..e3 | e4..e7 | e8, pad
+};
+static_assert(sizeof(ModelRow) == 96, "ModelRow must be three sectors");
+
+__global__ void __launch_bounds__(256) k_pad_models(const double* __restrict__ E, long long htotal, ModelRow* __restrict__ rows) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= htotal) return;
+    const double* e = E + 9 * i;
+    ModelRow r;
+    r.a = make_double4(e[0], e[1], e[2], e[3]);
+    r.b = make_double4(e[4], e[5], e[6], e[7]);
+    r.c = make_double4(e[8], 0.0, 0.0, 0.0);
+    rows[i] = r;
+}
+
 struct ScoreArgs {
     const Corr* pts;           // K-normalised correspondences (exact scorer)
     const void* spts;          // screening copy: Corr (xa/s, ya/s, xb, yb), or Corr32 for the fp32 pre-filter
@@ -132,6 +151,7 @@ struct ScoreArgs {
     long long n;
     const long long* offsets;  // [npairs+1] or null (single pair of n records)
     const double* E;           // [npairs][h][9]
+    const ModelRow* rows;      // [npairs][h] padded copies of E for the survivor path
     long long h;
     double thr, thr_pre, s;    // s = sqrt(thr_pre) (SCREEN)
     double kappa_coef;         // kKappaCoef * (1 + thr)
@@ -292,7 +312,7 @@ k_score(const ScoreArgs a) {
         // this warp's hypotheses: lane l, slot j  ->  hyp_w + 32*j + l
         const long long hyp_w = (long long)hw * (32 * HPT);
         const double* Ep = a.E + 9 * (long long)pair * a.h;
-        const double* Ew = Ep + 9 * hyp_w;   // this warp's models
+        const ModelRow* Rw = a.rows + (long long)pair * a.h + hyp_w;  // this warp's models, padded (survivor path)
         const Corr* pbeg = a.pts + begin;    // this item's correspondences (exact copies)
         const P* src = reinterpret_cast<const P*>(SCREEN ? a.spts : (const void*)a.pts);
 
@@ -373,10 +393,10 @@ k_score(const ScoreArgs a) {
                 const unsigned rel = act ? (rj.y & 0x3fffffu) + (unsigned)(i / HPT) : 0u;
                 // padding hypotheses never survive the screen, so an active entry is a real hypothesis
                 const unsigned hl = act ? (unsigned)(32 * slot + owner) : 0u;
-                const double* er = Ew + 9u * hl;
-                double eo[9];
-#pragma unroll
-                for (int kk = 0; kk < 9; ++kk) eo[kk] = __ldg(er + kk);
+                const ModelRow* er = Rw + hl;
+                const double4 r0 = er->a, r1 = er->b;
+                const double r2 = er->c.x;
+                const double eo[9] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2};
                 const Corr c = pbeg[rel];
                 const double sv = sed_exact(eo, c.xa, c.ya, c.xb, c.yb);
                 if (act && (sv <= a.thr)) {  // ransac.py:73  score <= threshold

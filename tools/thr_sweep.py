@@ -17,11 +17,14 @@ eng.fit(want_E=False)
 eng.enable_timing(True)
 print("thr        variant   ms      evals/s     mean inliers per hypothesis")
 for thr in (1.5e-8, 1.5e-7, 1.5e-6, 1.5e-5, 1.5e-4, 1.5e-3):
-    for v, hpt, g in (("screen", 2, 16), ("full", 2, 16), ("screen32", 4, 8)):
+    shapes = (("screen", 2, 16), ("full", 2, 16), ("screen32", 4, 8))
+    if "--shapes" in sys.argv:
+        shapes = (("screen", 1, 32), ("screen", 2, 16), ("screen", 4, 8), ("full", 1, 32), ("full", 4, 8))
+    for v, hpt, g in shapes:
         eng.set_score_variant(v, hpt, g)
         ts = []
         for r in range(3):
             cnt, _, _, _ = eng.score(thr, 10, "rms")
             t, _ = eng.get_timing()
             ts.append(t["score"])
-        print(f"{thr:8.1e}  {v:9s} {min(ts[1:]):7.3f}  {n * h / min(ts[1:]) * 1e3:.3e}   {np.maximum(cnt, 0).mean():.1f}")
+        print(f"{thr:8.1e}  {v:9s} hpt {hpt} {min(ts[1:]):7.3f}  {n * h / min(ts[1:]) * 1e3:.3e}   {np.maximum(cnt, 0).mean():.1f}")

@@ -58,8 +58,11 @@ int sfm_device_count(void);
 int sfm_create(int device, sfm_ctx **out);
 int sfm_destroy(sfm_ctx *ctx);
 /* Use an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the
- * context's own stream. */
+ * context's own (non-blocking) stream. */
 int sfm_set_stream(sfm_ctx *ctx, void *cuda_stream);
+/* Use the legacy default stream (cudaStreamLegacy) - what a framework's "default stream" handle 0 means; needed
+ * when the context's work has to be ordered with that stream's work (NCCL collectives, timing events). */
+int sfm_use_default_stream(sfm_ctx *ctx);
 int sfm_synchronize(sfm_ctx *ctx);
 /* hyps_per_thread: essential matrices per thread (1, 2, 4; fp32 pre-filter: 2, 4, 8); group:
  * correspondences per vote (hyps_per_thread * group <= 32 tests per lane and vote); 0 keeps the

@@ -46,6 +46,7 @@ _SIGNATURES = {
     "sfm_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "sfm_destroy": (C.c_int, [_P]),
     "sfm_set_stream": (C.c_int, [_P, _P]),
+    "sfm_use_default_stream": (C.c_int, [_P]),
     "sfm_synchronize": (C.c_int, [_P]),
     "sfm_set_score_variant": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     "sfm_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(_P)]),
@@ -171,7 +172,15 @@ class Engine:
             pass
 
     def set_stream(self, cuda_stream_ptr):
-        self._ck(self.lib.sfm_set_stream(self.h, _P(cuda_stream_ptr) if cuda_stream_ptr else None), "sfm_set_stream")
+        """Run on an external stream: a cudaStream_t handle, 0 = the legacy default stream (what
+        ``torch.cuda.default_stream().cuda_stream`` is), None = back to the engine's own non-blocking stream.  The
+        engine must share a stream with whatever it has to be ordered with (NCCL collectives, timing events)."""
+        if cuda_stream_ptr is None:
+            self._ck(self.lib.sfm_set_stream(self.h, None), "sfm_set_stream")
+        elif int(cuda_stream_ptr) == 0:
+            self._ck(self.lib.sfm_use_default_stream(self.h), "sfm_use_default_stream")
+        else:
+            self._ck(self.lib.sfm_set_stream(self.h, _P(int(cuda_stream_ptr))), "sfm_set_stream")
 
     def synchronize(self):
         self._ck(self.lib.sfm_synchronize(self.h), "sfm_synchronize")

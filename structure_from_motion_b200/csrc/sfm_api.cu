@@ -280,6 +280,12 @@ int sfm_set_stream(sfm_ctx* c, void* s) {
     return 0;
 }
 
+int sfm_use_default_stream(sfm_ctx* c) {
+    if (int r = use(c)) return r;
+    c->stream = cudaStreamLegacy;
+    return 0;
+}
+
 int sfm_synchronize(sfm_ctx* c) {
     if (int r = use(c)) return r;
     CU(cudaStreamSynchronize(c->stream));

@@ -325,4 +325,4 @@ def test_device_side_merge_of_sharded_records(engine):
         b, owner, poses, num, idx, ok, X = engine.sharded_fetch()
         assert owner == -1 and b.index == -1 and num == 0 and np.isinf(b.err)
     finally:
-        engine.set_stream(0)
+        engine.set_stream(None)

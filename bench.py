@@ -318,7 +318,7 @@ def main():
     eng = _native.get_engine(local_rank)
     eng.set_score_variant(args.variant, args.hpt, args.group)
     stream = torch.cuda.current_stream()
-    eng.set_stream(stream.cuda_stream)
+    eng.set_stream(stream.cuda_stream)  # torch's default stream: the flush, the timing events, NCCL and the engine in one order
 
     def barrier():
         if world > 1:

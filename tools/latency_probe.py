@@ -10,6 +10,8 @@ from structure_from_motion_b200 import _native  # noqa: E402
 from structure_from_motion_b200.scenes import make_scene  # noqa: E402
 
 eng = _native.get_engine(0)
+if os.environ.get("SFM_PROBE_DEFAULT_STREAM"):
+    eng.set_stream(0)
 K, x1, x2, *_ = make_scene(200, 0.3, seed=0)
 
 

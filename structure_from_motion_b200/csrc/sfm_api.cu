@@ -80,7 +80,7 @@ struct sfm_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     // data
     Buf raw, pts, offsets, Ks, table, E, valid, eig;
-    Buf acc, count_extra, S1, S2, err, blocks, best, invalid, winnerE, spts, bounds, fitflag, record, merged, rows;
+    Buf acc, count_extra, S1, S2, err, blocks, best, invalid, winnerE, spts, bounds, fitflag, record, merged, rows, blockinv;
     Buf m_img, m_feat, m_W, m_ss, m_ok, m_S, m_out;
     Buf h_img, h_gx, h_gy, h_corner, h_alive, h_key, h_idx, h_small, h_xy;
     Buf mask, sed, poses, pass, X, idx, scan, tmp;
@@ -259,7 +259,7 @@ int sfm_destroy(sfm_ctx* c) {
     cudaStreamSynchronize(c->stream);
     Buf* bufs[] = {&c->raw, &c->pts, &c->offsets, &c->Ks, &c->table, &c->E, &c->valid, &c->eig, &c->acc,
                    &c->count_extra, &c->S1, &c->S2, &c->err, &c->blocks, &c->best,
-                   &c->invalid, &c->winnerE, &c->record, &c->merged, &c->rows, &c->mask, &c->sed, &c->poses, &c->pass, &c->X, &c->idx,
+                   &c->invalid, &c->winnerE, &c->record, &c->merged, &c->rows, &c->blockinv, &c->mask, &c->sed, &c->poses, &c->pass, &c->X, &c->idx,
                    &c->scan, &c->tmp, &c->spts, &c->bounds, &c->fitflag,
                    &c->m_img, &c->m_feat, &c->m_W, &c->m_ss, &c->m_ok, &c->m_S, &c->m_out,
                    &c->h_img, &c->h_gx, &c->h_gy, &c->h_corner, &c->h_alive, &c->h_key, &c->h_idx, &c->h_small, &c->h_xy};
@@ -730,10 +730,12 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
     f.S2 = c->S2.as<double>();
     f.err = c->err.as<double>();
     f.block_out = c->blocks.as<Best>();
+    if (int r = c->blockinv.reserve((size_t)fblocks * P * 16)) return r;
+    f.block_inv = c->blockinv.as<long long>();
     k_finalise<<<dim3((unsigned)fblocks, (unsigned)P), 256, 0, c->stream>>>(f);
     if (int r = check_launch(c, "k_finalise")) return r;
     if (int r = c->record.reserve((size_t)P * sizeof(SelectRecord))) return r;
-    k_select<<<(unsigned)P, 256, 0, c->stream>>>(c->blocks.as<Best>(), fblocks, mode, c->valid.as<uint8_t>(), h,
+    k_select<<<(unsigned)P, 256, 0, c->stream>>>(c->blocks.as<Best>(), fblocks, mode, c->blockinv.as<long long>(), h,
                                                   idx_offset, c->best.as<Best>(), c->invalid.as<long long>(),
                                                   c->E.as<double>(), c->record.as<SelectRecord>());
     if (int r = check_launch(c, "k_select")) return r;

@@ -612,6 +612,7 @@ struct FinalArgs {
     double* S2;
     double* err;
     Best* block_out;
+    long long* block_inv;  // [npairs][blocks][2]: invalid hypotheses in the block, smallest global index among them
 };
 
 __global__ void __launch_bounds__(256) k_finalise(const FinalArgs a) {
@@ -661,14 +662,27 @@ __global__ void __launch_bounds__(256) k_finalise(const FinalArgs a) {
         a.err[i] = cand ? err : __longlong_as_double(0x7ff0000000000000LL);
         if (cand) { b.err = err; b.idx = a.idx_offset + li; b.count = (int)cnt; }
     }
+    // invalid hypotheses of this block (ransac.py:65 has no try/except: one degenerate sample aborts the reference run,
+    // so the host needs their number and the earliest one)
+    __shared__ long long s_first;
+    if (threadIdx.x == 0) s_first = 0x7fffffffffffffffLL;
+    const bool inv = (li < a.h) && a.valid && (a.valid[i] == 0);
+    const int ninv = __syncthreads_count(inv);
+    if (inv) atomicMin(&s_first, a.idx_offset + li);
     b = block_best(b, a.mode, sm);
-    if (threadIdx.x == 0) a.block_out[(long long)blockIdx.y * gridDim.x + blockIdx.x] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const long long blk = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+        a.block_out[blk] = b;
+        a.block_inv[2 * blk] = ninv;
+        a.block_inv[2 * blk + 1] = s_first;
+    }
 }
 
 // Single block: reduce per-block bests; also counts invalid hypotheses (ransac.py:65 has no
 // try/except around the fitter, so one degenerate sample aborts the reference run).
 __global__ void __launch_bounds__(256)
-k_select(const Best* __restrict__ blocks, int nblocks, int mode, const uint8_t* __restrict__ valid,
+k_select(const Best* __restrict__ blocks, int nblocks, int mode, const long long* __restrict__ block_inv,
          long long h, long long idx_offset, Best* __restrict__ out, long long* __restrict__ invalid_out,
          const double* __restrict__ E, SelectRecord* __restrict__ record) {
     __shared__ Best sm[32];
@@ -677,7 +691,7 @@ k_select(const Best* __restrict__ blocks, int nblocks, int mode, const uint8_t* 
     __syncthreads();
     // blockIdx.x = image pair
     blocks += (long long)blockIdx.x * nblocks;
-    if (valid) valid += (long long)blockIdx.x * h;
+    block_inv += 2 * (long long)blockIdx.x * nblocks;
     out += blockIdx.x;
     invalid_out += 2 * (long long)blockIdx.x;
     Best b;
@@ -687,14 +701,13 @@ k_select(const Best* __restrict__ blocks, int nblocks, int mode, const uint8_t* 
         if (better(o, b, mode)) b = o;
     }
     long long ninv = 0, first = 0x7fffffffffffffffLL;
-    if (valid) {
-        for (long long i = threadIdx.x; i < h; i += blockDim.x) {
-            if (!valid[i]) { ++ninv; if (i + idx_offset < first) first = i + idx_offset; }
-        }
-        if (ninv) {
-            atomicAdd((unsigned long long*)&s_ninv, (unsigned long long)ninv);
-            atomicMin(&s_first, first);
-        }
+    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) {  // per-block counts from k_finalise
+        ninv += block_inv[2 * i];
+        if (block_inv[2 * i + 1] < first) first = block_inv[2 * i + 1];
+    }
+    if (ninv) {
+        atomicAdd((unsigned long long*)&s_ninv, (unsigned long long)ninv);
+        atomicMin(&s_first, first);
     }
     b = block_best(b, mode, sm);
     __syncthreads();

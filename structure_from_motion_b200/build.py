@@ -8,6 +8,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "sfm_api.cu")
+HOST_SRC = os.path.join(HERE, "csrc", "sfm_sampler.cpp")  # host-only translation unit (straight to the host compiler)
 SO = os.path.join(HERE, "libsfm_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -39,7 +40,7 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return SO
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", SO + ".tmp", SRC]
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", SO + ".tmp", SRC, HOST_SRC]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

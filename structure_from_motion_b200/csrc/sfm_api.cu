@@ -39,6 +39,16 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
+}  // namespace
+
+// error setter for the host-only translation units (sfm_sampler.cpp)
+int sfm_internal_set_error(int code, const char* message) {
+    g_err = message;
+    return code;
+}
+
+namespace {
+
 #define CU(call)                                                                                   \
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \
@@ -164,46 +174,6 @@ const void* score_kernel(int variant, int hpt, int group) {
     return nullptr;
 }
 
-// ---------------------------------------------------------------------------------------
-// CPython random: MT19937 + shuffle()  (lib/ransac/ransac.py:62 uses random.shuffle)
-// ---------------------------------------------------------------------------------------
-struct PyMT {
-    uint32_t mt[624];
-    uint32_t out[624];  // tempered outputs of the current block (filled per twist: straight-line, vectorisable)
-    int pos;
-    static inline uint32_t twist(uint32_t u, uint32_t v, uint32_t m) {
-        const uint32_t y = (u & 0x80000000u) | (v & 0x7fffffffu);
-        return m ^ (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu);
-    }
-    void temper_block() {
-        for (int k = 0; k < 624; ++k) {
-            uint32_t y = mt[k];
-            y ^= y >> 11;
-            y ^= (y << 7) & 0x9d2c5680u;
-            y ^= (y << 15) & 0xefc60000u;
-            y ^= y >> 18;
-            out[k] = y;
-        }
-    }
-    void regenerate() {
-        int k = 0;
-        for (; k < 624 - 397; ++k) mt[k] = twist(mt[k], mt[k + 1], mt[k + 397]);
-        for (; k < 623; ++k) mt[k] = twist(mt[k], mt[k + 1], mt[k - (624 - 397)]);
-        mt[623] = twist(mt[623], mt[0], mt[396]);
-        temper_block();
-        pos = 0;
-    }
-    void load(const uint32_t* state625) {
-        memcpy(mt, state625, 624 * sizeof(uint32_t));
-        pos = (int)state625[624];
-        temper_block();
-    }
-    inline uint32_t next() {
-        if (pos >= 624) regenerate();
-        return out[pos++];
-    }
-};
-
 }  // namespace
 
 extern "C" {
@@ -321,59 +291,6 @@ int sfm_host_free(void* p) {
 }
 
 // ---- sampling ---------------------------------------------------------------------------
-// cumulative Fisher-Yates iterations on `perm` (random.shuffle, CPython semantics); row `it` of `table` receives the
-// first 8 entries after iteration `it`
-static void mt_shuffle_rounds(PyMT& g, int32_t* pp, int64_t n, int64_t h, int32_t* table, int64_t perm_at, int32_t* perm_out) {
-    for (int64_t it = 0; it < h; ++it) {
-        // j = _randbelow(i + 1) = the first getrandbits(bit_length(i + 1)) that is <= i.  Branch-free form: every
-        // stream word is consumed; a rejected one swaps position i with itself and leaves i where it is.
-        for (uint32_t i = (uint32_t)n - 1; i >= 1;) {
-            const uint32_t r = g.next() >> __builtin_clz(i + 1);
-            const uint32_t acc = r <= i ? 1u : 0u;
-            const uint32_t j = acc ? r : i;
-            const int32_t t = pp[i];
-            pp[i] = pp[j];
-            pp[j] = t;
-            i -= acc;
-        }
-        if (table) memcpy(table + 8 * it, pp, 8 * sizeof(int32_t));
-        if (perm_out && it == perm_at) memcpy(perm_out, pp, (size_t)n * sizeof(int32_t));
-    }
-}
-
-static int mt_check(const uint32_t* state625, int64_t n, int64_t h) {
-    if (!state625) return fail(SFM_ERR_ARG, "null argument");
-    if (n < 8 || n > 0x7fffffff) return fail(SFM_ERR_ARG, "need 8 <= n < 2^31 correspondences, got %lld", (long long)n);
-    if (h < 0) return fail(SFM_ERR_ARG, "negative hypothesis count");
-    if ((int)state625[624] < 0 || (int)state625[624] > 624) return fail(SFM_ERR_ARG, "bad MT position %d", (int)state625[624]);
-    return 0;
-}
-
-int sfm_mt_shuffle_table(uint32_t* state625, int64_t n, int64_t h, int32_t* table, int64_t perm_at,
-                         int32_t* perm_out) {
-    if (!table) return fail(SFM_ERR_ARG, "null argument");
-    if (int r = mt_check(state625, n, h)) return r;
-    PyMT g;
-    g.load(state625);
-    std::vector<int32_t> perm((size_t)n);
-    for (int64_t i = 0; i < n; ++i) perm[(size_t)i] = (int32_t)i;
-    mt_shuffle_rounds(g, perm.data(), n, h, table, perm_at, perm_out);
-    memcpy(state625, g.mt, 624 * sizeof(uint32_t));
-    state625[624] = (uint32_t)g.pos;
-    return 0;
-}
-
-int sfm_mt_shuffle_resume(uint32_t* state625, int64_t n, int64_t h, int32_t* table, int32_t* perm_inout) {
-    if (!perm_inout) return fail(SFM_ERR_ARG, "null permutation");
-    if (int r = mt_check(state625, n, h)) return r;
-    PyMT g;
-    g.load(state625);
-    mt_shuffle_rounds(g, perm_inout, n, h, table, -1, nullptr);
-    memcpy(state625, g.mt, 624 * sizeof(uint32_t));
-    state625[624] = (uint32_t)g.pos;
-    return 0;
-}
-
 int sfm_set_table(sfm_ctx* c, const int32_t* table, int64_t h) {
     if (int r = use(c)) return r;
     if (!table || h <= 0) return fail(SFM_ERR_ARG, "bad table");

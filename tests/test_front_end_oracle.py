@@ -157,3 +157,47 @@ def test_front_end_matches_live_reference(matching_golden, harris_golden):
     corners = ref.harris.detect_harris_corners(img, num_corners=15)
     xy, _, _ = fe.harris_corners(img, 15)
     assert sorted((float(c.x), float(c.y)) for c in corners) == sorted(map(tuple, xy))
+
+
+# ---- property-based checks (the reference's own suite uses hypothesis for its geometry tests) ----
+from hypothesis import given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+_scores = st.lists(st.one_of(st.integers(0, 6).map(float), st.floats(0, 2, allow_nan=False), st.just(float("inf"))),
+                   min_size=1, max_size=80)
+
+
+@settings(max_examples=150, deadline=None)
+@given(_scores)
+def test_heap_closed_form_property(scores):
+    """heap[0] / heap[1] of the reference's per-feature heapq, without the heap: any length, ties, infinities."""
+    assert fe.heap_top2(scores) == fe.heap_top2_closed_form(scores)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(1, 14), st.integers(1, 14), st.integers(0, 2 ** 32 - 1), st.booleans())
+def test_nms_fixed_point_property(rows, cols, seed, ties):
+    """The parallel fixed point equals the reference's in-place row-major scan on arbitrary non-negative images."""
+    rng = np.random.default_rng(seed)
+    v = rng.integers(0, 4, (rows, cols)).astype(float) if ties else rng.random((rows, cols))
+    seq = v.copy()
+    fe.non_max_suppress(seq)
+    fp, sweeps = fe.non_max_suppress_fixed_point(v)
+    assert np.array_equal(seq, fp) and sweeps <= rows * cols + 1
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(2, 12), st.integers(1, 12), st.integers(0, 2 ** 32 - 1), st.booleans(), st.booleans(),
+       st.floats(0.05, 1.5))
+def test_matcher_cross_check_is_an_injection(na, nb, seed, ratio, many_ties, thr):
+    """With CROSSCHECK every feature of B is used at most once and each kept match is the lowest-scored (earliest on
+    ties) surviving match of its B feature (matching.py:100-118)."""
+    rng = np.random.default_rng(seed)
+    S = rng.integers(0, 3, (na, nb)).astype(float) if many_ties else rng.random((na, nb))
+    kept = fe.match_from_scores(S, ratio, True, thr)
+    bs = [b for _, b, _ in kept]
+    assert len(set(bs)) == len(bs)
+    survivors = fe.match_from_scores(S, ratio, False, thr)
+    for a, b, s in kept:
+        rivals = [(s2, a2) for a2, b2, s2 in survivors if b2 == b]
+        assert (s, a) == min(rivals)

@@ -635,9 +635,9 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
     f.idx_offset = idx_offset;
     f.htotal = (long long)H;
     f.acc = acc_dev;
-    f.inv_scale1 = ldexp(1.0, e2 - 63);
+    f.inv_scale1 = ldexp(1.0, e2 - kFixedBits);
     f.sums = sums;
-    f.inv_scale2 = ldexp(1.0, 2 * e2 - 63);
+    f.inv_scale2 = ldexp(1.0, 2 * e2 - kFixedBits);
     f.thr = thr;
     f.min_extra = min_extra;
     f.agg = agg;

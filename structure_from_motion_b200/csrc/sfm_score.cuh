@@ -116,7 +116,8 @@ constexpr int kTile = SFM_SCORE_TILE;     // correspondences per stage (2 KB)
 constexpr int kStages = SFM_SCORE_STAGES;
 constexpr int kRing = 64;     // survivor records per warp: < 32 pending + <= 32 new
 constexpr unsigned kMaxPoints = 1u << 25;
-constexpr int kChunks = 3;             // 21-bit chunks of a 63-bit fixed-point term
+constexpr int kChunks = 4;             // 21-bit chunks of an 84-bit fixed-point term
+constexpr int kFixedBits = 21 * kChunks;  // 2^kFixedBits = scaled value of 2^e (thr < 2^e)
 constexpr int kChunkBits = 21;
 constexpr int kAccWords = 1 + 2 * kChunks;  // count, sum(sed), sum(sed^2)
 constexpr long long kMaxItemPoints = 1ll << 11;  // 2^11 adds of < 2^21 cannot overflow a 32-bit word
@@ -184,13 +185,18 @@ __device__ __forceinline__ unsigned lanemask_lt() {
     return m;
 }
 
-// three 21-bit chunks of V = rn(x * scale) < 2^63 (x <= thr < 2^e, scale = 2^(63-e)): c[2] is the most
-// significant.  One multiply, one conversion, five integer instructions.
+// four 21-bit chunks of V = floor(x * 2^(84-e)) < 2^84 (x <= thr < 2^e; `scale` = 2^(63-e)): c[3] is the most
+// significant.  The top 63 bits come from one conversion, the low 21 from the exact remainder, so terms down to
+// 2^-84 of the threshold scale enter the sum (a 63-bit term lost up to 1e-7 of a sum of squares whose inliers were
+// a thousand times tighter than the threshold).  Truncation keeps every chunk < 2^21.
 __device__ __forceinline__ void chunks21(double x, double scale, unsigned (&c)[kChunks]) {
-    const unsigned long long v = __double2ull_rn(x * scale);
-    c[0] = (unsigned)v & 0x1fffffu;
-    c[1] = (unsigned)(v >> kChunkBits) & 0x1fffffu;
-    c[2] = (unsigned)(v >> (2 * kChunkBits));
+    const double t = x * scale;                            // < 2^63
+    const unsigned long long v = __double2ull_rz(t);       // floor (t >= 0)
+    const double rem = t - __ull2double_rz(v);             // exact: v == t when t >= 2^53
+    c[0] = (unsigned)__double2uint_rz(rem * 2097152.0);    // 2^21
+    c[1] = (unsigned)v & 0x1fffffu;
+    c[2] = (unsigned)(v >> kChunkBits) & 0x1fffffu;
+    c[3] = (unsigned)(v >> (2 * kChunkBits));
 }
 
 // fp32 twin of the screening record
@@ -583,7 +589,7 @@ __device__ __forceinline__ Best block_best(Best b, int mode, Best* sm /* 32 */) 
     return b;  // valid in thread 0
 }
 
-// sum_k plane[k] * 2^(21k) as a double; plane sums are < 2^21 * N each, the total < 2^63 * N.
+// sum_k plane[k] * 2^(21k) as a double; plane sums are < 2^21 * N each, the total < 2^84 * N < 2^128.
 __device__ __forceinline__ double fixed_to_double(const unsigned long long* acc, long long stride) {
     unsigned __int128 v = 0;
 #pragma unroll

@@ -96,13 +96,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 //   (>= u^2 [2113 thr B^2 + 16640 A^2 B^2]); ~2 % more survivors than the fp64 screen.
 //
 // Order-independent accumulation.  An inlier's sed (or sed^2 — only the sum the aggregation
-// method needs is accumulated unless both are requested) is converted to a 63-bit fixed-point
-// integer scaled so that thr < 2^e maps below 2^63, split into three 21-bit chunks and added with
+// method needs is accumulated unless both are requested) is converted to an 84-bit fixed-point
+// integer scaled so that thr < 2^e maps below 2^84, split into four 21-bit chunks and added with
 // native 32-bit shared-memory atomics (a word cannot overflow within an item of <= 2^11
 // correspondences); chunks are folded into 64-bit global accumulators at the end of the item.
 // Integer addition is associative, so the sums are independent of warp scheduling, split count
 // and GPU count — run-to-run deterministic by construction; every term >= thr * 2^-10 enters
-// without rounding, smaller ones are rounded at 2^-63 of the scale (<= 1e-19 thr per term).
+// without rounding, smaller ones are truncated at 2^-84 of the scale (<= 6e-26 thr per term).
 // ------------------------------------------------------------------------------------
 constexpr int kScoreThreads = 128;
 constexpr int kScoreWarps = kScoreThreads / 32;

@@ -1,7 +1,8 @@
 """Randomised parity sweeps (tools/fuzz_scorer.py, tools/fuzz_pipeline.py) in a size that fits the test budget: random
 problem sizes (8 .. 20 000 correspondences, 1 .. 4 097 hypotheses), thresholds over ten decades, outlier fractions
 0 .. 0.9, every scoring variant and aggregation method — counts bit-equal to the exact C scorer, sums within 1e-12,
-same winner; and the whole estimate (winner, E, inliers, pose, points, no-model cases) against the numpy restatement."""
+same winner; the whole estimate (winner, E, inliers, pose, points, no-model cases) against the numpy restatement;
+the matcher (scores, selection, validations) and the Harris detector against oracle/front_end.py."""
 import os
 import subprocess
 import sys
@@ -12,7 +13,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("script,cases", [("fuzz_scorer.py", 25), ("fuzz_pipeline.py", 12)])
+@pytest.mark.parametrize("script,cases", [("fuzz_scorer.py", 25), ("fuzz_pipeline.py", 12), ("fuzz_front_end.py", 30)])
 def test_fuzz(script, cases):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", script), str(cases)], capture_output=True, text=True,
                          timeout=900, cwd=ROOT)

@@ -3,7 +3,8 @@ problem sizes (8 .. 20 000 correspondences, 1 .. 4 097 hypotheses), thresholds o
 0 .. 0.9, every scoring variant and aggregation method — counts bit-equal to the exact C scorer, sums within 1e-12,
 same winner; the whole estimate (winner, E, inliers, pose, points, no-model cases) against the numpy restatement;
 the matcher (scores, selection, validations) and the Harris detector against oracle/front_end.py; ragged pair batches
-(empty pairs, fewer than eight correspondences, every selection mode) against the single-pair pipeline."""
+(empty pairs, fewer than eight correspondences, every selection mode) against the single-pair pipeline; the drop-in list API (E, inlier pairs in order, global RNG state, exception types)
+against the restatement."""
 import os
 import subprocess
 import sys
@@ -14,7 +15,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("script,cases", [("fuzz_scorer.py", 25), ("fuzz_pipeline.py", 12), ("fuzz_front_end.py", 30), ("fuzz_batch.py", 15)])
+@pytest.mark.parametrize("script,cases", [("fuzz_scorer.py", 25), ("fuzz_pipeline.py", 12), ("fuzz_front_end.py", 30), ("fuzz_batch.py", 15), ("fuzz_list_api.py", 24)])
 def test_fuzz(script, cases):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", script), str(cases)], capture_output=True, text=True,
                          timeout=900, cwd=ROOT)

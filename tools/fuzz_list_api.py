@@ -1,0 +1,80 @@
+"""One-off fuzz of the drop-in entry point (lists of Feature / Match, CPython-exact sampling on the global ``random``
+state) against the numpy restatement of the reference: same E, same inlier pairs in the same order, same RNG state
+afterwards, same exception type in the failure cases (no model, degenerate minimal sample).
+usage: python tools/fuzz_list_api.py [cases]"""
+import os
+import random
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from lib.common.feature import Feature  # noqa: E402
+from lib.epipolar.eight_point import EightPointCalculationError  # noqa: E402
+from lib.epipolar.epipolar_ransac import estimate_essential_mat_with_ransac  # noqa: E402
+from lib.feature_matching.matching import Match  # noqa: E402
+from lib.ransac.ransac import ErrorAggregationMethod  # noqa: E402
+from oracle import restatement as o  # noqa: E402
+from structure_from_motion_b200.scenes import make_scene  # noqa: E402
+
+cases = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+rng = np.random.default_rng(31337)
+bad = 0
+for k in range(cases):
+    n = int(rng.choice([8, 9, 20, 60, 150, 400]))
+    h = int(rng.choice([1, 5, 40, 120]))
+    thr = float(10.0 ** rng.uniform(-7, -4))
+    min_extra = [None, 0, 3, 10][k % 4]
+    agg = [None, ErrorAggregationMethod.SUM, ErrorAggregationMethod.SQUARE, ErrorAggregationMethod.MEAN, ErrorAggregationMethod.RMS][k % 5]
+    K, x1, x2, *_ = make_scene(n, float(rng.choice([0.0, 0.3])), seed=2000 + k)
+    if k % 6 == 5:  # duplicated correspondences: some minimal samples are degenerate and the reference aborts
+        dup = rng.choice(n, max(2, n // 2), replace=False)
+        x1[dup] = x1[dup[0]]
+        x2[dup] = x2[dup[0]]
+    perm = rng.permutation(n)  # matches in a shuffled order, indices into the feature lists
+    fa = [Feature(x=float(p[0]), y=float(p[1])) for p in x1]
+    fb = [Feature(x=float(p[0]), y=float(p[1])) for p in x2]
+    ms = [Match(a_index=int(i), b_index=int(i), match_score=0.1) for i in perm]
+    seed = int(rng.integers(0, 10 ** 6))
+    random.seed(seed)
+    ref, ref_exc = None, None
+    try:
+        ref = o.ransac_essential(K, x1[perm, 0], x1[perm, 1], x2[perm, 0], x2[perm, 1], thr, min_extra,
+                                 None if agg is None else agg.value, None if h == 40 else h)
+    except ValueError as e:
+        ref_exc = "ValueError"
+    except o.OracleEightPointError:
+        ref_exc = "EightPointCalculationError"
+    state_ref = random.getstate()
+    random.seed(seed)
+    got, got_exc = None, None
+    try:
+        got = estimate_essential_mat_with_ransac(K, fa, fb, ms, thr, min_num_extra_inliers=min_extra,
+                                                 error_aggregation_method=agg, max_iterations=None if h == 40 else h)
+    except EightPointCalculationError:
+        got_exc = "EightPointCalculationError"
+    except ValueError:
+        got_exc = "ValueError"
+    msg = ""
+    if ref_exc != got_exc:
+        msg = f"exception {got_exc} vs {ref_exc}"
+    elif random.getstate() != state_ref:
+        msg = "RNG state differs"
+    elif ref is not None:
+        e, pairs = got
+        a, b = e.reshape(-1), ref["E"].reshape(-1)
+        want = [(float(x1[perm[i], 0]), float(x1[perm[i], 1]), float(x2[perm[i], 0]), float(x2[perm[i], 1])) for i in ref["inlier_indices"]]
+        have = [(p[0].x, p[0].y, p[1].x, p[1].y) for p in pairs]
+        if np.abs(a / np.linalg.norm(a) - b / np.linalg.norm(b)).max() > 1e-6:
+            msg = "E differs"
+        elif n == 8 and sorted(have) == sorted(want):
+            # every iteration fits the same eight pairs exactly: the "errors" are rounding noise (~1e-32) and which
+            # iteration wins depends on the last bit of the solver, so only the set of pairs can be compared
+            pass
+        elif have != want:
+            msg = f"inlier pairs differ ({len(have)} vs {len(want)})"
+    bad += bool(msg)
+    print(f"{k:3d} n {n:4d} h {h:4d} thr {thr:.1e} min_extra {min_extra} agg {None if agg is None else agg.value}  "
+          f"{ref_exc or ('winner %d, %d inliers' % (ref['best_index'], len(ref['inlier_indices'])))}  {msg or 'ok'}")
+print("mismatches:", bad)
+sys.exit(1 if bad else 0)

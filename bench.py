@@ -19,7 +19,7 @@ winner -> decomposition + cheirality vote -> triangulation of the passing inlier
 * ``cpu_baseline`` the oracle port (numpy eight-point + threaded C scorer) on the host cores, on a
                 bounded sample of the same workload.
 N > 1 (torchrun): hypotheses are sharded — every rank scores its own 64k hypotheses of the same
-pair (weak scaling); the 112-byte selection records are all-gathered device-to-device by NCCL (the one collective),
+pair (weak scaling); the 144-byte selection records are all-gathered device-to-device by NCCL (the one collective),
 merged by a kernel, and the tail runs behind it without a host round trip.
 """
 from __future__ import annotations
@@ -90,6 +90,11 @@ def parse():
     ap.add_argument("--cpu-sample-hyps", type=int, default=0, help="reference arm: hypotheses per step (0 = auto)")
     ap.add_argument("--cpu-step-seconds", type=float, default=2.0, help="reference arm: target seconds per step")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0, help="native arm: cpu_baseline sample length")
+    ap.add_argument("--true-reference-seconds", type=float, default=10.0,
+                    help="CPU legs: budget for timing the unmodified reference on one core")
+    ap.add_argument("--no-true-reference", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the sub-records (config3_strong, config5_strong, config4_pairs, parity_multi)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fp32-variant", action="store_true")
@@ -231,6 +236,44 @@ class CpuPort:
         self.pool.join()
 
 
+def time_true_reference(K, x1, x2, budget_s: float):
+    """The UNMODIFIED reference (baseline/_ref or /root/reference, through oracle/reference_shims.py) on ONE core:
+    estimate_essential_mat_with_ransac (lib/epipolar/epipolar_ransac.py:45-70) as is - list-of-Feature inputs, its own
+    random.shuffle per iteration - on ALL correspondences of the workload for a bounded number of iterations, reported
+    as hypothesis x correspondence evaluations per second (linear in H, so this is the rate of the full run)."""
+    import random
+
+    from oracle import reference_shims
+
+    if not reference_shims.reference_available():
+        return None
+    ref = reference_shims.load()
+    F, M = ref.feature.Feature, ref.matching.Match
+    n = x1.shape[0]
+    fa = [F(x=float(p[0]), y=float(p[1])) for p in x1]
+    fb = [F(x=float(p[0]), y=float(p[1])) for p in x2]
+    ms = [M(a_index=i, b_index=i) for i in range(n)]
+
+    def run(iters):
+        random.seed(5)
+        t0 = time.perf_counter()
+        try:
+            ref.epipolar_ransac.estimate_essential_mat_with_ransac(
+                K, fa, fb, ms, THR, min_num_extra_inliers=MIN_EXTRA,
+                error_aggregation_method=ref.ransac.ErrorAggregationMethod.RMS, max_iterations=iters)
+        except ValueError:
+            pass  # "No model could be found" after so few iterations: the work was done all the same
+        return time.perf_counter() - t0
+
+    t1 = run(1)
+    iters = int(max(2, min(32, budget_s / max(t1, 1e-3))))
+    dt = run(iters)
+    return {"value": iters * float(n - 8) / dt, "unit": UNIT, "cores": 1, "kind": "reference",
+            "sample": f"the unmodified reference ({os.path.relpath(reference_shims.REFERENCE_ROOT, ROOT)}), "
+                      f"{iters} iterations x all {n} correspondences incl. its shuffle, {dt:.1f} s; the full run is "
+                      "this rate extrapolated linearly in the iteration count"}
+
+
 def run_reference_arm(args):
     """--impl reference: the CPU implementation of the path on the host cores.  The reference is
     pure Python (2.5e4 evals/s on one core), has nothing to compile into oracle/_ref,
@@ -263,6 +306,7 @@ def run_reference_arm(args):
     port.close()
     value = evals / secs
     sample_h = done
+    true_ref = None if args.no_true_reference else time_true_reference(K, x1, x2, args.true_reference_seconds)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
@@ -274,6 +318,10 @@ def run_reference_arm(args):
                                    f"{args.steps} steps, {secs:.1f} s"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if true_ref is not None:
+        line["cpu_baseline"]["reference"] = true_ref
+    else:
+        line["cpu_baseline"]["reference"] = {"unavailable": "no baseline/_ref and no /root/reference on this box"}
     emit(line)
     return line
 
@@ -282,13 +330,141 @@ def cpu_baseline_subprocess(args, workload):
     """cpu_baseline leg of the native arm: the reference arm in a fresh process (no CUDA context to
     fork), one step of ~args.cpu_baseline_seconds."""
     cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload, "--steps", "1",
-           "--warmup", "1", "--cpu-step-seconds", str(args.cpu_baseline_seconds)]
+           "--warmup", "1", "--cpu-step-seconds", str(args.cpu_baseline_seconds),
+           "--true-reference-seconds", str(args.true_reference_seconds)]
+    if args.no_true_reference:
+        cmd.append("--no-true-reference")
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
     out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
     for ln in reversed(out.stdout.strip().splitlines()):
         if ln.startswith("{"):
             return json.loads(ln)["cpu_baseline"]
     raise RuntimeError("cpu baseline failed: " + out.stderr[-2000:])
+
+
+
+# ----------------------------------------------------------------------------------------------
+# sub-records of the default line: the north_star's other multi-GPU configurations + multi-rank parity
+# ----------------------------------------------------------------------------------------------
+def _timed(torch, dist, world, stream, barrier, flush_l2, steps, fn):
+    """steps timed calls of fn(step) bracketed by barrier + synchronize, L2 flushed between steps; ms total, max over ranks."""
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    for s in range(steps):
+        flush_l2()
+        stream.synchronize()
+        ev[s][0].record(stream)
+        fn(s)
+        ev[s][1].record(stream)
+    barrier()
+    ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.cpu()[0])
+
+
+def run_extras(args, eng, world, rank, barrier, flush_l2, torch, dist, per_gpu_rate):
+    """config3_strong (65 536 hypotheses split over the ranks), config5_strong (1M x 1M split over the ranks),
+    config4_pairs (4 096 pairs split over the ranks, host buffers, pose + triangulation per pair) and parity_multi
+    (the merged multi-rank result against a single-rank evaluation of the union of the hypotheses, untimed).
+    ``per_gpu_rate`` = evaluations/s of ONE GPU on config 3 measured in this run (the denominator of `efficiency`)."""
+    from structure_from_motion_b200 import _native, distributed
+    from structure_from_motion_b200.scenes import make_scene
+
+    out = {}
+    stream = torch.cuda.current_stream()
+
+    def sharded_step(h_rank, seed):
+        if world == 1:
+            eng.sample_device(seed, h_rank)
+            best, *_rest = eng.two_view(THR, MIN_EXTRA, AGG, "min_error", 50.0, want_mask=False, want_sed=False)
+            return int(best.index)
+        r = distributed.two_view_sharded(THR, MIN_EXTRA, AGG, h_rank, seed, engine=eng, rank=rank, world=world)
+        return int(r["index"])
+
+    # ---- parity_multi: every rank must return the single-GPU answer for the union of the hypotheses ----
+    if world > 1:
+        ok = 1
+        K, x1, x2, *_ = make_scene(100_000, 0.4, seed=0)
+        eng.upload_pairs(x1, x2, K)
+        hs = 4096
+        for seed in (11, 12, 13):
+            r = distributed.two_view_sharded(THR, MIN_EXTRA, AGG, hs, seed, engine=eng, rank=rank, world=world)
+            eng.sample_device(seed, hs * world)  # the union on this one GPU (the sampler is keyed by the global index)
+            best, _, _, poses, num, idx, okb, X = eng.two_view(THR, MIN_EXTRA, AGG, "min_error", 50.0, want_mask=False,
+                                                                want_sed=False)
+            same = (r["index"] == best.index and r["err"] == best.err and r["count"] == best.count_extra
+                    and np.array_equal(r["E"].reshape(9), np.array(best.E)) and r["num_inliers"] == num
+                    and np.array_equal(r["inlier_idx"], idx) and np.array_equal(r["pass_bits"], okb)
+                    and np.array_equal(r["points"], X, equal_nan=True) and int(r["poses"].best) == int(poses.best)
+                    and list(r["poses"].counts) == list(poses.counts))
+            ok &= int(bool(same))
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        out["parity_multi"] = bool(int(flag.cpu()[0]))
+        out["parity_multi_note"] = (f"3 estimates, {hs} hypotheses per rank x {world} ranks over NCCL: (index, error, count, E, "
+                                    "inlier list, cheirality bits, vote, triangulated points) bit-identical on EVERY rank "
+                                    "to one GPU evaluating the union")
+
+    # ---- config3_strong: BASELINE configs[2] with its 65 536 hypotheses split over the ranks ----
+    n, h, frac = WORKLOADS["config3"]
+    K, x1, x2, *_ = make_scene(n, frac, seed=0)
+    eng.upload_pairs(x1, x2, K)
+    h_rank = h // world
+    for w in range(3):
+        sharded_step(h_rank, 500 + w)
+    steps = max(5, min(args.steps, 20))
+    ms = _timed(torch, dist, world, stream, barrier, flush_l2, steps, lambda s: sharded_step(h_rank, s))
+    rate = float(n) * h_rank * world * steps / (ms * 1e-3)
+    out["config3_strong"] = {"workload": f"{n} correspondences x {h} hypotheses split over {world} GPU(s) ({h_rank} each) + tail",
+                             "ms_per_estimate": ms / steps, "value": rate, "unit": UNIT, "steps": steps, "scaling": "strong",
+                             "efficiency_vs_one_gpu": rate / (world * per_gpu_rate)}
+
+    # ---- config5_strong: 1M correspondences x 1M hypotheses split over the ranks ----
+    n, h, frac = WORKLOADS["config5"]
+    K, x1, x2, *_ = make_scene(n, frac, seed=0)
+    eng.upload_pairs(x1, x2, K)
+    h_rank = h // world
+    sharded_step(h_rank, 600)
+    steps = 2
+    ms = _timed(torch, dist, world, stream, barrier, flush_l2, steps, lambda s: sharded_step(h_rank, s))
+    rate = float(n) * h_rank * world * steps / (ms * 1e-3)
+    out["config5_strong"] = {"workload": f"{n} correspondences x {h} hypotheses split over {world} GPU(s) ({h_rank} each) + tail",
+                             "ms_per_estimate": ms / steps, "value": rate, "unit": UNIT, "steps": steps, "scaling": "strong",
+                             "efficiency_vs_one_gpu": rate / (world * per_gpu_rate)}
+
+    # ---- config4_pairs: 4 096 image pairs x 2 000 matches x 2 000 hypotheses, pair-sharded, host buffers ----
+    P_total, n, h = 4096, 2000, 2000
+    P = P_total // world
+    base = make_scene(n, 0.4, seed=0)
+    rng = np.random.default_rng(rank)
+    pa = _native.pinned_empty((P * n, 2))
+    pb = _native.pinned_empty((P * n, 2))
+    for p in range(P):  # cheap per-pair variation of one scene (generation is not what is measured)
+        perm = rng.permutation(n)
+        pa[p * n:(p + 1) * n] = base[1][perm]
+        pb[p * n:(p + 1) * n] = base[2][perm]
+    offsets = np.arange(P + 1, dtype=np.int64) * n
+    Ks = np.stack([base[0]] * P)
+    pipe = distributed.PairPipeline(depth=2)
+    try:
+        def pstep(seed):
+            return pipe.batch_two_view(pa, pb, offsets, Ks, h, seed, THR, MIN_EXTRA, AGG, pair_id0=rank * P, chunk_pairs=256)
+
+        for w in range(2):
+            res = pstep(700 + w)
+        steps = 5
+        ms = _timed(torch, dist, world, stream, barrier, flush_l2, steps, pstep)
+    finally:
+        pipe.close()
+    rate = float(P) * n * h * world * steps / (ms * 1e-3)
+    out["config4_pairs"] = {"workload": f"{P_total} image pairs x {n} correspondences x {h} hypotheses, pair-sharded over {world} "
+                                        f"GPU(s) ({P} each), HOST buffers (H2D inside the timed region), per pair: E, inlier "
+                                        "mask, 4-pose cheirality vote, triangulated inliers back on the host",
+                            "ms_per_step": ms / steps, "value": rate, "unit": UNIT, "steps": steps, "scaling": "strong",
+                            "models_found": int((res["best_index"] >= 0).sum()), "pairs_per_s": P * world * steps / (ms * 1e-3),
+                            "efficiency_vs_one_gpu_config3": rate / (world * per_gpu_rate)}
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
@@ -451,6 +627,12 @@ def main():
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
     ms_total, e2e_max, score_ms, f32_ms, f32_score_ms = (float(v) for v in vals.cpu())
 
+    extras = {}
+    if args.workload == "config3" and not args.no_extras:
+        # one GPU's config-3 rate in this run: every rank did the full config 3 in the (weak) headline leg
+        extras = run_extras(args, eng, world, rank, barrier, flush_l2, torch, dist,
+                            float(n) * h_rank * args.steps / (ms_total * 1e-3))
+
     if rank == 0:
         evals_per_step = float(n) * h_rank * world
         value = evals_per_step * args.steps / (ms_total * 1e-3)
@@ -481,7 +663,7 @@ def main():
                             f"vote + triangulation of the {num_inl} inliers",
                 "sampler": "device (Philox)", "score_variant": args.variant, "hyps_per_thread": args.hpt, "group": args.group,
                 "l2": "flushed (256 MiB memset) between timed steps",
-                "parallelism": f"hypothesis-sharded x{world}, one 112 B/rank device-to-device all-gather + merge kernel" if world > 1 else "single GPU",
+                "parallelism": f"hypothesis-sharded x{world}, one 144 B/rank device-to-device all-gather + merge kernel" if world > 1 else "single GPU",
             },
             "ms_per_estimate": ms_total / args.steps,
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
@@ -494,7 +676,10 @@ def main():
                 "algorithmic_flop_per_eval": FLOP_PER_EVAL,
                 "executed_fp64_slots_per_eval": 11.0 if args.variant.startswith("screen") else 21.0,
                 "fp64_pipe_busy_frac_est": kern_evals * (11.0 if args.variant.startswith("screen") else 21.0) / fp64_peak_dfma,
-                "hbm_achieved_gbs": algo_bytes / (score_ms_per_launch * 1e-3) / 1e9,
+                "l2_to_smem_stream_gbs": algo_bytes / (score_ms_per_launch * 1e-3) / 1e9,
+                "l2_to_smem_note": "32 B per correspondence per hypothesis-group pass, served by L2 (the working set is L2-resident); NOT HBM traffic",
+                "dram_gbs": (traffic / (score_ms_per_launch * 1e-3) / 1e9) if traffic else None,
+                "dram_note": "traffic = dram__bytes_read+write per k_score launch from the committed ncu --set full capture (profiles/k_score_dram_traffic.json), divided by this run's launch duration",
                 "hbm_peak_gbs": peaks.get("hbm_gbs"),
             },
             "clocks": clk,
@@ -514,6 +699,7 @@ def main():
                            "h2d_bytes_per_step": int(n * 32 + 72), "d2h_bytes_per_step": int(d2h)}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_subprocess(args, args.workload)
+        line.update(extras)
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -114,6 +114,9 @@ int sfm_get_normalised(sfm_ctx *ctx, double *out, int64_t n);
  * EightPointCalculationError, eight_point.py:414-421); eig_out: double[h][9] or NULL
  * (eigenvalues of Y^T Y, diagnostics). */
 int sfm_fit(sfm_ctx *ctx, double *E_out, uint8_t *valid_out, double *eig_out);
+/* The fitted (or uploaded) models [first, first+count) back to the host: E_out double[count][9], valid_out uint8[count]
+ * (either may be NULL). */
+int sfm_get_models(sfm_ctx *ctx, int64_t first, int64_t count, double *E_out, uint8_t *valid_out);
 /* Replace the fitted models by caller-supplied ones (scorer-only parity tests). */
 int sfm_set_models(sfm_ctx *ctx, const double *E, const uint8_t *valid /* or NULL */, int64_t h);
 
@@ -141,6 +144,13 @@ int sfm_get_best(sfm_ctx *ctx, sfm_best *out);
 /* Tell the context which hypothesis won (hypothesis-sharded runs: after the cross-rank
  * merge).  local_index < 0 = the winner lives on another rank; E then supplies the model. */
 int sfm_set_winner(sfm_ctx *ctx, int64_t local_index, const double *E);
+/* SURVEY.md H1 (ransac.py:83,96-108: strict < on errors summed in LIST order): the local indices of the hypotheses
+ * of the last score whose error is <= best * (1 + rel_tol), unordered, at most cap of them; *count is their total
+ * number.  The Python mirror re-evaluates such near-ties in the reference's own summation order. */
+int sfm_near_ties(sfm_ctx *ctx, double rel_tol, int64_t cap, int64_t *idx_out, int64_t *count);
+/* How many hypotheses of the last score went through K3's exact double-double rescore (their inliers were more than
+ * 2^31 times tighter than the threshold, so the 84-bit fixed-point sums of K2 would have lost precision). */
+int sfm_get_rescored(sfm_ctx *ctx, int64_t *count);
 /* Inlier mask (sed <= threshold) and SED value of every correspondence under the current
  * winner.  mask uint8[n], sed double[n]; either may be NULL. */
 int sfm_inlier_mask(sfm_ctx *ctx, double threshold, uint8_t *mask, double *sed);
@@ -203,18 +213,34 @@ int sfm_batch_ransac(sfm_ctx *ctx, const double *xa, const double *ya, const dou
                      double min_extra, int aggregation, int selection, double *E, int64_t *best_index,
                      double *best_err, int32_t *count_extra, int64_t *num_invalid);
 
+/* The same batch carried through the rest of the path (apps/sfm.py:118-186 per pair): for every pair's winner the
+ * inlier list (sed <= threshold plus the 8 sample points, ransac.py:70-76, ascending pair-relative indices), the four
+ * candidate poses with the cheirality vote (lib/epipolar/eight_point.py:65-96, 181-280, 449-488; poses[p].best = the
+ * voted candidate, -2 = the pair has no model) and the triangulated points of the inliers that pass the voted pose
+ * (lib/epipolar/triangulation.py:42-62, pixel coordinates with the pair's K; NaN for the others).  Per-inlier results
+ * are packed densely: pair p owns [inlier_offsets[p], inlier_offsets[p+1]) of inlier_idx int32[cap], pass uint8[cap]
+ * (bit q = passes candidate q) and X double[cap][3]; cap >= offsets[npairs] always suffices. */
+int sfm_batch_two_view(sfm_ctx *ctx, const double *xa, const double *ya, const double *xb, const double *yb,
+                       int64_t stride, const int64_t *offsets, int64_t npairs, const double *Ks, int64_t h,
+                       uint64_t seed, uint64_t pair_id0, double threshold, double min_extra, int aggregation,
+                       int selection, double distance_threshold, double *E, int64_t *best_index, double *best_err,
+                       int32_t *count_extra, int64_t *num_invalid, sfm_poses *poses, int64_t *inlier_offsets,
+                       int64_t cap, int32_t *inlier_idx, uint8_t *pass, double *X);
+
 /* ---- hypothesis-sharded estimates without a host round trip ---------- */
 /* One rank of a run whose hypotheses are split over `world` GPUs (correspondences replicated):
  *   1. sfm_score_async  : fit + score + select of this rank's hypotheses, nothing synchronised; *record_dev is the
  *                         DEVICE address of this rank's SFM_RECORD_BYTES-byte selection record;
  *   2. the caller all-gathers the records of all ranks into one device buffer on the context's stream
- *      (ncclAllGather / torch.distributed.all_gather_into_tensor - the path's only collective, 112 bytes per rank);
+ *      (ncclAllGather / torch.distributed.all_gather_into_tensor - the path's only collective, SFM_RECORD_BYTES per rank);
+ *      a record = {err f64, index i64, count i32, pad, num_invalid i64, first_invalid i64, E f64[9], sample i32[8]}:
+ *      the winner's model AND its minimal sample travel with it, so every rank finishes with identical results;
  *   3. sfm_sharded_tail : merges the records on the device with the reference's rule (ransac.py:83: smallest error,
  *                         earliest GLOBAL iteration = rank * hyps_per_rank + local index on ties) and enqueues the
  *                         inlier mask, pose vote and triangulation of the global winner;
  *   4. sfm_sharded_fetch: the single synchronisation; best->index is the global index, *owner the rank that fitted
  *                         the winner (-1: no model anywhere). */
-#define SFM_RECORD_BYTES 112
+#define SFM_RECORD_BYTES 144
 int sfm_score_async(sfm_ctx *ctx, double threshold, double min_extra, int aggregation, int selection,
                     void **record_dev);
 int sfm_sharded_tail(sfm_ctx *ctx, const void *gathered_records_dev, int world, int rank, int64_t hyps_per_rank,

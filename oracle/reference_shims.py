@@ -1,10 +1,11 @@
 """TEST INFRASTRUCTURE ONLY — load the UNMODIFIED reference behind import shims.
 
-The reference (Bazs/structure_from_motion) is pure Python and lives at
-``/root/reference`` in the build container only; it does not travel to the GPU box.
-This loader is used (a) by ``tests/golden/make_golden.py`` to generate the committed
-golden vectors and (b) by container-only tests (skipped when the reference is absent)
-that pin ``oracle/restatement.py`` against the real thing.
+The reference (Bazs/structure_from_motion) is pure Python.  It lives at ``/root/reference`` in the
+build container; ``baseline/install_reference.py`` pip-installs it, unmodified, into the git-ignored
+``baseline/_ref/`` so that a copy travels to the GPU box.  This loader is used (a) by
+``tests/golden/make_golden.py`` to generate the committed golden vectors, (b) by tests (skipped when
+the reference is absent) that pin ``oracle/restatement.py`` against the real thing and (c) by
+``bench.py``'s CPU legs, which time the reference itself beside the GPU.
 
 Four shims are needed because of dependency drift; none of them
 touches hot-path arithmetic:
@@ -24,8 +25,22 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("SFM_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = "_sfm_reference"
+
+
+def _find_root() -> str:
+    """SFM_REFERENCE_ROOT, else baseline/_ref (the pip-staged copy that travels to the GPU box, see
+    baseline/install_reference.py), else /root/reference (build container)."""
+    cands = [os.environ.get("SFM_REFERENCE_ROOT"), os.path.join(os.path.dirname(_HERE), "baseline", "_ref"),
+             "/root/reference"]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "lib", "ransac", "ransac.py")):
+            return c
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:

@@ -61,9 +61,12 @@ _SIGNATURES = {
     "sfm_get_normalised": (C.c_int, [_P, _P, C.c_int64]),
     "sfm_fit": (C.c_int, [_P, _P, _P, _P]),
     "sfm_set_models": (C.c_int, [_P, _P, _P, C.c_int64]),
+    "sfm_get_models": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
     "sfm_score": (C.c_int, [_P, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int64, _P, _P, _P, _P]),
     "sfm_get_best": (C.c_int, [_P, C.POINTER(Best)]),
     "sfm_set_winner": (C.c_int, [_P, C.c_int64, _P]),
+    "sfm_near_ties": (C.c_int, [_P, C.c_double, C.c_int64, _P, C.POINTER(C.c_int64)]),
+    "sfm_get_rescored": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "sfm_inlier_mask": (C.c_int, [_P, C.c_double, _P, _P]),
     "sfm_ransac_essential": (C.c_int, [_P, C.c_double, C.c_double, C.c_int, C.c_int, C.POINTER(Best), _P, _P]),
     "sfm_decompose_essential": (C.c_int, [_P, _P, C.POINTER(Poses)]),
@@ -81,6 +84,9 @@ _SIGNATURES = {
                                     C.POINTER(C.c_int64), _P, _P, _P]),
     "sfm_batch_ransac": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P, C.c_int64, _P, C.c_int64, C.c_uint64,
                                    C.c_uint64, C.c_double, C.c_double, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
+    "sfm_batch_two_view": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P, C.c_int64, _P, C.c_int64, C.c_uint64,
+                                     C.c_uint64, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, _P, _P, _P, _P, _P,
+                                     _P, _P, C.c_int64, _P, _P, _P]),
     "sfm_match_brute_force": (C.c_int, [_P, _P, _P, C.c_int, C.c_int64, C.c_int64, _P, C.c_int64, _P, C.c_int64, C.c_int,
                                         C.c_int, C.c_int, C.c_double, _P, _P, _P, _P]),
     "sfm_match_from_scores": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int, C.c_double, _P, _P, _P]),
@@ -152,7 +158,6 @@ class Engine:
             raise NativeError(f"sfm_create(device={device}) -> {rc}: {msg}")
         self.h = h
         self.device = int(device)
-        self._keep = None  # host arrays referenced by the last upload
         self.n = 0
 
     # -- helpers -------------------------------------------------------------------------
@@ -247,6 +252,13 @@ class Engine:
         self._ck(self.lib.sfm_fit(self.h, _ptr(E), _ptr(valid), _ptr(eig)), "sfm_fit")
         return E, valid.astype(bool), eig
 
+    def get_models(self, first=0, count=None):
+        count = self.h_count - first if count is None else int(count)
+        E = np.empty((count, 3, 3), dtype=np.float64)
+        valid = np.empty(count, dtype=np.uint8)
+        self._ck(self.lib.sfm_get_models(self.h, int(first), count, _ptr(E), _ptr(valid)), "sfm_get_models")
+        return E, valid.astype(bool)
+
     def set_models(self, E, valid=None):
         E = _f64(E).reshape(-1, 9)
         v = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint8)
@@ -276,6 +288,19 @@ class Engine:
     def set_winner(self, local_index, E=None):
         Ea = None if E is None else _f64(E).reshape(9)
         self._ck(self.lib.sfm_set_winner(self.h, int(local_index), _ptr(Ea)), "sfm_set_winner")
+
+    def near_ties(self, rel_tol=1e-12, cap=64):
+        """Local indices (ascending) of the hypotheses whose error is within rel_tol of the winner's, and their
+        total number (which may exceed ``cap``)."""
+        idx = np.empty(cap, dtype=np.int64)
+        n = C.c_int64(0)
+        self._ck(self.lib.sfm_near_ties(self.h, float(rel_tol), int(cap), _ptr(idx), C.byref(n)), "sfm_near_ties")
+        return np.sort(idx[:min(int(n.value), cap)]), int(n.value)
+
+    def rescored(self) -> int:
+        n = C.c_int64(0)
+        self._ck(self.lib.sfm_get_rescored(self.h, C.byref(n)), "sfm_get_rescored")
+        return int(n.value)
 
     def inlier_mask(self, threshold, want_sed=True):
         mask = np.empty(self.n, dtype=np.uint8)
@@ -362,7 +387,7 @@ class Engine:
         return b, mask, sed, p, int(num.value), idx[:m], ok[:m], X[:m]
 
     # -- hypothesis-sharded runs: nothing synchronises between scoring and the final fetch ----
-    RECORD_BYTES = 112  # include/sfm_b200.h SFM_RECORD_BYTES
+    RECORD_BYTES = 144  # include/sfm_b200.h SFM_RECORD_BYTES
 
     def score_async(self, threshold, min_extra=0.0, aggregation="rms", selection="min_error") -> int:
         """fit + score + select, enqueued only.  Returns the DEVICE address of this rank's selection record."""
@@ -407,6 +432,47 @@ class Engine:
                                            AGG[aggregation], SELECT[selection], _ptr(E), _ptr(bi), _ptr(be), _ptr(ce),
                                            _ptr(ni)), "sfm_batch_ransac")
         return dict(E=E, best_index=bi, best_err=be, count_extra=ce, num_invalid=ni)
+
+    def batch_two_view(self, pts_a, pts_b, offsets, Ks, h, seed, threshold, min_extra=0.0, aggregation="rms",
+                       selection="min_error", distance_threshold=50.0, pair_id0=0):
+        """batch_ransac + per pair: inlier list, pose vote, triangulation.  Returns the batch_ransac dict plus
+        R [P,3,3], t [P,3] (NaN without a model), counts [P,4], pose_index [P], inlier_offsets [P+1], inlier_idx
+        (pair-relative), pass_bits, points [total,3]."""
+        pa, pb = _split_xy(pts_a), _split_xy(pts_b)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        P = offsets.shape[0] - 1
+        Ks = _f64(Ks).reshape(P, 9)
+        E = np.empty((P, 3, 3), dtype=np.float64)
+        bi = np.empty(P, dtype=np.int64)
+        be = np.empty(P, dtype=np.float64)
+        ce = np.empty(P, dtype=np.int32)
+        ni = np.empty(P, dtype=np.int64)
+        poses = (Poses * P)()
+        ioff = np.empty(P + 1, dtype=np.int64)
+        cap = int(offsets[-1])
+        idx = np.empty(cap, dtype=np.int32)
+        ok = np.empty(cap, dtype=np.uint8)
+        X = np.empty((cap, 3), dtype=np.float64)
+        a, b = pa.ctypes.data, pb.ctypes.data
+        self._ck(self.lib.sfm_batch_two_view(self.h, _P(a), _P(a + 8), _P(b), _P(b + 8), 2, _ptr(offsets), P, _ptr(Ks),
+                                             int(h), int(seed), int(pair_id0), float(threshold), float(min_extra),
+                                             AGG[aggregation], SELECT[selection], float(distance_threshold), _ptr(E),
+                                             _ptr(bi), _ptr(be), _ptr(ce), _ptr(ni), C.cast(poses, _P), _ptr(ioff), cap,
+                                             _ptr(idx), _ptr(ok), _ptr(X)), "sfm_batch_two_view")
+        raw = np.frombuffer(poses, dtype=np.uint8).reshape(P, C.sizeof(Poses))
+        dbl = raw[:, :(36 + 12 + 3) * 8].copy().view(np.float64)
+        R4, t4 = dbl[:, :36].reshape(P, 4, 3, 3), dbl[:, 36:48].reshape(P, 4, 3)
+        counts = raw[:, 51 * 8:55 * 8].copy().view(np.int64).reshape(P, 4)
+        pose_index = raw[:, 55 * 8:55 * 8 + 4].copy().view(np.int32).reshape(P)
+        sel = np.clip(pose_index, 0, 3)
+        R = R4[np.arange(P), sel].copy()
+        t = t4[np.arange(P), sel].copy()
+        R[pose_index < 0] = np.nan
+        t[pose_index < 0] = np.nan
+        total = int(ioff[-1])
+        return dict(E=E, best_index=bi, best_err=be, count_extra=ce, num_invalid=ni, R=R, t=t, counts=counts,
+                    pose_index=pose_index, inlier_offsets=ioff, inlier_idx=idx[:total], pass_bits=ok[:total],
+                    points=X[:total])
 
     # -- front end: brute-force matcher (N1) ---------------------------------------------------
     def match_brute_force(self, image_a, image_b, feats_a, feats_b, kind="ncc", window=None, ratio_test=False,
@@ -583,11 +649,14 @@ def default_device() -> int:
 
 
 def get_engine(device: int | None = None) -> Engine:
-    """Process-wide engine for a device (created on first use)."""
+    """The calling THREAD's engine for a device (created on first use).  An Engine is a stateful context (upload ->
+    table -> estimate -> fetch on one stream with shared buffers) and is not thread-safe, so every thread that goes
+    through the module-level API gets its own; pass ``engine=`` explicitly to share one under your own lock."""
     dev = default_device() if device is None else int(device)
+    key = (dev, threading.get_ident())
     with _engine_lock:
-        eng = _engines.get(dev)
+        eng = _engines.get(key)
         if eng is None:
             eng = Engine(dev)
-            _engines[dev] = eng
+            _engines[key] = eng
         return eng

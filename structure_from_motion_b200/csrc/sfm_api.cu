@@ -15,6 +15,7 @@
 #include "sfm_linalg.cuh"
 #include "sfm_score.cuh"
 #include "sfm_pose.cuh"
+#include "sfm_tail.cuh"
 #include "sfm_misc.cuh"
 #include "sfm_match.cuh"
 #include "sfm_harris.cuh"
@@ -93,13 +94,14 @@ struct sfm_ctx {
     Buf acc, count_extra, S1, S2, err, blocks, best, invalid, winnerE, spts, bounds, fitflag, record, merged, rows, blockinv;
     Buf m_img, m_feat, m_W, m_ss, m_ok, m_S, m_out;
     Buf h_img, h_gx, h_gy, h_corner, h_alive, h_key, h_idx, h_small, h_xy;
-    Buf mask, sed, poses, pass, X, idx, scan, tmp;
+    Buf mask, sed, poses, pass, X, idx, scan, tmp, tailstate, num, winrec, bout;
     long long n = 0, h = 0, npairs = 1;
     long long raw_stride = 1;
     bool batched = false, has_pts = false, has_table = false, has_models = false, has_score = false;
     double Kstage[9] = {0};
     const void* occ_fn = nullptr;  // scoring kernel whose launch configuration is cached
     int occ_blocks = 0;
+    const unsigned long long* rescored_dev = nullptr;  // K3's rescore counter of the last scoring call
     long long winner_local = -1;  // index into E of the current winner, -1 = use winnerE
     bool winner_set = false;
     long long last_idx_offset = 0;
@@ -230,7 +232,7 @@ int sfm_destroy(sfm_ctx* c) {
     Buf* bufs[] = {&c->raw, &c->pts, &c->offsets, &c->Ks, &c->table, &c->E, &c->valid, &c->eig, &c->acc,
                    &c->count_extra, &c->S1, &c->S2, &c->err, &c->blocks, &c->best,
                    &c->invalid, &c->winnerE, &c->record, &c->merged, &c->rows, &c->blockinv, &c->mask, &c->sed, &c->poses, &c->pass, &c->X, &c->idx,
-                   &c->scan, &c->tmp, &c->spts, &c->bounds, &c->fitflag,
+                   &c->scan, &c->tmp, &c->tailstate, &c->num, &c->winrec, &c->bout, &c->spts, &c->bounds, &c->fitflag,
                    &c->m_img, &c->m_feat, &c->m_W, &c->m_ss, &c->m_ok, &c->m_S, &c->m_out,
                    &c->h_img, &c->h_gx, &c->h_gy, &c->h_corner, &c->h_alive, &c->h_key, &c->h_idx, &c->h_small, &c->h_xy};
     for (Buf* b : bufs) b->release();
@@ -377,7 +379,7 @@ int sfm_upload_pairs(sfm_ctx* c, const double* xa, const double* ya, const doubl
                      int64_t stride, int64_t n, const double* K) {
     if (int r = use(c)) return r;
     if (!xa || !ya || !xb || !yb || !K) return fail(SFM_ERR_ARG, "null argument");
-    if (n <= 0 || (uint64_t)n >= kMaxPoints) return fail(SFM_ERR_ARG, "need 0 < n < 2^26 correspondences, got %lld", (long long)n);
+    if (n <= 0 || (uint64_t)n >= kMaxPoints) return fail(SFM_ERR_ARG, "need 0 < n < 2^25 correspondences, got %lld", (long long)n);
     c->tic(T_UPLOAD);
     c->batched = false;
     c->npairs = 1;
@@ -401,7 +403,7 @@ int sfm_upload_pairs_d(sfm_ctx* c, const double* xa, const double* ya, const dou
                        int64_t stride, int64_t n, const double* K) {
     if (int r = use(c)) return r;
     if (!xa || !ya || !xb || !yb || !K) return fail(SFM_ERR_ARG, "null argument");
-    if (n <= 0 || (uint64_t)n >= kMaxPoints) return fail(SFM_ERR_ARG, "need 0 < n < 2^26 correspondences, got %lld", (long long)n);
+    if (n <= 0 || (uint64_t)n >= kMaxPoints) return fail(SFM_ERR_ARG, "need 0 < n < 2^25 correspondences, got %lld", (long long)n);
     c->tic(T_UPLOAD);
     c->batched = false;
     c->npairs = 1;
@@ -479,6 +481,17 @@ int sfm_fit(sfm_ctx* c, double* E_out, uint8_t* valid_out, double* eig_out) {
     return 0;
 }
 
+int sfm_get_models(sfm_ctx* c, int64_t first, int64_t count, double* E_out, uint8_t* valid_out) {
+    if (int r = use(c)) return r;
+    const int64_t total = c->h * c->npairs;
+    if (!c->has_models || first < 0 || count < 0 || first + count > total)
+        return fail(SFM_ERR_STATE, "no models [%lld, %lld)", (long long)first, (long long)(first + count));
+    if (E_out) CU(cudaMemcpyAsync(E_out, c->E.as<double>() + 9 * first, (size_t)count * 72, cudaMemcpyDeviceToHost, c->stream));
+    if (valid_out) CU(cudaMemcpyAsync(valid_out, c->valid.as<uint8_t>() + first, (size_t)count, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 int sfm_set_models(sfm_ctx* c, const double* E, const uint8_t* valid, int64_t h) {
     if (int r = use(c)) return r;
     if (!E || h <= 0) return fail(SFM_ERR_ARG, "bad models");
@@ -506,8 +519,11 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
     if (use_table && !c->has_table) return fail(SFM_ERR_STATE, "sample rule requested but no table is loaded");
     if (agg < 0 || agg > 3) return fail(SFM_ERR_ARG, "bad aggregation %d", agg);
     if (mode < 0 || mode > 2) return fail(SFM_ERR_ARG, "bad selection %d", mode);
-    if (!(thr >= 0.0)) return fail(SFM_ERR_ARG, "threshold must be >= 0");
-    if (thr > 1e100) return fail(SFM_ERR_ARG, "threshold too large for the fixed-point accumulators");
+    // ransac.py accepts any float: a negative (or NaN) threshold means "no extra inliers" (score <= thr is never true),
+    // +inf "every finite score".  K2's fixed-point sums cover thresholds up to 1e100; outside that range K2 is
+    // skipped and K3 counts and sums every hypothesis with its exact double-double pass.
+    const bool skip_k2 = !(thr >= 0.0) || thr > 1e100;
+    const int force_rescore = (thr > 1e100) ? 1 : 0;
     const long long h = c->h, P = c->npairs;
     const int hpt = (c->variant == SFM_SCORE_SCREEN32 && thr > 1e6) ? 2 : c->hpt;
     const int G = (c->variant == SFM_SCORE_SCREEN32 && thr > 1e6) ? 16 : c->group;
@@ -522,7 +538,7 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
     if (int r = c->best.reserve((size_t)P * sizeof(Best))) return r;
     if (int r = c->invalid.reserve((size_t)P * 16)) return r;
     int e2 = 0;
-    if (thr > 0.0) (void)frexp(thr, &e2);  // thr = m * 2^e2, m in [0.5, 1)  =>  thr < 2^e2
+    if (thr > 0.0 && !skip_k2) (void)frexp(thr, &e2);  // thr = m * 2^e2, m in [0.5, 1)  =>  thr < 2^e2
     if (e2 < -400) e2 = -400;
     // rounding guard of the screening tests: relative slack + an absolute term that covers a
     // cancelling residual r at the 1-ulp level (only matters for thr -> 0)
@@ -557,10 +573,10 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         }
         const long long grid_blocks = (long long)c->sm_count * occ;
         const long long tiles = (max_len + kTile - 1) / kTile;
-        static const int items_per_warp = getenv("SFM_ITEMS_PER_WARP") ? atoi(getenv("SFM_ITEMS_PER_WARP")) : 32;  // tuning knob: 12 -> 32 shortens the end-of-launch tail (+1 % on config 3)
+        constexpr int items_per_warp = 32;  // 12 -> 32 shortens the end-of-launch tail (+1 % on config 3)
         const long long target_items = grid_blocks * kScoreWarps * items_per_warp;
         long long nsplit = (target_items + hblocks * P - 1) / (hblocks * P);
-        static const int min_tiles = getenv("SFM_MIN_TILES_PER_ITEM") ? atoi(getenv("SFM_MIN_TILES_PER_ITEM")) : 2;  // 8 -> 2: mid-size pairs (config 2) get enough items to balance the warps (+6 %)
+        constexpr int min_tiles = 2;  // 8 -> 2: mid-size pairs (config 2) get enough items to balance the warps (+6 %)
         const long long max_split = tiles / min_tiles > 0 ? tiles / min_tiles : 1;  // keep >= min_tiles x 64 correspondences per item
         if (nsplit > max_split) nsplit = max_split;
         const long long min_split = (max_len + kMaxItemPoints - 1) / kMaxItemPoints;  // 32-bit chunk sums cannot overflow
@@ -570,7 +586,9 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         nsplit = (max_len + chunk - 1) / chunk;
         if (nsplit < 1) nsplit = 1;
         const long long total_items = hblocks * nsplit * P;
-        if (int r = c->acc.reserve(H * kAccWords * 8 + 64)) return r;
+        // tail of the accumulator buffer (zeroed with it): work counter | rescored counter | K3 tickets [P]
+        const size_t acc_tail = 64 + (size_t)P * 4;
+        if (int r = c->acc.reserve(H * kAccWords * 8 + acc_tail)) return r;
         const long long npts = c->n;  // total records (all pairs)
         if (int r = c->bounds.reserve(16)) return r;
         if (screen) { if (int r = c->spts.reserve((size_t)npts * (f32 ? sizeof(Corr32) : sizeof(Corr)))) return r; }
@@ -581,7 +599,6 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         a.s = s_scale;
         a.kappa_coef = kKappaCoef * (1.0 + thr);
         a.kappa32_coef = kKappa32Coef * (1.0 + thr);
-        a.debug_flags = getenv("SFM_DEBUG_FLAGS") ? atoi(getenv("SFM_DEBUG_FLAGS")) : 0;
         a.n = c->n;
         a.offsets = c->batched ? c->offsets.as<long long>() : nullptr;
         a.E = c->E.as<double>();
@@ -602,10 +619,12 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         a.work_counter = reinterpret_cast<unsigned*>(a.acc + H * kAccWords);
         acc_dev = a.acc;
         c->tic(T_SCORE);
-        CU(cudaMemsetAsync(c->acc.p, 0, H * kAccWords * 8 + 64, c->stream));
+        CU(cudaMemsetAsync(c->acc.p, 0, H * kAccWords * 8 + acc_tail, c->stream));
+        if (!skip_k2) {
         k_pad_models<<<(unsigned)((H + 255) / 256), 256, 0, c->stream>>>(c->E.as<double>(), (long long)H, c->rows.as<ModelRow>());
         if (int r = check_launch(c, "k_pad_models")) return r;
-        if (screen) {
+        }
+        if (screen && !skip_k2) {
             CU(cudaMemsetAsync(c->bounds.p, 0, 16, c->stream));
             if (f32)
                 k_screen_pts<true><<<(unsigned)((npts + 255) / 256), 256, 0, c->stream>>>(
@@ -618,8 +637,10 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         const long long want_blocks = (total_items + kScoreWarps - 1) / kScoreWarps;
         const long long launch_blocks = grid_blocks < want_blocks ? grid_blocks : want_blocks;
         void* kargs[] = {(void*)&a};
-        CU(cudaLaunchKernel(fn, dim3((unsigned)launch_blocks), dim3(kScoreThreads), kargs, smem, c->stream));
-        if (int r = check_launch(c, "k_score")) return r;
+        if (!skip_k2) {
+            CU(cudaLaunchKernel(fn, dim3((unsigned)launch_blocks), dim3(kScoreThreads), kargs, smem, c->stream));
+            if (int r = check_launch(c, "k_score")) return r;
+        }
         c->toc(T_SCORE);
     }
 
@@ -649,13 +670,16 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
     f.block_out = c->blocks.as<Best>();
     if (int r = c->blockinv.reserve((size_t)fblocks * P * 16)) return r;
     f.block_inv = c->blockinv.as<long long>();
+    if (int r = c->record.reserve((size_t)P * sizeof(SelectRecord))) return r;
+    f.force_rescore = force_rescore;
+    f.rescored = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(acc_dev + H * kAccWords) + 8);
+    f.tickets = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(acc_dev + H * kAccWords) + 64);
+    c->rescored_dev = f.rescored;
+    f.out = c->best.as<Best>();
+    f.invalid_out = c->invalid.as<long long>();
+    f.record = c->record.as<SelectRecord>();
     k_finalise<<<dim3((unsigned)fblocks, (unsigned)P), 256, 0, c->stream>>>(f);
     if (int r = check_launch(c, "k_finalise")) return r;
-    if (int r = c->record.reserve((size_t)P * sizeof(SelectRecord))) return r;
-    k_select<<<(unsigned)P, 256, 0, c->stream>>>(c->blocks.as<Best>(), fblocks, mode, c->blockinv.as<long long>(), h,
-                                                  idx_offset, c->best.as<Best>(), c->invalid.as<long long>(),
-                                                  c->E.as<double>(), c->record.as<SelectRecord>());
-    if (int r = check_launch(c, "k_select")) return r;
     c->toc(T_SELECT);
     c->has_score = true;
     c->last_idx_offset = idx_offset;
@@ -705,6 +729,41 @@ int sfm_get_best(sfm_ctx* c, sfm_best* out) {
     if (!out) return fail(SFM_ERR_ARG, "out is null");
     if (!c->has_score || c->batched) return fail(SFM_ERR_STATE, "no single-pair score to read");
     return fetch_best(c, out);
+}
+
+int sfm_near_ties(sfm_ctx* c, double rel_tol, int64_t cap, int64_t* idx_out, int64_t* count) {
+    if (int r = use(c)) return r;
+    if (!idx_out || !count || cap <= 0 || cap > 4096) return fail(SFM_ERR_ARG, "bad near-tie arguments");
+    if (!c->has_score || c->batched) return fail(SFM_ERR_STATE, "no single-pair score to read");
+    if (int r = c->tmp.reserve((size_t)cap * 8 + 16)) return r;
+    unsigned* cnt = c->tmp.as<unsigned>();
+    long long* out = reinterpret_cast<long long*>(c->tmp.as<char>() + 16);
+    CU(cudaMemsetAsync(cnt, 0, 16, c->stream));
+    const int blocks = (int)((c->h + 255) / 256 < 4 * c->sm_count ? (c->h + 255) / 256 : 4 * c->sm_count);
+    k_near_ties<<<blocks, 256, 0, c->stream>>>(c->err.as<double>(), c->h, c->record.as<SelectRecord>(), rel_tol, (int)cap, out, cnt);
+    if (int r = check_launch(c, "k_near_ties")) return r;
+    if (int r = ensure_pinned(c, (size_t)cap * 8 + 16)) return r;
+    CU(cudaMemcpyAsync(c->hpin, c->tmp.p, (size_t)cap * 8 + 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    unsigned n;
+    memcpy(&n, c->hpin, 4);
+    *count = n;  // may exceed cap: only the first cap entries were kept
+    const int64_t take = n < (unsigned)cap ? n : cap;
+    memcpy(idx_out, (char*)c->hpin + 16, (size_t)take * 8);
+    return 0;
+}
+
+int sfm_get_rescored(sfm_ctx* c, int64_t* count) {
+    if (int r = use(c)) return r;
+    if (!count) return fail(SFM_ERR_ARG, "null argument");
+    if (!c->rescored_dev) return fail(SFM_ERR_STATE, "no scoring call yet");
+    if (int r = ensure_pinned(c, 8)) return r;
+    CU(cudaMemcpyAsync(c->hpin, c->rescored_dev, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    unsigned long long v;
+    memcpy(&v, c->hpin, 8);
+    *count = (int64_t)v;
+    return 0;
 }
 
 int sfm_set_winner(sfm_ctx* c, int64_t local_index, const double* E) {
@@ -885,74 +944,86 @@ int sfm_triangulate(sfm_ctx* c, const double* P1, const double* P2, const double
     return 0;
 }
 
-// The tail of apps/sfm.py:133-186 for the current winner: inlier mask -> compaction -> decomposition -> 4-pose
-// cheirality vote -> triangulation of the passing inliers.  best_dev != null: the winner is read from K3's device
-// output, so everything is enqueued without waiting for the selection to reach the host.
-static int pose_tail_launch(sfm_ctx* c, double thr, double dist_thr, const Best* best_dev, uint8_t* mask_host = nullptr,
-                            double* sed_host = nullptr, const double* E_override = nullptr) {
-    const long long n = c->n;
-    if (int r = mask_launch(c, thr, best_dev, E_override)) return r;
-    // the caller's mask is "sed <= thr" (copied before the sample points are forced in below)
-    if (mask_host) CU(cudaMemcpyAsync(mask_host, c->mask.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
-    if (sed_host) CU(cudaMemcpyAsync(sed_host, c->sed.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
-    const bool have_row = c->has_table && (best_dev || c->winner_local >= 0);
-    if (have_row) {
-        if (best_dev)
-            k_mark_samples_dev<<<1, 32, 0, c->stream>>>(c->table.as<int32_t>(), best_dev, c->last_idx_offset, c->mask.as<uint8_t>());
-        else
-            k_mark_samples<<<1, 32, 0, c->stream>>>(c->table.as<int32_t>() + 8 * c->winner_local, c->mask.as<uint8_t>());
-        if (int r = check_launch(c, "k_mark_samples")) return r;
-    }
-    // compact the winner's inliers (ascending index): block counts -> scan -> scatter
-    const int cblocks = (int)((n + 1023) / 1024);
-    if (int r = c->scan.reserve((size_t)(cblocks + 2) * 8)) return r;
+// Device buffer that must read as zero before its first use (self-cleaning kernel state).
+static int reserve_zeroed(sfm_ctx* c, Buf& b, size_t bytes) {
+    if (bytes <= b.cap) return 0;
+    if (int r = b.reserve(bytes)) return r;
+    CU(cudaMemsetAsync(b.p, 0, b.cap, c->stream));
+    return 0;
+}
+
+// The tail of apps/sfm.py:133-186 for the winner described by rec_dev (one SelectRecord per pair on the device):
+// T1 inlier mask + ordered compaction + decomposition, T2 4-pose cheirality + vote, T3 triangulation of the passing
+// inliers - three launches, nothing synchronised (see sfm_tail.cuh).  max_len = the longest pair.
+static int pose_tail_launch(sfm_ctx* c, double thr, double dist_thr, const SelectRecord* rec_dev, long long max_len,
+                            uint8_t* mask_host = nullptr, double* sed_host = nullptr) {
+    const long long n = c->n, P = c->npairs;
+    if (max_len < 1) max_len = 1;
+    const int nblk = (int)((max_len + kTailPerBlock - 1) / kTailPerBlock);
+    if (int r = c->mask.reserve((size_t)n)) return r;
+    if (int r = c->sed.reserve((size_t)n * 8)) return r;
     if (int r = c->idx.reserve((size_t)n * 8)) return r;
-    if (int r = c->poses.reserve(sizeof(PoseSet))) return r;
+    if (int r = c->num.reserve((size_t)P * 8)) return r;
+    if (int r = c->poses.reserve((size_t)P * sizeof(PoseSet))) return r;
     if (int r = c->pass.reserve((size_t)n + 1)) return r;
     if (int r = c->X.reserve((size_t)n * 24)) return r;
+    const size_t state_bytes = (size_t)P * nblk * 8 + (size_t)P * 8;
+    if (int r = reserve_zeroed(c, c->tailstate, state_bytes)) return r;
+    TailArgs a;
+    a.pts = c->pts.as<Corr>();
+    a.offsets = c->batched ? c->offsets.as<long long>() : nullptr;
+    a.n = n;
+    a.rec = rec_dev;
+    a.thr = thr;
+    a.dist_thr = dist_thr;
+    a.mask = c->mask.as<uint8_t>();
+    a.sed = c->sed.as<double>();
+    a.idx = c->idx.as<long long>();
+    a.num = c->num.as<long long>();
+    a.agg = c->tailstate.as<unsigned long long>();
+    a.ticket = reinterpret_cast<unsigned*>(a.agg + (size_t)P * nblk);
+    a.done = a.ticket + P;
+    a.poses = c->poses.as<PoseSet>();
+    a.pass = c->pass.as<uint8_t>();
+    const double* d = c->raw.as<double>();
+    if (c->raw_stride == 1) { a.xa = d; a.ya = d + n; a.xb = d + 2 * n; a.yb = d + 3 * n; }
+    else { a.xa = d; a.ya = d + 1; a.xb = d + 2 * n; a.yb = d + 2 * n + 1; }
+    a.stride = c->raw_stride;
+    a.Ks = c->Ks.as<double>();
+    a.X = c->X.as<double>();
+    c->tic(T_MASK);
+    k_tail_mask<<<dim3((unsigned)nblk, (unsigned)P), kTailBlock, 0, c->stream>>>(a);
+    if (int r = check_launch(c, "k_tail_mask")) return r;
+    c->toc(T_MASK);
+    // the caller's mask is "sed <= thr" (the forced sample points live in the compacted list only)
+    if (mask_host) CU(cudaMemcpyAsync(mask_host, c->mask.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    if (sed_host) CU(cudaMemcpyAsync(sed_host, c->sed.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
     c->tic(T_POSE);
-    k_compact_count<<<cblocks, 256, 0, c->stream>>>(c->mask.as<uint8_t>(), n, c->scan.as<long long>());
-    if (int r = check_launch(c, "k_compact_count")) return r;
-    k_compact_scan<<<1, 1024, 0, c->stream>>>(c->scan.as<long long>(), cblocks);
-    if (int r = check_launch(c, "k_compact_scan")) return r;
-    k_compact_scatter<<<cblocks, 256, 0, c->stream>>>(c->mask.as<uint8_t>(), n, c->scan.as<long long>(), c->idx.as<long long>());
-    if (int r = check_launch(c, "k_compact_scatter")) return r;
-    if (E_override)
-        k_decompose<<<1, 32, 0, c->stream>>>(E_override, nullptr, 0, c->poses.as<PoseSet>(), 1);
-    else if (best_dev)
-        k_decompose<<<1, 32, 0, c->stream>>>(c->E.as<double>(), best_dev, c->last_idx_offset, c->poses.as<PoseSet>(), 1);
-    else
-        k_decompose<<<1, 32, 0, c->stream>>>(winner_E_dev(c), nullptr, 0, c->poses.as<PoseSet>(), 1);
-    if (int r = check_launch(c, "k_decompose")) return r;
-    // the number of inliers stays on the device: launch over n and let threads beyond it exit
-    const long long* cnt_dev = c->scan.as<long long>() + cblocks;
-    const int32_t* quirk = !have_row ? nullptr : (best_dev ? c->table.as<int32_t>() : c->table.as<int32_t>() + 8 * c->winner_local);
-    k_cheirality<<<(unsigned)((4 * n + 127) / 128), 128, 0, c->stream>>>(
-        c->pts.as<Corr>(), -1, c->idx.as<long long>(), cnt_dev, c->poses.as<PoseSet>(), dist_thr, c->pass.as<uint8_t>(),
-        quirk, have_row ? best_dev : nullptr, c->last_idx_offset);
-    if (int r = check_launch(c, "k_cheirality")) return r;
-    k_vote<<<1, 32, 0, c->stream>>>(c->poses.as<PoseSet>());
-    if (int r = check_launch(c, "k_vote")) return r;
+    k_tail_cheirality<<<dim3((unsigned)((4 * max_len + 127) / 128), (unsigned)P), 128, 0, c->stream>>>(a);
+    if (int r = check_launch(c, "k_tail_cheirality")) return r;
     c->toc(T_POSE);
     c->tic(T_TRI);
-    const double* d = c->raw.as<double>();
-    const double *sxa, *sya, *sxb, *syb;
-    if (c->raw_stride == 1) { sxa = d; sya = d + n; sxb = d + 2 * n; syb = d + 3 * n; }
-    else { sxa = d; sya = d + 1; sxb = d + 2 * n; syb = d + 2 * n + 1; }
-    k_triangulate<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(sxa, sya, sxb, syb, c->raw_stride, -1, cnt_dev,
-                                                                      nullptr, nullptr, c->Ks.as<double>(),
-                                                                      c->poses.as<PoseSet>(), c->pass.as<uint8_t>(), 1,
-                                                                      c->X.as<double>(), c->idx.as<long long>());
-    if (int r = check_launch(c, "k_triangulate")) return r;
+    k_tail_triangulate<<<dim3((unsigned)((max_len + 127) / 128), (unsigned)P), 128, 0, c->stream>>>(a);
+    if (int r = check_launch(c, "k_tail_triangulate")) return r;
     c->toc(T_TRI);
+    return 0;
+}
+
+// the record of a winner the host chose (sfm_get_best / sfm_set_winner) for the tail
+static int host_winner_record(sfm_ctx* c, const SelectRecord** out) {
+    if (int r = c->winrec.reserve(sizeof(SelectRecord))) return r;
+    const int32_t* row = (c->has_table && c->winner_local >= 0) ? c->table.as<int32_t>() + 8 * c->winner_local : nullptr;
+    k_make_record<<<1, 32, 0, c->stream>>>(winner_E_dev(c), row, c->winner_local >= 0 ? c->winner_local : 0,
+                                           c->winrec.as<SelectRecord>());
+    if (int r = check_launch(c, "k_make_record")) return r;
+    *out = c->winrec.as<SelectRecord>();
     return 0;
 }
 
 // results of pose_tail_launch to the host: fixed-size part first (one synchronisation), then the per-inlier arrays
 static int pose_tail_fetch(sfm_ctx* c, sfm_poses* poses, int64_t cap, int64_t* num_inliers, int64_t* inlier_idx,
                            uint8_t* pass, double* X, sfm_best* best /* may be null */) {
-    const int cblocks = (int)((c->n + 1023) / 1024);
-    const long long* cnt_dev = c->scan.as<long long>() + cblocks;
+    const long long* cnt_dev = c->num.as<long long>();
     if (int r = ensure_pinned(c, 64 + sizeof(SelectRecord))) return r;
     CU(cudaMemcpyAsync(c->hpin, cnt_dev, 8, cudaMemcpyDeviceToHost, c->stream));
     if (best) CU(cudaMemcpyAsync((char*)c->hpin + 64, c->record.p, sizeof(SelectRecord), cudaMemcpyDeviceToHost, c->stream));
@@ -994,7 +1065,9 @@ int sfm_pose_and_triangulate(sfm_ctx* c, double thr, double dist_thr, sfm_poses*
     if (!poses || !num_inliers) return fail(SFM_ERR_ARG, "null argument");
     if (!c->has_pts || c->batched) return fail(SFM_ERR_STATE, "no single-pair correspondences loaded");
     if (!c->winner_set) return fail(SFM_ERR_STATE, "no winner: run sfm_ransac_essential / sfm_get_best first");
-    if (int r = pose_tail_launch(c, thr, dist_thr, nullptr)) return r;
+    const SelectRecord* rec = nullptr;
+    if (int r = host_winner_record(c, &rec)) return r;
+    if (int r = pose_tail_launch(c, thr, dist_thr, rec, c->n)) return r;
     return pose_tail_fetch(c, poses, cap, num_inliers, inlier_idx, pass, X, nullptr);
 }
 
@@ -1008,7 +1081,7 @@ int sfm_two_view(sfm_ctx* c, double thr, double min_extra, int agg, int mode, do
     if (int r = score_launch(c, thr, min_extra, agg, mode, true, 0, c->n)) return r;
     // the winner stays on the device: mask, compaction, decomposition, vote and triangulation are enqueued right
     // behind the selection, and the host synchronises once for all fixed-size results
-    if (int r = pose_tail_launch(c, thr, dist_thr, c->best.as<Best>(), mask, sed)) return r;
+    if (int r = pose_tail_launch(c, thr, dist_thr, c->record.as<SelectRecord>(), c->n, mask, sed)) return r;
     return pose_tail_fetch(c, poses, cap, num_inliers, inlier_idx, pass, X, best);
 }
 
@@ -1036,7 +1109,7 @@ int sfm_sharded_tail(sfm_ctx* c, const void* gathered_records_dev, int world, in
     k_merge_records<<<1, 32, 0, c->stream>>>(reinterpret_cast<const SelectRecord*>(gathered_records_dev), world, rank,
                                              (long long)hyps_per_rank, mode, merged, owner, c->winnerE.as<double>(), local_best);
     if (int r = check_launch(c, "k_merge_records")) return r;
-    return pose_tail_launch(c, thr, dist_thr, local_best, nullptr, nullptr, c->winnerE.as<double>());
+    return pose_tail_launch(c, thr, dist_thr, merged, c->n);
 }
 
 int sfm_sharded_fetch(sfm_ctx* c, sfm_best* best, int32_t* owner, sfm_poses* poses, int64_t cap, int64_t* num_inliers,
@@ -1044,8 +1117,7 @@ int sfm_sharded_fetch(sfm_ctx* c, sfm_best* best, int32_t* owner, sfm_poses* pos
     if (int r = use(c)) return r;
     if (!best || !owner || !poses || !num_inliers) return fail(SFM_ERR_ARG, "null argument");
     if (!c->merged.p) return fail(SFM_ERR_STATE, "sfm_sharded_tail first");
-    const int cblocks = (int)((c->n + 1023) / 1024);
-    const long long* cnt_dev = c->scan.as<long long>() + cblocks;
+    const long long* cnt_dev = c->num.as<long long>();
     const size_t mbytes = sizeof(SelectRecord) + sizeof(Best) + 16;
     if (int r = ensure_pinned(c, 64 + mbytes)) return r;
     CU(cudaMemcpyAsync(c->hpin, cnt_dev, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1083,11 +1155,10 @@ int sfm_sharded_fetch(sfm_ctx* c, sfm_best* best, int32_t* owner, sfm_poses* pos
 }
 
 // ---- batched pairs ------------------------------------------------------------------------
-int sfm_batch_ransac(sfm_ctx* c, const double* xa, const double* ya, const double* xb, const double* yb,
-                     int64_t stride, const int64_t* offsets, int64_t npairs, const double* Ks, int64_t h,
-                     uint64_t seed, uint64_t pair_id0, double thr, double min_extra, int agg, int mode, double* E,
-                     int64_t* best_index, double* best_err, int32_t* count_extra, int64_t* num_invalid) {
-    if (int r = use(c)) return r;
+// upload -> device sampler -> fit -> score + select of P independent pairs (nothing synchronised)
+static int batch_core(sfm_ctx* c, const double* xa, const double* ya, const double* xb, const double* yb, int64_t stride,
+                      const int64_t* offsets, int64_t npairs, const double* Ks, int64_t h, uint64_t seed, uint64_t pair_id0,
+                      double thr, double min_extra, int agg, int mode, long long* max_len_out) {
     if (!xa || !ya || !xb || !yb || !offsets || !Ks) return fail(SFM_ERR_ARG, "null argument");
     if (npairs <= 0 || npairs > 65535) return fail(SFM_ERR_ARG, "need 1 <= npairs <= 65535 per call");
     if (h <= 0) return fail(SFM_ERR_ARG, "need h > 0");
@@ -1115,29 +1186,97 @@ int sfm_batch_ransac(sfm_ctx* c, const double* xa, const double* ya, const doubl
     if (int r = sample_device(c, seed, pair_id0, 0, h)) return r;
     if (int r = fit_launch(c, false)) return r;
     if (int r = score_launch(c, thr, min_extra, agg, mode, true, 0, max_len)) return r;
-    // gather per-pair winners
-    if (int r = c->tmp.reserve((size_t)npairs * 72)) return r;
-    k_gather_winners<<<(unsigned)((npairs + 127) / 128), 128, 0, c->stream>>>(c->best.as<Best>(), c->E.as<double>(), h,
-                                                                              (int)npairs, c->tmp.as<double>());
-    if (int r = check_launch(c, "k_gather_winners")) return r;
-    const size_t bytes = (size_t)npairs * (sizeof(Best) + 16 + 72);
-    if (int r = ensure_pinned(c, bytes)) return r;
+    *max_len_out = max_len;
+    return 0;
+}
+
+// per-pair winners of the last batch score -> host arrays (the selection records hold everything)
+static int batch_fetch_winners(sfm_ctx* c, int64_t npairs, double* E, int64_t* best_index, double* best_err,
+                               int32_t* count_extra, int64_t* num_invalid, size_t extra_pinned, char** extra) {
+    const size_t rbytes = (size_t)npairs * sizeof(SelectRecord);
+    if (int r = ensure_pinned(c, rbytes + extra_pinned + 64)) return r;
     char* hp = (char*)c->hpin;
-    CU(cudaMemcpyAsync(hp, c->best.p, (size_t)npairs * sizeof(Best), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(hp + npairs * sizeof(Best), c->invalid.p, (size_t)npairs * 16, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(hp + npairs * (sizeof(Best) + 16), c->tmp.p, (size_t)npairs * 72, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    const Best* hb = reinterpret_cast<const Best*>(hp);
-    const long long* hinv = reinterpret_cast<const long long*>(hp + npairs * sizeof(Best));
-    const double* hE = reinterpret_cast<const double*>(hp + npairs * (sizeof(Best) + 16));
+    CU(cudaMemcpyAsync(hp, c->record.p, rbytes, cudaMemcpyDeviceToHost, c->stream));
+    if (extra) *extra = hp + ((rbytes + 63) / 64) * 64;
+    return 0;
+}
+
+static void batch_unpack_winners(const char* hp, int64_t npairs, double* E, int64_t* best_index, double* best_err,
+                                 int32_t* count_extra, int64_t* num_invalid) {
+    const SelectRecord* hr = reinterpret_cast<const SelectRecord*>(hp);
     for (int64_t p = 0; p < npairs; ++p) {
-        if (best_index) best_index[p] = hb[p].idx;
-        if (best_err) best_err[p] = hb[p].idx >= 0 ? hb[p].err : __builtin_inf();
-        if (count_extra) count_extra[p] = hb[p].idx >= 0 ? hb[p].count : -1;
-        if (num_invalid) num_invalid[p] = hinv[2 * p];
-        if (E) memcpy(E + 9 * p, hE + 9 * p, 72);
+        const bool ok = hr[p].best.idx >= 0;
+        if (best_index) best_index[p] = hr[p].best.idx;
+        if (best_err) best_err[p] = ok ? hr[p].best.err : __builtin_inf();
+        if (count_extra) count_extra[p] = ok ? hr[p].best.count : -1;
+        if (num_invalid) num_invalid[p] = hr[p].num_invalid;
+        if (E) memcpy(E + 9 * p, hr[p].E, 72);
     }
+}
+
+int sfm_batch_ransac(sfm_ctx* c, const double* xa, const double* ya, const double* xb, const double* yb,
+                     int64_t stride, const int64_t* offsets, int64_t npairs, const double* Ks, int64_t h,
+                     uint64_t seed, uint64_t pair_id0, double thr, double min_extra, int agg, int mode, double* E,
+                     int64_t* best_index, double* best_err, int32_t* count_extra, int64_t* num_invalid) {
+    if (int r = use(c)) return r;
+    long long max_len = 0;
+    if (int r = batch_core(c, xa, ya, xb, yb, stride, offsets, npairs, Ks, h, seed, pair_id0, thr, min_extra, agg, mode,
+                           &max_len)) return r;
+    if (int r = batch_fetch_winners(c, npairs, E, best_index, best_err, count_extra, num_invalid, 0, nullptr)) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    batch_unpack_winners((const char*)c->hpin, npairs, E, best_index, best_err, count_extra, num_invalid);
     c->has_score = false;  // per-hypothesis single-pair getters do not apply to batches
+    c->winner_set = false;
+    return 0;
+}
+
+// The whole path per pair (apps/sfm.py:110-186 for every pair of the batch): RANSAC E, then for each pair's winner the
+// inlier list, the 4-pose cheirality vote and the triangulation of the passing inliers - the same three tail kernels as
+// the single-pair call, with the pair as blockIdx.y.  Per-inlier results come back densely packed:
+// inlier_offsets[p] .. inlier_offsets[p+1] index inlier_idx (pair-relative, ascending), pass and X.
+int sfm_batch_two_view(sfm_ctx* c, const double* xa, const double* ya, const double* xb, const double* yb,
+                       int64_t stride, const int64_t* offsets, int64_t npairs, const double* Ks, int64_t h,
+                       uint64_t seed, uint64_t pair_id0, double thr, double min_extra, int agg, int mode,
+                       double dist_thr, double* E, int64_t* best_index, double* best_err, int32_t* count_extra,
+                       int64_t* num_invalid, sfm_poses* poses, int64_t* inlier_offsets, int64_t cap,
+                       int32_t* inlier_idx, uint8_t* pass, double* X) {
+    if (int r = use(c)) return r;
+    if (!poses || !inlier_offsets) return fail(SFM_ERR_ARG, "null argument");
+    long long max_len = 0;
+    if (int r = batch_core(c, xa, ya, xb, yb, stride, offsets, npairs, Ks, h, seed, pair_id0, thr, min_extra, agg, mode,
+                           &max_len)) return r;
+    if (int r = pose_tail_launch(c, thr, dist_thr, c->record.as<SelectRecord>(), max_len)) return r;
+    // dense packing of the per-pair inlier segments
+    const long long n = c->n;
+    const size_t o_off = 0, o_idx = ((size_t)(npairs + 1) * 8 + 63) / 64 * 64, o_pass = o_idx + ((size_t)n * 4 + 63) / 64 * 64,
+                 o_X = o_pass + ((size_t)n + 63) / 64 * 64;
+    if (int r = c->bout.reserve(o_X + (size_t)n * 24)) return r;
+    char* bo = c->bout.as<char>();
+    long long* d_off = reinterpret_cast<long long*>(bo + o_off);
+    k_batch_offsets<<<1, 1024, 0, c->stream>>>(c->num.as<long long>(), (int)npairs, d_off);
+    if (int r = check_launch(c, "k_batch_offsets")) return r;
+    const unsigned gx = (unsigned)((max_len + 255) / 256 > 0 ? (max_len + 255) / 256 : 1);
+    k_batch_pack<<<dim3(gx, (unsigned)npairs), 256, 0, c->stream>>>(
+        c->offsets.as<long long>(), c->num.as<long long>(), d_off, c->idx.as<long long>(), c->pass.as<uint8_t>(),
+        c->X.as<double>(), reinterpret_cast<int32_t*>(bo + o_idx), reinterpret_cast<uint8_t*>(bo + o_pass),
+        reinterpret_cast<double*>(bo + o_X));
+    if (int r = check_launch(c, "k_batch_pack")) return r;
+    char* extra = nullptr;
+    const size_t pose_bytes = (size_t)npairs * sizeof(PoseSet);
+    if (int r = batch_fetch_winners(c, npairs, E, best_index, best_err, count_extra, num_invalid, pose_bytes, &extra)) return r;
+    CU(cudaMemcpyAsync(poses, c->poses.p, pose_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(inlier_offsets, d_off, (size_t)(npairs + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    batch_unpack_winners((const char*)c->hpin, npairs, E, best_index, best_err, count_extra, num_invalid);
+    const long long total = inlier_offsets[npairs];
+    const long long take = total < cap ? total : cap;
+    if (take > 0) {
+        if (inlier_idx) CU(cudaMemcpyAsync(inlier_idx, bo + o_idx, (size_t)take * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (pass) CU(cudaMemcpyAsync(pass, bo + o_pass, (size_t)take, cudaMemcpyDeviceToHost, c->stream));
+        if (X) CU(cudaMemcpyAsync(X, bo + o_X, (size_t)take * 24, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    c->has_score = false;
     c->winner_set = false;
     return 0;
 }

@@ -174,7 +174,8 @@ k_cheirality(const Corr* __restrict__ pts, long long m, const long long* __restr
         // the count_nonzero-of-indices quirk (:228-230): the correspondence at list position 0
         // never counts.  In the fused pipeline position 0 is the winner's first sample point
         // (lib/ransac/ransac.py:76 returns the samples first).
-        counts = ok && !(quirk_row ? (gi == quirk_row[0]) : (i == 0));
+        const bool has_row = quirk_row && quirk_row[0] >= 0;  // a row of -1 = no sample table
+        counts = ok && !(has_row ? (gi == quirk_row[0]) : (i == 0));
     }
     const unsigned lane = threadIdx.x & 31u;
     const unsigned okb = __ballot_sync(0xffffffffu, ok);

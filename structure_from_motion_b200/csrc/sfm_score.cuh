@@ -165,7 +165,6 @@ struct ScoreArgs {
     long long htotal;          // npairs * h
     unsigned* work_counter;
     unsigned long long* acc;   // [kAccWords][htotal] exact integer accumulators (pre-zeroed)
-    int debug_flags;           // experiments only: 1 = discard survivors instead of scoring them
 };
 
 __device__ __forceinline__ unsigned atom_add_acq_rel_shared(unsigned* p, unsigned v) {
@@ -389,7 +388,7 @@ k_score(const ScoreArgs a) {
                 for (; take > 0; --take) pm &= pm - 1u;
                 q[(head + lane) & (kRing - 1)].x = pm;
             }
-            if (!(a.debug_flags & 1)) {
+            {
                 unsigned pmj = rj.x;
                 for (int k = (int)(o >> 8); k > 0; --k) pmj &= pmj - 1u;  // drop the k lowest set bits
                 const int bit = act ? (__ffs(pmj) - 1) : 0;
@@ -428,7 +427,6 @@ k_score(const ScoreArgs a) {
 
         // one record per lane with survivors in this batch (ballot-compacted: no atomics, no loop)
         auto push = [&](unsigned pm, unsigned rel0) {
-            if (a.debug_flags & 4) return;
             const unsigned vote = __ballot_sync(full, pm != 0u);
             if (pm) q[(tail + __popc(vote & lt)) & (kRing - 1)] = make_uint2(pm, ((unsigned)lane << 27) | rel0);
             tail += __popc(vote);
@@ -542,6 +540,7 @@ struct SelectRecord {
     Best best;
     long long num_invalid, first_invalid;
     double E[9];
+    int32_t sample[8];  // the winner's minimal sample (its table row; ransac.py:63), -1 without a table or a winner
 };
 
 __device__ __forceinline__ bool better(const Best& x, const Best& y, int mode) {
@@ -589,11 +588,31 @@ __device__ __forceinline__ Best block_best(Best b, int mode, Best* sm /* 32 */) 
     return b;  // valid in thread 0
 }
 
-// sum_k plane[k] * 2^(21k) as a double; plane sums are < 2^21 * N each, the total < 2^84 * N < 2^128.
-__device__ __forceinline__ double fixed_to_double(const unsigned long long* acc, long long stride) {
+// ---- double-double helpers for the exact rescore (error-free transformations, Knuth two-sum) ----
+struct dd { double hi, lo; };
+__device__ __forceinline__ void dd_add(dd& s, double x) {
+    const double t = __dadd_rn(s.hi, x);
+    const double bb = __dsub_rn(t, s.hi);
+    const double e = __dadd_rn(__dsub_rn(s.hi, __dsub_rn(t, bb)), __dsub_rn(x, bb));
+    s.hi = t;
+    s.lo = __dadd_rn(s.lo, e);
+}
+__device__ __forceinline__ void dd_merge(dd& s, const dd& o) {
+    dd_add(s, o.hi);
+    s.lo = __dadd_rn(s.lo, o.lo);
+    const double t = __dadd_rn(s.hi, s.lo);  // renormalise
+    s.lo = __dsub_rn(s.lo, __dsub_rn(t, s.hi));
+    s.hi = t;
+}
+
+// exact 128-bit value of a fixed-point sum: sum_k plane[k] * 2^(21k)
+__device__ __forceinline__ unsigned __int128 fixed_value(const unsigned long long* acc, long long stride) {
     unsigned __int128 v = 0;
 #pragma unroll
     for (int k = kChunks - 1; k >= 0; --k) v = (v << kChunkBits) + acc[(long long)k * stride];
+    return v;
+}
+__device__ __forceinline__ double u128_to_double(unsigned __int128 v) {
     const unsigned long long hi = (unsigned long long)(v >> 64), lo = (unsigned long long)v;
     return fma((double)hi, 18446744073709551616.0, (double)lo);
 }
@@ -609,8 +628,9 @@ struct FinalArgs {
     long long idx_offset;  // global index of hypothesis 0 (hypothesis-sharded runs)
     long long htotal;                 // npairs * h (stride of the accumulator planes)
     const unsigned long long* acc;    // [kAccWords][htotal] exact sums from K2
-    double inv_scale1, inv_scale2;    // 2^(e-63), 2^(2e-63)
+    double inv_scale1, inv_scale2;    // 2^(e-84), 2^(2e-84)
     int sums;                         // which sums K2 accumulated (the other one is reported as NaN)
+    int force_rescore;                // K2 did not run (threshold outside the fixed-point range): rescore everything
     double thr, min_extra;
     int agg, mode;
     int32_t* count_extra;
@@ -619,122 +639,222 @@ struct FinalArgs {
     double* err;
     Best* block_out;
     long long* block_inv;  // [npairs][blocks][2]: invalid hypotheses in the block, smallest global index among them
+    unsigned* tickets;     // [npairs], zero on entry, zero again on exit
+    Best* out;             // [npairs]
+    long long* invalid_out;  // [npairs][2]
+    SelectRecord* record;    // [npairs]
+    unsigned long long* rescored;  // [1] number of hypotheses that went through the exact rescore (diagnostic)
 };
 
+// the sample rule + aggregation + candidate test of one hypothesis (ransac.py:63-64, 70-76, 96-108), given the count and
+// the sums over ALL correspondences with sed <= thr
+__device__ __forceinline__ bool finalise_one(const FinalArgs& a, const Corr* pts, long long i, long long npts, bool valid,
+                                             long long cnt, double s1, double s2, double& err_out, long long& cnt_out,
+                                             double& s1_out, double& s2_out) {
+    const double msac = __dadd_rn(s1, __dmul_rn(a.thr, (double)(npts - cnt)));  // K2 saw every correspondence
+    if (a.table && valid) {
+        double e[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) e[k] = a.E[9 * i + k];
+        for (int k = 0; k < 8; ++k) {
+            const Corr c = pts[a.table[8 * i + k]];
+            const double sv = sed_exact(e, c.xa, c.ya, c.xb, c.yb);
+            if (sv <= a.thr) {
+                cnt -= 1;  // was counted by K2, but samples are not "extra" inliers
+            } else {
+                s1 = __dadd_rn(s1, sv);  // not counted by K2, but always part of the error
+                s2 = __dadd_rn(s2, __dmul_rn(sv, sv));
+            }
+        }
+    }
+    const double n = (double)((a.table ? 8 : 0) + cnt);
+    double err;
+    switch (a.agg) {
+        case AGG_SUM: err = s1; break;
+        case AGG_SQUARE: err = s2; break;
+        case AGG_MEAN: err = s1 / n; break;
+        default: err = sqrt(s2 / n); break;
+    }
+    if (a.mode == SELECT_MSAC) err = msac;
+    err_out = err; cnt_out = cnt; s1_out = s1; s2_out = s2;
+    return valid && (a.min_extra <= (double)cnt) && (err == err);
+}
+
+// K3, one launch.  Thread per hypothesis: integer accumulators -> one rounding, sample rule, aggregation, candidate
+// test.  A hypothesis whose fixed-point sum carries fewer than 53 significant bits per term (its inliers are more than
+// 2^31 times tighter than the threshold - noise-free data, the reference's own RANSAC test) is RESCORED by the whole
+// block: exact scorer over all correspondences, double-double sums in a fixed order (strided partials, fixed tree), so
+// the result is still independent of scheduling, sharding and scoring variant.  Block arg-min, then the last block of
+// the pair to finish (ticket) reduces the per-block results into the selection record.
 __global__ void __launch_bounds__(256) k_finalise(const FinalArgs a) {
     __shared__ Best sm[32];
-    const long long li = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    __shared__ int s_list[256];
+    __shared__ int s_nlist;
+    __shared__ dd s_dd[2][8];
+    __shared__ long long s_cnt[8];
+    __shared__ long long s_first;
+    __shared__ int s_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long li = blockIdx.x * (long long)blockDim.x + tid;
     const long long i = (long long)blockIdx.y * a.h + li;  // blockIdx.y = image pair
     const Corr* pts = a.pts + (a.offsets ? a.offsets[blockIdx.y] : 0);
+    const long long npts = a.offsets ? a.offsets[blockIdx.y + 1] - a.offsets[blockIdx.y] : a.n;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    const double pinf = __longlong_as_double(0x7ff0000000000000LL);
+    if (tid == 0) { s_nlist = 0; s_first = 0x7fffffffffffffffLL; }
+    __syncthreads();
     Best b;
     b.err = 0.0; b.idx = -1; b.count = 0; b.pad = 0;
     if (li < a.h) {
-        // exact integer sums -> one rounding each
-        long long cnt = (long long)a.acc[i];
-        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-        double s1 = (a.sums & SUM_S1) ? fixed_to_double(a.acc + 1 * a.htotal + i, a.htotal) * a.inv_scale1 : qnan;
-        double s2 = (a.sums & SUM_S2) ? fixed_to_double(a.acc + (1 + kChunks) * a.htotal + i, a.htotal) * a.inv_scale2 : qnan;
         const bool valid = a.valid ? (a.valid[i] != 0) : true;
-        const long long npts = a.offsets ? a.offsets[blockIdx.y + 1] - a.offsets[blockIdx.y] : a.n;
-        const double msac = __dadd_rn(s1, __dmul_rn(a.thr, (double)(npts - cnt)));  // K2 saw every correspondence
-        if (a.table && valid) {
-            double e[9];
+        const long long cnt = (long long)a.acc[i];
+        const unsigned __int128 v1 = (a.sums & SUM_S1) ? fixed_value(a.acc + 1 * a.htotal + i, a.htotal) : 0;
+        const unsigned __int128 v2 = (a.sums & SUM_S2) ? fixed_value(a.acc + (1 + kChunks) * a.htotal + i, a.htotal) : 0;
+        // truncation loses < 1 unit per term: the sum is good to 2^-53 relative iff V >= cnt * 2^53
+        const unsigned __int128 need = (unsigned __int128)(unsigned long long)cnt << 53;
+        const bool coarse = cnt > 0 && (((a.sums & SUM_S1) && v1 < need) || ((a.sums & SUM_S2) && v2 < need));
+        if (valid && (a.force_rescore || coarse)) {
+            s_list[atomicAdd(&s_nlist, 1)] = tid;
+        } else {
+            const double s1 = (a.sums & SUM_S1) ? u128_to_double(v1) * a.inv_scale1 : qnan;
+            const double s2 = (a.sums & SUM_S2) ? u128_to_double(v2) * a.inv_scale2 : qnan;
+            double err, s1o, s2o;
+            long long c2;
+            const bool cand = finalise_one(a, pts, i, npts, valid, cnt, s1, s2, err, c2, s1o, s2o);
+            a.count_extra[i] = valid ? (int32_t)c2 : -1;
+            a.S1[i] = s1o;
+            a.S2[i] = s2o;
+            a.err[i] = cand ? err : pinf;
+            if (cand) { b.err = err; b.idx = a.idx_offset + li; b.count = (int)c2; }
+        }
+    }
+    __syncthreads();
+    // exact rescore of the listed hypotheses, one after the other, by all threads of the block
+    const int nlist = s_nlist;
+    for (int q = 0; q < nlist; ++q) {
+        const int owner = s_list[q];
+        const long long hi_ = (long long)blockIdx.y * a.h + blockIdx.x * (long long)blockDim.x + owner;
+        double e[9];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) e[k] = a.E[9 * i + k];
-            for (int k = 0; k < 8; ++k) {
-                const Corr c = pts[a.table[8 * i + k]];
-                const double sv = sed_exact(e, c.xa, c.ya, c.xb, c.yb);
-                if (sv <= a.thr) {
-                    cnt -= 1;  // was counted by K2, but samples are not "extra" inliers
-                } else {
-                    s1 = __dadd_rn(s1, sv);  // not counted by K2, but always part of the error
-                    s2 = __dadd_rn(s2, __dmul_rn(sv, sv));
-                }
+        for (int k = 0; k < 9; ++k) e[k] = a.E[9 * hi_ + k];
+        dd p1{0.0, 0.0}, p2{0.0, 0.0};
+        long long pc = 0;
+        for (long long j = tid; j < npts; j += 256) {
+            const Corr c = pts[j];
+            const double sv = sed_exact(e, c.xa, c.ya, c.xb, c.yb);
+            if (sv <= a.thr) {  // ransac.py:73
+                pc += 1;
+                dd_add(p1, sv);
+                dd_add(p2, __dmul_rn(sv, sv));
             }
         }
-        const double n = (double)((a.table ? 8 : 0) + cnt);
-        double err;
-        switch (a.agg) {
-            case AGG_SUM: err = s1; break;
-            case AGG_SQUARE: err = s2; break;
-            case AGG_MEAN: err = s1 / n; break;
-            default: err = sqrt(s2 / n); break;
+        // fixed reduction tree: lanes (xor 16..1), then warps 0..7 in order
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            dd o1, o2;
+            o1.hi = __shfl_xor_sync(0xffffffffu, p1.hi, d); o1.lo = __shfl_xor_sync(0xffffffffu, p1.lo, d);
+            o2.hi = __shfl_xor_sync(0xffffffffu, p2.hi, d); o2.lo = __shfl_xor_sync(0xffffffffu, p2.lo, d);
+            pc += __shfl_xor_sync(0xffffffffu, pc, d);
+            // keep the merge symmetric so that both partners compute the same value: lower lane's partial first
+            if (lane & d) { dd t1 = o1, t2 = o2; dd_merge(t1, p1); dd_merge(t2, p2); p1 = t1; p2 = t2; }
+            else { dd_merge(p1, o1); dd_merge(p2, o2); }
         }
-        if (a.mode == SELECT_MSAC) err = msac;
-        const bool cand = valid && (a.min_extra <= (double)cnt) && (err == err);
-        a.count_extra[i] = valid ? (int32_t)cnt : -1;
-        a.S1[i] = s1;
-        a.S2[i] = s2;
-        a.err[i] = cand ? err : __longlong_as_double(0x7ff0000000000000LL);
-        if (cand) { b.err = err; b.idx = a.idx_offset + li; b.count = (int)cnt; }
+        if (lane == 0) { s_dd[0][warp] = p1; s_dd[1][warp] = p2; s_cnt[warp] = pc; }
+        __syncthreads();
+        if (tid == owner) {
+            dd t1 = s_dd[0][0], t2 = s_dd[1][0];
+            long long c = s_cnt[0];
+            for (int w = 1; w < 8; ++w) { dd_merge(t1, s_dd[0][w]); dd_merge(t2, s_dd[1][w]); c += s_cnt[w]; }
+            double err, s1o, s2o;
+            long long c2;
+            const bool cand = finalise_one(a, pts, hi_, npts, true, c, (a.sums & SUM_S1) ? t1.hi : qnan,
+                                           (a.sums & SUM_S2) ? t2.hi : qnan, err, c2, s1o, s2o);
+            a.count_extra[hi_] = (int32_t)c2;
+            a.S1[hi_] = s1o;
+            a.S2[hi_] = s2o;
+            a.err[hi_] = cand ? err : pinf;
+            if (cand) { b.err = err; b.idx = a.idx_offset + (hi_ - (long long)blockIdx.y * a.h); b.count = (int)c2; }
+        }
+        __syncthreads();
     }
+    if (tid == 0 && nlist) atomicAdd(a.rescored, (unsigned long long)nlist);
     // invalid hypotheses of this block (ransac.py:65 has no try/except: one degenerate sample aborts the reference run,
     // so the host needs their number and the earliest one)
-    __shared__ long long s_first;
-    if (threadIdx.x == 0) s_first = 0x7fffffffffffffffLL;
     const bool inv = (li < a.h) && a.valid && (a.valid[i] == 0);
     const int ninv = __syncthreads_count(inv);
     if (inv) atomicMin(&s_first, a.idx_offset + li);
     b = block_best(b, a.mode, sm);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const long long blk = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+    const int nblocks = gridDim.x;
+    if (tid == 0) {
+        const long long blk = (long long)blockIdx.y * nblocks + blockIdx.x;
         a.block_out[blk] = b;
         a.block_inv[2 * blk] = ninv;
         a.block_inv[2 * blk + 1] = s_first;
+        __threadfence();
+        s_last = (atomicAdd(&a.tickets[blockIdx.y], 1u) == (unsigned)(nblocks - 1)) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    // ---- last block of the pair: reduce the per-block results into the selection record ----
+    __threadfence();
+    __shared__ long long s_ninv, s_first2;
+    if (tid == 0) { s_ninv = 0; s_first2 = 0x7fffffffffffffffLL; a.tickets[blockIdx.y] = 0; }
+    __syncthreads();
+    const volatile Best* blocks = a.block_out + (long long)blockIdx.y * nblocks;
+    const volatile long long* binv = a.block_inv + 2 * (long long)blockIdx.y * nblocks;
+    Best g;
+    g.err = 0.0; g.idx = -1; g.count = 0; g.pad = 0;
+    long long tn = 0, tf = 0x7fffffffffffffffLL;
+    for (int k = tid; k < nblocks; k += 256) {
+        Best o;
+        o.err = blocks[k].err; o.idx = blocks[k].idx; o.count = blocks[k].count; o.pad = 0;
+        if (better(o, g, a.mode)) g = o;
+        tn += binv[2 * k];
+        const long long f = binv[2 * k + 1];
+        if (f < tf) tf = f;
+    }
+    if (tn) {
+        atomicAdd((unsigned long long*)&s_ninv, (unsigned long long)tn);
+        atomicMin(&s_first2, tf);
+    }
+    g = block_best(g, a.mode, sm);
+    __syncthreads();
+    if (tid == 0) {
+        a.out[blockIdx.y] = g;
+        a.invalid_out[2 * blockIdx.y] = s_ninv;
+        a.invalid_out[2 * blockIdx.y + 1] = s_ninv ? s_first2 : -1;
+        // everything the host wants about this pair in one record (one D2H copy, one synchronisation)
+        SelectRecord& r = a.record[blockIdx.y];
+        r.best = g;
+        r.num_invalid = s_ninv;
+        r.first_invalid = s_ninv ? s_first2 : -1;
+        const long long w = (long long)blockIdx.y * a.h + (g.idx >= 0 ? g.idx - a.idx_offset : 0);
+        for (int k = 0; k < 9; ++k) r.E[k] = g.idx >= 0 ? a.E[9 * w + k] : 0.0;
+        for (int k = 0; k < 8; ++k) r.sample[k] = (a.table && g.idx >= 0) ? a.table[8 * w + k] : -1;
     }
 }
 
-// Single block: reduce per-block bests; also counts invalid hypotheses (ransac.py:65 has no
-// try/except around the fitter, so one degenerate sample aborts the reference run).
-__global__ void __launch_bounds__(256)
-k_select(const Best* __restrict__ blocks, int nblocks, int mode, const long long* __restrict__ block_inv,
-         long long h, long long idx_offset, Best* __restrict__ out, long long* __restrict__ invalid_out,
-         const double* __restrict__ E, SelectRecord* __restrict__ record) {
-    __shared__ Best sm[32];
-    __shared__ long long s_ninv, s_first;
-    if (threadIdx.x == 0) { s_ninv = 0; s_first = 0x7fffffffffffffffLL; }
-    __syncthreads();
-    // blockIdx.x = image pair
-    blocks += (long long)blockIdx.x * nblocks;
-    block_inv += 2 * (long long)blockIdx.x * nblocks;
-    out += blockIdx.x;
-    invalid_out += 2 * (long long)blockIdx.x;
-    Best b;
-    b.err = 0.0; b.idx = -1; b.count = 0; b.pad = 0;
-    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) {
-        const Best o = blocks[i];
-        if (better(o, b, mode)) b = o;
-    }
-    long long ninv = 0, first = 0x7fffffffffffffffLL;
-    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) {  // per-block counts from k_finalise
-        ninv += block_inv[2 * i];
-        if (block_inv[2 * i + 1] < first) first = block_inv[2 * i + 1];
-    }
-    if (ninv) {
-        atomicAdd((unsigned long long*)&s_ninv, (unsigned long long)ninv);
-        atomicMin(&s_first, first);
-    }
-    b = block_best(b, mode, sm);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        *out = b;
-        invalid_out[0] = s_ninv;
-        invalid_out[1] = s_ninv ? s_first : -1;
-        // everything the host wants about this pair in one 112-byte record (one D2H copy, one synchronisation)
-        SelectRecord& r = record[blockIdx.x];
-        r.best = b;
-        r.num_invalid = s_ninv;
-        r.first_invalid = s_ninv ? s_first : -1;
-        const double* e = E + 9 * ((long long)blockIdx.x * h + (b.idx >= 0 ? b.idx - idx_offset : 0));
-        for (int k = 0; k < 9; ++k) r.E[k] = b.idx >= 0 ? e[k] : 0.0;
+// candidates whose error is within rel_tol of the winner's (ransac.py:83 compares errors that were
+// summed in list order; the host re-evaluates near-ties in that order).  Appends up to cap local indices, unordered.
+__global__ void __launch_bounds__(256) k_near_ties(const double* __restrict__ err, long long h, const SelectRecord* __restrict__ rec,
+                                                   double rel_tol, int cap, long long* __restrict__ out, unsigned* __restrict__ count) {
+    const double best = rec->best.err;
+    if (rec->best.idx < 0) return;
+    const double lim = best + fabs(best) * rel_tol;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < h; i += (long long)gridDim.x * blockDim.x) {
+        if (err[i] <= lim) {
+            const unsigned pos = atomicAdd(count, 1u);
+            if (pos < (unsigned)cap) out[pos] = i;
+        }
     }
 }
 
 // Hypothesis-sharded runs: every rank's SelectRecord, gathered by one NCCL all-gather, is merged on
 // the device with the reference's rule (smallest error, earliest GLOBAL iteration on ties, ransac.py:83; or the
 // non-default modes) so that the tail can be enqueued without a host round trip.  One thread.
-//   merged      : winner with its global index (idx = owner * hyps_per_rank + local idx), this rank's invalid counters
+//   merged      : winner with its global index (idx = owner * hyps_per_rank + local idx), its model and sample row,
+//                 this rank's invalid counters
 //   winner_E    : the winning model (the tail reads it from here whichever rank fitted it)
 //   local_best  : Best whose idx is this rank's local index if it owns the winner, else -1 (sample-row lookups)
 __global__ void k_merge_records(const SelectRecord* __restrict__ gathered, int world, int rank, long long hyps_per_rank,
@@ -757,6 +877,9 @@ __global__ void k_merge_records(const SelectRecord* __restrict__ gathered, int w
         merged->E[k] = v;
         winner_E[k] = v;
     }
+    // the winner's sample row travels with the record: every rank forces the same 8 points into the inlier set
+    // (ransac.py:76) and applies the same index-0 quirk of the vote (eight_point.py:228-230)
+    for (int k = 0; k < 8; ++k) merged->sample[k] = owner >= 0 ? gathered[owner].sample[k] : -1;
     *owner_out = owner;
     Best lb = b;
     lb.idx = (owner == rank) ? gathered[rank].best.idx : -1;

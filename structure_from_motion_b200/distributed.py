@@ -120,7 +120,7 @@ def two_view_sharded(threshold, min_num_extra_inliers, aggregation, hyps_per_ran
                      world: int, selection: str = "min_error", distance_threshold: float = 50.0, group=None):
     """One complete estimate (RANSAC E -> cheirality vote -> triangulation) with the hypotheses sharded over ``world``
     GPUs and NO host round trip between scoring and the final results: every rank scores its hypotheses
-    (``sfm_score_async``), the 112-byte selection records are all-gathered device-to-device by NCCL on the engine's
+    (``sfm_score_async``), the 144-byte selection records are all-gathered device-to-device by NCCL on the engine's
     stream — the path's only collective — and merged by a kernel with the reference's rule (``sfm_sharded_tail``),
     which also enqueues the inlier mask, pose vote and triangulation of the global winner.  The correspondences must
     already be resident (``engine.upload_pairs``) and the engine must run on torch's current stream.
@@ -129,9 +129,12 @@ def two_view_sharded(threshold, min_num_extra_inliers, aggregation, hyps_per_ran
     import torch.distributed as dist
 
     n_doubles = engine.RECORD_BYTES // 8
+    dev = torch.device("cuda", engine.device)
+    # the all-gather reads the record K3 writes and the tail reads what the all-gather writes: everything has to be
+    # enqueued on ONE stream - torch's current stream of the engine's device, which NCCL orders itself with
+    engine.set_stream(torch.cuda.current_stream(dev).cuda_stream)
     engine.sample_device(seed, hyps_per_rank, hyp_offset=rank * hyps_per_rank)
     rec_ptr = engine.score_async(threshold, float(min_num_extra_inliers or 0), aggregation, selection)
-    dev = torch.device("cuda", engine.device)
     mine = torch.as_tensor(_DeviceBuffer(rec_ptr, n_doubles), device=dev)
     if world > 1:
         gathered = torch.empty(world * n_doubles, dtype=torch.float64, device=dev)
@@ -203,6 +206,42 @@ class PairPipeline:
         parts = dict(kv for res in self.pool.map(worker, range(depth)) for kv in res)
         keys = parts[0].keys()
         return {key: np.concatenate([parts[k][key] for k in range(len(bounds) - 1)]) for key in keys}
+
+    def batch_two_view(self, pts_a, pts_b, offsets, Ks, h, seed, threshold, min_extra=0.0, aggregation="rms",
+                       selection="min_error", distance_threshold=50.0, pair_id0=0, chunk_pairs: Optional[int] = None):
+        """``Engine.batch_two_view`` (RANSAC E + inlier list + pose vote + triangulation per pair) over chunks of
+        pairs that alternate between the contexts; identical to one call over all pairs."""
+        offsets = np.asarray(offsets, dtype=np.int64)
+        P = len(offsets) - 1
+        Ks = np.asarray(Ks, dtype=np.float64).reshape(P, 3, 3)
+        depth = len(self.engines)
+        if chunk_pairs is None:
+            chunk_pairs = max(1, -(-P // (4 * depth)))
+        bounds = list(range(0, P, chunk_pairs)) + [P]
+
+        def run(k):
+            p0, p1 = bounds[k], bounds[k + 1]
+            lo, hi = int(offsets[p0]), int(offsets[p1])
+            return self.engines[k % depth].batch_two_view(pts_a[lo:hi], pts_b[lo:hi], offsets[p0:p1 + 1] - lo, Ks[p0:p1],
+                                                          h, seed, threshold, min_extra, aggregation, selection,
+                                                          distance_threshold, pair_id0=pair_id0 + p0)
+
+        def worker(e):
+            return [(k, run(k)) for k in range(e, len(bounds) - 1, depth)]
+
+        parts = dict(kv for res in self.pool.map(worker, range(depth)) for kv in res)
+        nchunks = len(bounds) - 1
+        out = {}
+        for key in parts[0].keys():
+            if key == "inlier_offsets":
+                base, segs = 0, [np.zeros(1, dtype=np.int64)]
+                for k in range(nchunks):
+                    segs.append(parts[k][key][1:] + base)
+                    base += int(parts[k][key][-1])
+                out[key] = np.concatenate(segs)
+            else:
+                out[key] = np.concatenate([parts[k][key] for k in range(nchunks)])
+        return out
 
     def close(self):
         self.pool.shutdown()

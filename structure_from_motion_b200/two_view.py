@@ -37,7 +37,38 @@ class RansacResult:
 def _agg_name(method) -> str:
     if method is None:
         return "rms"  # ransac.py:50-51
-    return method.value if isinstance(method, ErrorAggregationMethod) else str(method)
+    # the reference compares ``.value`` (ransac.py:99-105), so any Enum with the same values is accepted
+    return str(getattr(method, "value", method))
+
+
+def _reference_error(errors, agg: str) -> float:
+    """_aggregate_error (lib/ransac/ransac.py:96-108) on a python list in [samples..., extra inliers...] order:
+    the reference's own summation order (python ``sum`` / numpy pairwise) — used only to settle near-ties."""
+    if agg == "sum":
+        return sum(errors)
+    if agg == "square":
+        return np.sum(np.square(errors)).item()
+    if agg == "mean":
+        return np.mean(errors).item()
+    return np.sqrt(np.mean(np.square(errors))).item()
+
+
+def _resolve_near_ties(eng, ties, threshold, agg, rows, order_after):
+    """SURVEY.md H1.  The GPU selects on exactly rounded sums; the reference keeps ``model_error < best_model_error``
+    (ransac.py:83) on errors summed in list order.  For the hypotheses whose errors agree to 1e-12 the list-order error
+    is recomputed here from the device's exact per-correspondence scores and the strict ``<`` is replayed in iteration
+    order.  rows(t) -> the 8 sample indices of hypothesis t; order_after(t) -> the correspondences that follow the
+    samples in that iteration's list (the permutation tail for the reference sampler).  Returns the local index."""
+    best_t, best_err = None, float("inf")
+    for t in ties:  # ascending = iteration order
+        eng.set_winner(int(t))
+        _, sed = eng.inlier_mask(threshold)
+        rest = order_after(int(t))
+        errs = [float(v) for v in sed[rows(int(t))]] + [float(v) for v in sed[rest][sed[rest] <= threshold]]
+        e = _reference_error(errs, agg)
+        if e < best_err:
+            best_t, best_err = int(t), e
+    return best_t, best_err
 
 
 def _get_state_words():
@@ -127,6 +158,37 @@ def ransac_essential_arrays(
         raise EightPointCalculationError(EIGHT_POINT_ERROR_MESSAGE)  # eight_point.py:417-421
     if best.index < 0:
         raise no_model()
+
+    if sampler != "device" and selection == "min_error":
+        # H1: a definite list order exists (reference sampler: the permutation; table: samples then ascending), so
+        # near-ties are settled in the reference's own summation order
+        ties, total = eng.near_ties(1e-12, 64)
+        if total > 1 and total <= 64:
+            def rows(t):
+                return np.asarray(table[t], dtype=np.int64)
+
+            def order_after(t):
+                if sampler == "reference":
+                    return ref_sampler.after(t)[1][8:].astype(np.int64)
+                keep = np.ones(n, dtype=bool)
+                keep[table[t]] = False
+                return np.nonzero(keep)[0]
+
+            t, _ = _resolve_near_ties(eng, ties, threshold, agg, rows, order_after)
+            if t is not None and t != int(best.index):
+                E_t, _ = eng.get_models(t, 1)
+                best.index = t
+                best.E[:] = tuple(E_t.reshape(9))
+                eng.set_winner(t)
+                m2, sed = eng.inlier_mask(threshold)
+                mask = m2.astype(np.uint8)
+                best.count_extra = int(m2.sum() - m2[table[t]].sum())
+                errs = [float(v) for v in sed[rows(t)]] + [float(v) for v in sed[order_after(t)][sed[order_after(t)] <= threshold]]
+                best.err = _reference_error(errs, agg)
+                if _tail is not None:
+                    _tail["out"] = list(eng.pose_and_triangulate(threshold, _tail["distance_threshold"]))
+            else:
+                eng.set_winner(int(best.index))
 
     mask = mask.astype(bool)
     local = int(best.index)

@@ -160,6 +160,59 @@ def test_config3_winner_count_equals_mask(engine, config3):
     assert np.array_equal(sed, csed.sed_exact_many(E, nxa, nya, nxb, nyb))
 
 
+def test_config3_full_size_counts_against_oracle(engine, config3):
+    """BASELINE.json configs[2] at full size against the oracle, not against itself: ALL 65 536 models the GPU fitted
+    are scored by the exact C scorer over all 100 000 correspondences (6.5e9 evaluations, threaded): extra-inlier
+    counts bit-exact, sum of squares to 1e-12, the same winner as the oracle's arg-min, and the triangulated points of
+    the winner's inliers within 1e-6 relative of the oracle's DLT (lib/epipolar/triangulation.py:9-62)."""
+    import os
+
+    c = config3
+    n, h = c["n"], c["h"]
+    engine.upload_pairs(c["x1"], c["x2"], c["K"])
+    engine.sample_device(seed=3, h=h)
+    best, _, _, poses, num, idx, ok, X = engine.two_view(THR, 10, "rms", "min_error", 50.0)
+    E, valid = engine.get_models()
+    table = engine.get_table()
+    assert valid.all()
+    nxa, nya, nxb, nyb = _norm(c["K"], c["x1"], c["x2"])
+    cnt_o, s1_o, s2_o = csed.score_batch(E.reshape(-1, 9), nxa, nya, nxb, nyb, THR, table=table,
+                                         nthreads=os.cpu_count() or 8)
+    assert np.array_equal(c["cnt"], cnt_o)
+    np.testing.assert_allclose(c["s2"], s2_o, rtol=1e-12, atol=0)
+    err_o = np.where(cnt_o >= 10, np.sqrt(s2_o / (8 + cnt_o)), np.inf)
+    win = int(np.argmin(err_o))
+    assert best.index == win == c["best"].index
+    assert abs(best.err - err_o[win]) <= 1e-12 * err_o[win]
+    # the winner's inliers (samples included, ransac.py:76), ascending
+    sed_o = csed.sed_exact_many(E[win], nxa, nya, nxb, nyb)
+    m = sed_o <= THR
+    m[table[win]] = True
+    assert num == int(m.sum()) and np.array_equal(idx, np.nonzero(m)[0])
+    # pose: the oracle's candidates from the same E; ours is one of them, the vote picked the one most points pass
+    R1, R2, t1 = o.recover_all_r_t(E[win])
+    b = int(poses.best)
+    Rg = np.array(poses.R, dtype=np.float64).reshape(4, 3, 3)[b]
+    tg = np.array(poses.t, dtype=np.float64).reshape(4, 3)[b]
+    assert min(np.abs(Rg - R).max() for R in (R1, R2)) <= 1e-9
+    assert min(np.abs(tg - t).max() for t in (t1, -t1)) <= 1e-9
+    sub = idx[:: max(1, len(idx) // 400)]  # the oracle's per-point python check on a sample of the inliers
+    passing_sub = ((ok >> b) & 1).astype(bool)[:: max(1, len(idx) // 400)]
+    want = [o.cheirality_check(nxa[i], nya[i], nxb[i], nyb[i], Rg, tg, 50.0) for i in sub]
+    assert passing_sub.tolist() == [bool(w) for w in want]
+    # triangulation of every passing inlier against the oracle's DLT
+    passing = ((ok >> b) & 1).astype(bool)
+    pi = idx[passing]
+    X_o = o.triangulate_points(c["x1"][pi, 0], c["x1"][pi, 1], c["x2"][pi, 0], c["x2"][pi, 1], c["K"], o.tmat(Rg, tg))
+    rel = np.linalg.norm(X[passing] - X_o, axis=1) / np.linalg.norm(X_o, axis=1)
+    assert rel.max() <= 1e-6, rel.max()
+    assert np.isnan(X[~passing]).all()
+    # leave the engine as the fixture left it
+    engine.sample_device(seed=3, h=h)
+    engine.fit(want_E=False)
+    engine.score(THR, min_extra=10, aggregation="rms", want_arrays=False)
+
+
 def test_config4_batch_matches_single_pairs(engine):
     """Ragged batch (a pair with too few correspondences and an empty pair included): every pair's
     winner equals the single-pair pipeline on the same (seed, pair id) sample table."""
@@ -252,13 +305,17 @@ def test_config5_scale_invariants(engine):
     assert n_extra == best.count_extra == cnt[best.index - lo]
     ssum = float(np.sum(sed[mask] ** 2) + np.sum(sed[samples][~mask[samples]] ** 2))
     assert abs(np.sqrt(ssum / (8 + n_extra)) - best.err) <= 1e-11 * best.err
-    # exact C scorer on a few hypotheses of the shard, all 1M correspondences
+    # exact C scorer on EVERY hypothesis of this rank's shard, all 1M correspondences (1.7e10 evaluations, threaded)
+    import os
+
     nxa, nya, nxb, nyb = _norm(K, x1, x2)
-    pick = np.array([0, 1, 4097, shard - 1, best.index - lo])
     table = engine.get_table()
-    cnt_o, s1_o, s2_o = csed.score_batch(E[pick].reshape(-1, 9), nxa, nya, nxb, nyb, THR, table=table[pick], nthreads=8)
-    assert np.array_equal(cnt[pick], cnt_o)
-    np.testing.assert_allclose(s2[pick], s2_o, rtol=1e-11)
+    cnt_o, s1_o, s2_o = csed.score_batch(E.reshape(-1, 9), nxa, nya, nxb, nyb, THR, table=table,
+                                         nthreads=os.cpu_count() or 8)
+    assert np.array_equal(cnt, cnt_o)
+    np.testing.assert_allclose(s2, s2_o, rtol=1e-12, atol=0)
+    err_o = np.where(cnt_o >= 10, np.sqrt(s2_o / (8 + cnt_o)), np.inf)
+    assert best.index - lo == int(np.argmin(err_o))
     # tail: cheirality vote + triangulation of the winner's inliers; the pose is the scene's (to the accuracy of an
     # eight-point fit on one minimal sample selected by min-RMS, which is what the reference computes)
     poses, num, idx, ok, X = engine.pose_and_triangulate(THR, 50.0)
@@ -294,9 +351,9 @@ def test_device_side_merge_of_sharded_records(engine):
         H = 600
         engine.sample_device(4, H, hyp_offset=1 * H)
         ptr = engine.score_async(THR, 10, "rms")
-        mine = torch.as_tensor(distributed._DeviceBuffer(ptr, 14), device="cuda").clone()
+        mine = torch.as_tensor(distributed._DeviceBuffer(ptr, engine.RECORD_BYTES // 8), device="cuda").clone()
         torch.cuda.synchronize()
-        rec = mine.cpu().numpy().copy()  # [err, idx(bits), count|pad(bits), ninv, first, E[9]]
+        rec = mine.cpu().numpy().copy()  # [err, idx(bits), count|pad(bits), ninv, first, E[9], sample int32[8]]
         as_i64 = rec.view(np.int64)
         rows = []
         for rank_r, (err_scale, idx_local) in enumerate([(None, -1), (1.0, int(as_i64[1])), (0.5, 7), (0.5, 3)]):
@@ -307,16 +364,19 @@ def test_device_side_merge_of_sharded_records(engine):
             else:
                 row[0] = rec[0] * err_scale
                 ri[1] = idx_local
-                row[5:] = rec[5:] * (1.0 + rank_r)  # a recognisable E per rank
+                row[5:14] = rec[5:14] * (1.0 + rank_r)  # a recognisable E per rank
+                row[14:].view(np.int32)[:] = np.arange(8) + 10 * rank_r  # and a recognisable sample row
             rows.append(row)
         gathered = torch.from_numpy(np.concatenate(rows)).cuda()
         engine.sharded_tail(gathered.data_ptr(), 4, 1, H, THR, 50.0)
         b, owner, poses, num, idx, ok, X = engine.sharded_fetch()
         want = distributed.merge_best(np.array([distributed.pack_local_best(
             rows[k][0], (k * H + int(rows[k].view(np.int64)[1])) if rows[k].view(np.int64)[1] >= 0 else -1,
-            int(rows[k].view(np.int32)[4]), rows[k][5:]) for k in range(4)]))
+            int(rows[k].view(np.int32)[4]), rows[k][5:14]) for k in range(4)]))
         assert owner == want[0] == 2 and b.index == want[2] == 2 * H + 7 and b.err == want[1]
-        assert np.array_equal(np.array(b.E), rows[2][5:])
+        assert np.array_equal(np.array(b.E), rows[2][5:14])
+        # the winner's sample row (rank 2's: 20..27) was forced into the inlier set on this non-owner rank (ransac.py:76)
+        assert set(range(20, 28)) <= set(idx.tolist())
         # all ranks empty
         for row in rows:
             row.view(np.int64)[1] = -1

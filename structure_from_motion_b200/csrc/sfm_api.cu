@@ -98,6 +98,8 @@ struct sfm_ctx {
     long long n = 0, h = 0, npairs = 1;
     long long raw_stride = 1;
     bool batched = false, has_pts = false, has_table = false, has_models = false, has_score = false;
+    bool acc_clean = false;  // K2's accumulators (+ tail words) are zero: the fit kernel cleared them
+    size_t acc_planes_for = 0;  // hypotheses (all pairs) the cleared accumulators were laid out for
     double Kstage[9] = {0};
     const void* occ_fn = nullptr;  // scoring kernel whose launch configuration is cached
     int occ_blocks = 0;
@@ -140,6 +142,14 @@ int ensure_pinned(sfm_ctx* c, size_t bytes) {
 int use(sfm_ctx* c) {
     if (!c) return fail(SFM_ERR_ARG, "null context");
     CU(cudaSetDevice(c->device));
+    return 0;
+}
+
+// Device buffer that must read as zero before its first use (self-cleaning kernel state).
+int reserve_zeroed(sfm_ctx* c, Buf& b, size_t bytes) {
+    if (bytes <= b.cap) return 0;
+    if (int r = b.reserve(bytes)) return r;
+    CU(cudaMemsetAsync(b.p, 0, b.cap, c->stream));
     return 0;
 }
 
@@ -347,10 +357,12 @@ int sfm_get_table(sfm_ctx* c, int32_t* table, int64_t first, int64_t h) {
 static int normalise_from(sfm_ctx* c, const double* xa, const double* ya, const double* xb, const double* yb,
                           int64_t stride, int64_t n, int64_t max_len) {
     if (int r = c->pts.reserve((size_t)n * sizeof(Corr))) return r;
+    if (int r = c->bounds.reserve(16)) return r;
+    CU(cudaMemsetAsync(c->bounds.p, 0, 16, c->stream));
     dim3 grid((unsigned)((max_len + 255) / 256), (unsigned)c->npairs);
     k_normalise<<<grid, 256, 0, c->stream>>>(xa, ya, xb, yb, stride, n,
                                              c->batched ? c->offsets.as<long long>() : nullptr,
-                                             c->Ks.as<double>(), c->pts.as<Corr>());
+                                             c->Ks.as<double>(), c->pts.as<Corr>(), c->bounds.as<unsigned long long>());
     return check_launch(c, "k_normalise");
 }
 
@@ -444,7 +456,11 @@ static int fit_launch(sfm_ctx* c, bool want_eig) {
     if (int r = c->valid.reserve(H)) return r;
     if (want_eig)
         if (int r = c->eig.reserve(H * 9 * sizeof(double))) return r;
-    if (int r = c->fitflag.reserve(16)) return r;
+    if (int r = reserve_zeroed(c, c->fitflag, 16)) return r;  // K3 resets it after use
+    if (int r = c->rows.reserve(H * sizeof(ModelRow))) return r;
+    // K2's accumulators are cleared by the fit itself: layout [kAccWords][H] | work counter, rescore counter, tickets
+    const size_t acc_tail = 64 + (size_t)c->npairs * 4;
+    if (int r = c->acc.reserve(H * kAccWords * 8 + acc_tail)) return r;
     c->tic(T_FIT);
     const long long* off = c->batched ? c->offsets.as<long long>() : nullptr;
     dim3 grid((unsigned)((c->h + kFitThreads - 1) / kFitThreads), (unsigned)c->npairs);
@@ -452,17 +468,21 @@ static int fit_launch(sfm_ctx* c, bool want_eig) {
     if (!want_eig) {
         // fast path: Householder null vector in registers; flags the (rare) samples whose validity
         // test is too close to call, which the Y^T Y Jacobi kernel then redoes
-        CU(cudaMemsetAsync(c->fitflag.p, 0, 16, c->stream));
         dim3 gq((unsigned)((c->h + kFitQrThreads - 1) / kFitQrThreads), (unsigned)c->npairs);
         k_fit_qr<<<gq, kFitQrThreads, 0, c->stream>>>(c->pts.as<Corr>(), off, c->table.as<int32_t>(), c->h,
                                                       c->E.as<double>(), c->valid.as<uint8_t>(),
-                                                      c->fitflag.as<unsigned>());
+                                                      c->fitflag.as<unsigned>(), c->rows.as<ModelRow>(),
+                                                      c->acc.as<unsigned long long>(), kAccWords, (int)((acc_tail + 7) / 8));
         if (int r = check_launch(c, "k_fit_qr")) return r;
         only = c->fitflag.as<unsigned>();
+        c->acc_clean = true;
+        c->acc_planes_for = H;
+    } else {
+        c->acc_clean = false;
     }
     k_fit<<<grid, kFitThreads, kFitThreads * kFitSmemDoubles * sizeof(double), c->stream>>>(
         c->pts.as<Corr>(), off, c->table.as<int32_t>(), c->h, c->E.as<double>(), c->valid.as<uint8_t>(),
-        want_eig ? c->eig.as<double>() : nullptr, only);
+        want_eig ? c->eig.as<double>() : nullptr, only, c->rows.as<ModelRow>());
     if (int r = check_launch(c, "k_fit")) return r;
     c->toc(T_FIT);
     c->has_models = true;
@@ -502,10 +522,14 @@ int sfm_set_models(sfm_ctx* c, const double* E, const uint8_t* valid, int64_t h)
     CU(cudaMemcpyAsync(c->E.p, E, (size_t)h * 72, cudaMemcpyHostToDevice, c->stream));
     if (valid) CU(cudaMemcpyAsync(c->valid.p, valid, (size_t)h, cudaMemcpyHostToDevice, c->stream));
     else CU(cudaMemsetAsync(c->valid.p, 1, (size_t)h, c->stream));
+    if (int r = c->rows.reserve((size_t)h * sizeof(ModelRow))) return r;
+    k_pad_models<<<(unsigned)((h + 255) / 256), 256, 0, c->stream>>>(c->E.as<double>(), (long long)h, c->rows.as<ModelRow>());
+    if (int r = check_launch(c, "k_pad_models")) return r;
     CU(cudaStreamSynchronize(c->stream));
     c->h = h;
     c->has_models = true;
     c->has_score = false;
+    c->acc_clean = false;
     return 0;
 }
 
@@ -590,20 +614,19 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         const size_t acc_tail = 64 + (size_t)P * 4;
         if (int r = c->acc.reserve(H * kAccWords * 8 + acc_tail)) return r;
         const long long npts = c->n;  // total records (all pairs)
-        if (int r = c->bounds.reserve(16)) return r;
-        if (screen) { if (int r = c->spts.reserve((size_t)npts * (f32 ? sizeof(Corr32) : sizeof(Corr)))) return r; }
+        if (f32) { if (int r = c->spts.reserve((size_t)npts * sizeof(Corr32))) return r; }
         ScoreArgs a;
         a.pts = c->pts.as<Corr>();
-        a.spts = screen ? c->spts.p : c->pts.p;
+        a.spts = f32 ? c->spts.p : c->pts.p;
         a.bounds = c->bounds.as<double>();
         a.s = s_scale;
+        a.inv_s = 1.0 / s_scale;
         a.kappa_coef = kKappaCoef * (1.0 + thr);
         a.kappa32_coef = kKappa32Coef * (1.0 + thr);
         a.n = c->n;
         a.offsets = c->batched ? c->offsets.as<long long>() : nullptr;
         a.E = c->E.as<double>();
-        if (int r = c->rows.reserve(H * sizeof(ModelRow))) return r;
-        a.rows = c->rows.as<ModelRow>();
+        a.rows = c->rows.as<ModelRow>();  // written by the fit kernels / sfm_set_models
         a.h = h;
         a.thr = thr;
         a.thr_pre = thr_pre;
@@ -619,20 +642,14 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         a.work_counter = reinterpret_cast<unsigned*>(a.acc + H * kAccWords);
         acc_dev = a.acc;
         c->tic(T_SCORE);
-        CU(cudaMemsetAsync(c->acc.p, 0, H * kAccWords * 8 + acc_tail, c->stream));
-        if (!skip_k2) {
-        k_pad_models<<<(unsigned)((H + 255) / 256), 256, 0, c->stream>>>(c->E.as<double>(), (long long)H, c->rows.as<ModelRow>());
-        if (int r = check_launch(c, "k_pad_models")) return r;
-        }
-        if (screen && !skip_k2) {
-            CU(cudaMemsetAsync(c->bounds.p, 0, 16, c->stream));
-            if (f32)
-                k_screen_pts<true><<<(unsigned)((npts + 255) / 256), 256, 0, c->stream>>>(
-                    c->pts.as<Corr>(), npts, 1.0 / s_scale, c->spts.p, c->bounds.as<unsigned long long>());
-            else
-                k_screen_pts<false><<<(unsigned)((npts + 255) / 256), 256, 0, c->stream>>>(
-                    c->pts.as<Corr>(), npts, 1.0 / s_scale, c->spts.p, c->bounds.as<unsigned long long>());
-            if (int r = check_launch(c, "k_screen_pts")) return r;
+        // the fit kernel leaves the accumulators cleared; a second score of the same models (or uploaded models) clears here
+        if (!(c->acc_clean && c->acc_planes_for == H))
+            CU(cudaMemsetAsync(c->acc.p, 0, H * kAccWords * 8 + acc_tail, c->stream));
+        c->acc_clean = false;
+        if (f32 && !skip_k2) {
+            k_screen_pts32<<<(unsigned)((npts + 255) / 256), 256, 0, c->stream>>>(c->pts.as<Corr>(), npts, 1.0 / s_scale,
+                                                                                  reinterpret_cast<Corr32*>(c->spts.p));
+            if (int r = check_launch(c, "k_screen_pts32")) return r;
         }
         const long long want_blocks = (total_items + kScoreWarps - 1) / kScoreWarps;
         const long long launch_blocks = grid_blocks < want_blocks ? grid_blocks : want_blocks;
@@ -678,6 +695,7 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
     f.out = c->best.as<Best>();
     f.invalid_out = c->invalid.as<long long>();
     f.record = c->record.as<SelectRecord>();
+    f.fitflag = c->fitflag.as<unsigned>();
     k_finalise<<<dim3((unsigned)fblocks, (unsigned)P), 256, 0, c->stream>>>(f);
     if (int r = check_launch(c, "k_finalise")) return r;
     c->toc(T_SELECT);
@@ -894,7 +912,7 @@ static int recover_pose_impl(sfm_ctx* c, const double* E, const double* K9, cons
         } else {
             return fail(SFM_ERR_ARG, "unsupported layout: stride must be 1 or 2");
         }
-        k_normalise<<<dim3((unsigned)((m + 255) / 256), 1), 256, 0, c->stream>>>(sxa, sya, sxb, syb, stride, m, nullptr, dK, dpts);
+        k_normalise<<<dim3((unsigned)((m + 255) / 256), 1), 256, 0, c->stream>>>(sxa, sya, sxb, syb, stride, m, nullptr, dK, dpts, nullptr);
         if (int r = check_launch(c, "k_normalise")) return r;
         k_cheirality<<<(unsigned)((4 * m + 127) / 128), 128, 0, c->stream>>>(dpts, m, nullptr, nullptr, c->poses.as<PoseSet>(),
                                                                         dist_thr, c->pass.as<uint8_t>(), nullptr);
@@ -941,14 +959,6 @@ int sfm_triangulate(sfm_ctx* c, const double* P1, const double* P2, const double
     c->toc(T_TRI);
     CU(cudaMemcpyAsync(X, c->X.p, (size_t)m * 24, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    return 0;
-}
-
-// Device buffer that must read as zero before its first use (self-cleaning kernel state).
-static int reserve_zeroed(sfm_ctx* c, Buf& b, size_t bytes) {
-    if (bytes <= b.cap) return 0;
-    if (int r = b.reserve(bytes)) return r;
-    CU(cudaMemsetAsync(b.p, 0, b.cap, c->stream));
     return 0;
 }
 

@@ -18,6 +18,22 @@ struct __align__(32) Corr {
     double xa, ya, xb, yb;
 };
 
+// One model padded to 96 bytes = three 32-byte sectors: the survivor path gathers a candidate's row with three
+// 256-bit loads (one sector each) instead of nine 8-byte loads that straddle 3-4 sectors - the gather was the
+// L1TEX-bound part of the drain (ncu at a 7 % inlier rate: l1tex 76 % busy).
+struct __align__(32) ModelRow {
+    double4 a, b, c;  // e0..e3 | e4..e7 | e8, pad
+};
+static_assert(sizeof(ModelRow) == 96, "ModelRow must be three sectors");
+
+__device__ __forceinline__ void store_model_row(ModelRow* rows, long long i, const double (&e)[9], bool ok) {
+    ModelRow r;
+    r.a = ok ? make_double4(e[0], e[1], e[2], e[3]) : make_double4(0.0, 0.0, 0.0, 0.0);
+    r.b = ok ? make_double4(e[4], e[5], e[6], e[7]) : make_double4(0.0, 0.0, 0.0, 0.0);
+    r.c = make_double4(ok ? e[8] : 0.0, 0.0, 0.0, 0.0);
+    rows[i] = r;
+}
+
 // ------------------------------------------------------------------------------------
 // Symmetric epipolar distance — lib/epipolar/sed.py:7-30
 // ------------------------------------------------------------------------------------

@@ -16,20 +16,38 @@ namespace sfm {
 __global__ void k_normalise(const double* __restrict__ xa, const double* __restrict__ ya,
                             const double* __restrict__ xb, const double* __restrict__ yb,
                             long long stride, long long n, const long long* __restrict__ offsets,
-                            const double* __restrict__ Ks, Corr* __restrict__ out) {
+                            const double* __restrict__ Ks, Corr* __restrict__ out,
+                            unsigned long long* __restrict__ bounds /* [2] or null, zero on entry */) {
     const long long base = offsets ? offsets[blockIdx.y] : 0;
     const long long len = offsets ? offsets[blockIdx.y + 1] - base : n;
     const long long li = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (li >= len) return;
-    const long long i = base + li;
-    const double* K = Ks + 9 * (long long)blockIdx.y;
-    const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
-    Corr c;
-    c.xa = __ddiv_rn(__dsub_rn(xa[i * stride], cx), fx);
-    c.ya = __ddiv_rn(__dsub_rn(ya[i * stride], cy), fy);
-    c.xb = __ddiv_rn(__dsub_rn(xb[i * stride], cx), fx);
-    c.yb = __ddiv_rn(__dsub_rn(yb[i * stride], cy), fy);
-    out[i] = c;
+    double a2 = 0.0, b2 = 0.0;
+    if (li < len) {
+        const long long i = base + li;
+        const double* K = Ks + 9 * (long long)blockIdx.y;
+        const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+        Corr c;
+        c.xa = __ddiv_rn(__dsub_rn(xa[i * stride], cx), fx);
+        c.ya = __ddiv_rn(__dsub_rn(ya[i * stride], cy), fy);
+        c.xb = __ddiv_rn(__dsub_rn(xb[i * stride], cx), fx);
+        c.yb = __ddiv_rn(__dsub_rn(yb[i * stride], cy), fy);
+        out[i] = c;
+        a2 = fma(c.xa, c.xa, fma(c.ya, c.ya, 1.0));
+        b2 = fma(c.xb, c.xb, fma(c.yb, c.yb, 1.0));
+    }
+    if (!bounds) return;
+    // max |(x, y, 1)|^2 per image over all correspondences: the rounding bound kappa of the K2 screen (sfm_score.cuh).
+    // Non-negative doubles order like their bit patterns; NaN coordinates poison the bound (kappa = NaN => d = NaN,
+    // sign clear) exactly like they poison the reference's score (NaN <= thr is False)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        a2 = fmax(a2, __shfl_xor_sync(0xffffffffu, a2, d));
+        b2 = fmax(b2, __shfl_xor_sync(0xffffffffu, b2, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(bounds, (unsigned long long)__double_as_longlong(a2));
+        atomicMax(bounds + 1, (unsigned long long)__double_as_longlong(b2));
+    }
 }
 
 // ------------------------------------------------------------------------------------
@@ -260,14 +278,24 @@ constexpr int kFitQrThreads = 64;
 __global__ void __launch_bounds__(kFitQrThreads, SFM_FIT_MINB)
 k_fit_qr(const Corr* __restrict__ pts, const long long* __restrict__ offsets, const int32_t* __restrict__ table,
          long long h, double* __restrict__ E_out, uint8_t* __restrict__ valid_out,
-         unsigned* __restrict__ ambiguous_count) {
+         unsigned* __restrict__ ambiguous_count, ModelRow* __restrict__ rows,
+         unsigned long long* __restrict__ acc, int acc_planes, int acc_tail_words) {
     const long long li = blockIdx.x * (long long)kFitQrThreads + threadIdx.x;
     if (li >= h) return;
     const long long i = (long long)blockIdx.y * h + li;  // blockIdx.y = image pair
+    if (acc) {
+        // K2's exact integer accumulators of this hypothesis start at zero (saves the scoring call a 4.7 MB memset);
+        // the first thread also clears the work counter / rescore counter / K3 tickets behind the planes
+        const long long htotal = (long long)gridDim.y * h;
+        for (int k = 0; k < acc_planes; ++k) acc[(long long)k * htotal + i] = 0ull;
+        if (i == 0)
+            for (int k = 0; k < acc_tail_words; ++k) acc[(long long)acc_planes * htotal + k] = 0ull;
+    }
     if (offsets) {
         if (offsets[blockIdx.y + 1] - offsets[blockIdx.y] < 8) {
             for (int k = 0; k < 9; ++k) E_out[9 * i + k] = 0.0;
             valid_out[i] = FIT_INVALID;
+            if (rows) { const double z[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; store_model_row(rows, i, z, false); }
             return;
         }
         pts += offsets[blockIdx.y];
@@ -282,6 +310,7 @@ k_fit_qr(const Corr* __restrict__ pts, const long long* __restrict__ offsets, co
     const int status = eight_point_fit_qr(c, E);
 #pragma unroll
     for (int k = 0; k < 9; ++k) E_out[9 * i + k] = (status == FIT_VALID) ? E[k] : 0.0;
+    if (rows) store_model_row(rows, i, E, status == FIT_VALID);  // padded copy for K2's survivor path
     valid_out[i] = (uint8_t)status;
     if (status == FIT_AMBIGUOUS) atomicAdd(ambiguous_count, 1u);
 }
@@ -388,7 +417,7 @@ __global__ void __launch_bounds__(kFitThreads)
 k_fit(const Corr* __restrict__ pts, const long long* __restrict__ offsets,
       const int32_t* __restrict__ table, long long h, double* __restrict__ E_out,
       uint8_t* __restrict__ valid_out, double* __restrict__ eig_out,
-      const unsigned* __restrict__ only_ambiguous /* null = fit everything */) {
+      const unsigned* __restrict__ only_ambiguous /* null = fit everything */, ModelRow* __restrict__ rows) {
     extern __shared__ double fit_smem[];
     if (only_ambiguous && *only_ambiguous == 0u) return;  // the usual case: nothing was flagged
     const long long li = blockIdx.x * (long long)kFitThreads + threadIdx.x;
@@ -403,6 +432,7 @@ k_fit(const Corr* __restrict__ pts, const long long* __restrict__ offsets,
     if (!enough) {
         for (int k = 0; k < 9; ++k) E_out[9 * i + k] = 0.0;
         valid_out[i] = 0;
+        if (rows) { const double z[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; store_model_row(rows, i, z, false); }
         return;
     }
     Corr c[8];
@@ -415,6 +445,7 @@ k_fit(const Corr* __restrict__ pts, const long long* __restrict__ offsets,
     const bool valid = eight_point_fit(c, fit_smem + threadIdx.x, E, eig_out ? eig : nullptr);
 #pragma unroll
     for (int k = 0; k < 9; ++k) E_out[9 * i + k] = valid ? E[k] : 0.0;
+    if (rows) store_model_row(rows, i, E, valid);
     valid_out[i] = valid ? 1 : 0;
     if (eig_out)
         for (int k = 0; k < 9; ++k) eig_out[9 * i + k] = eig[k];

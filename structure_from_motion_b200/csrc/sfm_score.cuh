@@ -73,7 +73,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 //   SCREEN (default), 11 FP64 issue slots per evaluation.  sed <= thr implies
 //   r^2 <= thr * nb  (drop the image-A term), nb = lb0^2 + lb1^2, lb = E^T b, r = lb . a.
 //   With s = sqrt(thr'), the kernel keeps E with columns 0 and 1 pre-multiplied by s and
-//   streams a copy of the correspondences with (xa, ya) pre-divided by s, so that
+//   divides (xa, ya) of every tile by s once it has landed in shared memory, so that
 //       lb0' = s lb0, lb1' = s lb1, lb2   (6 DFMA)      r = lb0' xa' + lb1' ya' + lb2   (2 DFMA)
 //       m = lb1'^2 + kappa ; m = lb0'^2 + m   (2 DFMA)  d = r^2 - m                      (1 DFMA)
 //   and "d < 0" (sign bit) is the test.  thr' = thr (1 + 1e-9) and
@@ -126,14 +126,6 @@ constexpr double kKappaCoef = 4e-20;
 constexpr double kKappa32Coef = 1.2e-10;   // fp32 pre-filter, see the K2 header
 constexpr double kThr32Factor = 1.0316;   // (1 + 1/64)^2 (1 + 1e-4)
 
-// One model padded to 96 bytes = three 32-byte sectors: the survivor path gathers a candidate's row with three
-// 256-bit loads (one sector each) instead of nine 8-byte loads that straddle 3-4 sectors - the gather was the
-// L1TEX-bound part of the drain (ncu at a 7 % inlier rate: l1tex 76 % busy).
-struct __align__(32) ModelRow {
-    double4 a, b, c;  // e0..e3 | e4..e7 | e8, pad
-};
-static_assert(sizeof(ModelRow) == 96, "ModelRow must be three sectors");
-
 __global__ void __launch_bounds__(256) k_pad_models(const double* __restrict__ E, long long htotal, ModelRow* __restrict__ rows) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= htotal) return;
@@ -147,7 +139,7 @@ __global__ void __launch_bounds__(256) k_pad_models(const double* __restrict__ E
 
 struct ScoreArgs {
     const Corr* pts;           // K-normalised correspondences (exact scorer)
-    const void* spts;          // screening copy: Corr (xa/s, ya/s, xb, yb), or Corr32 for the fp32 pre-filter
+    const void* spts;          // fp32 pre-filter only: Corr32 copy (xa/s, ya/s, xb, yb); the fp64 screen scales its tiles in shared memory
     const double* bounds;      // [2]: max (xa^2+ya^2+1), max (xb^2+yb^2+1) over all correspondences
     long long n;
     const long long* offsets;  // [npairs+1] or null (single pair of n records)
@@ -155,6 +147,7 @@ struct ScoreArgs {
     const ModelRow* rows;      // [npairs][h] padded copies of E for the survivor path
     long long h;
     double thr, thr_pre, s;    // s = sqrt(thr_pre) (SCREEN)
+    double inv_s;              // 1 / s
     double kappa_coef;         // kKappaCoef * (1 + thr)
     double kappa32_coef;       // kKappa32Coef * (1 + thr)
     double scale1, scale2;     // 2^(63-e), 2^(63-2e) with thr < 2^e
@@ -203,39 +196,16 @@ struct __align__(16) Corr32 {
     float xa, ya, xb, yb;
 };
 
-// Screening copy of the correspondences + the coordinate bounds used by kappa (one pass
-// over N; thr-dependent, so it runs at the head of every scoring call).  F32: the copy is
-// rounded to fp32 (16-byte records) for the fp32 pre-filter.
-template <bool F32>
-__global__ void __launch_bounds__(256) k_screen_pts(const Corr* __restrict__ pts, long long n, double inv_s,
-                                                    void* __restrict__ spts, unsigned long long* __restrict__ bounds) {
+// fp32 pre-filter only: Corr32 copy of the correspondences with (xa, ya) pre-divided by s (thr-dependent, so it runs
+// at the head of every SCREEN32 scoring call).  The coordinate bounds used by kappa come from k_normalise.
+__global__ void __launch_bounds__(256) k_screen_pts32(const Corr* __restrict__ pts, long long n, double inv_s,
+                                                      Corr32* __restrict__ spts) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    double a2 = 0.0, b2 = 0.0;
-    if (i < n) {
-        Corr c = pts[i];
-        a2 = fma(c.xa, c.xa, fma(c.ya, c.ya, 1.0));
-        b2 = fma(c.xb, c.xb, fma(c.yb, c.yb, 1.0));
-        c.xa *= inv_s;
-        c.ya *= inv_s;
-        if (F32) {
-            Corr32 f;
-            f.xa = (float)c.xa; f.ya = (float)c.ya; f.xb = (float)c.xb; f.yb = (float)c.yb;
-            reinterpret_cast<Corr32*>(spts)[i] = f;
-        } else {
-            reinterpret_cast<Corr*>(spts)[i] = c;
-        }
-    }
-    // non-negative doubles order like their bit patterns; NaN coordinates poison the bound (kappa = NaN
-    // => d = NaN, sign clear) exactly like they poison the reference's score (NaN <= thr is False)
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        a2 = fmax(a2, __shfl_xor_sync(0xffffffffu, a2, d));
-        b2 = fmax(b2, __shfl_xor_sync(0xffffffffu, b2, d));
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicMax(bounds, (unsigned long long)__double_as_longlong(a2));
-        atomicMax(bounds + 1, (unsigned long long)__double_as_longlong(b2));
-    }
+    if (i >= n) return;
+    const Corr c = pts[i];
+    Corr32 f;
+    f.xa = (float)(c.xa * inv_s); f.ya = (float)(c.ya * inv_s); f.xb = (float)c.xb; f.yb = (float)c.yb;
+    spts[i] = f;
 }
 
 // Per-warp shared-memory state: every warp is an autonomous worker (own tile ring, own
@@ -319,7 +289,7 @@ k_score(const ScoreArgs a) {
         const double* Ep = a.E + 9 * (long long)pair * a.h;
         const ModelRow* Rw = a.rows + (long long)pair * a.h + hyp_w;  // this warp's models, padded (survivor path)
         const Corr* pbeg = a.pts + begin;    // this item's correspondences (exact copies)
-        const P* src = reinterpret_cast<const P*>(SCREEN ? a.spts : (const void*)a.pts);
+        const P* src = reinterpret_cast<const P*>(F32 ? a.spts : (const void*)a.pts);
 
         auto issue = [&](int t) {  // lane 0 only
             const int s = (int)((gt + (unsigned)t) % kStages);
@@ -329,8 +299,10 @@ k_score(const ScoreArgs a) {
             mbar_expect_tx(&ws.full_bar[s], bytes);
             bulk_g2s(&ws.tile[s][0], src + first, bytes, &ws.full_bar[s]);
         };
-        if (lane == 0)
+        if (lane == 0) {
+            if (SCREEN && !F32) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // tiles were scaled in place
             for (int t = 0; t < kStages && t < ntiles; ++t) issue(t);
+        }
 
         // register-resident models; SCREEN: columns 0 and 1 scaled by s, kappa per hypothesis;
         // SCREEN32: additionally normalised to |E|_F = 1 (sed is scale-invariant in E) and rounded to fp32
@@ -442,6 +414,19 @@ k_score(const ScoreArgs a) {
             const long long first = begin + (long long)t * kTile;
             const int np = (int)((end - first < kTile) ? (end - first) : kTile);
             const P* tp = reinterpret_cast<const P*>(&ws.tile[s][0]);
+            if (SCREEN && !F32) {
+                // the screen wants (xa, ya) / s (see the header): scale the freshly landed tile in place, two records
+                // per lane - 4 DMUL per lane and tile against 22 DFMA per lane and correspondence
+#pragma unroll
+                for (int r = 0; r < kTile; r += 32) {
+                    double2* q2 = reinterpret_cast<double2*>(&ws.tile[s][r + lane]);
+                    double2 v = *q2;
+                    v.x *= a.inv_s;
+                    v.y *= a.inv_s;
+                    *q2 = v;
+                }
+                __syncwarp();
+            }
             for (int p = 0; p < np; p += G) {
                 unsigned pm = 0;
 #pragma unroll
@@ -486,7 +471,12 @@ k_score(const ScoreArgs a) {
             }
             // every lane is done with the stage: refill it with the tile kStages ahead
             __syncwarp();
-            if (lane == 0 && t + kStages < ntiles) issue(t + kStages);
+            if (lane == 0 && t + kStages < ntiles) {
+                // the tile was rewritten through the generic proxy (scaling): order that before the bulk copy (async
+                // proxy) lands in the same bytes
+                if (SCREEN && !F32) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(t + kStages);
+            }
         }
         gt += (unsigned)ntiles;
 
@@ -644,6 +634,7 @@ struct FinalArgs {
     long long* invalid_out;  // [npairs][2]
     SelectRecord* record;    // [npairs]
     unsigned long long* rescored;  // [1] number of hypotheses that went through the exact rescore (diagnostic)
+    unsigned* fitflag;             // K1's ambiguous-sample counter: reset here for the next fit (may be null)
 };
 
 // the sample rule + aggregation + candidate test of one hypothesis (ransac.py:63-64, 70-76, 96-108), given the count and
@@ -799,7 +790,10 @@ __global__ void __launch_bounds__(256) k_finalise(const FinalArgs a) {
     // ---- last block of the pair: reduce the per-block results into the selection record ----
     __threadfence();
     __shared__ long long s_ninv, s_first2;
-    if (tid == 0) { s_ninv = 0; s_first2 = 0x7fffffffffffffffLL; a.tickets[blockIdx.y] = 0; }
+    if (tid == 0) {
+        s_ninv = 0; s_first2 = 0x7fffffffffffffffLL; a.tickets[blockIdx.y] = 0;
+        if (a.fitflag && blockIdx.y == 0) *a.fitflag = 0u;
+    }
     __syncthreads();
     const volatile Best* blocks = a.block_out + (long long)blockIdx.y * nblocks;
     const volatile long long* binv = a.block_inv + 2 * (long long)blockIdx.y * nblocks;

@@ -379,7 +379,7 @@ def run_extras(args, eng, world, rank, barrier, flush_l2, torch, dist, per_gpu_r
             eng.sample_device(seed, h_rank)
             best, *_rest = eng.two_view(THR, MIN_EXTRA, AGG, "min_error", 50.0, want_mask=False, want_sed=False)
             return int(best.index)
-        r = distributed.two_view_sharded(THR, MIN_EXTRA, AGG, h_rank, seed, engine=eng, rank=rank, world=world)
+        r = distributed.two_view_sharded(THR, MIN_EXTRA, AGG, h_rank, seed, engine=eng, rank=rank, world=world, native=True)
         return int(r["index"])
 
     # ---- parity_multi: every rank must return the single-GPU answer for the union of the hypotheses ----
@@ -389,7 +389,7 @@ def run_extras(args, eng, world, rank, barrier, flush_l2, torch, dist, per_gpu_r
         eng.upload_pairs(x1, x2, K)
         hs = 4096
         for seed in (11, 12, 13):
-            r = distributed.two_view_sharded(THR, MIN_EXTRA, AGG, hs, seed, engine=eng, rank=rank, world=world)
+            r = distributed.two_view_sharded(THR, MIN_EXTRA, AGG, hs, seed, engine=eng, rank=rank, world=world, native=True)
             eng.sample_device(seed, hs * world)  # the union on this one GPU (the sampler is keyed by the global index)
             best, _, _, poses, num, idx, okb, X = eng.two_view(THR, MIN_EXTRA, AGG, "min_error", 50.0, want_mask=False,
                                                                 want_sed=False)
@@ -494,7 +494,13 @@ def main():
     eng = _native.get_engine(local_rank)
     eng.set_score_variant(args.variant, args.hpt, args.group)
     stream = torch.cuda.current_stream()
-    eng.set_stream(stream.cuda_stream)  # torch's default stream: the flush, the timing events, NCCL and the engine in one order
+    eng.set_stream(stream.cuda_stream)  # torch's default stream: the flush, the timing events and the engine in one order
+    if world > 1:
+        # the data-path collective (one all-gather of the selection records) runs on the library's OWN communicator,
+        # behind the C ABI; torch.distributed only does the plumbing here (rendezvous, barriers, max over ranks)
+        uid = [_native.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.nccl_init(rank, world, uid[0])
 
     def barrier():
         if world > 1:
@@ -536,7 +542,7 @@ def main():
             return {"index": int(best.index)}, num
         # several GPUs: records all-gathered device-to-device (the one collective), merged by a kernel, tail enqueued
         # behind it - the host synchronises once per estimate
-        r = distributed.two_view_sharded(THR, MIN_EXTRA, AGG, h_rank, seed, engine=eng, rank=rank, world=world)
+        r = distributed.two_view_sharded(THR, MIN_EXTRA, AGG, h_rank, seed, engine=eng, rank=rank, world=world, native=True)
         if r["owner"] < 0:
             raise RuntimeError("no model found")
         return r, r["num_inliers"]
@@ -547,7 +553,7 @@ def main():
                                            on_degenerate="skip", engine=eng)
             return res.points.shape[0]
         eng.upload_pairs(pa, pb, K)  # every rank uploads the (replicated) correspondences from its host buffers
-        r = distributed.two_view_sharded(THR, MIN_EXTRA, AGG, h_rank, seed, engine=eng, rank=rank, world=world)
+        r = distributed.two_view_sharded(THR, MIN_EXTRA, AGG, h_rank, seed, engine=eng, rank=rank, world=world, native=True)
         mask, sed = eng.inlier_mask(THR)
         return r["num_inliers"]
 
@@ -663,7 +669,7 @@ def main():
                             f"vote + triangulation of the {num_inl} inliers",
                 "sampler": "device (Philox)", "score_variant": args.variant, "hyps_per_thread": args.hpt, "group": args.group,
                 "l2": "flushed (256 MiB memset) between timed steps",
-                "parallelism": f"hypothesis-sharded x{world}, one 144 B/rank device-to-device all-gather + merge kernel" if world > 1 else "single GPU",
+                "parallelism": f"hypothesis-sharded x{world}, one 144 B/rank ncclAllGather issued by the library (C ABI) + merge kernel" if world > 1 else "single GPU",
             },
             "ms_per_estimate": ms_total / args.steps,
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},

@@ -248,6 +248,20 @@ int sfm_sharded_tail(sfm_ctx *ctx, const void *gathered_records_dev, int world, 
 int sfm_sharded_fetch(sfm_ctx *ctx, sfm_best *best, int32_t *owner, sfm_poses *poses, int64_t cap,
                       int64_t *num_inliers, int64_t *inlier_idx, uint8_t *pass, double *X);
 
+/* The same without any host framework: the collective behind the C ABI (SURVEY.md 8(b) sfm_nccl_init /
+ * sfm_ransac_E_sharded).  libnccl.so.2 is resolved at run time (the copy already loaded in the process, else the
+ * system's).  Rank 0 calls sfm_nccl_unique_id and ships the SFM_NCCL_ID_BYTES bytes to its peers by any means; every
+ * rank calls sfm_nccl_init (collective).  sfm_two_view_sharded then enqueues one complete estimate - this rank's
+ * hypotheses [rank * hyps_per_rank, (rank+1) * hyps_per_rank) of the device sampler, ONE ncclAllGather of the
+ * selection records on the context's stream, merge kernel, tail - and sfm_sharded_fetch returns, on every rank, what
+ * one GPU returns for the union of the hypotheses (ransac.py:83 applied across ranks). */
+#define SFM_NCCL_ID_BYTES 128
+int sfm_nccl_unique_id(void *id_out);
+int sfm_nccl_init(sfm_ctx *ctx, int rank, int nranks, const void *unique_id);
+int sfm_nccl_destroy(sfm_ctx *ctx);
+int sfm_two_view_sharded(sfm_ctx *ctx, uint64_t seed, int64_t hyps_per_rank, double threshold, double min_extra,
+                         int aggregation, int selection, double distance_threshold);
+
 /* ---- the stage in front of the hot path: brute-force matcher ------ */
 /* lib/feature_matching/matching.py:36-118 match_brute_force with ncc.py:7-54 (score_kind 0, score
  * in [0,2], 2.0 when a window leaves the image) or ssd.py:7-36 (score_kind 1, +inf outside) as the

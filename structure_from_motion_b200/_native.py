@@ -82,6 +82,10 @@ _SIGNATURES = {
     "sfm_sharded_tail": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_double, C.c_double]),
     "sfm_sharded_fetch": (C.c_int, [_P, C.POINTER(Best), C.POINTER(C.c_int32), C.POINTER(Poses), C.c_int64,
                                     C.POINTER(C.c_int64), _P, _P, _P]),
+    "sfm_nccl_unique_id": (C.c_int, [_P]),
+    "sfm_nccl_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "sfm_nccl_destroy": (C.c_int, [_P]),
+    "sfm_two_view_sharded": (C.c_int, [_P, C.c_uint64, C.c_int64, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double]),
     "sfm_batch_ransac": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P, C.c_int64, _P, C.c_int64, C.c_uint64,
                                    C.c_uint64, C.c_double, C.c_double, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "sfm_batch_two_view": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P, C.c_int64, _P, C.c_int64, C.c_uint64,
@@ -414,6 +418,22 @@ class Engine:
         m = min(int(num.value), cap)
         return b, int(owner.value), p, int(num.value), idx[:m], ok[:m], X[:m]
 
+    # -- the collective behind the C ABI (no torch needed on the data path) --------------------------
+    def nccl_init(self, rank: int, world: int, unique_id: bytes):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._ck(self.lib.sfm_nccl_init(self.h, int(rank), int(world), C.cast(buf, _P)), "sfm_nccl_init")
+        self.nccl_world = int(world)
+
+    def nccl_destroy(self):
+        self._ck(self.lib.sfm_nccl_destroy(self.h), "sfm_nccl_destroy")
+
+    def two_view_sharded(self, seed, hyps_per_rank, threshold, min_extra=0.0, aggregation="rms", selection="min_error",
+                         distance_threshold=50.0):
+        """Enqueue one hypothesis-sharded estimate on the communicator of nccl_init; results via sharded_fetch()."""
+        self._ck(self.lib.sfm_two_view_sharded(self.h, int(seed), int(hyps_per_rank), float(threshold), float(min_extra),
+                                               AGG[aggregation], SELECT[selection], float(distance_threshold)),
+                 "sfm_two_view_sharded")
+
     # -- batches ----------------------------------------------------------------------------
     def batch_ransac(self, pts_a, pts_b, offsets, Ks, h, seed, threshold, min_extra=0.0, aggregation="rms",
                      selection="min_error", pair_id0=0):
@@ -622,6 +642,16 @@ class ReferenceSampler:
         if rc != 0:
             raise NativeError(f"sfm_mt_shuffle_resume -> {rc}: {lib.sfm_last_error().decode()}")
         return st, perm
+
+
+def nccl_unique_id() -> bytes:
+    """ncclGetUniqueId through the C ABI: 128 bytes that rank 0 hands to its peers (any transport)."""
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    rc = lib.sfm_nccl_unique_id(C.cast(buf, _P))
+    if rc != 0:
+        raise NativeError(f"sfm_nccl_unique_id -> {rc}: {lib.sfm_last_error().decode()}")
+    return buf.raw
 
 
 def pinned_empty(shape, dtype=np.float64):

@@ -2,6 +2,8 @@
 // device buffers, launch geometry, and the CPython-compatible MT19937 sampler.
 #include "../../include/sfm_b200.h"
 
+#include <dlfcn.h>
+
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -103,6 +105,9 @@ struct sfm_ctx {
     double Kstage[9] = {0};
     const void* occ_fn = nullptr;  // scoring kernel whose launch configuration is cached
     int occ_blocks = 0;
+    void* nccl_comm = nullptr;  // ncclComm_t of sfm_nccl_init (hypothesis-sharded runs without torch)
+    int nccl_rank = 0, nccl_world = 1;
+    Buf gathered;
     const unsigned long long* rescored_dev = nullptr;  // K3's rescore counter of the last scoring call
     long long winner_local = -1;  // index into E of the current winner, -1 = use winnerE
     bool winner_set = false;
@@ -242,7 +247,7 @@ int sfm_destroy(sfm_ctx* c) {
     Buf* bufs[] = {&c->raw, &c->pts, &c->offsets, &c->Ks, &c->table, &c->E, &c->valid, &c->eig, &c->acc,
                    &c->count_extra, &c->S1, &c->S2, &c->err, &c->blocks, &c->best,
                    &c->invalid, &c->winnerE, &c->record, &c->merged, &c->rows, &c->blockinv, &c->mask, &c->sed, &c->poses, &c->pass, &c->X, &c->idx,
-                   &c->scan, &c->tmp, &c->tailstate, &c->num, &c->winrec, &c->bout, &c->spts, &c->bounds, &c->fitflag,
+                   &c->scan, &c->tmp, &c->gathered, &c->tailstate, &c->num, &c->winrec, &c->bout, &c->spts, &c->bounds, &c->fitflag,
                    &c->m_img, &c->m_feat, &c->m_W, &c->m_ss, &c->m_ok, &c->m_S, &c->m_out,
                    &c->h_img, &c->h_gx, &c->h_gy, &c->h_corner, &c->h_alive, &c->h_key, &c->h_idx, &c->h_small, &c->h_xy};
     for (Buf* b : bufs) b->release();
@@ -250,6 +255,7 @@ int sfm_destroy(sfm_ctx* c) {
         cudaEventDestroy(c->ev0[i]);
         cudaEventDestroy(c->ev1[i]);
     }
+    sfm_nccl_destroy(c);
     if (c->hpin) cudaFreeHost(c->hpin);
     cudaStreamDestroy(c->own_stream);
     delete c;
@@ -615,9 +621,16 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         if (int r = c->acc.reserve(H * kAccWords * 8 + acc_tail)) return r;
         const long long npts = c->n;  // total records (all pairs)
         if (f32) { if (int r = c->spts.reserve((size_t)npts * sizeof(Corr32))) return r; }
+#if SFM_SCALE_MODE == 0
+        else if (screen) { if (int r = c->spts.reserve((size_t)npts * sizeof(Corr))) return r; }
+#endif
         ScoreArgs a;
         a.pts = c->pts.as<Corr>();
+#if SFM_SCALE_MODE == 0
+        a.spts = screen ? c->spts.p : c->pts.p;
+#else
         a.spts = f32 ? c->spts.p : c->pts.p;
+#endif
         a.bounds = c->bounds.as<double>();
         a.s = s_scale;
         a.inv_s = 1.0 / s_scale;
@@ -651,6 +664,13 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
                                                                                   reinterpret_cast<Corr32*>(c->spts.p));
             if (int r = check_launch(c, "k_screen_pts32")) return r;
         }
+#if SFM_SCALE_MODE == 0
+        else if (screen && !skip_k2) {
+            k_screen_pts64<<<(unsigned)((npts + 255) / 256), 256, 0, c->stream>>>(c->pts.as<Corr>(), npts, 1.0 / s_scale,
+                                                                                  reinterpret_cast<Corr*>(c->spts.p));
+            if (int r = check_launch(c, "k_screen_pts64")) return r;
+        }
+#endif
         const long long want_blocks = (total_items + kScoreWarps - 1) / kScoreWarps;
         const long long launch_blocks = grid_blocks < want_blocks ? grid_blocks : want_blocks;
         void* kargs[] = {(void*)&a};
@@ -1163,6 +1183,105 @@ int sfm_sharded_fetch(sfm_ctx* c, sfm_best* best, int32_t* owner, sfm_poses* pos
     }
     return 0;
 }
+
+}  // extern "C"
+
+// ---- NCCL behind the C ABI (sfm_nccl_init / sharded estimate without torch) ---------------------
+// libnccl is resolved at run time (dlopen): the library a host process already loaded (torch bundles one) is reused,
+// otherwise the system's libnccl.so.2.  Only four entry points are needed; their prototypes are restated here so that
+// the build does not depend on nccl.h.
+struct NcclId { char internal[128]; };  // ncclUniqueId, passed BY VALUE to ncclCommInitRank
+static_assert(sizeof(NcclId) == SFM_NCCL_ID_BYTES, "ncclUniqueId is 128 bytes");
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+
+int nccl_load() {
+    if (g_nccl.lib) return 0;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // already in the process (torch)?
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(SFM_ERR_STATE, "libnccl.so.2 not found: %s", dlerror());
+    g_nccl.GetUniqueId = reinterpret_cast<int (*)(void*)>(dlsym(h, "ncclGetUniqueId"));
+    g_nccl.CommInitRank = reinterpret_cast<int (*)(void**, int, NcclId, int)>(dlsym(h, "ncclCommInitRank"));
+    g_nccl.AllGather = reinterpret_cast<int (*)(const void*, void*, size_t, int, void*, cudaStream_t)>(dlsym(h, "ncclAllGather"));
+    g_nccl.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(h, "ncclCommDestroy"));
+    g_nccl.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(h, "ncclGetErrorString"));
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy)
+        return fail(SFM_ERR_STATE, "libnccl.so.2 lacks a required symbol");
+    g_nccl.lib = h;
+    return 0;
+}
+#define NC(call)                                                                                          \
+    do {                                                                                                  \
+        int e_ = (call);                                                                                  \
+        if (e_ != 0)                                                                                      \
+            return fail(SFM_ERR_CUDA, "%s failed: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(e_) : "?"); \
+    } while (0)
+}  // namespace
+
+extern "C" {
+
+int sfm_nccl_unique_id(void* id_out) {
+    if (!id_out) return fail(SFM_ERR_ARG, "null argument");
+    if (int r = nccl_load()) return r;
+    NC(g_nccl.GetUniqueId(id_out));
+    return 0;
+}
+
+int sfm_nccl_init(sfm_ctx* c, int rank, int nranks, const void* unique_id) {
+    if (int r = use(c)) return r;
+    if (!unique_id || nranks < 1 || rank < 0 || rank >= nranks) return fail(SFM_ERR_ARG, "bad communicator arguments");
+    if (int r = nccl_load()) return r;
+    if (c->nccl_comm) { g_nccl.CommDestroy(c->nccl_comm); c->nccl_comm = nullptr; }
+    NcclId id;
+    memcpy(&id, unique_id, sizeof id);
+    NC(g_nccl.CommInitRank(&c->nccl_comm, nranks, id, rank));
+    c->nccl_rank = rank;
+    c->nccl_world = nranks;
+    return 0;
+}
+
+int sfm_nccl_destroy(sfm_ctx* c) {
+    if (!c) return 0;
+    if (c->nccl_comm && g_nccl.lib) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        g_nccl.CommDestroy(c->nccl_comm);
+    }
+    c->nccl_comm = nullptr;
+    c->nccl_world = 1;
+    c->nccl_rank = 0;
+    return 0;
+}
+
+// One complete hypothesis-sharded estimate on the communicator of sfm_nccl_init, nothing synchronised: this rank's
+// hypotheses [rank * hyps_per_rank, (rank + 1) * hyps_per_rank) of the device sampler -> fit -> score -> select, ONE
+// ncclAllGather of the SFM_RECORD_BYTES selection records on the context's stream (the path's only collective), merge
+// kernel, tail.  Results through sfm_sharded_fetch.
+int sfm_two_view_sharded(sfm_ctx* c, uint64_t seed, int64_t hyps_per_rank, double thr, double min_extra, int agg,
+                         int mode, double dist_thr) {
+    if (int r = use(c)) return r;
+    if (!c->nccl_comm) return fail(SFM_ERR_STATE, "sfm_nccl_init first");
+    if (c->batched) return fail(SFM_ERR_STATE, "single-pair call on a batched context");
+    if (int r = sample_device(c, seed, 0, (int64_t)c->nccl_rank * hyps_per_rank, hyps_per_rank)) return r;
+    if (int r = fit_launch(c, false)) return r;
+    if (int r = score_launch(c, thr, min_extra, agg, mode, true, 0, c->n)) return r;
+    if (int r = c->gathered.reserve((size_t)c->nccl_world * sizeof(SelectRecord))) return r;
+    NC(g_nccl.AllGather(c->record.p, c->gathered.p, sizeof(SelectRecord), /* ncclUint8 */ 1, c->nccl_comm, c->stream));
+    return sfm_sharded_tail(c, c->gathered.p, c->nccl_world, c->nccl_rank, hyps_per_rank, mode, thr, dist_thr);
+}
+
+}  // extern "C"
+
+extern "C" {
 
 // ---- batched pairs ------------------------------------------------------------------------
 // upload -> device sampler -> fit -> score + select of P independent pairs (nothing synchronised)

@@ -104,6 +104,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 // and GPU count — run-to-run deterministic by construction; every term >= thr * 2^-10 enters
 // without rounding, smaller ones are truncated at 2^-84 of the scale (<= 6e-26 thr per term).
 // ------------------------------------------------------------------------------------
+// How the fp64 screen gets (xa, ya) / s:  0 = a scaled copy of the correspondences written by k_screen_pts64 at the head
+// of every scoring call (streamed instead of the exact records), 1 = the landed tile is scaled in place (+ proxy fence
+// before its refill), 3 = scaled (xa, ya) go to a separate per-warp buffer (the TMA tile is never written by the warp).
+#ifndef SFM_SCALE_MODE
+#define SFM_SCALE_MODE 0
+#endif
 constexpr int kScoreThreads = 128;
 constexpr int kScoreWarps = kScoreThreads / 32;
 #ifndef SFM_SCORE_TILE
@@ -196,6 +202,17 @@ struct __align__(16) Corr32 {
     float xa, ya, xb, yb;
 };
 
+// SFM_SCALE_MODE 0: fp64 screening copy (xa / s, ya / s, xb, yb)
+__global__ void __launch_bounds__(256) k_screen_pts64(const Corr* __restrict__ pts, long long n, double inv_s,
+                                                      Corr* __restrict__ spts) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Corr c = pts[i];
+    c.xa *= inv_s;
+    c.ya *= inv_s;
+    spts[i] = c;
+}
+
 // fp32 pre-filter only: Corr32 copy of the correspondences with (xa, ya) pre-divided by s (thr-dependent, so it runs
 // at the head of every SCREEN32 scoring call).  The coordinate bounds used by kappa come from k_normalise.
 __global__ void __launch_bounds__(256) k_screen_pts32(const Corr* __restrict__ pts, long long n, double inv_s,
@@ -213,6 +230,9 @@ __global__ void __launch_bounds__(256) k_screen_pts32(const Corr* __restrict__ p
 template <int HPT>
 struct alignas(128) ScoreWarpSmem {
     Corr tile[kStages][kTile];
+#if SFM_SCALE_MODE == 3
+    double2 sxy[kTile];  // (xa, ya) / s of the tile being processed
+#endif
     unsigned sacc[HPT][kAccWords][32];
     uint2 ring[kRing];
     unsigned short own[32];
@@ -289,7 +309,11 @@ k_score(const ScoreArgs a) {
         const double* Ep = a.E + 9 * (long long)pair * a.h;
         const ModelRow* Rw = a.rows + (long long)pair * a.h + hyp_w;  // this warp's models, padded (survivor path)
         const Corr* pbeg = a.pts + begin;    // this item's correspondences (exact copies)
+#if SFM_SCALE_MODE == 0
+        const P* src = reinterpret_cast<const P*>(SCREEN ? a.spts : (const void*)a.pts);
+#else
         const P* src = reinterpret_cast<const P*>(F32 ? a.spts : (const void*)a.pts);
+#endif
 
         auto issue = [&](int t) {  // lane 0 only
             const int s = (int)((gt + (unsigned)t) % kStages);
@@ -300,7 +324,9 @@ k_score(const ScoreArgs a) {
             bulk_g2s(&ws.tile[s][0], src + first, bytes, &ws.full_bar[s]);
         };
         if (lane == 0) {
+#if SFM_SCALE_MODE == 1
             if (SCREEN && !F32) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // tiles were scaled in place
+#endif
             for (int t = 0; t < kStages && t < ntiles; ++t) issue(t);
         }
 
@@ -414,6 +440,7 @@ k_score(const ScoreArgs a) {
             const long long first = begin + (long long)t * kTile;
             const int np = (int)((end - first < kTile) ? (end - first) : kTile);
             const P* tp = reinterpret_cast<const P*>(&ws.tile[s][0]);
+#if SFM_SCALE_MODE == 1 || SFM_SCALE_MODE == 2
             if (SCREEN && !F32) {
                 // the screen wants (xa, ya) / s (see the header): scale the freshly landed tile in place, two records
                 // per lane - 4 DMUL per lane and tile against 22 DFMA per lane and correspondence
@@ -427,11 +454,29 @@ k_score(const ScoreArgs a) {
                 }
                 __syncwarp();
             }
+#elif SFM_SCALE_MODE == 3
+            if (SCREEN && !F32) {
+                __syncwarp();  // every lane is done reading sxy of the previous tile
+#pragma unroll
+                for (int r = 0; r < kTile; r += 32) {
+                    const double2 v = *reinterpret_cast<const double2*>(&ws.tile[s][r + lane]);
+                    ws.sxy[r + lane] = make_double2(v.x * a.inv_s, v.y * a.inv_s);
+                }
+                __syncwarp();
+            }
+#endif
             for (int p = 0; p < np; p += G) {
                 unsigned pm = 0;
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    const P c = tp[p + g];
+                    P c = tp[p + g];
+#if SFM_SCALE_MODE == 3
+                    if constexpr (SCREEN && !F32) {
+                        const double2 sx = ws.sxy[p + g];
+                        c.xa = sx.x;
+                        c.ya = sx.y;
+                    }
+#endif
                     T d[HPT];
                     if (SCREEN) {
                         // hypothesis-innermost: consecutive FMAs share c.yb / c.xb / c.ya / c.xa
@@ -474,7 +519,9 @@ k_score(const ScoreArgs a) {
             if (lane == 0 && t + kStages < ntiles) {
                 // the tile was rewritten through the generic proxy (scaling): order that before the bulk copy (async
                 // proxy) lands in the same bytes
+#if SFM_SCALE_MODE == 1
                 if (SCREEN && !F32) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
                 issue(t + kStages);
             }
         }

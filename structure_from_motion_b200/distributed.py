@@ -117,14 +117,26 @@ class _DeviceBuffer:
 
 
 def two_view_sharded(threshold, min_num_extra_inliers, aggregation, hyps_per_rank: int, seed: int, *, engine, rank: int,
-                     world: int, selection: str = "min_error", distance_threshold: float = 50.0, group=None):
+                     world: int, selection: str = "min_error", distance_threshold: float = 50.0, group=None,
+                     native: bool = False):
     """One complete estimate (RANSAC E -> cheirality vote -> triangulation) with the hypotheses sharded over ``world``
     GPUs and NO host round trip between scoring and the final results: every rank scores its hypotheses
     (``sfm_score_async``), the 144-byte selection records are all-gathered device-to-device by NCCL on the engine's
     stream — the path's only collective — and merged by a kernel with the reference's rule (``sfm_sharded_tail``),
     which also enqueues the inlier mask, pose vote and triangulation of the global winner.  The correspondences must
-    already be resident (``engine.upload_pairs``) and the engine must run on torch's current stream.
+    already be resident (``engine.upload_pairs``).  ``native=True``: the all-gather is issued by the library itself on the
+    communicator of ``Engine.nccl_init`` (no torch involved); otherwise torch.distributed's NCCL group is used and the engine
+    is put on torch's current stream.
     Returns dict(err, index (global), count, E, owner, num_invalid, poses, num_inliers, inlier_idx, pass_bits, points)."""
+    if native:
+        # the communicator lives behind the C ABI (Engine.nccl_init): sample -> fit -> score -> ncclAllGather ->
+        # merge -> tail in ONE C call, no torch on the data path
+        engine.two_view_sharded(seed, hyps_per_rank, threshold, float(min_num_extra_inliers or 0), aggregation, selection,
+                                distance_threshold)
+        best, owner, poses, num, idx, ok, X = engine.sharded_fetch()
+        return dict(err=float(best.err), index=int(best.index), count=int(best.count_extra),
+                    E=np.array(best.E, dtype=np.float64).reshape(3, 3), owner=owner, num_invalid=int(best.num_invalid),
+                    poses=poses, num_inliers=num, inlier_idx=idx, pass_bits=ok, points=X)
     import torch
     import torch.distributed as dist
 

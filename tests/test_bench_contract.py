@@ -39,6 +39,6 @@ def test_native_arm_line():
     r = d["roofline"]
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and 0.5 < r["frac"] < 1.2
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["unit"] == "TFLOP/s"
-    assert d["gpu_launches"] >= 2 * 10 and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["kind"] == "port"
+    assert d["gpu_launches"] >= 2 * 6 and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["kind"] == "port"
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
     assert "workload" in d["config"] and "config3" in d["config"]["workload"]

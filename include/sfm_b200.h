@@ -101,6 +101,11 @@ int sfm_get_table(sfm_ctx *ctx, int32_t *table, int64_t first, int64_t h);
  * K: row-major 3x3; only fx, fy, cx, cy are used, as in the reference. */
 int sfm_upload_pairs(sfm_ctx *ctx, const double *xa, const double *ya, const double *xb,
                      const double *yb, int64_t stride, int64_t n, const double *K);
+/* The same without the trailing synchronisation: the copies out of the caller's arrays are only ENQUEUED, so the
+ * arrays must stay valid and unchanged until the next synchronising call on this context (sfm_two_view_fetch,
+ * sfm_synchronize, ...).  Lets the upload of one estimate overlap the kernels of another context. */
+int sfm_upload_pairs_async(sfm_ctx *ctx, const double *xa, const double *ya, const double *xb,
+                           const double *yb, int64_t stride, int64_t n, const double *K);
 /* Same, inputs already in device memory. */
 int sfm_upload_pairs_d(sfm_ctx *ctx, const double *xa_d, const double *ya_d, const double *xb_d,
                        const double *yb_d, int64_t stride, int64_t n, const double *K);
@@ -138,6 +143,7 @@ typedef struct sfm_best {
     int64_t num_invalid;   /* hypotheses the reference would have raised on           */
     int64_t first_invalid; /* lowest such index, -1 if none                            */
     double E[9];           /* the winning model (row-major), E[8] == 1                 */
+    int32_t sample[8];     /* the winner's minimal sample (ransac.py:63), -1 without a table or a winner */
 } sfm_best;
 /* Winner of the last sfm_score (ransac.py:83: minimum error, earliest iteration on ties). */
 int sfm_get_best(sfm_ctx *ctx, sfm_best *out);
@@ -201,6 +207,14 @@ int sfm_pose_and_triangulate(sfm_ctx *ctx, double threshold, double distance_thr
 int sfm_two_view(sfm_ctx *ctx, double threshold, double min_extra, int aggregation, int selection,
                  double distance_threshold, sfm_best *best, sfm_poses *poses, int64_t cap, int64_t *num_inliers,
                  int64_t *inlier_idx, uint8_t *pass, double *X, uint8_t *mask, double *sed);
+/* sfm_two_view in two halves: _async enqueues everything (device sampler or uploaded table -> fit -> score -> select ->
+ * tail, plus the copies of mask / sed into the caller's arrays when given) and returns at once; _fetch synchronises
+ * and returns the results.  With two contexts on one GPU the host buffers of estimate s+1 upload while estimate s is
+ * being scored (structure_from_motion_b200.two_view.TwoViewStream). */
+int sfm_two_view_async(sfm_ctx *ctx, double threshold, double min_extra, int aggregation, int selection,
+                       double distance_threshold, uint8_t *mask, double *sed);
+int sfm_two_view_fetch(sfm_ctx *ctx, sfm_best *best, sfm_poses *poses, int64_t cap, int64_t *num_inliers,
+                       int64_t *inlier_idx, uint8_t *pass, double *X);
 
 /* ---- batched image pairs (pair-sharded workloads) ------------------------------------ */
 /* P independent pairs; pair p owns correspondences [offsets[p], offsets[p+1]) of the

@@ -30,7 +30,7 @@ class NativeError(RuntimeError):
 class Best(C.Structure):
     _fields_ = [("err", C.c_double), ("index", C.c_int64), ("count_extra", C.c_int32),
                 ("reserved", C.c_int32), ("num_invalid", C.c_int64), ("first_invalid", C.c_int64),
-                ("E", C.c_double * 9)]
+                ("E", C.c_double * 9), ("sample", C.c_int32 * 8)]
 
 
 class Poses(C.Structure):
@@ -57,6 +57,7 @@ _SIGNATURES = {
     "sfm_sample_device": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64]),
     "sfm_get_table": (C.c_int, [_P, _P, C.c_int64, C.c_int64]),
     "sfm_upload_pairs": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P]),
+    "sfm_upload_pairs_async": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P]),
     "sfm_upload_pairs_d": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P]),
     "sfm_get_normalised": (C.c_int, [_P, _P, C.c_int64]),
     "sfm_fit": (C.c_int, [_P, _P, _P, _P]),
@@ -78,6 +79,8 @@ _SIGNATURES = {
                                            C.POINTER(C.c_int64), _P, _P, _P]),
     "sfm_two_view": (C.c_int, [_P, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.POINTER(Best), C.POINTER(Poses),
                                C.c_int64, C.POINTER(C.c_int64), _P, _P, _P, _P, _P]),
+    "sfm_two_view_async": (C.c_int, [_P, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, _P, _P]),
+    "sfm_two_view_fetch": (C.c_int, [_P, C.POINTER(Best), C.POINTER(Poses), C.c_int64, C.POINTER(C.c_int64), _P, _P, _P]),
     "sfm_score_async": (C.c_int, [_P, C.c_double, C.c_double, C.c_int, C.c_int, C.POINTER(_P)]),
     "sfm_sharded_tail": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_double, C.c_double]),
     "sfm_sharded_fetch": (C.c_int, [_P, C.POINTER(Best), C.POINTER(C.c_int32), C.POINTER(Poses), C.c_int64,
@@ -162,6 +165,7 @@ class Engine:
             raise NativeError(f"sfm_create(device={device}) -> {rc}: {msg}")
         self.h = h
         self.device = int(device)
+        self._keep = None  # host arrays an un-synchronised upload still reads from
         self.n = 0
 
     # -- helpers -------------------------------------------------------------------------
@@ -199,16 +203,18 @@ class Engine:
                  "sfm_set_score_variant")
 
     # -- correspondences ------------------------------------------------------------------
-    def upload_pairs(self, pts_a, pts_b, K):
-        """pts_a, pts_b: [n,2] pixel coordinates; K: 3x3."""
+    def upload_pairs(self, pts_a, pts_b, K, sync=True):
+        """pts_a, pts_b: [n,2] pixel coordinates; K: 3x3.  sync=False only enqueues the copies: the arrays (kept
+        referenced by the engine) must not change until the next synchronising call."""
         pa, pb = _split_xy(pts_a), _split_xy(pts_b)
         if pa.shape != pb.shape:
             raise ValueError("pts_a and pts_b must have the same shape")
         K = _f64(K).reshape(3, 3)
         n = pa.shape[0]
         base_a, base_b = pa.ctypes.data, pb.ctypes.data
-        self._ck(self.lib.sfm_upload_pairs(self.h, _P(base_a), _P(base_a + 8), _P(base_b), _P(base_b + 8), 2, n,
-                                           _ptr(K)), "sfm_upload_pairs")
+        fn = self.lib.sfm_upload_pairs if sync else self.lib.sfm_upload_pairs_async
+        self._ck(fn(self.h, _P(base_a), _P(base_a + 8), _P(base_b), _P(base_b + 8), 2, n, _ptr(K)), "sfm_upload_pairs")
+        self._keep = None if sync else (pa, pb)
         self.n = n
 
     def upload_pairs_soa(self, xa, ya, xb, yb, K):
@@ -389,6 +395,30 @@ class Engine:
                                        _ptr(ok), _ptr(X), _ptr(mask), _ptr(sed)), "sfm_two_view")
         m = min(int(num.value), cap)
         return b, mask, sed, p, int(num.value), idx[:m], ok[:m], X[:m]
+
+    def two_view_async(self, threshold, min_extra=0.0, aggregation="rms", selection="min_error", distance_threshold=50.0,
+                       want_mask=True, want_sed=True):
+        """Enqueue fit -> score -> select -> tail; nothing synchronises.  Returns the (mask, sed) arrays that the
+        enqueued copies will fill - valid after two_view_fetch()."""
+        mask = pinned_empty(self.n, np.uint8) if want_mask else None
+        sed = pinned_empty(self.n, np.float64) if want_sed else None
+        self._ck(self.lib.sfm_two_view_async(self.h, float(threshold), float(min_extra), AGG[aggregation],
+                                             SELECT[selection], float(distance_threshold), _ptr(mask), _ptr(sed)),
+                 "sfm_two_view_async")
+        return mask, sed
+
+    def two_view_fetch(self, cap=None):
+        cap = self.n if cap is None else int(cap)
+        b, p = Best(), Poses()
+        num = C.c_int64(0)
+        idx = np.empty(cap, dtype=np.int64)
+        ok = np.empty(cap, dtype=np.uint8)
+        X = np.empty((cap, 3), dtype=np.float64)
+        self._ck(self.lib.sfm_two_view_fetch(self.h, C.byref(b), C.byref(p), cap, C.byref(num), _ptr(idx), _ptr(ok),
+                                             _ptr(X)), "sfm_two_view_fetch")
+        self._keep = None
+        m = min(int(num.value), cap)
+        return b, p, int(num.value), idx[:m], ok[:m], X[:m]
 
     # -- hypothesis-sharded runs: nothing synchronises between scoring and the final fetch ----
     RECORD_BYTES = 144  # include/sfm_b200.h SFM_RECORD_BYTES

@@ -393,8 +393,21 @@ static int stage_raw(sfm_ctx* c, const double* xa, const double* ya, const doubl
     return 0;
 }
 
+static int upload_pairs_impl(sfm_ctx* c, const double* xa, const double* ya, const double* xb, const double* yb,
+                             int64_t stride, int64_t n, const double* K, bool sync);
+
 int sfm_upload_pairs(sfm_ctx* c, const double* xa, const double* ya, const double* xb, const double* yb,
                      int64_t stride, int64_t n, const double* K) {
+    return upload_pairs_impl(c, xa, ya, xb, yb, stride, n, K, true);
+}
+
+int sfm_upload_pairs_async(sfm_ctx* c, const double* xa, const double* ya, const double* xb, const double* yb,
+                           int64_t stride, int64_t n, const double* K) {
+    return upload_pairs_impl(c, xa, ya, xb, yb, stride, n, K, false);
+}
+
+static int upload_pairs_impl(sfm_ctx* c, const double* xa, const double* ya, const double* xb, const double* yb,
+                             int64_t stride, int64_t n, const double* K, bool sync) {
     if (int r = use(c)) return r;
     if (!xa || !ya || !xb || !yb || !K) return fail(SFM_ERR_ARG, "null argument");
     if (n <= 0 || (uint64_t)n >= kMaxPoints) return fail(SFM_ERR_ARG, "need 0 < n < 2^25 correspondences, got %lld", (long long)n);
@@ -405,12 +418,12 @@ int sfm_upload_pairs(sfm_ctx* c, const double* xa, const double* ya, const doubl
     if (int r = stage_raw(c, xa, ya, xb, yb, stride, n, &dxa, &dya, &dxb, &dyb)) return r;
     if (int r = c->Ks.reserve(9 * sizeof(double))) return r;
     memcpy(c->Khost, K, sizeof c->Khost);
-    CU(cudaMemcpyAsync(c->Ks.p, K, 9 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->Ks.p, c->Khost, 9 * sizeof(double), cudaMemcpyHostToDevice, c->stream));  // context-owned copy of K
     c->n = n;
     if (int r = normalise_from(c, dxa, dya, dxb, dyb, stride, n, n)) return r;
     c->toc(T_UPLOAD);
-    // K is read from caller memory by the async copy: finish before returning
-    CU(cudaStreamSynchronize(c->stream));
+    // the coordinate copies read caller memory: finish before returning unless the caller took that on (_async)
+    if (sync) CU(cudaStreamSynchronize(c->stream));
     c->has_pts = true;
     c->has_table = c->has_models = c->has_score = false;
     c->winner_set = false;
@@ -753,6 +766,7 @@ static int fetch_best(sfm_ctx* c, sfm_best* out) {
     out->num_invalid = r.num_invalid;
     out->first_invalid = r.first_invalid;
     memcpy(out->E, r.E, 72);
+    memcpy(out->sample, r.sample, 32);
     if (r.best.idx >= 0) {
         c->winner_local = r.best.idx - c->last_idx_offset;
         c->winner_set = true;
@@ -1071,6 +1085,7 @@ static int pose_tail_fetch(sfm_ctx* c, sfm_poses* poses, int64_t cap, int64_t* n
         best->num_invalid = r.num_invalid;
         best->first_invalid = r.first_invalid;
         memcpy(best->E, r.E, 72);
+        memcpy(best->sample, r.sample, 32);
         if (r.best.idx >= 0) {
             c->winner_local = r.best.idx - c->last_idx_offset;
             c->winner_set = true;
@@ -1101,18 +1116,31 @@ int sfm_pose_and_triangulate(sfm_ctx* c, double thr, double dist_thr, sfm_poses*
     return pose_tail_fetch(c, poses, cap, num_inliers, inlier_idx, pass, X, nullptr);
 }
 
-int sfm_two_view(sfm_ctx* c, double thr, double min_extra, int agg, int mode, double dist_thr, sfm_best* best,
-                 sfm_poses* poses, int64_t cap, int64_t* num_inliers, int64_t* inlier_idx, uint8_t* pass, double* X,
-                 uint8_t* mask, double* sed) {
+int sfm_two_view_async(sfm_ctx* c, double thr, double min_extra, int agg, int mode, double dist_thr, uint8_t* mask,
+                       double* sed) {
     if (int r = use(c)) return r;
-    if (!best || !poses || !num_inliers) return fail(SFM_ERR_ARG, "null argument");
     if (c->batched) return fail(SFM_ERR_STATE, "single-pair call on a batched context");
     if (int r = fit_launch(c, false)) return r;
     if (int r = score_launch(c, thr, min_extra, agg, mode, true, 0, c->n)) return r;
     // the winner stays on the device: mask, compaction, decomposition, vote and triangulation are enqueued right
-    // behind the selection, and the host synchronises once for all fixed-size results
-    if (int r = pose_tail_launch(c, thr, dist_thr, c->record.as<SelectRecord>(), c->n, mask, sed)) return r;
+    // behind the selection, and the host synchronises once for all fixed-size results (sfm_two_view_fetch)
+    return pose_tail_launch(c, thr, dist_thr, c->record.as<SelectRecord>(), c->n, mask, sed);
+}
+
+int sfm_two_view_fetch(sfm_ctx* c, sfm_best* best, sfm_poses* poses, int64_t cap, int64_t* num_inliers,
+                       int64_t* inlier_idx, uint8_t* pass, double* X) {
+    if (int r = use(c)) return r;
+    if (!best || !poses || !num_inliers) return fail(SFM_ERR_ARG, "null argument");
+    if (!c->has_score || c->batched) return fail(SFM_ERR_STATE, "sfm_two_view_async first");
     return pose_tail_fetch(c, poses, cap, num_inliers, inlier_idx, pass, X, best);
+}
+
+int sfm_two_view(sfm_ctx* c, double thr, double min_extra, int agg, int mode, double dist_thr, sfm_best* best,
+                 sfm_poses* poses, int64_t cap, int64_t* num_inliers, int64_t* inlier_idx, uint8_t* pass, double* X,
+                 uint8_t* mask, double* sed) {
+    if (!best || !poses || !num_inliers) return fail(SFM_ERR_ARG, "null argument");
+    if (int r = sfm_two_view_async(c, thr, min_extra, agg, mode, dist_thr, mask, sed)) return r;
+    return sfm_two_view_fetch(c, best, poses, cap, num_inliers, inlier_idx, pass, X);
 }
 
 // ---- hypothesis-sharded runs without a host round trip -----------------------
@@ -1169,6 +1197,7 @@ int sfm_sharded_fetch(sfm_ctx* c, sfm_best* best, int32_t* owner, sfm_poses* pos
     best->num_invalid = r.num_invalid;
     best->first_invalid = r.first_invalid;
     memcpy(best->E, r.E, 72);
+    memcpy(best->sample, r.sample, 32);
     *owner = own;
     c->winner_local = lb.idx >= 0 ? lb.idx : -1;  // -1: the model lives in winnerE
     c->winner_set = r.best.idx >= 0;

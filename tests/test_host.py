@@ -35,7 +35,7 @@ def test_abi_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert ctypes.sizeof(_native.Best) == 8 + 8 + 4 + 4 + 8 + 8 + 72
+    assert ctypes.sizeof(_native.Best) == 8 + 8 + 4 + 4 + 8 + 8 + 72 + 32
     assert ctypes.sizeof(_native.Poses) == 4 * 72 + 4 * 24 + 24 + 32 + 8
 
 

@@ -100,6 +100,9 @@ struct sfm_ctx {
     long long n = 0, h = 0, npairs = 1;
     long long raw_stride = 1;
     bool batched = false, has_pts = false, has_table = false, has_models = false, has_score = false;
+    bool table_pending = false;  // sfm_sample_device was called: the table is drawn by the fit kernel (or on demand)
+    unsigned long long smp_seed = 0, smp_stream = 0;
+    long long smp_offset = 0;
     bool acc_clean = false;  // K2's accumulators (+ tail words) are zero: the fit kernel cleared them
     size_t acc_planes_for = 0;  // hypotheses (all pairs) the cleared accumulators were laid out for
     double Kstage[9] = {0};
@@ -321,27 +324,39 @@ int sfm_set_table(sfm_ctx* c, const int32_t* table, int64_t h) {
     c->h = h;
     c->npairs = 1;
     c->has_table = true;
+    c->table_pending = false;
     c->has_models = false;
     c->has_score = false;
     return 0;
 }
 
+// The device sampler is lazy: the call records (seed, stream, offset) and the next fit draws every row inside the fit
+// kernel (one launch less per estimate); anything else that needs the table first materialises it with k_sample.
 static int sample_device(sfm_ctx* c, uint64_t seed, uint64_t stream, int64_t hyp_offset, int64_t h) {
     if (h <= 0) return fail(SFM_ERR_ARG, "need h > 0");
     if (!c->has_pts) return fail(SFM_ERR_STATE, "upload correspondences before sampling");
     if (!c->batched && c->n < 8) return fail(SFM_ERR_ARG, "need at least 8 correspondences");
     if (int r = c->table.reserve((size_t)h * c->npairs * 32)) return r;
-    c->tic(T_SAMPLE);
-    dim3 grid((unsigned)((h + 127) / 128), (unsigned)c->npairs);
-    k_sample<<<grid, 128, 0, c->stream>>>(seed, stream, hyp_offset, h, c->n,
-                                          c->batched ? c->offsets.as<long long>() : nullptr,
-                                          c->table.as<int32_t>());
-    if (int r = check_launch(c, "k_sample")) return r;
-    c->toc(T_SAMPLE);
+    c->smp_seed = seed;
+    c->smp_stream = stream;
+    c->smp_offset = hyp_offset;
+    c->table_pending = true;
     c->h = h;
     c->has_table = true;
     c->has_models = false;
     c->has_score = false;
+    return 0;
+}
+
+static int ensure_table(sfm_ctx* c) {
+    if (!c->table_pending) return 0;
+    c->tic(T_SAMPLE);
+    dim3 grid((unsigned)((c->h + 127) / 128), (unsigned)c->npairs);
+    k_sample<<<grid, 128, 0, c->stream>>>(c->smp_seed, c->smp_stream, c->smp_offset, c->h, c->n,
+                                          c->batched ? c->offsets.as<long long>() : nullptr, c->table.as<int32_t>());
+    if (int r = check_launch(c, "k_sample")) return r;
+    c->toc(T_SAMPLE);
+    c->table_pending = false;
     return 0;
 }
 
@@ -354,6 +369,7 @@ int sfm_get_table(sfm_ctx* c, int32_t* table, int64_t first, int64_t h) {
     if (int r = use(c)) return r;
     if (!c->has_table || first < 0 || h < 0 || first + h > c->h * c->npairs)
         return fail(SFM_ERR_STATE, "no table rows [%lld, %lld)", (long long)first, (long long)(first + h));
+    if (int r = ensure_table(c)) return r;
     CU(cudaMemcpyAsync(table, c->table.as<int32_t>() + 8 * first, (size_t)h * 32, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return 0;
@@ -426,6 +442,7 @@ static int upload_pairs_impl(sfm_ctx* c, const double* xa, const double* ya, con
     if (sync) CU(cudaStreamSynchronize(c->stream));
     c->has_pts = true;
     c->has_table = c->has_models = c->has_score = false;
+    c->table_pending = false;
     c->winner_set = false;
     return 0;
 }
@@ -455,6 +472,7 @@ int sfm_upload_pairs_d(sfm_ctx* c, const double* xa, const double* ya, const dou
     CU(cudaStreamSynchronize(c->stream));
     c->has_pts = true;
     c->has_table = c->has_models = c->has_score = false;
+    c->table_pending = false;
     c->winner_set = false;
     return 0;
 }
@@ -480,6 +498,8 @@ static int fit_launch(sfm_ctx* c, bool want_eig) {
     // K2's accumulators are cleared by the fit itself: layout [kAccWords][H] | work counter, rescore counter, tickets
     const size_t acc_tail = 64 + (size_t)c->npairs * 4;
     if (int r = c->acc.reserve(H * kAccWords * 8 + acc_tail)) return r;
+    if (want_eig)
+        if (int r = ensure_table(c)) return r;  // the Jacobi kernel reads the table
     c->tic(T_FIT);
     const long long* off = c->batched ? c->offsets.as<long long>() : nullptr;
     dim3 grid((unsigned)((c->h + kFitThreads - 1) / kFitThreads), (unsigned)c->npairs);
@@ -491,8 +511,11 @@ static int fit_launch(sfm_ctx* c, bool want_eig) {
         k_fit_qr<<<gq, kFitQrThreads, 0, c->stream>>>(c->pts.as<Corr>(), off, c->table.as<int32_t>(), c->h,
                                                       c->E.as<double>(), c->valid.as<uint8_t>(),
                                                       c->fitflag.as<unsigned>(), c->rows.as<ModelRow>(),
-                                                      c->acc.as<unsigned long long>(), kAccWords, (int)((acc_tail + 7) / 8));
+                                                      c->acc.as<unsigned long long>(), kAccWords, (int)((acc_tail + 7) / 8),
+                                                      c->table_pending ? 1 : 0, c->smp_seed, c->smp_stream, c->smp_offset,
+                                                      c->n);
         if (int r = check_launch(c, "k_fit_qr")) return r;
+        c->table_pending = false;  // the fit kernel wrote the rows it drew
         only = c->fitflag.as<unsigned>();
         c->acc_clean = true;
         c->acc_planes_for = H;
@@ -560,6 +583,8 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
     if (mode == SELECT_MSAC) sums |= SUM_S1;  // the MSAC cost is built from the sum of the inlier distances
     if (!c->has_pts || !c->has_models) return fail(SFM_ERR_STATE, "score needs correspondences and fitted models");
     if (use_table && !c->has_table) return fail(SFM_ERR_STATE, "sample rule requested but no table is loaded");
+    if (use_table)
+        if (int r = ensure_table(c)) return r;
     if (agg < 0 || agg > 3) return fail(SFM_ERR_ARG, "bad aggregation %d", agg);
     if (mode < 0 || mode > 2) return fail(SFM_ERR_ARG, "bad selection %d", mode);
     // ransac.py accepts any float: a negative (or NaN) threshold means "no extra inliers" (score <= thr is never true),
@@ -1011,7 +1036,7 @@ static int pose_tail_launch(sfm_ctx* c, double thr, double dist_thr, const Selec
     if (int r = c->poses.reserve((size_t)P * sizeof(PoseSet))) return r;
     if (int r = c->pass.reserve((size_t)n + 1)) return r;
     if (int r = c->X.reserve((size_t)n * 24)) return r;
-    const size_t state_bytes = (size_t)P * nblk * 8 + (size_t)P * 8;
+    const size_t state_bytes = (size_t)P * nblk * 8 + (size_t)P * 12;
     if (int r = reserve_zeroed(c, c->tailstate, state_bytes)) return r;
     TailArgs a;
     a.pts = c->pts.as<Corr>();
@@ -1027,6 +1052,7 @@ static int pose_tail_launch(sfm_ctx* c, double thr, double dist_thr, const Selec
     a.agg = c->tailstate.as<unsigned long long>();
     a.ticket = reinterpret_cast<unsigned*>(a.agg + (size_t)P * nblk);
     a.done = a.ticket + P;
+    a.tri_done = a.done + P;
     a.poses = c->poses.as<PoseSet>();
     a.pass = c->pass.as<uint8_t>();
     const double* d = c->raw.as<double>();
@@ -1043,11 +1069,14 @@ static int pose_tail_launch(sfm_ctx* c, double thr, double dist_thr, const Selec
     if (mask_host) CU(cudaMemcpyAsync(mask_host, c->mask.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     if (sed_host) CU(cudaMemcpyAsync(sed_host, c->sed.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
     c->tic(T_POSE);
-    k_tail_cheirality<<<dim3((unsigned)((4 * max_len + 127) / 128), (unsigned)P), 128, 0, c->stream>>>(a);
+    // grids sized for the machine (grid-stride inside): the number of inliers is only known on the device
+    const long long cap_blocks = P >= 64 ? 8 : 2ll * c->sm_count;
+    const long long g2 = (4 * max_len + 127) / 128, g3 = (max_len + 127) / 128;
+    k_tail_cheirality<<<dim3((unsigned)(g2 < cap_blocks ? g2 : cap_blocks), (unsigned)P), 128, 0, c->stream>>>(a);
     if (int r = check_launch(c, "k_tail_cheirality")) return r;
     c->toc(T_POSE);
     c->tic(T_TRI);
-    k_tail_triangulate<<<dim3((unsigned)((max_len + 127) / 128), (unsigned)P), 128, 0, c->stream>>>(a);
+    k_tail_triangulate<<<dim3((unsigned)(g3 < cap_blocks ? g3 : cap_blocks), (unsigned)P), 128, 0, c->stream>>>(a);
     if (int r = check_launch(c, "k_tail_triangulate")) return r;
     c->toc(T_TRI);
     return 0;
@@ -1056,6 +1085,8 @@ static int pose_tail_launch(sfm_ctx* c, double thr, double dist_thr, const Selec
 // the record of a winner the host chose (sfm_get_best / sfm_set_winner) for the tail
 static int host_winner_record(sfm_ctx* c, const SelectRecord** out) {
     if (int r = c->winrec.reserve(sizeof(SelectRecord))) return r;
+    if (c->has_table)
+        if (int r = ensure_table(c)) return r;
     const int32_t* row = (c->has_table && c->winner_local >= 0) ? c->table.as<int32_t>() + 8 * c->winner_local : nullptr;
     k_make_record<<<1, 32, 0, c->stream>>>(winner_E_dev(c), row, c->winner_local >= 0 ? c->winner_local : 0,
                                            c->winrec.as<SelectRecord>());

@@ -279,7 +279,8 @@ __global__ void __launch_bounds__(kFitQrThreads, SFM_FIT_MINB)
 k_fit_qr(const Corr* __restrict__ pts, const long long* __restrict__ offsets, const int32_t* __restrict__ table,
          long long h, double* __restrict__ E_out, uint8_t* __restrict__ valid_out,
          unsigned* __restrict__ ambiguous_count, ModelRow* __restrict__ rows,
-         unsigned long long* __restrict__ acc, int acc_planes, int acc_tail_words) {
+         unsigned long long* __restrict__ acc, int acc_planes, int acc_tail_words,
+         int draw, unsigned long long seed, unsigned long long stream0, long long hyp_offset, long long n) {
     const long long li = blockIdx.x * (long long)kFitQrThreads + threadIdx.x;
     if (li >= h) return;
     const long long i = (long long)blockIdx.y * h + li;  // blockIdx.y = image pair
@@ -296,14 +297,33 @@ k_fit_qr(const Corr* __restrict__ pts, const long long* __restrict__ offsets, co
             for (int k = 0; k < 9; ++k) E_out[9 * i + k] = 0.0;
             valid_out[i] = FIT_INVALID;
             if (rows) { const double z[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; store_model_row(rows, i, z, false); }
+            if (draw) {  // a pair too short to sample from gets a row of zeros, as k_sample writes
+                int4* t = reinterpret_cast<int4*>(const_cast<int32_t*>(table) + 8 * i);
+                t[0] = make_int4(0, 0, 0, 0);
+                t[1] = make_int4(0, 0, 0, 0);
+            }
             return;
         }
         pts += offsets[blockIdx.y];
     }
     Corr c[8];
-    const int4 t0 = reinterpret_cast<const int4*>(table + 8 * i)[0];
-    const int4 t1 = reinterpret_cast<const int4*>(table + 8 * i)[1];
-    const int idx[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+    int idx[8];
+    if (draw) {
+        // the device sampler (k_sample) folded in: this hypothesis draws its own row and records it in the table
+        const long long len = offsets ? offsets[blockIdx.y + 1] - offsets[blockIdx.y] : n;
+        int32_t row[8];
+        philox_sample8(seed, stream0 + blockIdx.y, (unsigned long long)(hyp_offset + li), (unsigned)len, row);
+        int4* t = reinterpret_cast<int4*>(const_cast<int32_t*>(table) + 8 * i);
+        t[0] = make_int4(row[0], row[1], row[2], row[3]);
+        t[1] = make_int4(row[4], row[5], row[6], row[7]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) idx[k] = row[k];
+    } else {
+        const int4 t0 = reinterpret_cast<const int4*>(table + 8 * i)[0];
+        const int4 t1 = reinterpret_cast<const int4*>(table + 8 * i)[1];
+        idx[0] = t0.x; idx[1] = t0.y; idx[2] = t0.z; idx[3] = t0.w;
+        idx[4] = t1.x; idx[5] = t1.y; idx[6] = t1.z; idx[7] = t1.w;
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) c[k] = pts[idx[k]];
     double E[9];

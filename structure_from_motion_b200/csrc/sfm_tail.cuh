@@ -31,6 +31,7 @@ struct TailArgs {
     unsigned long long* agg;     // [P][nblk] look-back state, zero on entry and on exit
     unsigned* ticket;            // [P] zero on entry and on exit
     unsigned* done;              // [P] zero on entry and on exit
+    unsigned* tri_done;          // [P] set by T2 when it triangulated the pair itself
     PoseSet* poses;              // [P]
     uint8_t* pass;               // [n_total] bit p = inlier k passes pose p (at compact position offsets[p] + k)
     // triangulation
@@ -156,6 +157,40 @@ __global__ void __launch_bounds__(kTailBlock) k_tail_mask(const TailArgs a) {
     }
 }
 
+// DLT of inlier i of the pair in pixel coordinates under the voted pose b (triangulation.py:42-62); NaN when the inlier
+// does not pass that pose.
+__device__ __forceinline__ void tail_triangulate_one(const TailArgs& a, int pair, long long pbase, long long i, int b,
+                                                     uint8_t passbits) {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    double* Xo = a.X + 3 * (pbase + i);
+    if (b < 0 || !((passbits >> b) & 1u)) {
+        Xo[0] = nan; Xo[1] = nan; Xo[2] = nan;
+        return;
+    }
+    const PoseSet* poses = a.poses + pair;
+    const double* Kmat = a.Ks + 9 * (long long)pair;
+    const double* R = poses->R[b];
+    const double* t = poses->t[b];
+    double P1[12], P2[12];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            // K_ext @ Tmat: K[r,:] . [R|t][:,c]   (triangulation.py:52-56)
+            const double a0 = (c < 3) ? R[c] : t[0], a1 = (c < 3) ? R[3 + c] : t[1], a2 = (c < 3) ? R[6 + c] : t[2];
+            P2[4 * r + c] = fma(Kmat[3 * r + 2], a2, fma(Kmat[3 * r + 1], a1, Kmat[3 * r] * a0));
+            P1[4 * r + c] = (c < 3) ? Kmat[3 * r + c] : 0.0;
+        }
+    const long long gi = (pbase + a.idx[pbase + i]) * a.stride;
+    double Xr[3];
+    dlt_triangulate(a.xa[gi], a.ya[gi], a.xb[gi], a.yb[gi], P1, P2, Xr);
+    Xo[0] = Xr[0]; Xo[1] = Xr[1]; Xo[2] = Xr[2];
+}
+
+constexpr long long kTailSmallTri = 512;  // up to this many inliers the block that takes the vote also triangulates
+
+// Grid-stride: the grid is sized for the machine, not for the (unknown to the host) number of inliers - a config-3
+// winner has ~100 inliers, and 3 000 blocks that only find that out cost 30 us.
 __global__ void __launch_bounds__(128) k_tail_cheirality(const TailArgs a) {
     __shared__ int s_cnt[4];
     __shared__ int s_last;
@@ -163,13 +198,13 @@ __global__ void __launch_bounds__(128) k_tail_cheirality(const TailArgs a) {
     const long long pbase = a.offsets ? a.offsets[pair] : 0;
     const long long m = a.num[pair];
     PoseSet* poses = a.poses + pair;
-    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long i = t >> 2;
-    const int p = (int)(t & 3);
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
     __syncthreads();
-    const bool any = blockIdx.x * (long long)blockDim.x < 4 * m;  // block-uniform
-    if (any) {
+    const int r0 = a.rec[pair].sample[0];
+    for (long long t0 = blockIdx.x * (long long)blockDim.x; t0 < 4 * m; t0 += (long long)gridDim.x * blockDim.x) {
+        const long long t = t0 + threadIdx.x;
+        const long long i = t >> 2;
+        const int p = (int)(t & 3);
         bool ok = false, counts = false;
         if (i < m) {
             const long long gi = a.idx[pbase + i];
@@ -191,7 +226,6 @@ __global__ void __launch_bounds__(128) k_tail_cheirality(const TailArgs a) {
             // np.count_nonzero of the passing INDICES (:228-230): list position 0 never counts.  The list is the RANSAC
             // inlier list (apps/sfm.py:118-133), whose position 0 is the winner's first sample (ransac.py:76); without
             // a sample row it is the first correspondence.
-            const int r0 = a.rec[pair].sample[0];
             counts = ok && !(r0 >= 0 ? (gi == (long long)r0) : (i == 0));
         }
         const unsigned lane = threadIdx.x & 31u;
@@ -202,10 +236,10 @@ __global__ void __launch_bounds__(128) k_tail_cheirality(const TailArgs a) {
             const int n = __popc(cb & (0x11111111u << lane));  // lanes with pose == lane
             if (n) atomicAdd(&s_cnt[lane], n);
         }
-        __syncthreads();
-        if (threadIdx.x < 4 && s_cnt[threadIdx.x])
-            atomicAdd((unsigned long long*)&poses->counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
     }
+    __syncthreads();
+    if (threadIdx.x < 4 && s_cnt[threadIdx.x])
+        atomicAdd((unsigned long long*)&poses->counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
     // np.argmax(num_good_correspondences) (:237), first maximum: by the last block of the pair
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -213,50 +247,39 @@ __global__ void __launch_bounds__(128) k_tail_cheirality(const TailArgs a) {
         s_last = (atomicAdd(&a.done[pair], 1u) == gridDim.x - 1) ? 1 : 0;
     }
     __syncthreads();
-    if (s_last && threadIdx.x == 0) {
-        __threadfence();
+    if (!s_last) return;
+    __threadfence();
+    __shared__ int s_best;
+    if (threadIdx.x == 0) {
         a.done[pair] = 0;
-        if (poses->best != -2) {
+        int bst = poses->best;
+        if (bst != -2) {
             const volatile long long* cn = poses->counts;
-            int bst = 0;
+            bst = 0;
             for (int q = 1; q < 4; ++q)
                 if (cn[q] > cn[bst]) bst = q;
             poses->best = bst;
         }
+        s_best = bst;
+        a.tri_done[pair] = (m <= kTailSmallTri) ? 1u : 0u;
+    }
+    __syncthreads();
+    // a short inlier list is triangulated right here (same code, already in the instruction cache); a long one by T3
+    if (m <= kTailSmallTri) {
+        const int bst = s_best;
+        for (long long i = threadIdx.x; i < m; i += blockDim.x)
+            tail_triangulate_one(a, pair, pbase, i, bst, __ldcg(a.pass + pbase + i));
     }
 }
 
 __global__ void __launch_bounds__(128) k_tail_triangulate(const TailArgs a) {
     const int pair = blockIdx.y;
+    if (a.tri_done[pair]) return;  // T2 already did it
     const long long pbase = a.offsets ? a.offsets[pair] : 0;
     const long long m = a.num[pair];
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    const PoseSet* poses = a.poses + pair;
-    const int b = poses->best;
-    const double nan = __longlong_as_double(0x7ff8000000000000LL);
-    double* Xo = a.X + 3 * (pbase + i);
-    if (b < 0 || !((a.pass[pbase + i] >> b) & 1u)) {
-        Xo[0] = nan; Xo[1] = nan; Xo[2] = nan;
-        return;
-    }
-    const double* Kmat = a.Ks + 9 * (long long)pair;
-    const double* R = poses->R[b];
-    const double* t = poses->t[b];
-    double P1[12], P2[12];
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            // K_ext @ Tmat: K[r,:] . [R|t][:,c]   (triangulation.py:52-56)
-            const double a0 = (c < 3) ? R[c] : t[0], a1 = (c < 3) ? R[3 + c] : t[1], a2 = (c < 3) ? R[6 + c] : t[2];
-            P2[4 * r + c] = fma(Kmat[3 * r + 2], a2, fma(Kmat[3 * r + 1], a1, Kmat[3 * r] * a0));
-            P1[4 * r + c] = (c < 3) ? Kmat[3 * r + c] : 0.0;
-        }
-    const long long gi = (pbase + a.idx[pbase + i]) * a.stride;
-    double Xr[3];
-    dlt_triangulate(a.xa[gi], a.ya[gi], a.xb[gi], a.yb[gi], P1, P2, Xr);
-    Xo[0] = Xr[0]; Xo[1] = Xr[1]; Xo[2] = Xr[2];
+    const int b = a.poses[pair].best;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x)
+        tail_triangulate_one(a, pair, pbase, i, b, a.pass[pbase + i]);
 }
 
 // ---- batch: per-pair results packed densely for the copy back to the host -------------------

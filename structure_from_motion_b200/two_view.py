@@ -192,7 +192,7 @@ def ransac_essential_arrays(
 
     mask = mask.astype(bool)
     local = int(best.index)
-    sample = eng.get_table(1, first=local)[0] if sampler == "device" else table[local]
+    sample = np.array(best.sample, dtype=np.int32) if sampler == "device" else table[local]
     is_sample = np.zeros(n, dtype=bool)
     is_sample[sample] = True
     if sampler == "reference":
@@ -422,3 +422,62 @@ def image_pair_arrays(image_a, image_b, camera_matrix, *, num_harris_corners: in
     tv = two_view_arrays(camera_matrix, ca[ia], cb[ib], sed_inlier_threshold, min_num_extra_inliers,
                          error_aggregation_method, max_iterations, sampler=sampler, seed=seed, engine=eng)
     return ImagePairResult(corners_a=ca, corners_b=cb, match_a=ia, match_b=ib, match_score=best_s[ia], two_view=tv)
+
+
+class TwoViewStream:
+    """Back-to-back estimates from HOST buffers with the transfers of one estimate hidden behind the kernels of
+    another: ``depth`` contexts on the same GPU (each its own stream); ``submit`` only ENQUEUES the upload of the
+    correspondences, the device sampler, fit, score, selection and tail on the next context and returns a ticket;
+    ``result`` synchronises that context and builds the ``TwoViewResult``.  While context A scores estimate s, the copy
+    engine moves the correspondences of estimate s+1 and the host unpacks estimate s-1.  Device sampler only (the
+    reference sampler is a sequential host computation); results are identical to ``two_view_arrays(...,
+    sampler="device")``."""
+
+    def __init__(self, depth: int = 2, device: Optional[int] = None):
+        dev = _native.default_device() if device is None else int(device)
+        self.engines = [_native.Engine(dev) for _ in range(depth)]
+        self._next = 0
+        self._pending = {}
+
+    def set_score_variant(self, *a, **k):
+        for e in self.engines:
+            e.set_score_variant(*a, **k)
+
+    def submit(self, camera_matrix, pts_a, pts_b, threshold, min_num_extra_inliers=0, error_aggregation_method="rms",
+               max_iterations: int = 100, distance_threshold: float = 50.0, seed: int = 0, selection: str = "min_error"):
+        k = self._next
+        eng = self.engines[k % len(self.engines)]
+        if any(t % len(self.engines) == k % len(self.engines) for t in self._pending):
+            raise RuntimeError("fetch the estimate submitted to this context before submitting another one")
+        self._next += 1
+        eng.upload_pairs(pts_a, pts_b, camera_matrix, sync=False)
+        eng.sample_device(seed, int(max_iterations))
+        mask, sed = eng.two_view_async(threshold, float(min_num_extra_inliers or 0), _agg_name(error_aggregation_method),
+                                       selection, float(distance_threshold))
+        self._pending[k] = (eng, mask, sed, min_num_extra_inliers or 0)
+        return k
+
+    def result(self, ticket) -> TwoViewResult:
+        eng, mask, sed, min_extra = self._pending.pop(ticket)
+        best, p, num, idx, ok, X = eng.two_view_fetch()
+        if best.index < 0:
+            raise ValueError(f"No model could be found with at least {min_extra + 8} inliers.")
+        _check_decomposition(p)
+        counts = np.array(p.counts, dtype=np.int64)
+        if 0 == np.count_nonzero(counts):
+            raise EightPointCalculationError("None of the transformations pass the cheirality check.")
+        sample = np.array(best.sample, dtype=np.int32)
+        extra = idx[~np.isin(idx, sample)]  # the tail's compacted list = sed <= thr plus the samples, ascending
+        b = int(p.best)
+        res = RansacResult(E=np.array(best.E, dtype=np.float64).reshape(3, 3), best_index=int(best.index),
+                           error=float(best.err), count_extra=int(best.count_extra),
+                           inlier_indices=np.concatenate([sample.astype(np.int64), extra]), mask=mask.view(bool),
+                           sed=sed, sample=sample, num_invalid=int(best.num_invalid), first_invalid=int(best.first_invalid))
+        R = np.array(p.R, dtype=np.float64).reshape(4, 3, 3)[b].copy()
+        t = np.array(p.t, dtype=np.float64).reshape(4, 3)[b].copy()
+        return TwoViewResult(ransac=res, R=R, t=t, inlier_indices=idx, passing=((ok >> b) & 1).astype(bool), points=X,
+                             counts=counts)
+
+    def close(self):
+        for e in self.engines:
+            e.close()

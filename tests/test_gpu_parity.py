@@ -370,3 +370,29 @@ def test_fused_two_view_call_equals_the_two_step_sequence(engine, min_extra):
     assert np.array_equal(X_a, X_b, equal_nan=True)
     assert poses_a.best == poses_b.best and list(poses_a.counts) == list(poses_b.counts)
     assert np.array_equal(np.array(poses_a.R), np.array(poses_b.R))
+
+
+def test_two_view_stream_equals_blocking_calls(engine):
+    """two_view.TwoViewStream (two contexts, un-synchronised uploads, results fetched one estimate behind) returns what
+    the blocking two_view_arrays call returns, estimate by estimate."""
+    K, x1, x2, *_ = make_scene(6000, 0.4, seed=14)
+    want = [two_view.two_view_arrays(K, x1, x2, THR, 10, "rms", 1200, sampler="device", seed=s, on_degenerate="skip",
+                                     engine=engine) for s in range(5)]
+    ts = two_view.TwoViewStream(depth=2)
+    try:
+        got, prev = [], ts.submit(K, x1, x2, THR, 10, "rms", 1200, 50.0, seed=0)
+        for s in range(1, 5):
+            cur = ts.submit(K, x1, x2, THR, 10, "rms", 1200, 50.0, seed=s)
+            got.append(ts.result(prev))
+            prev = cur
+        got.append(ts.result(prev))
+    finally:
+        ts.close()
+    for w, g in zip(want, got):
+        assert g.ransac.best_index == w.ransac.best_index and g.ransac.error == w.ransac.error
+        assert np.array_equal(g.ransac.E, w.ransac.E) and g.ransac.count_extra == w.ransac.count_extra
+        assert np.array_equal(g.ransac.inlier_indices, w.ransac.inlier_indices)
+        assert np.array_equal(g.ransac.mask, w.ransac.mask) and np.array_equal(g.ransac.sed, w.ransac.sed)
+        assert np.array_equal(g.R, w.R) and np.array_equal(g.t, w.t) and np.array_equal(g.counts, w.counts)
+        assert np.array_equal(g.inlier_indices, w.inlier_indices) and np.array_equal(g.passing, w.passing)
+        assert np.array_equal(g.points, w.points, equal_nan=True)

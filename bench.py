@@ -83,7 +83,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="config3", choices=list(WORKLOADS) + ["config1", "config4", "frontend"])
-    ap.add_argument("--variant", default=os.environ.get("SFM_SCORE_VARIANT", "screen"), choices=["screen", "full", "screen32"])
+    ap.add_argument("--variant", default=os.environ.get("SFM_SCORE_VARIANT", "auto"), choices=["auto", "screen", "full", "screen32"])
     ap.add_argument("--hpt", type=int, default=int(os.environ.get("SFM_SCORE_HPT", "2")))
     ap.add_argument("--group", type=int, default=int(os.environ.get("SFM_SCORE_GROUP", "16")))
     ap.add_argument("--pairs", type=int, default=512, help="config4: image pairs per GPU per step")
@@ -694,7 +694,7 @@ def main():
                 "workload": f"{args.workload}: {n} correspondences x {h_rank} hypotheses per GPU "
                             f"({h_rank * world} total), 40% outliers, thr 1.5e-6, RMS, min_extra 10, + cheirality "
                             f"vote + triangulation of the {num_inl} inliers",
-                "sampler": "device (Philox)", "score_variant": args.variant, "hyps_per_thread": args.hpt, "group": args.group,
+                "sampler": "device (Philox)", "score_variant": args.variant + (" (device pilot: survivor rate 1.6 % -> 11-slot one-sided screen)" if args.variant == "auto" else ""), "hyps_per_thread": args.hpt, "group": args.group,
                 "l2": "flushed (256 MiB memset) between timed steps",
                 "parallelism": f"hypothesis-sharded x{world}, one 144 B/rank ncclAllGather issued by the library (C ABI) + merge kernel" if world > 1 else "single GPU",
             },
@@ -707,8 +707,8 @@ def main():
                 "traffic": traffic,
                 "peak_source": "DFMA microbenchmark in this run (sfm_measure_fp64_peak); MEASURED_PEAKS.json has no fp64 entry",
                 "algorithmic_flop_per_eval": FLOP_PER_EVAL,
-                "executed_fp64_slots_per_eval": 11.0 if args.variant.startswith("screen") else 21.0,
-                "fp64_pipe_busy_frac_est": kern_evals * (11.0 if args.variant.startswith("screen") else 21.0) / fp64_peak_dfma,
+                "executed_fp64_slots_per_eval": 21.0 if args.variant == "full" else 11.0,
+                "fp64_pipe_busy_frac_est": kern_evals * (21.0 if args.variant == "full" else 11.0) / fp64_peak_dfma,
                 "l2_to_smem_stream_gbs": algo_bytes / (score_ms_per_launch * 1e-3) / 1e9,
                 "l2_to_smem_note": "32 B per correspondence per hypothesis-group pass, served by L2 (the working set is L2-resident); NOT HBM traffic",
                 "dram_gbs": (traffic / (score_ms_per_launch * 1e-3) / 1e9) if traffic else None,

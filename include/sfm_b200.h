@@ -49,7 +49,7 @@ enum sfm_selection { SFM_SELECT_MIN_ERROR = 0, SFM_SELECT_MAX_INLIERS = 1, SFM_S
  *   FULL      fp64 two-sided division-free decision (21 slots) + exact re-check
  *   SCREEN32  the screen evaluated in fp32 as a pre-filter (rigorous guard band, ~2 % more
  *             survivors) + exact fp64 re-check; reported separately from the fp64 headline */
-enum sfm_score_variant { SFM_SCORE_SCREEN = 0, SFM_SCORE_FULL = 1, SFM_SCORE_SCREEN32 = 2 };
+enum sfm_score_variant { SFM_SCORE_SCREEN = 0, SFM_SCORE_FULL = 1, SFM_SCORE_SCREEN32 = 2, SFM_SCORE_AUTO = 3 };
 
 /* ---- context ------------------------------------------------------------------------ */
 int sfm_version(void);

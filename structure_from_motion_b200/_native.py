@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("SFM_B200_LIB") or os.path.join(_HERE, "libsfm_b200.so
 
 AGG = {"sum": 0, "square": 1, "mean": 2, "rms": 3}
 SELECT = {"min_error": 0, "max_inliers": 1, "msac": 2}
-VARIANT = {"screen": 0, "full": 1, "screen32": 2}
+VARIANT = {"screen": 0, "full": 1, "screen32": 2, "auto": 3}
 
 
 class NativeUnavailableError(RuntimeError):
@@ -198,7 +198,7 @@ class Engine:
     def synchronize(self):
         self._ck(self.lib.sfm_synchronize(self.h), "sfm_synchronize")
 
-    def set_score_variant(self, variant="screen", hyps_per_thread=0, group=0):
+    def set_score_variant(self, variant="auto", hyps_per_thread=0, group=0):
         self._ck(self.lib.sfm_set_score_variant(self.h, VARIANT[variant], int(hyps_per_thread), int(group)),
                  "sfm_set_score_variant")
 

@@ -98,6 +98,7 @@ struct sfm_ctx {
     Buf h_img, h_gx, h_gy, h_corner, h_alive, h_key, h_idx, h_small, h_xy;
     Buf mask, sed, poses, pass, X, idx, scan, tmp, tailstate, num, winrec, bout;
     long long n = 0, h = 0, npairs = 1;
+    long long first_len = 0;  // batched: correspondences of the first pair (what the AUTO pilot samples)
     long long raw_stride = 1;
     bool batched = false, has_pts = false, has_table = false, has_models = false, has_score = false;
     bool table_pending = false;  // sfm_sample_device was called: the table is drawn by the fit kernel (or on demand)
@@ -106,8 +107,9 @@ struct sfm_ctx {
     bool acc_clean = false;  // K2's accumulators (+ tail words) are zero: the fit kernel cleared them
     size_t acc_planes_for = 0;  // hypotheses (all pairs) the cleared accumulators were laid out for
     double Kstage[9] = {0};
-    const void* occ_fn = nullptr;  // scoring kernel whose launch configuration is cached
-    int occ_blocks = 0;
+    const void* occ_fn[4] = {nullptr, nullptr, nullptr, nullptr};  // scoring kernels whose launch configuration is cached
+    int occ_blocks[4] = {0, 0, 0, 0};
+    int occ_next = 0;
     void* nccl_comm = nullptr;  // ncclComm_t of sfm_nccl_init (hypothesis-sharded runs without torch)
     int nccl_rank = 0, nccl_world = 1;
     Buf gathered;
@@ -117,7 +119,7 @@ struct sfm_ctx {
     long long last_idx_offset = 0;
     double Khost[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     // config
-    int variant = SFM_SCORE_SCREEN, hpt = 2, group = 16;
+    int variant = SFM_SCORE_AUTO, hpt = 2, group = 16;  // AUTO: a pilot on the device picks SCREEN or FULL per call
     // timing
     bool timing = false;
     cudaEvent_t ev0[T_COUNT], ev1[T_COUNT];
@@ -285,7 +287,7 @@ int sfm_synchronize(sfm_ctx* c) {
 
 int sfm_set_score_variant(sfm_ctx* c, int variant, int hpt, int group) {
     if (!c) return fail(SFM_ERR_ARG, "null context");
-    if (variant != SFM_SCORE_SCREEN && variant != SFM_SCORE_FULL && variant != SFM_SCORE_SCREEN32)
+    if (variant != SFM_SCORE_SCREEN && variant != SFM_SCORE_FULL && variant != SFM_SCORE_SCREEN32 && variant != SFM_SCORE_AUTO)
         return fail(SFM_ERR_ARG, "bad variant %d", variant);
     // hyps_per_thread == 0: keep the current shape, or the variant's default when the arithmetic changes
     int nh = hpt ? hpt : c->hpt, ng = group ? group : c->group;
@@ -293,7 +295,8 @@ int sfm_set_score_variant(sfm_ctx* c, int variant, int hpt, int group) {
         nh = variant == SFM_SCORE_SCREEN32 ? 4 : 2;
         ng = variant == SFM_SCORE_SCREEN32 ? 8 : 16;
     }
-    if (!score_kernel(variant, nh, ng))
+    if (!score_kernel(variant == SFM_SCORE_AUTO ? SFM_SCORE_SCREEN : variant, nh, ng) ||
+        (variant == SFM_SCORE_AUTO && !score_kernel(SFM_SCORE_FULL, nh, ng)))
         return fail(SFM_ERR_ARG, "unsupported combination: hyps_per_thread %d, group %d", nh, ng);
     c->variant = variant;
     c->hpt = nh;
@@ -611,7 +614,10 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
     // rounding guard of the screening tests: relative slack + an absolute term that covers a
     // cancelling residual r at the 1-ulp level (only matters for thr -> 0)
     // the fp32 pre-filter needs s = sqrt(thr32) and 1/s inside the fp32 range: huge thresholds use the fp64 screen
-    int variant = c->variant;
+    // AUTO: the one-sided screen is prepared and launched as usual, the two-sided one right behind it; a pilot that
+    // rides on the screening-copy kernel measures the survivor rate and one of the two scoring kernels exits at once
+    const bool autov = c->variant == SFM_SCORE_AUTO;
+    int variant = autov ? SFM_SCORE_SCREEN : c->variant;
     if (variant == SFM_SCORE_SCREEN32 && thr > 1e6) variant = SFM_SCORE_SCREEN;  // with hpt 2 / group 16, see above
     const bool f32 = variant == SFM_SCORE_SCREEN32;
     const bool screen = variant != SFM_SCORE_FULL;
@@ -629,16 +635,26 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         const void* fn = score_kernel(variant, hpt, G);
         if (!fn) return fail(SFM_ERR_ARG, "unsupported scoring configuration (variant %d, hpt %d, group %d)", variant, hpt, G);
         const size_t smem = (size_t)kScoreWarps * score_warp_smem(hpt);
+        // attribute set and occupancy queried once per kernel instantiation (small cache)
+        auto occupancy = [&](const void* f, int* out) -> int {
+            for (int k = 0; k < 4; ++k)
+                if (c->occ_fn[k] == f) { *out = c->occ_blocks[k]; return 0; }
+            int o = 0;
+            CU(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, f, kScoreThreads, smem));
+            if (o < 1) o = 1;
+            c->occ_fn[c->occ_next] = f;
+            c->occ_blocks[c->occ_next] = o;
+            c->occ_next = (c->occ_next + 1) & 3;
+            *out = o;
+            return 0;
+        };
         int occ = 0;
-        if (c->occ_fn == fn) {
-            occ = c->occ_blocks;  // attribute set and occupancy queried once per kernel instantiation
-        } else {
-            CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kScoreThreads, smem));
-            if (occ < 1) occ = 1;
-            c->occ_fn = fn;
-            c->occ_blocks = occ;
-        }
+        if (int r = occupancy(fn, &occ)) return r;
+        const void* fn_full = autov ? score_kernel(SFM_SCORE_FULL, hpt, G) : nullptr;
+        int occ_full = 0;
+        if (fn_full)
+            if (int r = occupancy(fn_full, &occ_full)) return r;
         const long long grid_blocks = (long long)c->sm_count * occ;
         const long long tiles = (max_len + kTile - 1) / kTile;
         constexpr int items_per_warp = 32;  // 12 -> 32 shortens the end-of-launch tail (+1 % on config 3)
@@ -691,6 +707,9 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         a.htotal = (long long)H;
         a.acc = c->acc.as<unsigned long long>();
         a.work_counter = reinterpret_cast<unsigned*>(a.acc + H * kAccWords);
+        // tail words behind the planes: +0 work counter, +8 rescore counter, +16 pilot totals, +24 pilot ticket, +32 mode
+        char* tailp = reinterpret_cast<char*>(a.acc + H * kAccWords);
+        a.mode_flag = autov ? reinterpret_cast<const int*>(tailp + 32) : nullptr;
         acc_dev = a.acc;
         c->tic(T_SCORE);
         // the fit kernel leaves the accumulators cleared; a second score of the same models (or uploaded models) clears here
@@ -704,8 +723,15 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         }
 #if SFM_SCALE_MODE == 0
         else if (screen && !skip_k2) {
+            PilotArgs pa;
+            pa.E = c->E.as<double>();
+            pa.h = h;
+            pa.plen = c->batched ? c->first_len : c->n;  // batches: the pilot looks at the first pair
+            pa.thr_pre = thr_pre;
+            pa.counters = reinterpret_cast<unsigned*>(tailp + 16);
+            pa.mode_flag = autov ? reinterpret_cast<int*>(tailp + 32) : nullptr;
             k_screen_pts64<<<(unsigned)((npts + 255) / 256), 256, 0, c->stream>>>(c->pts.as<Corr>(), npts, 1.0 / s_scale,
-                                                                                  reinterpret_cast<Corr*>(c->spts.p));
+                                                                                  reinterpret_cast<Corr*>(c->spts.p), pa);
             if (int r = check_launch(c, "k_screen_pts64")) return r;
         }
 #endif
@@ -715,6 +741,16 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         if (!skip_k2) {
             CU(cudaLaunchKernel(fn, dim3((unsigned)launch_blocks), dim3(kScoreThreads), kargs, smem, c->stream));
             if (int r = check_launch(c, "k_score")) return r;
+            if (fn_full) {  // AUTO: the two-sided screen on the unscaled records; exits at once unless the pilot chose it
+                ScoreArgs a2 = a;
+                a2.thr_pre = thr * (1.0 + 1e-9) + 1e-22;
+                a2.spts = c->pts.p;
+                const long long gb2 = (long long)c->sm_count * occ_full;
+                const long long lb2 = gb2 < want_blocks ? gb2 : want_blocks;
+                void* kargs2[] = {(void*)&a2};
+                CU(cudaLaunchKernel(fn_full, dim3((unsigned)lb2), dim3(kScoreThreads), kargs2, smem, c->stream));
+                if (int r = check_launch(c, "k_score")) return r;
+            }
         }
         c->toc(T_SCORE);
     }
@@ -1363,6 +1399,7 @@ static int batch_core(sfm_ctx* c, const double* xa, const double* ya, const doub
     c->batched = true;
     c->npairs = npairs;
     c->n = n;
+    c->first_len = offsets[1] - offsets[0];
     if (int r = c->offsets.reserve((size_t)(npairs + 1) * 8)) return r;
     if (int r = c->Ks.reserve((size_t)npairs * 72)) return r;
     CU(cudaMemcpyAsync(c->offsets.p, offsets, (size_t)(npairs + 1) * 8, cudaMemcpyHostToDevice, c->stream));

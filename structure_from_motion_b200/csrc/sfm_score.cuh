@@ -128,6 +128,7 @@ constexpr int kChunkBits = 21;
 constexpr int kAccWords = 1 + 2 * kChunks;  // count, sum(sed), sum(sed^2)
 constexpr long long kMaxItemPoints = 1ll << 11;  // 2^11 adds of < 2^21 cannot overflow a 32-bit word
 enum { SUM_S1 = 1, SUM_S2 = 2 };       // which sums a launch accumulates
+enum { MODE_FULL = 0, MODE_SCREEN = 1, MODE_SCREEN32 = 2 };
 constexpr double kKappaCoef = 4e-20;
 constexpr double kKappa32Coef = 1.2e-10;   // fp32 pre-filter, see the K2 header
 constexpr double kThr32Factor = 1.0316;   // (1 + 1/64)^2 (1 + 1e-4)
@@ -164,6 +165,7 @@ struct ScoreArgs {
     long long htotal;          // npairs * h
     unsigned* work_counter;
     unsigned long long* acc;   // [kAccWords][htotal] exact integer accumulators (pre-zeroed)
+    const int* mode_flag;      // AUTO variant: the MODE the pilot selected (the other kernel exits at once); else null
 };
 
 __device__ __forceinline__ unsigned atom_add_acq_rel_shared(unsigned* p, unsigned v) {
@@ -202,15 +204,75 @@ struct __align__(16) Corr32 {
     float xa, ya, xb, yb;
 };
 
-// SFM_SCALE_MODE 0: fp64 screening copy (xa / s, ya / s, xb, yb)
+// fp64 screening copy (xa / s, ya / s, xb, yb) written at the head of every SCREEN scoring call - and, for the AUTO
+// variant, the PILOT that chooses between the two fp64 screens: the first kPilotBlocks blocks also run the one-sided
+// test on a sample (64 hypotheses spread over the range x ~2 000 correspondences of the first pair) and the last of
+// them to finish turns the pass rate into the MODE the scoring kernels check.  Above ~6.5 % survivors the exact
+// evaluation of the survivors dominates and the 21-slot two-sided screen (survivors = inliers) wins; below, the
+// 11-slot one-sided screen does (DESIGN.md, table against the threshold).
+constexpr int kPilotBlocks = 8;
+constexpr int kPilotHyps = 64;
+constexpr int kPilotPts = 2048;
+constexpr double kPilotFullAbove = 0.065;
+struct PilotArgs {
+    const double* E;      // models of the first pair
+    long long h;          // hypotheses per pair
+    long long plen;       // correspondences of the first pair
+    double thr_pre;
+    unsigned* counters;   // [0] passes, [1] ticket (zero on entry)
+    int* mode_flag;       // out
+};
 __global__ void __launch_bounds__(256) k_screen_pts64(const Corr* __restrict__ pts, long long n, double inv_s,
-                                                      Corr* __restrict__ spts) {
+                                                      Corr* __restrict__ spts, const PilotArgs pa) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Corr c = pts[i];
-    c.xa *= inv_s;
-    c.ya *= inv_s;
-    spts[i] = c;
+    if (i < n) {
+        Corr c = pts[i];
+        c.xa *= inv_s;
+        c.ya *= inv_s;
+        spts[i] = c;
+    }
+    if (!pa.mode_flag || blockIdx.x >= kPilotBlocks) return;
+    // pilot: thread t of block b -> hypothesis (t % 64) of the sample, correspondences (b * 4 + t / 64) + 32 k
+    const int nb = gridDim.x < kPilotBlocks ? gridDim.x : kPilotBlocks;
+    const long long nh = pa.h < kPilotHyps ? pa.h : kPilotHyps;
+    const int hs = threadIdx.x % kPilotHyps;
+    int pass = 0, tests = 0;
+    if (hs < nh && pa.plen > 0) {
+        const long long hyp = (pa.h / nh) * hs;
+        double e[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) e[k] = pa.E[9 * hyp + k];
+        const long long np = pa.plen < kPilotPts ? pa.plen : kPilotPts;
+        const long long step = pa.plen / np;
+        const int lanes = nb * (256 / kPilotHyps);
+        for (long long q = blockIdx.x * (256 / kPilotHyps) + threadIdx.x / kPilotHyps; q < np; q += lanes) {
+            const Corr c = pts[q * step];
+            pass += sed_screen(e, c.xa, c.ya, c.xb, c.yb, pa.thr_pre) < 0.0 ? 1 : 0;
+            tests += 1;
+        }
+    }
+    // pack (passes, tests) into one 64-bit add: tests <= 2^17 per launch
+    unsigned long long v = ((unsigned long long)pass << 32) | (unsigned)tests;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    __shared__ unsigned long long s_sum;
+    __shared__ int s_last;
+    if (threadIdx.x == 0) s_sum = 0ull;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_sum, v);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long* tot = reinterpret_cast<unsigned long long*>(pa.counters);
+        atomicAdd(tot, s_sum);
+        __threadfence();
+        s_last = atomicAdd(pa.counters + 2, 1u) == (unsigned)(nb - 1);
+        if (s_last) {
+            __threadfence();
+            const unsigned long long t = *reinterpret_cast<volatile unsigned long long*>(tot);
+            const double rate = (unsigned)t ? (double)(t >> 32) / (double)(unsigned)t : 0.0;
+            *pa.mode_flag = rate > kPilotFullAbove ? MODE_FULL : MODE_SCREEN;
+        }
+    }
 }
 
 // fp32 pre-filter only: Corr32 copy of the correspondences with (xa, ya) pre-divided by s (thr-dependent, so it runs
@@ -250,7 +312,6 @@ struct alignas(128) ScoreWarpSmem {
 #endif
 constexpr int score_min_blocks(int hpt) { return hpt >= 4 ? SFM_SCORE_MINB4 : (hpt == 2 ? SFM_SCORE_MINB2 : 8); }
 
-enum { MODE_FULL = 0, MODE_SCREEN = 1, MODE_SCREEN32 = 2 };
 
 __device__ __forceinline__ int sign_word(double d) { return __double2hiint(d); }
 __device__ __forceinline__ int sign_word(float f) { return __float_as_int(f); }
@@ -269,6 +330,7 @@ k_score(const ScoreArgs a) {
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(full, (int)(threadIdx.x >> 5), 0);  // tells the compiler it is warp-uniform
     const unsigned lt = lanemask_lt();
+    if (a.mode_flag && *a.mode_flag != MODE) return;  // AUTO: the pilot of k_screen_pts64 chose the other screen
     ScoreWarpSmem<HPT>& ws = reinterpret_cast<ScoreWarpSmem<HPT>*>(score_smem)[warp];
 
     if (lane == 0) {

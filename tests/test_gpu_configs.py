@@ -110,7 +110,7 @@ def test_config3_deterministic_and_variant_invariant(engine, config3):
         try:
             cnt, s1, s2, err = engine.score(THR, min_extra=10, aggregation="rms")
         finally:
-            engine.set_score_variant("screen")
+            engine.set_score_variant("auto")
         assert np.array_equal(cnt, c["cnt"]), variant
         # integer accumulation: the sums are bit-identical whatever the schedule or the variant
         assert np.array_equal(s1, c["s1"]) and np.array_equal(s2, c["s2"]), variant

@@ -80,7 +80,7 @@ def test_scorer_bit_exact_against_oracle(engine, variant, hpt, group):
         engine.set_models(E)
         cnt, s1, s2, err = engine.score(THR, min_extra=10, aggregation="rms")
     finally:
-        engine.set_score_variant("screen")
+        engine.set_score_variant("auto")
     assert np.array_equal(cnt, cnt_o)
     np.testing.assert_allclose(s1, s1_o, rtol=1e-12, atol=0)
     np.testing.assert_allclose(s2, s2_o, rtol=1e-12, atol=0)
@@ -118,7 +118,7 @@ def test_screen_never_drops_an_inlier(engine, thr, escale, variant):
     try:
         cnt, s1, s2, err = engine.score(thr, min_extra=0, aggregation="sum")
     finally:
-        engine.set_score_variant("screen")
+        engine.set_score_variant("auto")
     assert np.array_equal(cnt, cnt_o)
     np.testing.assert_allclose(s1, s1_o, rtol=1e-12, atol=0)
     np.testing.assert_allclose(s2, s2_o, rtol=1e-12, atol=0)
@@ -396,3 +396,26 @@ def test_two_view_stream_equals_blocking_calls(engine):
         assert np.array_equal(g.R, w.R) and np.array_equal(g.t, w.t) and np.array_equal(g.counts, w.counts)
         assert np.array_equal(g.inlier_indices, w.inlier_indices) and np.array_equal(g.passing, w.passing)
         assert np.array_equal(g.points, w.points, equal_nan=True)
+
+
+@pytest.mark.parametrize("thr", [1.5e-6, 1.5e-4, 1.5e-2])
+def test_auto_variant_matches_explicit_screens(engine, thr):
+    """variant "auto" (the default): a pilot on the device measures the survivor rate of the one-sided screen and one of
+    the two fp64 scoring kernels runs.  Whichever it picks, counts, sums, errors and the winner are bit-identical to
+    both explicit variants (every decision and every summed value comes from the exact scorer)."""
+    K, x1, x2, *_ = make_scene(20_000, 0.4, seed=27)
+    engine.upload_pairs(x1, x2, K)
+    engine.sample_device(seed=2, h=2048)
+    engine.fit(want_E=False)
+    got = {}
+    try:
+        for variant in ("auto", "screen", "full"):
+            engine.set_score_variant(variant, 2, 16)
+            got[variant] = engine.score(thr, min_extra=10, aggregation="rms") + (engine.get_best().index,)
+    finally:
+        engine.set_score_variant("auto")
+    for variant in ("screen", "full"):
+        for a, b in zip(got["auto"][:4], got[variant][:4]):
+            assert np.array_equal(a, b, equal_nan=True), (variant, thr)
+        assert got["auto"][4] == got[variant][4]
+    assert got["auto"][0].max() > 10

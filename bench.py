@@ -406,6 +406,53 @@ def run_extras(args, eng, world, rank, barrier, flush_l2, torch, dist, per_gpu_r
                                     "inlier list, cheirality bits, vote, triangulated points) bit-identical on EVERY rank "
                                     "to one GPU evaluating the union")
 
+    # ---- latency of the small configurations (one GPU): config 2 resident, config 1 through the reference signature ----
+    if world == 1:
+        n2, h2, frac2 = WORKLOADS["config2"]
+        K, x1, x2, *_ = make_scene(n2, frac2, seed=0)
+        eng.upload_pairs(x1, x2, K)
+        for w in range(3):
+            sharded_step(h2, 800 + w)
+        steps = 20
+        ms = _timed(torch, dist, world, stream, barrier, flush_l2, steps, lambda s: sharded_step(h2, s))
+        out["config2_latency"] = {"workload": f"{n2} correspondences x {h2} hypotheses + tail, resident, device sampler",
+                                  "ms_per_estimate": ms / steps, "value": float(n2) * h2 * steps / (ms * 1e-3), "unit": UNIT,
+                                  "steps": steps}
+        import random
+
+        from lib.common.feature import Feature
+        from lib.epipolar.epipolar_ransac import estimate_essential_mat_with_ransac
+        from lib.feature_matching.matching import Match
+        from lib.ransac.ransac import ErrorAggregationMethod
+
+        n1, h1 = 500, 1000
+        K, x1, x2, *_ = make_scene(n1, 0.3, seed=0)
+        fa = [Feature(x=float(p[0]), y=float(p[1])) for p in x1]
+        fb = [Feature(x=float(p[0]), y=float(p[1])) for p in x2]
+        mt = [Match(a_index=i, b_index=i) for i in range(n1)]
+
+        def list_step():
+            random.seed(5)
+            return estimate_essential_mat_with_ransac(K, fa, fb, mt, THR, min_num_extra_inliers=MIN_EXTRA,
+                                                      error_aggregation_method=ErrorAggregationMethod.RMS, max_iterations=h1)
+
+        for w in range(3):
+            e, pairs = list_step()
+        t0 = time.perf_counter()
+        steps = 20
+        for s in range(steps):
+            e, pairs = list_step()
+        dt = (time.perf_counter() - t0) * 1e3 / steps
+        golden = json.load(open(os.path.join(ROOT, "tests", "golden", "config1_known_answer.json")))
+        coords = {(f.x, f.y): i for i, f in enumerate(fa)}
+        out["config1_list_api"] = {
+            "workload": f"BASELINE configs[0]: {n1} correspondences x {h1} iterations through estimate_essential_mat_with_ransac("
+                        "list[Feature], list[Match]) with the CPython-exact sampler; host wall clock incl. marshalling",
+            "ms_per_estimate": dt, "value": float(n1 - 8) * h1 / (dt * 1e-3), "unit": UNIT, "steps": steps,
+            "parity_golden": bool(np.allclose(e, np.array(golden["E"]), rtol=1e-6, atol=1e-9)
+                                  and [coords[(p[0].x, p[0].y)] for p in pairs] == golden["inlier_indices"]),
+            "golden": "tests/golden/config1_known_answer.json (the unmodified reference: iteration 87, 23 inliers, same order)"}
+
     # ---- config3_strong: BASELINE configs[2] with its 65 536 hypotheses split over the ranks ----
     n, h, frac = WORKLOADS["config3"]
     K, x1, x2, *_ = make_scene(n, frac, seed=0)
@@ -565,10 +612,10 @@ def main():
     barrier()
 
     # ---- timed: resident ---------------------------------------------------------------------
-    eng.enable_timing(True)
+    # the library's per-stage event timers are instrumentation (16 extra event records per step): OFF while `value` is
+    # measured, ON in a second pass of the same steps that yields the stage breakdown and the k_score launch duration
     _, launches0 = eng.get_timing()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    stage_ms = {}
     num_inl = 0
     barrier()
     clocks.mark_begin()
@@ -577,14 +624,20 @@ def main():
         ev[s][0].record(stream)
         _, num_inl = step_resident(s)
         ev[s][1].record(stream)
-        t, _ = eng.get_timing()
-        for k, v in t.items():
-            stage_ms[k] = stage_ms.get(k, 0.0) + v
     barrier()
     clocks.mark_end()
     clk = clocks.stop()
     _, launches1 = eng.get_timing()
     ms_total = sum(a.elapsed_time(b) for a, b in ev)
+    eng.enable_timing(True)
+    stage_ms = {}
+    for s in range(args.steps):
+        flush_l2()
+        step_resident(s)
+        t, _ = eng.get_timing()
+        for k, v in t.items():
+            stage_ms[k] = stage_ms.get(k, 0.0) + v
+    barrier()
     eng.enable_timing(False)
 
     # ---- timed: end to end through the public API (host buffers) ---------------------------------

@@ -85,6 +85,13 @@ int sfm_mt_shuffle_table(uint32_t *state625, int64_t n, int64_t h, int32_t *tabl
  * lets the caller keep (state, permutation) snapshots every few iterations and replay only a short stretch to
  * recover the permutation of the winning iteration. */
 int sfm_mt_shuffle_resume(uint32_t *state625, int64_t n, int64_t h, int32_t *table, int32_t *perm_inout);
+/* sfm_mt_shuffle_table from the identity permutation that also records, before every iteration k * stride, the
+ * generator state (snap_states[k][625]) and the permutation (snap_perms[k][n]) - so that the permutation or the state
+ * after ANY iteration is recovered by replaying at most `stride` iterations (sfm_mt_shuffle_resume) instead of the
+ * whole run: the reference returns the inliers in that iteration's permutation order (ransac.py:70-76) and, when a
+ * degenerate sample aborts the run, leaves the generator where that iteration left it. */
+int sfm_mt_shuffle_snapshots(uint32_t *state625, int64_t n, int64_t h, int32_t *table, int64_t stride,
+                             uint32_t *snap_states, int32_t *snap_perms);
 /* Upload a sample table (h x 8 indices into the correspondences). */
 int sfm_set_table(sfm_ctx *ctx, const int32_t *table, int64_t h);
 /* Device sampler (Philox4x32-10 keyed by seed/stream/global hypothesis index): 8 distinct

@@ -53,6 +53,7 @@ _SIGNATURES = {
     "sfm_host_free": (C.c_int, [_P]),
     "sfm_mt_shuffle_table": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int64, _P]),
     "sfm_mt_shuffle_resume": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
+    "sfm_mt_shuffle_snapshots": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int64, _P, _P]),
     "sfm_set_table": (C.c_int, [_P, _P, C.c_int64]),
     "sfm_sample_device": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64]),
     "sfm_get_table": (C.c_int, [_P, _P, C.c_int64, C.c_int64]),
@@ -397,11 +398,15 @@ class Engine:
         return b, mask, sed, p, int(num.value), idx[:m], ok[:m], X[:m]
 
     def two_view_async(self, threshold, min_extra=0.0, aggregation="rms", selection="min_error", distance_threshold=50.0,
-                       want_mask=True, want_sed=True):
+                       want_mask=True, want_sed=True, out=None):
         """Enqueue fit -> score -> select -> tail; nothing synchronises.  Returns the (mask, sed) arrays that the
-        enqueued copies will fill - valid after two_view_fetch()."""
-        mask = pinned_empty(self.n, np.uint8) if want_mask else None
-        sed = pinned_empty(self.n, np.float64) if want_sed else None
+        enqueued copies will fill - valid after two_view_fetch().  ``out``: (uint8[n], float64[n]) to fill, ideally
+        pinned and reused (page-locking fresh memory per call costs more than the estimate's transfers)."""
+        if out is not None:
+            mask, sed = out
+        else:
+            mask = pinned_empty(self.n, np.uint8) if want_mask else None
+            sed = pinned_empty(self.n, np.float64) if want_sed else None
         self._ck(self.lib.sfm_two_view_async(self.h, float(threshold), float(min_extra), AGG[aggregation],
                                              SELECT[selection], float(distance_threshold), _ptr(mask), _ptr(sed)),
                  "sfm_two_view_async")
@@ -652,21 +657,20 @@ class ReferenceSampler:
         self.table = np.empty((self.h, 8), dtype=np.int32)
         st = np.ascontiguousarray(state625, dtype=np.uint32).copy()
         assert st.shape == (625,)
-        perm = np.arange(self.n, dtype=np.int32)
-        self._snap = []
-        for first in range(0, self.h, self.stride):
-            self._snap.append((st.copy(), perm.copy()))
-            count = min(self.stride, self.h - first)
-            rc = lib.sfm_mt_shuffle_resume(_ptr(st), self.n, count, _ptr(self.table[first:first + count]), _ptr(perm))
-            if rc != 0:
-                raise NativeError(f"sfm_mt_shuffle_resume -> {rc}: {lib.sfm_last_error().decode()}")
+        ns = -(-self.h // self.stride)
+        self._states = np.empty((ns, 625), dtype=np.uint32)
+        self._perms = np.empty((ns, self.n), dtype=np.int32)
+        rc = lib.sfm_mt_shuffle_snapshots(_ptr(st), self.n, self.h, _ptr(self.table), self.stride, _ptr(self._states),
+                                          _ptr(self._perms))  # one C call: table + snapshots
+        if rc != 0:
+            raise NativeError(f"sfm_mt_shuffle_snapshots -> {rc}: {lib.sfm_last_error().decode()}")
         self.final_state = st
 
     def after(self, iteration: int):
         """(state625, permutation) right after 0-based ``iteration``."""
         lib = load_library()
         k = int(iteration) // self.stride
-        st, perm = self._snap[k][0].copy(), self._snap[k][1].copy()
+        st, perm = self._states[k].copy(), self._perms[k].copy()
         count = int(iteration) - k * self.stride + 1
         rc = lib.sfm_mt_shuffle_resume(_ptr(st), self.n, count, None, _ptr(perm))
         if rc != 0:

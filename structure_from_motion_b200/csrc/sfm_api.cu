@@ -167,6 +167,13 @@ int check_launch(sfm_ctx* c, const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(SFM_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
     c->launches += 1;
+#ifdef SFM_TRACE  // debugging builds only (tools/bin/libsfm_trace.so): name every launch and wait for it
+    fprintf(stderr, "[sfm] %s ...", what);
+    fflush(stderr);
+    e = cudaStreamSynchronize(c->stream);
+    fprintf(stderr, " %s\n", e == cudaSuccess ? "ok" : cudaGetErrorString(e));
+    fflush(stderr);
+#endif
     return 0;
 }
 
@@ -651,7 +658,18 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         };
         int occ = 0;
         if (int r = occupancy(fn, &occ)) return r;
-        const void* fn_full = autov ? score_kernel(SFM_SCORE_FULL, hpt, G) : nullptr;
+#ifndef SFM_AUTO_SINGLE
+#define SFM_AUTO_SINGLE 1
+#endif
+        // AUTO: one kernel holding both screens (shapes 2x16 and 4x8), else the two-launch scheme
+        const void* fn_auto = nullptr;
+        if (autov && SFM_AUTO_SINGLE) {
+            if (hpt == 2 && G == 16) fn_auto = reinterpret_cast<const void*>(&k_score_auto<2, 16>);
+            if (hpt == 4 && G == 8) fn_auto = reinterpret_cast<const void*>(&k_score_auto<4, 8>);
+        }
+        if (fn_auto)
+            if (int r = occupancy(fn_auto, &occ)) return r;
+        const void* fn_full = (autov && !fn_auto) ? score_kernel(SFM_SCORE_FULL, hpt, G) : nullptr;
         int occ_full = 0;
         if (fn_full)
             if (int r = occupancy(fn_full, &occ_full)) return r;
@@ -738,7 +756,14 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         const long long want_blocks = (total_items + kScoreWarps - 1) / kScoreWarps;
         const long long launch_blocks = grid_blocks < want_blocks ? grid_blocks : want_blocks;
         void* kargs[] = {(void*)&a};
-        if (!skip_k2) {
+        if (!skip_k2 && fn_auto) {
+            ScoreArgs a2 = a;
+            a2.thr_pre = thr * (1.0 + 1e-9) + 1e-22;
+            a2.spts = c->pts.p;
+            void* kargs2[] = {(void*)&a, (void*)&a2};
+            CU(cudaLaunchKernel(fn_auto, dim3((unsigned)launch_blocks), dim3(kScoreThreads), kargs2, smem, c->stream));
+            if (int r = check_launch(c, "k_score_auto")) return r;
+        } else if (!skip_k2) {
             CU(cudaLaunchKernel(fn, dim3((unsigned)launch_blocks), dim3(kScoreThreads), kargs, smem, c->stream));
             if (int r = check_launch(c, "k_score")) return r;
             if (fn_full) {  // AUTO: the two-sided screen on the unscaled records; exits at once unless the pilot chose it

@@ -87,31 +87,27 @@ __host__ __device__ inline bool null_vector4_fast(const double (&g)[16], double 
         for (int i = 0; i < 4; ++i) v[i] *= s;
     };
     double v[4] = {0.41, 0.27, 0.73, 1.0};
-    // three plain steps (growth <= (1e15 / big)^2 each: no overflow), then checked pairs
-    solve(v);
-    normalise(v);
-    solve(v);
-    normalise(v);
-    solve(v);
-    normalise(v);
-    double prev[4];
+    // inverse iteration, convergence checked after steps 4 and 6.  A real loop on purpose (not unrolled): the tail
+    // kernels run this once per launch on ~100 inliers, where every straight-line instruction is a cold
+    // instruction-cache miss - one copy of the step body, executed six times, beats six copies executed once.
+    double prev[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+    for (int step = 1; step <= 6; ++step) {
+        if (step == 4 || step == 6) {
 #pragma unroll
-    for (int round = 0; round < 2; ++round) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) prev[i] = v[i];
+            for (int i = 0; i < 4; ++i) prev[i] = v[i];
+        }
         solve(v);
         normalise(v);
-        double diff = 0.0;
+        if (step == 4 || step == 6) {
+            double diff = 0.0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) diff = fmax(diff, fabs(v[i] - prev[i]));
-        if (diff <= 1e-13) {
+            for (int i = 0; i < 4; ++i) diff = fmax(diff, fabs(v[i] - prev[i]));
+            if (diff <= 1e-13) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) x[i] = v[i];
-            return true;
-        }
-        if (round == 0) {
-            solve(v);
-            normalise(v);
+                for (int i = 0; i < 4; ++i) x[i] = v[i];
+                return true;
+            }
         }
     }
     return false;

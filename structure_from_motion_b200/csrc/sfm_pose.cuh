@@ -115,9 +115,11 @@ __global__ void k_decompose(const double* __restrict__ E, const Best* __restrict
 // triangulate_point_correspondence (lib/epipolar/triangulation.py:9-39): 4x4 DLT system,
 // right singular vector of the smallest singular value, dehomogenise.  P1, P2 are 3x4
 // row-major (only rows 0-2 of the reference's 4x4 Tmat are used, :24-31).
-__device__ __forceinline__ void dlt_triangulate(double xa, double ya, double xb, double yb,
-                                                const double* __restrict__ P1,
-                                                const double* __restrict__ P2, double (&X)[3]) {
+// One copy per kernel (noinline): T2 calls it for the cheirality test and again for the short triangulation, and the
+// second use finds the code in the instruction cache.
+__device__ __noinline__ void dlt_triangulate(double xa, double ya, double xb, double yb,
+                                             const double* __restrict__ P1,
+                                             const double* __restrict__ P2, double (&X)[3]) {
     double g[16], v[16];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {

@@ -64,14 +64,23 @@ struct PyMT {
 
 
 // cumulative Fisher-Yates iterations on `perm` (random.shuffle, CPython semantics); row `it` of `table` receives the
-// first 8 entries after iteration `it`
-static void mt_shuffle_rounds(PyMT& g, int32_t* pp, int64_t n, int64_t h, int32_t* table, int64_t perm_at, int32_t* perm_out) {
+// first 8 entries after iteration `it`.  Two phases per iteration: the swap partners j_(n-1), ..., j_1 do not depend on
+// the permutation (j = _randbelow(i + 1) = the first getrandbits(bit_length(i + 1)) that is <= i; every stream word is
+// consumed, a rejected one just does not advance i), so they are drawn first - loop-carried chain: compare -> subtract,
+// words straight from the tempered block, shift constant while i + 1 keeps its bit length - and the swaps follow as a
+// plain pass (1.6-2x faster than the fused loop, whose loads and stores alias through the data-dependent index).
+static void mt_shuffle_rounds(PyMT& g, int32_t* pp, int64_t n, int64_t h, int32_t* table, int64_t perm_at, int32_t* perm_out,
+                              int64_t snap_stride = 0, uint32_t* snap_states = nullptr, int32_t* snap_perms = nullptr) {
+    std::vector<uint32_t> jbuf((size_t)n + 8);
     for (int64_t it = 0; it < h; ++it) {
-        // j = _randbelow(i + 1) = the first getrandbits(bit_length(i + 1)) that is <= i.  Every stream word is consumed;
-        // a rejected one swaps position i with itself and leaves i where it is (branch-free).  The shift only changes
-        // when i + 1 crosses a power of two, and the words are taken straight from the tempered block, so the
-        // loop-carried chain is just compare -> subtract.
+        if (snap_stride > 0 && it % snap_stride == 0) {  // (state, permutation) BEFORE iteration `it`
+            const int64_t k = it / snap_stride;
+            memcpy(snap_states + 625 * k, g.mt, 624 * sizeof(uint32_t));
+            snap_states[625 * k + 624] = (uint32_t)g.pos;
+            memcpy(snap_perms + n * k, pp, (size_t)n * sizeof(int32_t));
+        }
         uint32_t i = (uint32_t)n - 1;
+        uint32_t* jo = jbuf.data();
         while (i >= 1) {
             const int sh = __builtin_clz(i + 1);
             uint32_t lo = (1u << (31 - sh)) - 1u;  // smallest i whose i + 1 has the same bit length
@@ -84,14 +93,19 @@ static void mt_shuffle_rounds(PyMT& g, int32_t* pp, int64_t n, int64_t h, int32_
                 for (; k < avail && i >= lo; ++k) {
                     const uint32_t r = w[k] >> sh;
                     const uint32_t acc = r <= i ? 1u : 0u;
-                    const uint32_t j = acc ? r : i;
-                    const int32_t t = pp[i];
-                    pp[i] = pp[j];
-                    pp[j] = t;
+                    *jo = r;  // overwritten by the next word unless accepted
+                    jo += acc;
                     i -= acc;
                 }
                 g.pos += k;
             }
+        }
+        const uint32_t* jp = jbuf.data();
+        for (uint32_t q = (uint32_t)n - 1; q >= 1; --q) {
+            const uint32_t j = *jp++;
+            const int32_t t = pp[q];
+            pp[q] = pp[j];
+            pp[j] = t;
         }
         if (table) memcpy(table + 8 * it, pp, 8 * sizeof(int32_t));
         if (perm_out && it == perm_at) memcpy(perm_out, pp, (size_t)n * sizeof(int32_t));
@@ -135,5 +149,18 @@ int sfm_mt_shuffle_resume(uint32_t* state625, int64_t n, int64_t h, int32_t* tab
     return 0;
 }
 
+int sfm_mt_shuffle_snapshots(uint32_t* state625, int64_t n, int64_t h, int32_t* table, int64_t stride,
+                             uint32_t* snap_states, int32_t* snap_perms) {
+    if (!table || !snap_states || !snap_perms || stride < 1) return fail(SFM_ERR_ARG, "bad snapshot arguments");
+    if (int r = mt_check(state625, n, h)) return r;
+    PyMT g;
+    g.load(state625);
+    std::vector<int32_t> perm((size_t)n);
+    for (int64_t i = 0; i < n; ++i) perm[(size_t)i] = (int32_t)i;
+    mt_shuffle_rounds(g, perm.data(), n, h, table, -1, nullptr, stride, snap_states, snap_perms);
+    memcpy(state625, g.mt, 624 * sizeof(uint32_t));
+    state625[624] = (uint32_t)g.pos;
+    return 0;
+}
 
 }  // extern "C"

@@ -317,8 +317,7 @@ __device__ __forceinline__ int sign_word(double d) { return __double2hiint(d); }
 __device__ __forceinline__ int sign_word(float f) { return __float_as_int(f); }
 
 template <int HPT, int G, int MODE>
-__global__ void __launch_bounds__(kScoreThreads, score_min_blocks(MODE == MODE_SCREEN32 ? HPT / 2 : HPT))
-k_score(const ScoreArgs a) {
+__device__ __forceinline__ void score_body(const ScoreArgs& a) {
     constexpr bool SCREEN = MODE != MODE_FULL;
     constexpr bool F32 = MODE == MODE_SCREEN32;
     using T = typename std::conditional<F32, float, double>::type;       // arithmetic of the per-test work
@@ -330,7 +329,7 @@ k_score(const ScoreArgs a) {
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(full, (int)(threadIdx.x >> 5), 0);  // tells the compiler it is warp-uniform
     const unsigned lt = lanemask_lt();
-    if (a.mode_flag && *a.mode_flag != MODE) return;  // AUTO: the pilot of k_screen_pts64 chose the other screen
+    if (a.mode_flag && *a.mode_flag != MODE) return;  // AUTO in two launches: the pilot chose the other screen
     ScoreWarpSmem<HPT>& ws = reinterpret_cast<ScoreWarpSmem<HPT>*>(score_smem)[warp];
 
     if (lane == 0) {
@@ -611,6 +610,20 @@ k_score(const ScoreArgs a) {
         }
         __syncwarp();
     }
+}
+
+template <int HPT, int G, int MODE>
+__global__ void __launch_bounds__(kScoreThreads, score_min_blocks(MODE == MODE_SCREEN32 ? HPT / 2 : HPT))
+k_score(const ScoreArgs a) {
+    score_body<HPT, G, MODE>(a);
+}
+
+// AUTO variant, one launch: the pilot's verdict (k_screen_pts64) picks the body.  Both bodies live in one kernel, so
+// no second (empty) launch is needed; the register budget is the larger of the two.
+template <int HPT, int G>
+__global__ void __launch_bounds__(kScoreThreads, score_min_blocks(HPT)) k_score_auto(const ScoreArgs a, const ScoreArgs a_full) {
+    if (*a.mode_flag == MODE_FULL) score_body<HPT, G, MODE_FULL>(a_full);
+    else score_body<HPT, G, MODE_SCREEN>(a);
 }
 
 // ------------------------------------------------------------------------------------

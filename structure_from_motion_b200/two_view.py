@@ -438,6 +438,7 @@ class TwoViewStream:
         self.engines = [_native.Engine(dev) for _ in range(depth)]
         self._next = 0
         self._pending = {}
+        self._out = [None] * depth  # per-context pinned (mask, sed) the enqueued copies land in; allocated once per size
 
     def set_score_variant(self, *a, **k):
         for e in self.engines:
@@ -452,8 +453,11 @@ class TwoViewStream:
         self._next += 1
         eng.upload_pairs(pts_a, pts_b, camera_matrix, sync=False)
         eng.sample_device(seed, int(max_iterations))
+        slot = k % len(self.engines)
+        if self._out[slot] is None or self._out[slot][0].shape[0] != eng.n:  # page-locking is slow: do it once
+            self._out[slot] = (_native.pinned_empty(eng.n, np.uint8), _native.pinned_empty(eng.n, np.float64))
         mask, sed = eng.two_view_async(threshold, float(min_num_extra_inliers or 0), _agg_name(error_aggregation_method),
-                                       selection, float(distance_threshold))
+                                       selection, float(distance_threshold), out=self._out[slot])
         self._pending[k] = (eng, mask, sed, min_num_extra_inliers or 0)
         return k
 
@@ -471,8 +475,8 @@ class TwoViewStream:
         b = int(p.best)
         res = RansacResult(E=np.array(best.E, dtype=np.float64).reshape(3, 3), best_index=int(best.index),
                            error=float(best.err), count_extra=int(best.count_extra),
-                           inlier_indices=np.concatenate([sample.astype(np.int64), extra]), mask=mask.view(bool),
-                           sed=sed, sample=sample, num_invalid=int(best.num_invalid), first_invalid=int(best.first_invalid))
+                           inlier_indices=np.concatenate([sample.astype(np.int64), extra]), mask=mask.astype(bool),
+                           sed=sed.copy(), sample=sample, num_invalid=int(best.num_invalid), first_invalid=int(best.first_invalid))
         R = np.array(p.R, dtype=np.float64).reshape(4, 3, 3)[b].copy()
         t = np.array(p.t, dtype=np.float64).reshape(4, 3)[b].copy()
         return TwoViewResult(ransac=res, R=R, t=t, inlier_indices=idx, passing=((ok >> b) & 1).astype(bool), points=X,

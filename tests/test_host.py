@@ -317,7 +317,7 @@ def test_reference_sampler_snapshots(n, h, budget, monkeypatch):
     random.seed(17)
     st0 = np.array(random.getstate()[1], dtype=np.uint32)
     rs = _native.ReferenceSampler(st0, n, h)
-    assert rs.stride == max(1, -(-h // 64), -(-(h * n * 4) // budget)) and len(rs._snap) <= 64
+    assert rs.stride == max(1, -(-h // 64), -(-(h * n * 4) // budget)) and len(rs._states) <= 64
     w = st0.copy()
     table, _ = _native.mt_shuffle_table(w, n, h)
     assert np.array_equal(rs.table, table) and np.array_equal(rs.final_state, w)

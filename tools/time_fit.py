@@ -31,3 +31,14 @@ for r in range(5):
     t, _ = eng.get_timing()
     ts.append((t["fit"], t["score"]))
 print("config4 fit: %.4f ms  score %.4f ms" % min(ts[1:]))
+import time
+ts = []
+for r in range(5):
+    t0 = time.perf_counter()
+    out = eng.batch_two_view(pa, pb, off, Ks, h, r, 1.5e-6, 10, "rms")
+    wall = (time.perf_counter() - t0) * 1e3
+    t, _ = eng.get_timing()
+    ts.append((wall, t))
+wall, t = min(ts[1:], key=lambda x: x[0])
+print("config4 batch_two_view (512 pairs, pageable host arrays): wall %.3f ms  stages %s  inliers %d" % (
+    wall, {k: round(v, 3) for k, v in t.items()}, len(out["inlier_idx"])))

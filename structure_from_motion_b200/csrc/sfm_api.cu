@@ -1097,7 +1097,8 @@ static int pose_tail_launch(sfm_ctx* c, double thr, double dist_thr, const Selec
     if (int r = c->poses.reserve((size_t)P * sizeof(PoseSet))) return r;
     if (int r = c->pass.reserve((size_t)n + 1)) return r;
     if (int r = c->X.reserve((size_t)n * 24)) return r;
-    const size_t state_bytes = (size_t)P * nblk * 8 + (size_t)P * 12;
+    // every word of this state is zero between launches (the kernels clean up behind themselves), whatever P and nblk
+    const size_t state_bytes = (size_t)P * nblk * 8 + (size_t)P * 8;
     if (int r = reserve_zeroed(c, c->tailstate, state_bytes)) return r;
     TailArgs a;
     a.pts = c->pts.as<Corr>();
@@ -1113,7 +1114,6 @@ static int pose_tail_launch(sfm_ctx* c, double thr, double dist_thr, const Selec
     a.agg = c->tailstate.as<unsigned long long>();
     a.ticket = reinterpret_cast<unsigned*>(a.agg + (size_t)P * nblk);
     a.done = a.ticket + P;
-    a.tri_done = a.done + P;
     a.poses = c->poses.as<PoseSet>();
     a.pass = c->pass.as<uint8_t>();
     const double* d = c->raw.as<double>();

@@ -31,7 +31,6 @@ struct TailArgs {
     unsigned long long* agg;     // [P][nblk] look-back state, zero on entry and on exit
     unsigned* ticket;            // [P] zero on entry and on exit
     unsigned* done;              // [P] zero on entry and on exit
-    unsigned* tri_done;          // [P] set by T2 when it triangulated the pair itself
     PoseSet* poses;              // [P]
     uint8_t* pass;               // [n_total] bit p = inlier k passes pose p (at compact position offsets[p] + k)
     // triangulation
@@ -153,6 +152,7 @@ __global__ void __launch_bounds__(kTailBlock) k_tail_mask(const TailArgs a) {
             PoseSet& p = a.poses[pair];
             for (int q = 0; q < 4; ++q) p.counts[q] = 0;
             p.best = -2;
+            p.pad = 0;
         }
     }
 }
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(128) k_tail_cheirality(const TailArgs a) {
             poses->best = bst;
         }
         s_best = bst;
-        a.tri_done[pair] = (m <= kTailSmallTri) ? 1u : 0u;
+        poses->pad = (m <= kTailSmallTri) ? 1 : 0;  // tells T3 that the pair is already triangulated
     }
     __syncthreads();
     // a short inlier list is triangulated right here (same code, already in the instruction cache); a long one by T3
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(128) k_tail_cheirality(const TailArgs a) {
 
 __global__ void __launch_bounds__(128) k_tail_triangulate(const TailArgs a) {
     const int pair = blockIdx.y;
-    if (a.tri_done[pair]) return;  // T2 already did it
+    if (a.poses[pair].pad) return;  // T2 already did it
     const long long pbase = a.offsets ? a.offsets[pair] : 0;
     const long long m = a.num[pair];
     const int b = a.poses[pair].best;

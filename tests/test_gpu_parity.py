@@ -419,3 +419,20 @@ def test_auto_variant_matches_explicit_screens(engine, thr):
             assert np.array_equal(a, b, equal_nan=True), (variant, thr)
         assert got["auto"][4] == got[variant][4]
     assert got["auto"][0].max() > 10
+
+
+def test_tail_state_survives_changing_shapes(engine):
+    """The tail's look-back words, tickets and counters clean up behind themselves, whatever the sequence of problem
+    shapes (regression: a flag left behind by a one-block launch once sat where a two-block launch keeps its ticket)."""
+    for n in (700, 1025, 3000, 500, 2049, 64, 5000):
+        K, x1, x2, *_ = make_scene(n, 0.3, seed=n)
+        engine.upload_pairs(x1, x2, K)
+        engine.sample_device(seed=1, h=300)
+        best, mask, sed, poses, num, idx, ok, X = engine.two_view(THR, 5, "rms", "min_error", 50.0)
+        if best.index < 0:
+            assert num == 0
+            continue
+        want = mask.astype(bool)
+        want[np.array(best.sample)] = True
+        assert num == int(want.sum()) and np.array_equal(idx, np.nonzero(want)[0])
+        assert X.shape == (num, 3) and np.isfinite(X[((ok >> poses.best) & 1).astype(bool)]).all()

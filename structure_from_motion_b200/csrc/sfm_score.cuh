@@ -429,11 +429,16 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
             for (int d = 1; d < 32; d <<= 1) incl = scan_step(incl, d);
             const int total = __shfl_sync(full, incl, 31);
             const int m = total < 32 ? total : 32;  // survivors handled now
-            // survivor slot t in [excl, incl) of this lane's record -> owner table {record, rank in record}
+            // survivor slot t in [excl, incl) of this lane's record -> owner table {record, bit position}: the record's
+            // set bits are handed out lowest first, so what is left in pmw afterwards is exactly what a record that
+            // straddles the 32-survivor boundary keeps for the next drain
             const int excl = incl - cnt;
-            for (int t = excl; t < incl && t < 32; ++t) ws.own[t] = (unsigned short)(lane | ((t - excl) << 8));
-            // ring bookkeeping: records entirely inside the first 32 survivors are retired; the one
-            // straddling the boundary keeps its remaining (higher) bits
+            unsigned pmw = rec.x;
+            for (int t = excl; pmw && t < 32; ++t) {
+                ws.own[t] = (unsigned short)(lane | ((__ffs(pmw) - 1) << 8));
+                pmw &= pmw - 1u;
+            }
+            // ring bookkeeping: records entirely inside the first 32 survivors are retired
             const unsigned done_mask = __ballot_sync(full, (unsigned)lane < nrec && incl <= 32);
             const int ndone = __popc(done_mask);
             __syncwarp();
@@ -441,16 +446,9 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
             const unsigned o = act ? ws.own[lane] : 0u;
             const uint2 rj = q[(head + (o & 255u)) & (kRing - 1)];
             __syncwarp();
-            if (lane == ndone && (unsigned)lane < nrec) {  // first record not retired
-                int take = 32 - excl;                      // its survivors consumed now (may be <= 0)
-                unsigned pm = rec.x;
-                for (; take > 0; --take) pm &= pm - 1u;
-                q[(head + lane) & (kRing - 1)].x = pm;
-            }
+            if (lane == ndone && (unsigned)lane < nrec) q[(head + lane) & (kRing - 1)].x = pmw;  // first record not retired
             {
-                unsigned pmj = rj.x;
-                for (int k = (int)(o >> 8); k > 0; --k) pmj &= pmj - 1u;  // drop the k lowest set bits
-                const int bit = act ? (__ffs(pmj) - 1) : 0;
+                const int bit = (int)(o >> 8);
                 const int owner = (int)(rj.y >> 27);
                 const int i = NB - 1 - bit;                    // test index in the batch: g * HPT + j
                 const int slot = i % HPT;

@@ -375,6 +375,13 @@ def two_view_arrays(camera_matrix, pts_a, pts_b, threshold, min_num_extra_inlier
         distance_threshold = 50.0
     eng = kw.get("engine") or _native.get_engine()
     kw["engine"] = eng
+    if (kw.get("sampler") == "device" and kw.get("on_degenerate", "raise") == "skip" and kw.get("hyp_offset", 0) == 0
+            and np.asarray(pts_a).reshape(-1, 2).shape[0] >= 8 and (max_iterations or 100) > 0):
+        # device sampler, degenerate samples skipped: nothing on the host depends on intermediate results, so the
+        # whole estimate is enqueued in one go (un-synchronised upload included) and fetched once
+        return _two_view_device(eng, camera_matrix, pts_a, pts_b, threshold, min_num_extra_inliers or 0,
+                                _agg_name(error_aggregation_method), int(max_iterations or 100), float(distance_threshold),
+                                int(kw.get("seed", 0)), kw.get("selection", "min_error"))
     tail = {"distance_threshold": float(distance_threshold)}
     res = ransac_essential_arrays(camera_matrix, pts_a, pts_b, threshold, min_num_extra_inliers,
                                   error_aggregation_method, max_iterations, _tail=tail, **kw)
@@ -424,6 +431,52 @@ def image_pair_arrays(image_a, image_b, camera_matrix, *, num_harris_corners: in
     return ImagePairResult(corners_a=ca, corners_b=cb, match_a=ia, match_b=ib, match_score=best_s[ia], two_view=tv)
 
 
+def _device_submit(eng, out, camera_matrix, pts_a, pts_b, threshold, min_extra, agg, max_iterations, distance_threshold,
+                   seed, selection):
+    eng.upload_pairs(pts_a, pts_b, camera_matrix, sync=False)
+    eng.sample_device(seed, max_iterations)
+    return eng.two_view_async(threshold, float(min_extra), agg, selection, distance_threshold, out=out)
+
+
+def _device_result(eng, mask, sed, min_extra, copy: bool) -> "TwoViewResult":
+    best, p, num, idx, ok, X = eng.two_view_fetch()
+    if best.index < 0:
+        raise ValueError(f"No model could be found with at least {min_extra + 8} inliers.")
+    _check_decomposition(p)
+    counts = np.array(p.counts, dtype=np.int64)
+    if 0 == np.count_nonzero(counts):
+        raise EightPointCalculationError("None of the transformations pass the cheirality check.")
+    sample = np.array(best.sample, dtype=np.int32)
+    extra = idx[~np.isin(idx, sample)]  # the tail's compacted list = sed <= thr plus the samples, ascending
+    b = int(p.best)
+    res = RansacResult(E=np.array(best.E, dtype=np.float64).reshape(3, 3), best_index=int(best.index),
+                       error=float(best.err), count_extra=int(best.count_extra),
+                       inlier_indices=np.concatenate([sample.astype(np.int64), extra]), mask=mask.astype(bool),
+                       sed=sed.copy() if copy else sed, sample=sample, num_invalid=int(best.num_invalid),
+                       first_invalid=int(best.first_invalid))
+    R = np.array(p.R, dtype=np.float64).reshape(4, 3, 3)[b].copy()
+    t = np.array(p.t, dtype=np.float64).reshape(4, 3)[b].copy()
+    return TwoViewResult(ransac=res, R=R, t=t, inlier_indices=idx, passing=((ok >> b) & 1).astype(bool), points=X,
+                         counts=counts)
+
+
+_DEVICE_OUT: dict = {}
+
+
+def _two_view_device(eng, camera_matrix, pts_a, pts_b, threshold, min_extra, agg, max_iterations, distance_threshold, seed,
+                     selection):
+    n = np.asarray(pts_a).reshape(-1, 2).shape[0]
+    key = (id(eng), n)
+    out = _DEVICE_OUT.get(key)
+    if out is None:  # pinned landing buffers, one pair per (engine, size): page-locking per call would dominate
+        if len(_DEVICE_OUT) > 8:
+            _DEVICE_OUT.clear()
+        out = _DEVICE_OUT[key] = (_native.pinned_empty(n, np.uint8), _native.pinned_empty(n, np.float64))
+    mask, sed = _device_submit(eng, out, camera_matrix, pts_a, pts_b, threshold, min_extra, agg, max_iterations,
+                               distance_threshold, seed, selection)
+    return _device_result(eng, mask, sed, min_extra, copy=True)
+
+
 class TwoViewStream:
     """Back-to-back estimates from HOST buffers with the transfers of one estimate hidden behind the kernels of
     another: ``depth`` contexts on the same GPU (each its own stream); ``submit`` only ENQUEUES the upload of the
@@ -451,36 +504,19 @@ class TwoViewStream:
         if any(t % len(self.engines) == k % len(self.engines) for t in self._pending):
             raise RuntimeError("fetch the estimate submitted to this context before submitting another one")
         self._next += 1
-        eng.upload_pairs(pts_a, pts_b, camera_matrix, sync=False)
-        eng.sample_device(seed, int(max_iterations))
         slot = k % len(self.engines)
-        if self._out[slot] is None or self._out[slot][0].shape[0] != eng.n:  # page-locking is slow: do it once
-            self._out[slot] = (_native.pinned_empty(eng.n, np.uint8), _native.pinned_empty(eng.n, np.float64))
-        mask, sed = eng.two_view_async(threshold, float(min_num_extra_inliers or 0), _agg_name(error_aggregation_method),
-                                       selection, float(distance_threshold), out=self._out[slot])
+        n = np.asarray(pts_a).reshape(-1, 2).shape[0]
+        if self._out[slot] is None or self._out[slot][0].shape[0] != n:  # page-locking is slow: do it once
+            self._out[slot] = (_native.pinned_empty(n, np.uint8), _native.pinned_empty(n, np.float64))
+        mask, sed = _device_submit(eng, self._out[slot], camera_matrix, pts_a, pts_b, threshold, min_num_extra_inliers or 0,
+                                   _agg_name(error_aggregation_method), int(max_iterations), float(distance_threshold),
+                                   seed, selection)
         self._pending[k] = (eng, mask, sed, min_num_extra_inliers or 0)
         return k
 
     def result(self, ticket) -> TwoViewResult:
         eng, mask, sed, min_extra = self._pending.pop(ticket)
-        best, p, num, idx, ok, X = eng.two_view_fetch()
-        if best.index < 0:
-            raise ValueError(f"No model could be found with at least {min_extra + 8} inliers.")
-        _check_decomposition(p)
-        counts = np.array(p.counts, dtype=np.int64)
-        if 0 == np.count_nonzero(counts):
-            raise EightPointCalculationError("None of the transformations pass the cheirality check.")
-        sample = np.array(best.sample, dtype=np.int32)
-        extra = idx[~np.isin(idx, sample)]  # the tail's compacted list = sed <= thr plus the samples, ascending
-        b = int(p.best)
-        res = RansacResult(E=np.array(best.E, dtype=np.float64).reshape(3, 3), best_index=int(best.index),
-                           error=float(best.err), count_extra=int(best.count_extra),
-                           inlier_indices=np.concatenate([sample.astype(np.int64), extra]), mask=mask.astype(bool),
-                           sed=sed.copy(), sample=sample, num_invalid=int(best.num_invalid), first_invalid=int(best.first_invalid))
-        R = np.array(p.R, dtype=np.float64).reshape(4, 3, 3)[b].copy()
-        t = np.array(p.t, dtype=np.float64).reshape(4, 3)[b].copy()
-        return TwoViewResult(ransac=res, R=R, t=t, inlier_indices=idx, passing=((ok >> b) & 1).astype(bool), points=X,
-                             counts=counts)
+        return _device_result(eng, mask, sed, min_extra, copy=True)
 
     def close(self):
         for e in self.engines:

@@ -6,8 +6,8 @@
 //   null_vector4_fast   right singular vector of the smallest singular value of a 4x4 matrix (the DLT system of
 //                       lib/epipolar/triangulation.py:34-35): Householder QR, then inverse iteration on R^T R through
 //                       the triangular factor (never forming A^T A, so the accuracy is that of an SVD: eps * cond(A)).
-//                       Convergence is checked; the caller falls back to the Jacobi SVD when it is slow (sigma4 not
-//                       well below sigma3: a correspondence whose rays do not meet - never an inlier).
+//                       Convergence is checked; the caller falls back to the Jacobi SVD when 40 steps do not suffice
+//                       (sigma4 close to sigma3: a correspondence whose rays do not meet - never an inlier).
 //   svd3_rank2_frames   U, V of a 3x3 matrix with a (numerically) zero third singular value - what
 //                       _recover_all_r_t (lib/epipolar/eight_point.py:245-280) takes from np.linalg.svd(E): the null
 //                       vectors are cross products, the remaining 2x2 symmetric eigenproblem is one closed-form rotation.
@@ -87,19 +87,24 @@ __host__ __device__ inline bool null_vector4_fast(const double (&g)[16], double 
         for (int i = 0; i < 4; ++i) v[i] *= s;
     };
     double v[4] = {0.41, 0.27, 0.73, 1.0};
-    // inverse iteration, convergence checked after steps 4 and 6.  A real loop on purpose (not unrolled): the tail
-    // kernels run this once per launch on ~100 inliers, where every straight-line instruction is a cold
-    // instruction-cache miss - one copy of the step body, executed six times, beats six copies executed once.
+    // inverse iteration, convergence checked after step 4 and then every second step.  A real loop on purpose (not
+    // unrolled): the tail kernels run this once per launch on ~100 inliers, where every straight-line instruction is a
+    // cold instruction-cache miss - one copy of the step body executed a few times beats several copies executed once.
+    // Inliers converge in 4-6 steps (error factor (sigma4 / sigma3)^2 per step); the candidate poses that put the point
+    // near infinity (rays almost parallel: sigma3 small too) need more, and kMaxSteps of ~280 cycles each are still far
+    // cheaper than the ~30 k cycles of the Jacobi SVD the caller falls back to.
+    constexpr int kMaxSteps = 40;
     double prev[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
-    for (int step = 1; step <= 6; ++step) {
-        if (step == 4 || step == 6) {
+    for (int step = 1; step <= kMaxSteps; ++step) {
+        const bool check = step >= 4 && (step & 1) == 0;
+        if (check) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) prev[i] = v[i];
         }
         solve(v);
         normalise(v);
-        if (step == 4 || step == 6) {
+        if (check) {
             double diff = 0.0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) diff = fmax(diff, fabs(v[i] - prev[i]));

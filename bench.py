@@ -493,10 +493,14 @@ def run_extras(args, eng, world, rank, barrier, flush_l2, torch, dist, per_gpu_r
         pb[p * n:(p + 1) * n] = base[2][perm]
     offsets = np.arange(P + 1, dtype=np.int64) * n
     Ks = np.stack([base[0]] * P)
-    pipe = distributed.PairPipeline(depth=2)
+    # four contexts, chunks of up to 512 pairs: H2D of one chunk, kernels of another and D2H of a third overlap
+    # (profiles/r2_pair_pipeline_depth.txt: 0.64e12 against 0.56e12 with two contexts and 256-pair chunks)
+    depth = 4
+    chunk = int(min(512, max(128, P // depth)))
+    pipe = distributed.PairPipeline(depth=depth)
     try:
         def pstep(seed):
-            return pipe.batch_two_view(pa, pb, offsets, Ks, h, seed, THR, MIN_EXTRA, AGG, pair_id0=rank * P, chunk_pairs=256)
+            return pipe.batch_two_view(pa, pb, offsets, Ks, h, seed, THR, MIN_EXTRA, AGG, pair_id0=rank * P, chunk_pairs=chunk)
 
         for w in range(2):
             res = pstep(700 + w)
@@ -507,7 +511,8 @@ def run_extras(args, eng, world, rank, barrier, flush_l2, torch, dist, per_gpu_r
     rate = float(P) * n * h * world * steps / (ms * 1e-3)
     out["config4_pairs"] = {"workload": f"{P_total} image pairs x {n} correspondences x {h} hypotheses, pair-sharded over {world} "
                                         f"GPU(s) ({P} each), HOST buffers (H2D inside the timed region), per pair: E, inlier "
-                                        "mask, 4-pose cheirality vote, triangulated inliers back on the host",
+                                        f"mask, 4-pose cheirality vote, triangulated inliers back on the host; {depth} contexts x "
+                                        f"{chunk}-pair chunks",
                             "ms_per_step": ms / steps, "value": rate, "unit": UNIT, "steps": steps, "scaling": "strong",
                             "models_found": int((res["best_index"] >= 0).sum()), "pairs_per_s": P * world * steps / (ms * 1e-3),
                             "efficiency_vs_one_gpu_config3": rate / (world * per_gpu_rate)}

@@ -344,7 +344,6 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
     __syncwarp();
     uint2* q = ws.ring;
     unsigned head = 0, tail = 0;  // ring positions (records): warp-uniform, monotone, tail - head < 64
-    unsigned pending = 0;         // queued survivors (set bits of the queued records)
     unsigned gt = 0;              // tiles consumed so far by this warp (drives stage + parity)
     const double ab2 = SCREEN ? a.bounds[0] * a.bounds[1] * (F32 ? a.kappa32_coef : a.kappa_coef) : 0.0;
 
@@ -415,7 +414,7 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
 
         // The survivor ring holds one RECORD per (lane, batch) with survivors: {batch mask pm, owner
         // lane | first correspondence of the batch (item-relative)}; bit NB-1-i of pm <-> test
-        // i = g*HPT + j.  `pending` counts queued survivors (bits).  drain() expands the first <= 32
+        // i = g*HPT + j.  drain() expands the first <= 32
         // records into <= 32 survivors, one per lane (prefix sum of the popcounts, binary search of
         // the owning record by shuffles, n-th set bit), and evaluates them with the exact scorer: the
         // candidate's E comes from global memory (L1/L2 hits), its correspondence by index.
@@ -478,18 +477,18 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
                 }
             }
             head += (unsigned)ndone;
-            pending -= (unsigned)m;
             __syncwarp();
         };
 
-        // one record per lane with survivors in this batch (ballot-compacted: no atomics, no loop)
-        auto push = [&](unsigned pm, unsigned rel0) {
-            const unsigned vote = __ballot_sync(full, pm != 0u);
+        // one record per lane with survivors in this batch (ballot-compacted: no atomics, no loop).  The queue is
+        // drained whenever 32 RECORDS are waiting - every record holds at least one survivor, so a drain always finds
+        // its 32 survivors, retires at least one record, and the ring (< 32 waiting + <= 32 new) cannot overflow; the
+        // trigger needs no reduction over the lanes (a REDUX per batch sat on the critical path before)
+        auto push = [&](unsigned vote, unsigned pm, unsigned rel0) {
             if (pm) q[(tail + __popc(vote & lt)) & (kRing - 1)] = make_uint2(pm, ((unsigned)lane << 27) | rel0);
             tail += __popc(vote);
-            pending += __reduce_add_sync(full, (unsigned)__popc(pm));
             __syncwarp();
-            while (pending >= 32u) drain();
+            while (tail - head >= 32u) drain();
         };
 
         for (int t = 0; t < ntiles; ++t) {
@@ -571,7 +570,8 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
                 }
                 const int v = np - p;  // a partial last batch evaluated stale records: drop their bits
                 if (v < G) pm &= 0xffffffffu << (NB - v * HPT);
-                if (__any_sync(full, pm != 0u)) push(pm, (unsigned)(first - begin) + (unsigned)p);
+                const unsigned vote = __ballot_sync(full, pm != 0u);
+                if (vote) push(vote, pm, (unsigned)(first - begin) + (unsigned)p);
             }
             // every lane is done with the stage: refill it with the tile kStages ahead
             __syncwarp();
@@ -587,7 +587,7 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
         gt += (unsigned)ntiles;
 
         // tail of the queue, then publish this item's exact sums
-        while (pending) drain();
+        while (tail != head) drain();
 #pragma unroll
         for (int j = 0; j < HPT; ++j) {
             const long long hyp = hyp_w + 32 * j + lane;

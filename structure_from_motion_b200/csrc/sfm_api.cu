@@ -1157,19 +1157,32 @@ static int host_winner_record(sfm_ctx* c, const SelectRecord** out) {
 }
 
 // results of pose_tail_launch to the host: fixed-size part first (one synchronisation), then the per-inlier arrays
+// A winner of the reference's selection rule (minimum error) usually has ~100 inliers: the first kSpecInliers entries of
+// the per-inlier arrays ride along with the fixed-size results, so that the common case needs ONE synchronisation.
+constexpr long long kSpecInliers = 2048;
+
 static int pose_tail_fetch(sfm_ctx* c, sfm_poses* poses, int64_t cap, int64_t* num_inliers, int64_t* inlier_idx,
                            uint8_t* pass, double* X, sfm_best* best /* may be null */) {
     const long long* cnt_dev = c->num.as<long long>();
-    if (int r = ensure_pinned(c, 64 + sizeof(SelectRecord))) return r;
-    CU(cudaMemcpyAsync(c->hpin, cnt_dev, 8, cudaMemcpyDeviceToHost, c->stream));
-    if (best) CU(cudaMemcpyAsync((char*)c->hpin + 64, c->record.p, sizeof(SelectRecord), cudaMemcpyDeviceToHost, c->stream));
+    const long long spec = c->n < kSpecInliers ? c->n : kSpecInliers;
+    const size_t o_idx = 64 + ((sizeof(SelectRecord) + 63) / 64) * 64, o_pass = o_idx + (size_t)spec * 8,
+                 o_X = ((o_pass + (size_t)spec + 63) / 64) * 64;
+    if (int r = ensure_pinned(c, o_X + (size_t)spec * 24)) return r;
+    char* hp = (char*)c->hpin;
+    CU(cudaMemcpyAsync(hp, cnt_dev, 8, cudaMemcpyDeviceToHost, c->stream));
+    if (best) CU(cudaMemcpyAsync(hp + 64, c->record.p, sizeof(SelectRecord), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(poses, c->poses.p, sizeof(PoseSet), cudaMemcpyDeviceToHost, c->stream));
+    if (spec > 0) {
+        if (inlier_idx) CU(cudaMemcpyAsync(hp + o_idx, c->idx.p, (size_t)spec * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (pass) CU(cudaMemcpyAsync(hp + o_pass, c->pass.p, (size_t)spec, cudaMemcpyDeviceToHost, c->stream));
+        if (X) CU(cudaMemcpyAsync(hp + o_X, c->X.p, (size_t)spec * 24, cudaMemcpyDeviceToHost, c->stream));
+    }
     CU(cudaStreamSynchronize(c->stream));
     long long m;
-    memcpy(&m, c->hpin, 8);
+    memcpy(&m, hp, 8);
     if (best) {
         SelectRecord r;
-        memcpy(&r, (char*)c->hpin + 64, sizeof r);
+        memcpy(&r, hp + 64, sizeof r);
         best->err = r.best.idx >= 0 ? r.best.err : __builtin_inf();
         best->index = r.best.idx;
         best->count_extra = r.best.count;
@@ -1187,7 +1200,11 @@ static int pose_tail_fetch(sfm_ctx* c, sfm_poses* poses, int64_t cap, int64_t* n
     }
     *num_inliers = m;
     const long long take = m < cap ? m : cap;
-    if (take > 0) {
+    if (take > 0 && take <= spec) {  // everything already sits in the pinned scratch
+        if (inlier_idx) memcpy(inlier_idx, hp + o_idx, (size_t)take * 8);
+        if (pass) memcpy(pass, hp + o_pass, (size_t)take);
+        if (X) memcpy(X, hp + o_X, (size_t)take * 24);
+    } else if (take > 0) {
         if (inlier_idx) CU(cudaMemcpyAsync(inlier_idx, c->idx.p, (size_t)take * 8, cudaMemcpyDeviceToHost, c->stream));
         if (pass) CU(cudaMemcpyAsync(pass, c->pass.p, (size_t)take, cudaMemcpyDeviceToHost, c->stream));
         if (X) CU(cudaMemcpyAsync(X, c->X.p, (size_t)take * 24, cudaMemcpyDeviceToHost, c->stream));

@@ -66,7 +66,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 // test; the sign bits of a BATCH of HPT*G (<= 32) tests are collected in one register per
 // lane and the warp votes once per batch.  Lanes with survivors (~1 % of the tests survive)
 // append one {mask, origin} record to a 64-record per-warp ring (ballot-compacted, positions
-// are warp-uniform registers: no atomics); whenever 32 survivors are queued all lanes expand
+// are warp-uniform registers: no atomics); whenever 32 records are queued all lanes expand
 // the records and process them 32 at a time (dense, no divergence): the exact reference-order
 // SED is evaluated and compared with thr.
 //
@@ -183,6 +183,17 @@ __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
+}
+
+// position of the r-th (0-based) set bit of m; m must have more than r set bits (binary search on popcounts)
+__device__ __forceinline__ int nth_set_bit(unsigned m, int r) {
+    int pos = 0, c;
+    c = __popc(m & 0xffffu); if (r >= c) { r -= c; pos += 16; m >>= 16; }
+    c = __popc(m & 0xffu);   if (r >= c) { r -= c; pos += 8;  m >>= 8; }
+    c = __popc(m & 0xfu);    if (r >= c) { r -= c; pos += 4;  m >>= 4; }
+    c = __popc(m & 0x3u);    if (r >= c) { r -= c; pos += 2;  m >>= 2; }
+    c = (int)(m & 1u);       if (r >= c) pos += 1;
+    return pos;
 }
 
 // four 21-bit chunks of V = floor(x * 2^(84-e)) < 2^84 (x <= thr < 2^e; `scale` = 2^(63-e)): c[3] is the most
@@ -428,24 +439,49 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
             for (int d = 1; d < 32; d <<= 1) incl = scan_step(incl, d);
             const int total = __shfl_sync(full, incl, 31);
             const int m = total < 32 ? total : 32;  // survivors handled now
-            // survivor slot t in [excl, incl) of this lane's record -> owner table {record, bit position}: the record's
-            // set bits are handed out lowest first, so what is left in pmw afterwards is exactly what a record that
-            // straddles the 32-survivor boundary keeps for the next drain
             const int excl = incl - cnt;
-            unsigned pmw = rec.x;
-            for (int t = excl; pmw && t < 32; ++t) {
-                ws.own[t] = (unsigned short)(lane | ((__ffs(pmw) - 1) << 8));
-                pmw &= pmw - 1u;
-            }
             // ring bookkeeping: records entirely inside the first 32 survivors are retired
             const unsigned done_mask = __ballot_sync(full, (unsigned)lane < nrec && incl <= 32);
             const int ndone = __popc(done_mask);
-            __syncwarp();
             const bool act = lane < m;
-            const unsigned o = act ? ws.own[lane] : 0u;
-            const uint2 rj = q[(head + (o & 255u)) & (kRing - 1)];
-            __syncwarp();
-            if (lane == ndone && (unsigned)lane < nrec) q[(head + lane) & (kRing - 1)].x = pmw;  // first record not retired
+            uint2 rj;
+            unsigned o;  // {record (low byte), bit position of this lane's survivor in it}
+            if constexpr (MODE == MODE_FULL) {
+                // Two-sided screen = survivor-rich regime (the AUTO pilot sends > 6.5 % survivors here): records hold
+                // many bits, and handing them out one by one (the table below) was a quarter of all instructions at a
+                // 17 % inlier rate (ncu: 364 M iterations of its loop).  Instead every lane finds its record by binary
+                // search over the inclusive counts (5 shuffles) and its bit by binary search over popcounts: a fixed
+                // ~45 instructions, no shared memory, no warp barrier.
+                int lo = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const int v = __shfl_sync(full, incl, lo + step - 1);
+                    if (v <= lane) lo += step;
+                }
+                const int j = lo < 31 ? lo : 31;  // lanes past the last survivor are inactive anyway
+                const int before = __shfl_sync(full, excl, j);
+                rj.x = __shfl_sync(full, rec.x, j);
+                rj.y = __shfl_sync(full, rec.y, j);
+                o = (unsigned)j | ((unsigned)(act ? nth_set_bit(rj.x, lane - before) : 0) << 8);
+                // the record that straddles the 32-survivor boundary keeps its bits above the last one consumed
+                const int take = 32 - excl;
+                if (lane == ndone && (unsigned)lane < nrec && take > 0)
+                    q[(head + lane) & (kRing - 1)].x = rec.x & ~((2u << nth_set_bit(rec.x, take - 1)) - 1u);
+            } else {
+                // survivor slot t in [excl, incl) of this lane's record -> owner table {record, bit position}: the
+                // record's set bits are handed out lowest first (1.3 bits per record at a 1 % survivor rate), so what
+                // is left in pmw afterwards is exactly what a record that straddles the boundary keeps for the next drain
+                unsigned pmw = rec.x;
+                for (int t = excl; pmw && t < 32; ++t) {
+                    ws.own[t] = (unsigned short)(lane | ((__ffs(pmw) - 1) << 8));
+                    pmw &= pmw - 1u;
+                }
+                __syncwarp();
+                o = act ? ws.own[lane] : 0u;
+                rj = q[(head + (o & 255u)) & (kRing - 1)];
+                __syncwarp();
+                if (lane == ndone && (unsigned)lane < nrec) q[(head + lane) & (kRing - 1)].x = pmw;  // first record not retired
+            }
             {
                 const int bit = (int)(o >> 8);
                 const int owner = (int)(rj.y >> 27);

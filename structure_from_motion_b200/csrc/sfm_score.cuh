@@ -217,13 +217,13 @@ struct __align__(16) Corr32 {
 
 // fp64 screening copy (xa / s, ya / s, xb, yb) written at the head of every SCREEN scoring call - and, for the AUTO
 // variant, the PILOT that chooses between the two fp64 screens: the first kPilotBlocks blocks also run the one-sided
-// test on a sample (64 hypotheses spread over the range x ~2 000 correspondences of the first pair) and the last of
+// test on a sample (64 hypotheses spread over the range x ~1 000 correspondences of the first pair, 8 tests per thread) and the last of
 // them to finish turns the pass rate into the MODE the scoring kernels check.  Above ~6.5 % survivors the exact
 // evaluation of the survivors dominates and the 21-slot two-sided screen (survivors = inliers) wins; below, the
 // 11-slot one-sided screen does (DESIGN.md, table against the threshold).
-constexpr int kPilotBlocks = 8;
+constexpr int kPilotBlocks = 32;
 constexpr int kPilotHyps = 64;
-constexpr int kPilotPts = 2048;
+constexpr int kPilotPts = 1024;
 constexpr double kPilotFullAbove = 0.065;
 struct PilotArgs {
     const double* E;      // models of the first pair
@@ -256,11 +256,20 @@ __global__ void __launch_bounds__(256) k_screen_pts64(const Corr* __restrict__ p
         const long long np = pa.plen < kPilotPts ? pa.plen : kPilotPts;
         const long long step = pa.plen / np;
         const int lanes = nb * (256 / kPilotHyps);
-        for (long long q = blockIdx.x * (256 / kPilotHyps) + threadIdx.x / kPilotHyps; q < np; q += lanes) {
-            const Corr c = pts[q * step];
-            pass += sed_screen(e, c.xa, c.ya, c.xb, c.yb, pa.thr_pre) < 0.0 ? 1 : 0;
-            tests += 1;
+        // at most 8 correspondences per thread, loads issued back to back (the kernel is pure latency otherwise)
+        Corr cs[8];
+        int got = 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const long long q = blockIdx.x * (256 / kPilotHyps) + threadIdx.x / kPilotHyps + (long long)u * lanes;
+            if (q < np) { cs[u] = pts[q * step]; got = u + 1; }
         }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (u < got) {
+                pass += sed_screen(e, cs[u].xa, cs[u].ya, cs[u].xb, cs[u].yb, pa.thr_pre) < 0.0 ? 1 : 0;
+                tests += 1;
+            }
     }
     // pack (passes, tests) into one 64-bit add: tests <= 2^17 per launch
     unsigned long long v = ((unsigned long long)pass << 32) | (unsigned)tests;

@@ -693,19 +693,12 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         if (int r = c->acc.reserve(H * kAccWords * 8 + acc_tail)) return r;
         const long long npts = c->n;  // total records (all pairs)
         if (f32) { if (int r = c->spts.reserve((size_t)npts * sizeof(Corr32))) return r; }
-#if SFM_SCALE_MODE == 0
         else if (screen) { if (int r = c->spts.reserve((size_t)npts * sizeof(Corr))) return r; }
-#endif
         ScoreArgs a;
         a.pts = c->pts.as<Corr>();
-#if SFM_SCALE_MODE == 0
         a.spts = screen ? c->spts.p : c->pts.p;
-#else
-        a.spts = f32 ? c->spts.p : c->pts.p;
-#endif
         a.bounds = c->bounds.as<double>();
         a.s = s_scale;
-        a.inv_s = 1.0 / s_scale;
         a.kappa_coef = kKappaCoef * (1.0 + thr);
         a.kappa32_coef = kKappa32Coef * (1.0 + thr);
         a.n = c->n;
@@ -739,7 +732,6 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
                                                                                   reinterpret_cast<Corr32*>(c->spts.p));
             if (int r = check_launch(c, "k_screen_pts32")) return r;
         }
-#if SFM_SCALE_MODE == 0
         else if (screen && !skip_k2) {
             PilotArgs pa;
             pa.E = c->E.as<double>();
@@ -752,7 +744,6 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
                                                                                   reinterpret_cast<Corr*>(c->spts.p), pa);
             if (int r = check_launch(c, "k_screen_pts64")) return r;
         }
-#endif
         const long long want_blocks = (total_items + kScoreWarps - 1) / kScoreWarps;
         const long long launch_blocks = grid_blocks < want_blocks ? grid_blocks : want_blocks;
         void* kargs[] = {(void*)&a};

@@ -73,7 +73,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 //   SCREEN (default), 11 FP64 issue slots per evaluation.  sed <= thr implies
 //   r^2 <= thr * nb  (drop the image-A term), nb = lb0^2 + lb1^2, lb = E^T b, r = lb . a.
 //   With s = sqrt(thr'), the kernel keeps E with columns 0 and 1 pre-multiplied by s and
-//   divides (xa, ya) of every tile by s once it has landed in shared memory, so that
+//   streams a copy of the correspondences with (xa, ya) pre-divided by s (k_screen_pts64; scaling the
+//   tiles inside this kernel instead costs 5 %: profiles/r2_scale_modes.txt), so that
 //       lb0' = s lb0, lb1' = s lb1, lb2   (6 DFMA)      r = lb0' xa' + lb1' ya' + lb2   (2 DFMA)
 //       m = lb1'^2 + kappa ; m = lb0'^2 + m   (2 DFMA)  d = r^2 - m                      (1 DFMA)
 //   and "d < 0" (sign bit) is the test.  thr' = thr (1 + 1e-9) and
@@ -104,12 +105,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 // and GPU count — run-to-run deterministic by construction; every term >= thr * 2^-10 enters
 // without rounding, smaller ones are truncated at 2^-84 of the scale (<= 6e-26 thr per term).
 // ------------------------------------------------------------------------------------
-// How the fp64 screen gets (xa, ya) / s:  0 = a scaled copy of the correspondences written by k_screen_pts64 at the head
-// of every scoring call (streamed instead of the exact records), 1 = the landed tile is scaled in place (+ proxy fence
-// before its refill), 3 = scaled (xa, ya) go to a separate per-warp buffer (the TMA tile is never written by the warp).
-#ifndef SFM_SCALE_MODE
-#define SFM_SCALE_MODE 0
-#endif
 constexpr int kScoreThreads = 128;
 constexpr int kScoreWarps = kScoreThreads / 32;
 #ifndef SFM_SCORE_TILE
@@ -146,7 +141,7 @@ __global__ void __launch_bounds__(256) k_pad_models(const double* __restrict__ E
 
 struct ScoreArgs {
     const Corr* pts;           // K-normalised correspondences (exact scorer)
-    const void* spts;          // fp32 pre-filter only: Corr32 copy (xa/s, ya/s, xb, yb); the fp64 screen scales its tiles in shared memory
+    const void* spts;          // screening copy: Corr (xa/s, ya/s, xb, yb) for the fp64 screen, Corr32 for the fp32 pre-filter
     const double* bounds;      // [2]: max (xa^2+ya^2+1), max (xb^2+yb^2+1) over all correspondences
     long long n;
     const long long* offsets;  // [npairs+1] or null (single pair of n records)
@@ -154,7 +149,6 @@ struct ScoreArgs {
     const ModelRow* rows;      // [npairs][h] padded copies of E for the survivor path
     long long h;
     double thr, thr_pre, s;    // s = sqrt(thr_pre) (SCREEN)
-    double inv_s;              // 1 / s
     double kappa_coef;         // kKappaCoef * (1 + thr)
     double kappa32_coef;       // kKappa32Coef * (1 + thr)
     double scale1, scale2;     // 2^(63-e), 2^(63-2e) with thr < 2^e
@@ -312,9 +306,6 @@ __global__ void __launch_bounds__(256) k_screen_pts32(const Corr* __restrict__ p
 template <int HPT>
 struct alignas(128) ScoreWarpSmem {
     Corr tile[kStages][kTile];
-#if SFM_SCALE_MODE == 3
-    double2 sxy[kTile];  // (xa, ya) / s of the tile being processed
-#endif
     unsigned sacc[HPT][kAccWords][32];
     uint2 ring[kRing];
     unsigned short own[32];
@@ -389,11 +380,7 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
         const double* Ep = a.E + 9 * (long long)pair * a.h;
         const ModelRow* Rw = a.rows + (long long)pair * a.h + hyp_w;  // this warp's models, padded (survivor path)
         const Corr* pbeg = a.pts + begin;    // this item's correspondences (exact copies)
-#if SFM_SCALE_MODE == 0
         const P* src = reinterpret_cast<const P*>(SCREEN ? a.spts : (const void*)a.pts);
-#else
-        const P* src = reinterpret_cast<const P*>(F32 ? a.spts : (const void*)a.pts);
-#endif
 
         auto issue = [&](int t) {  // lane 0 only
             const int s = (int)((gt + (unsigned)t) % kStages);
@@ -404,9 +391,6 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
             bulk_g2s(&ws.tile[s][0], src + first, bytes, &ws.full_bar[s]);
         };
         if (lane == 0) {
-#if SFM_SCALE_MODE == 1
-            if (SCREEN && !F32) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // tiles were scaled in place
-#endif
             for (int t = 0; t < kStages && t < ntiles; ++t) issue(t);
         }
 
@@ -543,43 +527,11 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
             const long long first = begin + (long long)t * kTile;
             const int np = (int)((end - first < kTile) ? (end - first) : kTile);
             const P* tp = reinterpret_cast<const P*>(&ws.tile[s][0]);
-#if SFM_SCALE_MODE == 1 || SFM_SCALE_MODE == 2
-            if (SCREEN && !F32) {
-                // the screen wants (xa, ya) / s (see the header): scale the freshly landed tile in place, two records
-                // per lane - 4 DMUL per lane and tile against 22 DFMA per lane and correspondence
-#pragma unroll
-                for (int r = 0; r < kTile; r += 32) {
-                    double2* q2 = reinterpret_cast<double2*>(&ws.tile[s][r + lane]);
-                    double2 v = *q2;
-                    v.x *= a.inv_s;
-                    v.y *= a.inv_s;
-                    *q2 = v;
-                }
-                __syncwarp();
-            }
-#elif SFM_SCALE_MODE == 3
-            if (SCREEN && !F32) {
-                __syncwarp();  // every lane is done reading sxy of the previous tile
-#pragma unroll
-                for (int r = 0; r < kTile; r += 32) {
-                    const double2 v = *reinterpret_cast<const double2*>(&ws.tile[s][r + lane]);
-                    ws.sxy[r + lane] = make_double2(v.x * a.inv_s, v.y * a.inv_s);
-                }
-                __syncwarp();
-            }
-#endif
             for (int p = 0; p < np; p += G) {
                 unsigned pm = 0;
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    P c = tp[p + g];
-#if SFM_SCALE_MODE == 3
-                    if constexpr (SCREEN && !F32) {
-                        const double2 sx = ws.sxy[p + g];
-                        c.xa = sx.x;
-                        c.ya = sx.y;
-                    }
-#endif
+                    const P c = tp[p + g];
                     T d[HPT];
                     if (SCREEN) {
                         // hypothesis-innermost: consecutive FMAs share c.yb / c.xb / c.ya / c.xa
@@ -620,14 +572,7 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
             }
             // every lane is done with the stage: refill it with the tile kStages ahead
             __syncwarp();
-            if (lane == 0 && t + kStages < ntiles) {
-                // the tile was rewritten through the generic proxy (scaling): order that before the bulk copy (async
-                // proxy) lands in the same bytes
-#if SFM_SCALE_MODE == 1
-                if (SCREEN && !F32) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#endif
-                issue(t + kStages);
-            }
+            if (lane == 0 && t + kStages < ntiles) issue(t + kStages);
         }
         gt += (unsigned)ntiles;
 

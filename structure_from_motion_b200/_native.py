@@ -167,6 +167,7 @@ class Engine:
         self.h = h
         self.device = int(device)
         self._keep = None  # host arrays an un-synchronised upload still reads from
+        self._out_ptr, self._out_cap, self._out = None, 0, None  # pinned landing buffers of the async path
         self.n = 0
 
     # -- helpers -------------------------------------------------------------------------
@@ -178,6 +179,26 @@ class Engine:
         if getattr(self, "h", None):
             self.lib.sfm_destroy(self.h)
             self.h = None
+        if getattr(self, "_out_ptr", None):
+            self.lib.sfm_host_free(self._out_ptr)
+            self._out_ptr, self._out_cap, self._out = None, 0, None
+
+    def pinned_out(self, n: int):
+        """(uint8[n], float64[n]) views of engine-owned pinned memory for the results of two_view_async: allocated
+        once, grown geometrically, freed with the engine.  Valid until the next call that lands results in them."""
+        n = int(n)
+        if n > self._out_cap:
+            if self._out_ptr:
+                self.synchronize()
+                self.lib.sfm_host_free(self._out_ptr)
+            cap = max(n, self._out_cap + self._out_cap // 2, 1024)
+            p = _P()
+            self._ck(self.lib.sfm_host_alloc(9 * cap + 64, C.byref(p)), "sfm_host_alloc")
+            self._out_ptr, self._out_cap = p, cap
+            sed = np.frombuffer((C.c_char * (8 * cap)).from_address(p.value), dtype=np.float64, count=cap)
+            mask = np.frombuffer((C.c_char * cap).from_address(p.value + 8 * cap), dtype=np.uint8, count=cap)
+            self._out = (mask, sed)
+        return self._out[0][:n], self._out[1][:n]
 
     def __del__(self):  # pragma: no cover
         try:
@@ -402,11 +423,11 @@ class Engine:
         """Enqueue fit -> score -> select -> tail; nothing synchronises.  Returns the (mask, sed) arrays that the
         enqueued copies will fill - valid after two_view_fetch().  ``out``: (uint8[n], float64[n]) to fill, ideally
         pinned and reused (page-locking fresh memory per call costs more than the estimate's transfers)."""
-        if out is not None:
-            mask, sed = out
-        else:
-            mask = pinned_empty(self.n, np.uint8) if want_mask else None
-            sed = pinned_empty(self.n, np.float64) if want_sed else None
+        mask, sed = out if out is not None else self.pinned_out(self.n)
+        if not want_mask:
+            mask = None
+        if not want_sed:
+            sed = None
         self._ck(self.lib.sfm_two_view_async(self.h, float(threshold), float(min_extra), AGG[aggregation],
                                              SELECT[selection], float(distance_threshold), _ptr(mask), _ptr(sed)),
                  "sfm_two_view_async")
@@ -689,7 +710,8 @@ def nccl_unique_id() -> bytes:
 
 
 def pinned_empty(shape, dtype=np.float64):
-    """numpy array backed by pinned (page-locked) host memory from sfm_host_alloc."""
+    """numpy array backed by pinned (page-locked) host memory from sfm_host_alloc.  The memory lives until
+    ``pinned_free(array)`` (or the end of the process): meant for long-lived staging buffers, not per-call use."""
     lib = load_library()
     dtype = np.dtype(dtype)
     nbytes = int(np.prod(shape)) * dtype.itemsize
@@ -701,6 +723,13 @@ def pinned_empty(shape, dtype=np.float64):
     arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
     _PINNED[arr.ctypes.data] = p
     return arr
+
+
+def pinned_free(arr) -> None:
+    """Release an array obtained from pinned_empty (the array must not be used afterwards)."""
+    p = _PINNED.pop(arr.ctypes.data, None)
+    if p is not None:
+        load_library().sfm_host_free(p)
 
 
 _PINNED: dict = {}

@@ -460,18 +460,10 @@ def _device_result(eng, mask, sed, min_extra, copy: bool) -> "TwoViewResult":
                          counts=counts)
 
 
-_DEVICE_OUT: dict = {}
-
-
 def _two_view_device(eng, camera_matrix, pts_a, pts_b, threshold, min_extra, agg, max_iterations, distance_threshold, seed,
                      selection):
     n = np.asarray(pts_a).reshape(-1, 2).shape[0]
-    key = (id(eng), n)
-    out = _DEVICE_OUT.get(key)
-    if out is None:  # pinned landing buffers, one pair per (engine, size): page-locking per call would dominate
-        if len(_DEVICE_OUT) > 8:
-            _DEVICE_OUT.clear()
-        out = _DEVICE_OUT[key] = (_native.pinned_empty(n, np.uint8), _native.pinned_empty(n, np.float64))
+    out = eng.pinned_out(n)  # engine-owned pinned landing buffers: page-locking per call would dominate the transfers
     mask, sed = _device_submit(eng, out, camera_matrix, pts_a, pts_b, threshold, min_extra, agg, max_iterations,
                                distance_threshold, seed, selection)
     return _device_result(eng, mask, sed, min_extra, copy=True)
@@ -491,7 +483,6 @@ class TwoViewStream:
         self.engines = [_native.Engine(dev) for _ in range(depth)]
         self._next = 0
         self._pending = {}
-        self._out = [None] * depth  # per-context pinned (mask, sed) the enqueued copies land in; allocated once per size
 
     def set_score_variant(self, *a, **k):
         for e in self.engines:
@@ -504,11 +495,8 @@ class TwoViewStream:
         if any(t % len(self.engines) == k % len(self.engines) for t in self._pending):
             raise RuntimeError("fetch the estimate submitted to this context before submitting another one")
         self._next += 1
-        slot = k % len(self.engines)
         n = np.asarray(pts_a).reshape(-1, 2).shape[0]
-        if self._out[slot] is None or self._out[slot][0].shape[0] != n:  # page-locking is slow: do it once
-            self._out[slot] = (_native.pinned_empty(n, np.uint8), _native.pinned_empty(n, np.float64))
-        mask, sed = _device_submit(eng, self._out[slot], camera_matrix, pts_a, pts_b, threshold, min_num_extra_inliers or 0,
+        mask, sed = _device_submit(eng, eng.pinned_out(n), camera_matrix, pts_a, pts_b, threshold, min_num_extra_inliers or 0,
                                    _agg_name(error_aggregation_method), int(max_iterations), float(distance_threshold),
                                    seed, selection)
         self._pending[k] = (eng, mask, sed, min_num_extra_inliers or 0)

@@ -427,10 +427,26 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
             uint2 rec = make_uint2(0u, 0u);
             if ((unsigned)lane < nrec) rec = q[(head + lane) & (kRing - 1)];
             const int cnt = __popc(rec.x);
-            int incl = cnt;
+            int incl, total;
+            if constexpr (MODE == MODE_FULL) {
+                // survivor-rich body: the drain is bound by the MIO queue (shuffles, shared atomics - ncu: short
+                // scoreboard 31 % of its stall samples), so the prefix sum of the per-record counts (<= 32: six bit
+                // planes) is taken with warp votes, which do not go through it
+                incl = 0;
+                total = 0;
+                const unsigned le = lt | (1u << lane);
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) incl = scan_step(incl, d);
-            const int total = __shfl_sync(full, incl, 31);
+                for (int b = 0; b < 6; ++b) {
+                    const unsigned v = __ballot_sync(full, (cnt >> b) & 1);
+                    incl += __popc(v & le) << b;
+                    total += __popc(v) << b;
+                }
+            } else {
+                incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) incl = scan_step(incl, d);
+                total = __shfl_sync(full, incl, 31);
+            }
             const int m = total < 32 ? total : 32;  // survivors handled now
             const int excl = incl - cnt;
             // ring bookkeeping: records entirely inside the first 32 survivors are retired
@@ -442,22 +458,20 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
             if constexpr (MODE == MODE_FULL) {
                 // Two-sided screen = survivor-rich regime (the AUTO pilot sends > 6.5 % survivors here): records hold
                 // many bits, and handing them out one by one (the table below) was a quarter of all instructions at a
-                // 17 % inlier rate (ncu: 364 M iterations of its loop).  Instead every lane finds its record by binary
-                // search over the inclusive counts (5 shuffles) and its bit by binary search over popcounts: a fixed
-                // ~45 instructions, no shared memory, no warp barrier.
-                int lo = 0;
-#pragma unroll
-                for (int step = 16; step > 0; step >>= 1) {
-                    const int v = __shfl_sync(full, incl, lo + step - 1);
-                    if (v <= lane) lo += step;
-                }
-                const int j = lo < 31 ? lo : 31;  // lanes past the last survivor are inactive anyway
-                const int before = __shfl_sync(full, excl, j);
-                rj.x = __shfl_sync(full, rec.x, j);
-                rj.y = __shfl_sync(full, rec.y, j);
+                // 17 % inlier rate (ncu: 364 M iterations of its loop).  Instead every lane finds its record from a
+                // bit mask of the record starts and its bit by binary search over popcounts: a fixed ~40 instructions.
+                // S = start positions (exclusive counts) of the records inside this drain; every record holds at least
+                // one survivor, so the starts are distinct: survivor t belongs to record #(starts <= t) - 1 and that
+                // record starts at the highest start <= t.  One REDUX, then the record comes from the ring (one LDS).
+                const unsigned S = __reduce_or_sync(full, ((unsigned)lane < nrec && excl < 32) ? (1u << excl) : 0u);
+                const unsigned below = S & ((2u << lane) - 1u);
+                const int j = act ? __popc(below) - 1 : 0;
+                const int before = act ? 31 - __clz(below) : 0;
+                rj = q[(head + (unsigned)j) & (kRing - 1)];
                 o = (unsigned)j | ((unsigned)(act ? nth_set_bit(rj.x, lane - before) : 0) << 8);
                 // the record that straddles the 32-survivor boundary keeps its bits above the last one consumed
                 const int take = 32 - excl;
+                __syncwarp();  // every lane has read its record before the straddling one is rewritten
                 if (lane == ndone && (unsigned)lane < nrec && take > 0)
                     q[(head + lane) & (kRing - 1)].x = rec.x & ~((2u << nth_set_bit(rec.x, take - 1)) - 1u);
             } else {

@@ -328,3 +328,59 @@ def test_reference_sampler_snapshots(n, h, budget, monkeypatch):
         if it in (0, 1, h // 3, h - 2, h - 1):
             st, perm = rs.after(it)
             assert perm.tolist() == data and st.tolist() == list(random.getstate()[1])
+
+
+def test_reference_error_matches_the_reference_aggregation():
+    """two_view._reference_error is what settles near-ties: the same floating-point value as
+    _aggregate_error (lib/ransac/ransac.py:96-108) on the same list, for every aggregation."""
+    from oracle import restatement as o
+    from structure_from_motion_b200 import two_view
+
+    rng = np.random.default_rng(3)
+    for n in (1, 8, 9, 130, 4097):
+        errs = [float(v) for v in rng.uniform(0, 1e-6, n) ** 2]
+        for agg in ("sum", "square", "mean", "rms"):
+            assert two_view._reference_error(errs, agg) == o.aggregate_error(errs, agg)
+
+
+def test_aggregation_name_accepts_any_enum_with_the_reference_values():
+    """ransac.py:99-105 compares ``.value``: an Enum of another module with the same values must work."""
+    import enum
+
+    from structure_from_motion_b200 import two_view
+    from structure_from_motion_b200.ransac.ransac import ErrorAggregationMethod
+
+    class Foreign(enum.Enum):
+        SUM = "sum"
+        RMS = "rms"
+
+    assert two_view._agg_name(Foreign.SUM) == "sum" and two_view._agg_name(Foreign.RMS) == "rms"
+    assert two_view._agg_name(ErrorAggregationMethod.MEAN) == "mean" and two_view._agg_name(None) == "rms"
+    assert two_view._agg_name("square") == "square"
+
+
+def test_near_tie_replay_with_a_scripted_engine():
+    """_resolve_near_ties: strict < in iteration order on list-order sums (ransac.py:83), from per-hypothesis scores."""
+    from structure_from_motion_b200 import two_view
+
+    class Fake:
+        def __init__(self, seds):
+            self.seds, self.cur = seds, None
+
+        def set_winner(self, t):
+            self.cur = t
+
+        def inlier_mask(self, thr):
+            s = self.seds[self.cur]
+            return s <= thr, s
+
+    thr = 1.0
+    base = np.array([0.25, 0.5, 0.125, 2.0, 0.0625, 0.5, 0.25, 0.125, 0.5, 0.75])
+    seds = {3: base, 7: base.copy(), 9: base * (1 - 2 ** -40)}
+    rows = lambda t: np.arange(8)  # noqa: E731
+    after = lambda t: np.array([8, 9])  # noqa: E731
+    t, e = two_view._resolve_near_ties(Fake(seds), [3, 7, 9], thr, "sum", rows, after)
+    assert t == 9 and e == sum(float(v) for v in seds[9][[0, 1, 2, 3, 4, 5, 6, 7, 8, 9]] if True)
+    seds[9] = base.copy()
+    t, e = two_view._resolve_near_ties(Fake(seds), [3, 7, 9], thr, "rms", rows, after)
+    assert t == 3  # exact ties keep the earliest iteration

@@ -83,16 +83,22 @@ for k in range(cases):
                 msg = "inlier sets differ"
             if abs(res.ransac.error - ref["error"]) > 1e-9 * abs(ref["error"]):
                 msg = f"error {res.ransac.error} vs {ref['error']}"
-            inl = np.sort(ref["inlier_indices"])
+            # apps/sfm.py:118-133 hands the RANSAC inlier LIST (samples first, ransac.py:76) to recover_r_t_from_e: its
+            # position 0 - the correspondence np.count_nonzero never counts (eight_point.py:228-230) - is the first sample
+            lst = ref["inlier_indices"]
             try:
-                Rr, tr, mask, _ = o.recover_r_t_from_e(ref["E"], K, x1[inl, 0], x1[inl, 1], x2[inl, 0], x2[inl, 1])
+                Rr, tr, mask_l, _ = o.recover_r_t_from_e(ref["E"], K, x1[lst, 0], x1[lst, 1], x2[lst, 0], x2[lst, 1])
                 if not (np.allclose(res.R, Rr, atol=1e-6) and np.allclose(res.t, tr, atol=1e-6)):
                     msg = "pose differs"
                 else:
-                    X = o.triangulate_points(x1[inl[mask], 0], x1[inl[mask], 1], x2[inl[mask], 0], x2[inl[mask], 1], K, o.tmat(Rr, tr))
-                    Xg = res.points[res.passing]
-                    if len(X) != len(Xg) or (len(X) and (np.linalg.norm(X - Xg, axis=1) / np.linalg.norm(X, axis=1)).max() > 1e-6):
-                        msg = "points differ"
+                    pi = np.sort(lst[mask_l])
+                    if not np.array_equal(pi, res.inlier_indices[res.passing]):
+                        msg = "passing sets differ"
+                    else:
+                        X = o.triangulate_points(x1[pi, 0], x1[pi, 1], x2[pi, 0], x2[pi, 1], K, o.tmat(Rr, tr))
+                        Xg = res.points[res.passing]
+                        if len(X) and (np.linalg.norm(X - Xg, axis=1) / np.linalg.norm(X, axis=1)).max() > 1e-6:
+                            msg = "points differ"
             except Exception as e:  # the reference raised in the pose stage: the GPU path must have raised too
                 msg = f"oracle pose stage raised {type(e).__name__} but the GPU path returned"
     bad += bool(msg)

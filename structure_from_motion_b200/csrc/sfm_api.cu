@@ -177,11 +177,12 @@ int check_launch(sfm_ctx* c, const char* what) {
     return 0;
 }
 
-size_t score_warp_smem(int hpt) {
+// per-warp shared memory of a scoring body (the two-sided one has its own layout for hpt <= 2)
+size_t score_warp_smem(int hpt, bool full) {
     switch (hpt) {
-        case 1: return sizeof(ScoreWarpSmem<1>);
-        case 2: return sizeof(ScoreWarpSmem<2>);
-        case 4: return sizeof(ScoreWarpSmem<4>);
+        case 1: return full ? score_warp_bytes<1, MODE_FULL>() : sizeof(ScoreWarpSmem<1>);
+        case 2: return full ? score_warp_bytes<2, MODE_FULL>() : sizeof(ScoreWarpSmem<2>);
+        case 4: return full ? score_warp_bytes<4, MODE_FULL>() : sizeof(ScoreWarpSmem<4>);
         default: return sizeof(ScoreWarpSmem<8>);
     }
 }
@@ -641,14 +642,17 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
         // persistent blocks over (pair, split, hypothesis block) items
         const void* fn = score_kernel(variant, hpt, G);
         if (!fn) return fail(SFM_ERR_ARG, "unsupported scoring configuration (variant %d, hpt %d, group %d)", variant, hpt, G);
-        const size_t smem = (size_t)kScoreWarps * score_warp_smem(hpt);
+        const size_t smem_one = (size_t)kScoreWarps * score_warp_smem(hpt, false);
+        const size_t smem_two = (size_t)kScoreWarps * score_warp_smem(hpt, true);
+        const size_t smem_both = smem_one > smem_two ? smem_one : smem_two;  // AUTO in one launch holds either body
+        const size_t smem = screen ? smem_one : smem_two;
         // attribute set and occupancy queried once per kernel instantiation (small cache)
-        auto occupancy = [&](const void* f, int* out) -> int {
+        auto occupancy = [&](const void* f, size_t bytes, int* out) -> int {
             for (int k = 0; k < 4; ++k)
                 if (c->occ_fn[k] == f) { *out = c->occ_blocks[k]; return 0; }
             int o = 0;
-            CU(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, f, kScoreThreads, smem));
+            CU(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, f, kScoreThreads, bytes));
             if (o < 1) o = 1;
             c->occ_fn[c->occ_next] = f;
             c->occ_blocks[c->occ_next] = o;
@@ -657,7 +661,7 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
             return 0;
         };
         int occ = 0;
-        if (int r = occupancy(fn, &occ)) return r;
+        if (int r = occupancy(fn, smem, &occ)) return r;
 #ifndef SFM_AUTO_SINGLE
 #define SFM_AUTO_SINGLE 1
 #endif
@@ -668,11 +672,11 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
             if (hpt == 4 && G == 8) fn_auto = reinterpret_cast<const void*>(&k_score_auto<4, 8>);
         }
         if (fn_auto)
-            if (int r = occupancy(fn_auto, &occ)) return r;
+            if (int r = occupancy(fn_auto, smem_both, &occ)) return r;
         const void* fn_full = (autov && !fn_auto) ? score_kernel(SFM_SCORE_FULL, hpt, G) : nullptr;
         int occ_full = 0;
         if (fn_full)
-            if (int r = occupancy(fn_full, &occ_full)) return r;
+            if (int r = occupancy(fn_full, smem_two, &occ_full)) return r;
         const long long grid_blocks = (long long)c->sm_count * occ;
         const long long tiles = (max_len + kTile - 1) / kTile;
         constexpr int items_per_warp = 32;  // 12 -> 32 shortens the end-of-launch tail (+1 % on config 3)
@@ -752,7 +756,7 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
             a2.thr_pre = thr * (1.0 + 1e-9) + 1e-22;
             a2.spts = c->pts.p;
             void* kargs2[] = {(void*)&a, (void*)&a2};
-            CU(cudaLaunchKernel(fn_auto, dim3((unsigned)launch_blocks), dim3(kScoreThreads), kargs2, smem, c->stream));
+            CU(cudaLaunchKernel(fn_auto, dim3((unsigned)launch_blocks), dim3(kScoreThreads), kargs2, smem_both, c->stream));
             if (int r = check_launch(c, "k_score_auto")) return r;
         } else if (!skip_k2) {
             CU(cudaLaunchKernel(fn, dim3((unsigned)launch_blocks), dim3(kScoreThreads), kargs, smem, c->stream));
@@ -764,7 +768,7 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
                 const long long gb2 = (long long)c->sm_count * occ_full;
                 const long long lb2 = gb2 < want_blocks ? gb2 : want_blocks;
                 void* kargs2[] = {(void*)&a2};
-                CU(cudaLaunchKernel(fn_full, dim3((unsigned)lb2), dim3(kScoreThreads), kargs2, smem, c->stream));
+                CU(cudaLaunchKernel(fn_full, dim3((unsigned)lb2), dim3(kScoreThreads), kargs2, smem_two, c->stream));
                 if (int r = check_launch(c, "k_score")) return r;
             }
         }

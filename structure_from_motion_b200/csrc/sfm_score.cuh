@@ -312,6 +312,29 @@ struct alignas(128) ScoreWarpSmem {
     unsigned long long full_bar[kStages];
 };
 
+// Two-sided body, HPT <= 2 (the survivor-rich regime: AUTO sends > 6.5 % survivors here): the drain gathers nothing
+// from global memory.  Its models sit in shared memory (component-major: a gather of 32 models is nine LDS.64) and
+// its correspondences are read from the tile ring itself - the two-sided screen streams the UNSCALED records, and a
+// stage is refilled only after every record that points into it has been drained (one tile of slack: see the tile
+// loop).  Tiles are 32 records so that ring + models fit the same five blocks per SM.  ncu before this layout (17 %
+// inliers): 73 % of the drain's gathers missed L1 (60 KB next to 180 KB of shared memory, against 120 KB of model
+// rows per SM) and the first DMUL behind them carried 13 % of all stall samples.
+constexpr int kTileFS = 32;
+constexpr int kStagesFS = 3;
+template <int HPT>
+struct alignas(128) ScoreWarpSmemFS {
+    Corr tile[kStagesFS][kTileFS];
+    double model[32 * HPT][10];  // 80-byte rows: a gather is four LDS.128 + one LDS.64 per lane
+    unsigned sacc[HPT][kAccWords][32];  // column of (slot j, lane l) = l ^ 16 j: the two slots of a lane in different banks
+    uint2 ring[kRing];
+    unsigned long long full_bar[kStagesFS];
+};
+__host__ __device__ constexpr bool score_full_in_smem(int hpt) { return hpt <= 2; }
+template <int HPT, int MODE>
+constexpr size_t score_warp_bytes() {
+    return (MODE == MODE_FULL && score_full_in_smem(HPT)) ? sizeof(ScoreWarpSmemFS<HPT>) : sizeof(ScoreWarpSmem<HPT>);
+}
+
 // resident blocks per SM the register budget is shaped for (HPT 4 / 2 / 1): 16 / 20 / 32 warps.  Measured on
 // config 3: HPT 2 at 96 registers (5 blocks) beats 80 registers (6 blocks) by ~1.5 %: the extra registers let
 // ptxas keep more independent DFMA chains in flight, which is what the FP64 pipe's ~25-cycle latency needs.
@@ -334,18 +357,23 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
     using T = typename std::conditional<F32, float, double>::type;       // arithmetic of the per-test work
     using P = typename std::conditional<F32, Corr32, Corr>::type;       // record streamed through shared memory
     constexpr int NB = HPT * G;  // tests per lane and batch = survivor bits per vote
-    static_assert(NB <= 32 && (kTile % G) == 0, "a batch is at most 32 tests and divides a tile");
+    constexpr bool FS = MODE == MODE_FULL && score_full_in_smem(HPT);  // drain gathers from shared memory only
+    constexpr int TILE = FS ? kTileFS : kTile;
+    constexpr int STAGES = FS ? kStagesFS : kStages;
+    constexpr int AHEAD = FS ? STAGES - 1 : STAGES;  // tiles in flight; FS keeps the previous tile's stage for the drain
+    using WS = typename std::conditional<FS, ScoreWarpSmemFS<HPT>, ScoreWarpSmem<HPT>>::type;
+    static_assert(NB <= 32 && (TILE % G) == 0 && (kTile % TILE) == 0, "a batch is at most 32 tests and divides a tile");
     extern __shared__ __align__(128) unsigned char score_smem[];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(full, (int)(threadIdx.x >> 5), 0);  // tells the compiler it is warp-uniform
     const unsigned lt = lanemask_lt();
     if (a.mode_flag && *a.mode_flag != MODE) return;  // AUTO in two launches: the pilot chose the other screen
-    ScoreWarpSmem<HPT>& ws = reinterpret_cast<ScoreWarpSmem<HPT>*>(score_smem)[warp];
+    WS& ws = reinterpret_cast<WS*>(score_smem)[warp];
 
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < kStages; ++s) mbar_init(&ws.full_bar[s], 1);
+        for (int s = 0; s < STAGES; ++s) mbar_init(&ws.full_bar[s], 1);
         mbar_fence_init();
     }
 #pragma unroll
@@ -374,7 +402,7 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
         if (begin > plen) begin = plen;
         const long long end = pbase + ((begin + a.chunk < plen) ? begin + a.chunk : plen);
         begin += pbase;
-        const int ntiles = (int)((end - begin + kTile - 1) / kTile);
+        const int ntiles = (int)((end - begin + TILE - 1) / TILE);
         // this warp's hypotheses: lane l, slot j  ->  hyp_w + 32*j + l
         const long long hyp_w = (long long)hw * (32 * HPT);
         const double* Ep = a.E + 9 * (long long)pair * a.h;
@@ -383,15 +411,15 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
         const P* src = reinterpret_cast<const P*>(SCREEN ? a.spts : (const void*)a.pts);
 
         auto issue = [&](int t) {  // lane 0 only
-            const int s = (int)((gt + (unsigned)t) % kStages);
-            const long long first = begin + (long long)t * kTile;
+            const int s = (int)((gt + (unsigned)t) % STAGES);
+            const long long first = begin + (long long)t * TILE;
             const long long rem = end - first;
-            const uint32_t bytes = (uint32_t)((rem < kTile ? rem : kTile) * sizeof(P));
+            const uint32_t bytes = (uint32_t)((rem < TILE ? rem : TILE) * sizeof(P));
             mbar_expect_tx(&ws.full_bar[s], bytes);
             bulk_g2s(&ws.tile[s][0], src + first, bytes, &ws.full_bar[s]);
         };
         if (lane == 0) {
-            for (int t = 0; t < kStages && t < ntiles; ++t) issue(t);
+            for (int t = 0; t < AHEAD && t < ntiles; ++t) issue(t);
         }
 
         // register-resident models; SCREEN: columns 0 and 1 scaled by s, kappa per hypothesis;
@@ -406,6 +434,14 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
             for (int k = 0; k < 9; ++k) {
                 v[k] = real ? Ep[9 * hyp + k] : 0.0;
                 f2 = fma(v[k], v[k], f2);
+            }
+            if constexpr (FS) {  // the previous item's drains are complete (queue emptied at its end)
+                double2* mp = reinterpret_cast<double2*>(&ws.model[32 * j + lane][0]);
+                mp[0] = make_double2(v[0], v[1]);
+                mp[1] = make_double2(v[2], v[3]);
+                mp[2] = make_double2(v[4], v[5]);
+                mp[3] = make_double2(v[6], v[7]);
+                ws.model[32 * j + lane][8] = v[8];
             }
             const double nrm = F32 ? rsqrt(f2) : 1.0;  // inf/NaN models screen nothing out wrongly: see below
 #pragma unroll
@@ -495,18 +531,32 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
                 const int owner = (int)(rj.y >> 27);
                 const int i = NB - 1 - bit;                    // test index in the batch: g * HPT + j
                 const int slot = i % HPT;
+                // FS: the record's low bits are the batch's first position in the tile ring, else its item-relative index
                 const unsigned rel = act ? (rj.y & 0x3fffffu) + (unsigned)(i / HPT) : 0u;
                 // padding hypotheses never survive the screen, so an active entry is a real hypothesis
                 const unsigned hl = act ? (unsigned)(32 * slot + owner) : 0u;
-                const ModelRow* er = Rw + hl;
-                const double4 r0 = er->a, r1 = er->b;
-                const double r2 = er->c.x;
-                const double eo[9] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2};
-                const Corr c = pbeg[rel];
+                double eo[9];
+                Corr c;
+                if constexpr (FS) {
+                    const double2* mp = reinterpret_cast<const double2*>(&ws.model[hl][0]);
+                    const double2 m0 = mp[0], m1 = mp[1], m2 = mp[2], m3 = mp[3];
+                    eo[0] = m0.x; eo[1] = m0.y; eo[2] = m1.x; eo[3] = m1.y;
+                    eo[4] = m2.x; eo[5] = m2.y; eo[6] = m3.x; eo[7] = m3.y;
+                    eo[8] = ws.model[hl][8];
+                    c = (&ws.tile[0][0])[rel];
+                } else {
+                    const ModelRow* er = Rw + hl;
+                    const double4 r0 = er->a, r1 = er->b;
+                    eo[0] = r0.x; eo[1] = r0.y; eo[2] = r0.z; eo[3] = r0.w;
+                    eo[4] = r1.x; eo[5] = r1.y; eo[6] = r1.z; eo[7] = r1.w;
+                    eo[8] = er->c.x;
+                    c = pbeg[rel];
+                }
                 const double sv = sed_exact(eo, c.xa, c.ya, c.xb, c.yb);
                 if (act && (sv <= a.thr)) {  // ransac.py:73  score <= threshold
                     unsigned ch[kChunks];
-                    unsigned* dst = &ws.sacc[slot][0][owner];
+                    // same-address atomics serialise; FS also keeps the two slots of an owner in different banks
+                    unsigned* dst = &ws.sacc[slot][0][FS ? (owner ^ (slot << 4)) : owner];
                     atomicAdd(dst, 1u);
                     if (a.sums & SUM_S1) {
                         chunks21(sv, a.scale1, ch);
@@ -535,12 +585,13 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
             while (tail - head >= 32u) drain();
         };
 
+        unsigned mark = tail;  // FS: queue position behind the last record of the previous tile
         for (int t = 0; t < ntiles; ++t) {
             const unsigned gti = gt + (unsigned)t;
-            const int s = (int)(gti % kStages);
-            mbar_wait(&ws.full_bar[s], (gti / kStages) & 1u);
-            const long long first = begin + (long long)t * kTile;
-            const int np = (int)((end - first < kTile) ? (end - first) : kTile);
+            const int s = (int)(gti % STAGES);
+            mbar_wait(&ws.full_bar[s], (gti / STAGES) & 1u);
+            const long long first = begin + (long long)t * TILE;
+            const int np = (int)((end - first < TILE) ? (end - first) : TILE);
             const P* tp = reinterpret_cast<const P*>(&ws.tile[s][0]);
             for (int p = 0; p < np; p += G) {
                 unsigned pm = 0;
@@ -583,11 +634,17 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
                 const int v = np - p;  // a partial last batch evaluated stale records: drop their bits
                 if (v < G) pm &= 0xffffffffu << (NB - v * HPT);
                 const unsigned vote = __ballot_sync(full, pm != 0u);
-                if (vote) push(vote, pm, (unsigned)(first - begin) + (unsigned)p);
+                if (vote) push(vote, pm, FS ? (unsigned)(s * TILE + p) : (unsigned)(first - begin) + (unsigned)p);
             }
-            // every lane is done with the stage: refill it with the tile kStages ahead
+            if constexpr (FS) {
+                // the stage of tile t - 1 is refilled next: records that still point into it go first (never the case in
+                // the survivor-rich regime - a tile leaves < 32 records behind and they are its own)
+                while ((int)(mark - head) > 0) drain();
+                mark = tail;
+            }
+            // every lane is done with the stage: refill it (FS: the previous tile's) with the tile AHEAD tiles on
             __syncwarp();
-            if (lane == 0 && t + kStages < ntiles) issue(t + kStages);
+            if (lane == 0 && t + AHEAD < ntiles) issue(t + AHEAD);
         }
         gt += (unsigned)ntiles;
 
@@ -596,17 +653,18 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
 #pragma unroll
         for (int j = 0; j < HPT; ++j) {
             const long long hyp = hyp_w + 32 * j + lane;
-            const unsigned cnt = ws.sacc[j][0][lane];
+            const int col = FS ? (lane ^ ((j & 1) << 4)) : lane;
+            const unsigned cnt = ws.sacc[j][0][col];
             if (cnt) {  // only real hypotheses can have inliers
                 unsigned long long* dst = a.acc + (long long)pair * a.h + hyp;
                 atomicAdd(dst, (unsigned long long)cnt);
-                ws.sacc[j][0][lane] = 0;
+                ws.sacc[j][0][col] = 0;
 #pragma unroll
                 for (int k = 1; k < kAccWords; ++k) {
-                    const unsigned v = ws.sacc[j][k][lane];
+                    const unsigned v = ws.sacc[j][k][col];
                     if (v) {
                         atomicAdd(dst + (long long)k * a.htotal, (unsigned long long)v);
-                        ws.sacc[j][k][lane] = 0;
+                        ws.sacc[j][k][col] = 0;
                     }
                 }
             }

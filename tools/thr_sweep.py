@@ -16,8 +16,13 @@ eng.sample_device(0, h)
 eng.fit(want_E=False)
 eng.enable_timing(True)
 print("thr        variant   ms      evals/s     mean inliers per hypothesis")
-for thr in (1.5e-8, 1.5e-7, 1.5e-6, 1.5e-5, 1.5e-4, 1.5e-3):
+thrs = (1.5e-8, 1.5e-7, 1.5e-6, 1.5e-5, 1.5e-4, 1.5e-3)
+if "--cliff" in sys.argv:  # the two inlier-rich points and the headline, auto and two-sided only
+    thrs = (1.5e-6, 1.5e-4, 1.5e-3)
+for thr in thrs:
     shapes = (("auto", 2, 16), ("screen", 2, 16), ("full", 2, 16), ("screen32", 4, 8))
+    if "--cliff" in sys.argv:
+        shapes = (("auto", 2, 16), ("full", 2, 16))
     if "--shapes" in sys.argv:
         shapes = (("screen", 1, 32), ("screen", 2, 16), ("screen", 4, 8), ("full", 1, 32), ("full", 4, 8))
     for v, hpt, g in shapes:

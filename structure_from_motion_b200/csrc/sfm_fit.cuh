@@ -133,7 +133,7 @@ __device__ __forceinline__ void finish_fit(double (&F)[9], double s1, double c1x
         double G[9], W[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) G[i] = F[i];
-        jacobi_svd_onesided<3, 3>(G, W, 30);
+        jacobi_svd_onesided<3, 3, true>(G, W, 30);
         double nrm[3];
 #pragma unroll
         for (int j = 0; j < 3; ++j) nrm[j] = fma(G[6 + j], G[6 + j], fma(G[3 + j], G[3 + j], G[j] * G[j]));

@@ -20,6 +20,18 @@ __device__ __forceinline__ void sym_schur(double app, double aqq, double apq, do
     s = t * c;
 }
 
+// The same rotation with three long-latency operations instead of five (one sqrt, one divide, one rsqrt): with
+// d = aqq - app and g = 2 apq,  t = sgn(d g) |g| / (|d| + sqrt(d^2 + g^2)).  For inputs whose squares neither
+// overflow nor underflow (the fitter's 3x3 estimate has unit Frobenius norm).
+__device__ __forceinline__ void sym_schur_short(double app, double aqq, double apq, double& c, double& s) {
+    const double d = aqq - app, g = apq + apq;
+    const double den = fabs(d) + sqrt(fma(d, d, g * g));
+    const double tt = den > 0.0 ? fabs(g) / den : 1.0;
+    const double t = ((d < 0.0) != (g < 0.0)) ? -tt : tt;
+    c = rsqrt(fma(t, t, 1.0));
+    s = t * c;
+}
+
 // Cyclic Jacobi eigen-decomposition of a symmetric NxN matrix held in registers
 // (a: row-major full matrix, only the upper triangle is referenced; v receives the
 // eigenvectors as columns).  Fully unrolled: indices are compile-time constants.
@@ -81,7 +93,9 @@ __device__ __forceinline__ void jacobi_eig_reg(double (&a)[N * N], double (&v)[N
 // On exit the columns of g are U*Sigma (mutually orthogonal), v holds the right singular
 // vectors as columns.  No A^T A is formed, so small singular directions keep full relative
 // accuracy — this is what the DLT null vector (triangulation.py:34-35) needs.
-template <int M, int N>
+// SHORT: the fitter's variant - sym_schur_short and an orthogonality test without the square root
+// (gamma^2 <= 1e-30 alpha beta, i.e. cos(angle between the columns) <= 1e-15).
+template <int M, int N, bool SHORT = false>
 __device__ __forceinline__ void jacobi_svd_onesided(double (&g)[M * N], double (&v)[N * N],
                                                     int max_sweeps) {
 #pragma unroll
@@ -102,10 +116,12 @@ __device__ __forceinline__ void jacobi_svd_onesided(double (&g)[M * N], double (
                     gamma = fma(g[k * N + p], g[k * N + q], gamma);
                 }
                 // columns already orthogonal to working precision?
-                if (gamma == 0.0 || fabs(gamma) <= 1e-16 * sqrt(alpha * beta)) continue;
+                if (SHORT ? (gamma * gamma <= 1e-30 * (alpha * beta))
+                          : (gamma == 0.0 || fabs(gamma) <= 1e-16 * sqrt(alpha * beta))) continue;
                 rotated = true;
                 double c, s, t;
-                sym_schur(alpha, beta, gamma, c, s, t);
+                if (SHORT) sym_schur_short(alpha, beta, gamma, c, s);
+                else sym_schur(alpha, beta, gamma, c, s, t);
 #pragma unroll
                 for (int k = 0; k < M; ++k) {
                     const double x = g[k * N + p], y = g[k * N + q];

@@ -273,7 +273,7 @@ __device__ __forceinline__ int eight_point_fit_qr(const Corr (&c)[8], double (&E
 constexpr int kFitQrThreads = 64;
 
 #ifndef SFM_FIT_MINB
-#define SFM_FIT_MINB 6  // 168 registers + 0.7 KB of L1-resident spills: 12 warps/SM instead of 8 hide the sqrt/div latency chains (config 4: 0.54 -> 0.44 ms)
+#define SFM_FIT_MINB 6  // 168 registers + 0.5 KB of L1-resident spills: 12 warps/SM hide the sqrt/div latency chains better than 8 warps without spills (222 registers: config 4 0.39 vs 0.34 ms) or 14 warps with 1 KB of spills (144 registers: 0.38 ms)
 #endif
 __global__ void __launch_bounds__(kFitQrThreads, SFM_FIT_MINB)
 k_fit_qr(const Corr* __restrict__ pts, const long long* __restrict__ offsets, const int32_t* __restrict__ table,

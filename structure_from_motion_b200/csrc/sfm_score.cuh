@@ -458,7 +458,65 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
         // records into <= 32 survivors, one per lane (prefix sum of the popcounts, binary search of
         // the owning record by shuffles, n-th set bit), and evaluates them with the exact scorer: the
         // candidate's E comes from global memory (L1/L2 hits), its correspondence by index.
+        // Two-sided body (FS): the ring holds one 32-bit ENTRY per survivor - {owner lane, slot, position of the
+        // correspondence in the tile ring} - so a drain is "lane l takes entry head + l": no prefix sum over record
+        // counts, no search for the n-th set bit, no record straddling a drain.  The bits of a batch are handed out in
+        // rounds, one bit per lane and round (ballot-compacted), which costs ~12 instructions per round and as many
+        // rounds as the fullest lane has survivors; ncu of the record scheme at 17 % inliers: 130 of the drain's 237
+        // instructions were that bookkeeping, with the n-th-set-bit search its longest dependent chain.
+        unsigned* qe = reinterpret_cast<unsigned*>(ws.ring);
+        auto drain_entries = [&]() {
+            if constexpr (FS) {
+                const unsigned navail = tail - head;  // 1..63
+                const bool act = (unsigned)lane < navail;
+                const unsigned en = act ? qe[(head + (unsigned)lane) & (kRing - 1)] : 0u;
+                const int owner = (int)(en >> 12), slot = (int)((en >> 11) & 1u);
+                const unsigned hl = (unsigned)(32 * slot + owner);
+                const double2* mp = reinterpret_cast<const double2*>(&ws.model[hl][0]);
+                const double2 m0 = mp[0], m1 = mp[1], m2 = mp[2], m3 = mp[3];
+                const double eo[9] = {m0.x, m0.y, m1.x, m1.y, m2.x, m2.y, m3.x, m3.y, ws.model[hl][8]};
+                const Corr c = (&ws.tile[0][0])[en & 0x7ffu];
+                const double sv = sed_exact(eo, c.xa, c.ya, c.xb, c.yb);
+                if (act && (sv <= a.thr)) {  // ransac.py:73  score <= threshold
+                    unsigned ch[kChunks];
+                    unsigned* dst = &ws.sacc[slot][0][owner ^ (slot << 4)];
+                    atomicAdd(dst, 1u);
+                    if (a.sums & SUM_S1) {
+                        chunks21(sv, a.scale1, ch);
+#pragma unroll
+                        for (int kk = 0; kk < kChunks; ++kk) atomicAdd(dst + 32 * (1 + kk), ch[kk]);
+                    }
+                    if (a.sums & SUM_S2) {
+                        chunks21(__dmul_rn(sv, sv), a.scale2, ch);
+#pragma unroll
+                        for (int kk = 0; kk < kChunks; ++kk) atomicAdd(dst + 32 * (1 + kChunks + kk), ch[kk]);
+                    }
+                }
+                head += navail < 32u ? navail : 32u;
+                __syncwarp();
+            }
+        };
+        // pm: bit NB-1-i <-> test i = g * HPT + j of the batch whose first correspondence sits at pos0 in the tile ring
+        auto push_entries = [&](unsigned pm, unsigned pos0) {
+            if constexpr (FS) {
+                unsigned vote;
+                while ((vote = __ballot_sync(full, pm != 0u)) != 0u) {
+                    if (pm) {
+                        const int bit = 31 - __clz(pm);
+                        pm ^= 1u << bit;
+                        const unsigned i = (unsigned)(NB - 1 - bit);
+                        qe[(tail + __popc(vote & lt)) & (kRing - 1)] =
+                            ((unsigned)lane << 12) | ((i % HPT) << 11) | (pos0 + i / HPT);
+                    }
+                    tail += __popc(vote);
+                    __syncwarp();
+                    if (tail - head >= 32u) drain_entries();
+                }
+            }
+        };
+
         auto drain = [&]() {
+            if constexpr (FS) { drain_entries(); return; }
             const unsigned nrec = tail - head;  // 1..63
             uint2 rec = make_uint2(0u, 0u);
             if ((unsigned)lane < nrec) rec = q[(head + lane) & (kRing - 1)];
@@ -634,7 +692,10 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
                 const int v = np - p;  // a partial last batch evaluated stale records: drop their bits
                 if (v < G) pm &= 0xffffffffu << (NB - v * HPT);
                 const unsigned vote = __ballot_sync(full, pm != 0u);
-                if (vote) push(vote, pm, FS ? (unsigned)(s * TILE + p) : (unsigned)(first - begin) + (unsigned)p);
+                if (vote) {
+                    if constexpr (FS) push_entries(pm, (unsigned)(s * TILE + p));
+                    else push(vote, pm, (unsigned)(first - begin) + (unsigned)p);
+                }
             }
             if constexpr (FS) {
                 // the stage of tile t - 1 is refilled next: records that still point into it go first (never the case in

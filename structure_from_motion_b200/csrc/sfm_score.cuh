@@ -179,17 +179,6 @@ __device__ __forceinline__ unsigned lanemask_lt() {
     return m;
 }
 
-// position of the r-th (0-based) set bit of m; m must have more than r set bits (binary search on popcounts)
-__device__ __forceinline__ int nth_set_bit(unsigned m, int r) {
-    int pos = 0, c;
-    c = __popc(m & 0xffffu); if (r >= c) { r -= c; pos += 16; m >>= 16; }
-    c = __popc(m & 0xffu);   if (r >= c) { r -= c; pos += 8;  m >>= 8; }
-    c = __popc(m & 0xfu);    if (r >= c) { r -= c; pos += 4;  m >>= 4; }
-    c = __popc(m & 0x3u);    if (r >= c) { r -= c; pos += 2;  m >>= 2; }
-    c = (int)(m & 1u);       if (r >= c) pos += 1;
-    return pos;
-}
-
 // four 21-bit chunks of V = floor(x * 2^(84-e)) < 2^84 (x <= thr < 2^e; `scale` = 2^(63-e)): c[3] is the most
 // significant.  The top 63 bits come from one conversion, the low 21 from the exact remainder, so terms down to
 // 2^-84 of the threshold scale enter the sum (a 63-bit term lost up to 1e-7 of a sum of squares whose inliers were
@@ -358,6 +347,7 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
     using P = typename std::conditional<F32, Corr32, Corr>::type;       // record streamed through shared memory
     constexpr int NB = HPT * G;  // tests per lane and batch = survivor bits per vote
     constexpr bool FS = MODE == MODE_FULL && score_full_in_smem(HPT);  // drain gathers from shared memory only
+    constexpr bool ENTRY = MODE == MODE_FULL;  // survivor ring of per-survivor entries instead of per-lane records
     constexpr int TILE = FS ? kTileFS : kTile;
     constexpr int STAGES = FS ? kStagesFS : kStages;
     constexpr int AHEAD = FS ? STAGES - 1 : STAGES;  // tiles in flight; FS keeps the previous tile's stage for the drain
@@ -452,127 +442,107 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
             else kap[j] = (T)(real ? f2 * ab2 : -1.0);
         }
 
-        // The survivor ring holds one RECORD per (lane, batch) with survivors: {batch mask pm, owner
-        // lane | first correspondence of the batch (item-relative)}; bit NB-1-i of pm <-> test
-        // i = g*HPT + j.  drain() expands the first <= 32
-        // records into <= 32 survivors, one per lane (prefix sum of the popcounts, binary search of
-        // the owning record by shuffles, n-th set bit), and evaluates them with the exact scorer: the
-        // candidate's E comes from global memory (L1/L2 hits), its correspondence by index.
-        // Two-sided body (FS): the ring holds one 32-bit ENTRY per survivor - {owner lane, slot, position of the
-        // correspondence in the tile ring} - so a drain is "lane l takes entry head + l": no prefix sum over record
-        // counts, no search for the n-th set bit, no record straddling a drain.  The bits of a batch are handed out in
-        // rounds, one bit per lane and round (ballot-compacted), which costs ~12 instructions per round and as many
-        // rounds as the fullest lane has survivors; ncu of the record scheme at 17 % inliers: 130 of the drain's 237
-        // instructions were that bookkeeping, with the n-th-set-bit search its longest dependent chain.
-        unsigned* qe = reinterpret_cast<unsigned*>(ws.ring);
-        auto drain_entries = [&]() {
-            if constexpr (FS) {
-                const unsigned navail = tail - head;  // 1..63
-                const bool act = (unsigned)lane < navail;
-                const unsigned en = act ? qe[(head + (unsigned)lane) & (kRing - 1)] : 0u;
-                const int owner = (int)(en >> 12), slot = (int)((en >> 11) & 1u);
-                const unsigned hl = (unsigned)(32 * slot + owner);
-                const double2* mp = reinterpret_cast<const double2*>(&ws.model[hl][0]);
-                const double2 m0 = mp[0], m1 = mp[1], m2 = mp[2], m3 = mp[3];
-                const double eo[9] = {m0.x, m0.y, m1.x, m1.y, m2.x, m2.y, m3.x, m3.y, ws.model[hl][8]};
-                const Corr c = (&ws.tile[0][0])[en & 0x7ffu];
-                const double sv = sed_exact(eo, c.xa, c.ya, c.xb, c.yb);
-                if (act && (sv <= a.thr)) {  // ransac.py:73  score <= threshold
-                    unsigned ch[kChunks];
-                    unsigned* dst = &ws.sacc[slot][0][owner ^ (slot << 4)];
-                    atomicAdd(dst, 1u);
-                    if (a.sums & SUM_S1) {
-                        chunks21(sv, a.scale1, ch);
+        // Exact evaluation of <= 32 survivors, one per lane (the reference's arithmetic, sed_exact), and the sums.
+        auto accumulate = [&](bool act, double sv, int slot, int owner) {
+            if (act && (sv <= a.thr)) {  // ransac.py:73  score <= threshold
+                unsigned ch[kChunks];
+                // same-address atomics serialise; FS also keeps the two slots of an owner in different banks
+                unsigned* dst = &ws.sacc[slot][0][FS ? (owner ^ (slot << 4)) : owner];
+                atomicAdd(dst, 1u);
+                if (a.sums & SUM_S1) {
+                    chunks21(sv, a.scale1, ch);
 #pragma unroll
-                        for (int kk = 0; kk < kChunks; ++kk) atomicAdd(dst + 32 * (1 + kk), ch[kk]);
-                    }
-                    if (a.sums & SUM_S2) {
-                        chunks21(__dmul_rn(sv, sv), a.scale2, ch);
-#pragma unroll
-                        for (int kk = 0; kk < kChunks; ++kk) atomicAdd(dst + 32 * (1 + kChunks + kk), ch[kk]);
-                    }
+                    for (int kk = 0; kk < kChunks; ++kk) atomicAdd(dst + 32 * (1 + kk), ch[kk]);
                 }
-                head += navail < 32u ? navail : 32u;
-                __syncwarp();
+                if (a.sums & SUM_S2) {
+                    chunks21(__dmul_rn(sv, sv), a.scale2, ch);
+#pragma unroll
+                    for (int kk = 0; kk < kChunks; ++kk) atomicAdd(dst + 32 * (1 + kChunks + kk), ch[kk]);
+                }
             }
         };
-        // pm: bit NB-1-i <-> test i = g * HPT + j of the batch whose first correspondence sits at pos0 in the tile ring
-        auto push_entries = [&](unsigned pm, unsigned pos0) {
+        // candidate's E and correspondence: from global memory (L1/L2 hits) by index, or - FS - from shared memory
+        auto survivor_sed = [&](unsigned hl, unsigned pos) -> double {
+            double eo[9];
+            Corr c;
             if constexpr (FS) {
-                unsigned vote;
-                while ((vote = __ballot_sync(full, pm != 0u)) != 0u) {
-                    if (pm) {
-                        const int bit = 31 - __clz(pm);
-                        pm ^= 1u << bit;
-                        const unsigned i = (unsigned)(NB - 1 - bit);
-                        qe[(tail + __popc(vote & lt)) & (kRing - 1)] =
-                            ((unsigned)lane << 12) | ((i % HPT) << 11) | (pos0 + i / HPT);
-                    }
-                    tail += __popc(vote);
-                    __syncwarp();
-                    if (tail - head >= 32u) drain_entries();
+                const double2* mp = reinterpret_cast<const double2*>(&ws.model[hl][0]);
+                const double2 m0 = mp[0], m1 = mp[1], m2 = mp[2], m3 = mp[3];
+                eo[0] = m0.x; eo[1] = m0.y; eo[2] = m1.x; eo[3] = m1.y;
+                eo[4] = m2.x; eo[5] = m2.y; eo[6] = m3.x; eo[7] = m3.y;
+                eo[8] = ws.model[hl][8];
+                c = (&ws.tile[0][0])[pos];
+            } else {
+                const ModelRow* er = Rw + hl;  // padding hypotheses never survive the screen: an active entry is real
+                const double4 r0 = er->a, r1 = er->b;
+                eo[0] = r0.x; eo[1] = r0.y; eo[2] = r0.z; eo[3] = r0.w;
+                eo[4] = r1.x; eo[5] = r1.y; eo[6] = r1.z; eo[7] = r1.w;
+                eo[8] = er->c.x;
+                c = pbeg[pos];
+            }
+            return sed_exact(eo, c.xa, c.ya, c.xb, c.yb);
+        };
+
+        // ---- two-sided body: one ring ENTRY per survivor ------------------------------------------------------------
+        // {owner lane << 14 | slot << 11 | position}: position = the correspondence's place in the tile ring (FS) or its
+        // item-relative index.  A drain is "lane l takes entry head + l": no prefix sum over record counts, no search
+        // for the n-th set bit, no record straddling a drain.  The bits of a batch are handed out in rounds, one bit per
+        // lane and round (ballot-compacted): ~12 instructions per round, as many rounds as the fullest lane has
+        // survivors.  ncu of the record scheme below at 17 % inliers: 130 of the drain's 237 instructions were that
+        // bookkeeping, the n-th-set-bit search its longest dependent chain (0.30 -> 0.37e12 evaluations/s).  In the
+        // one-sided body (1 % survivors, 1.3 bits per record) the rounds cost more than they save (-5 %), so it keeps
+        // the records.
+        unsigned* qe = reinterpret_cast<unsigned*>(ws.ring);
+        auto drain_entries = [&]() {
+            const unsigned navail = tail - head;  // 1..63
+            const bool act = (unsigned)lane < navail;
+            const unsigned en = act ? qe[(head + (unsigned)lane) & (kRing - 1)] : 0u;
+            const int owner = (int)(en >> 14), slot = (int)((en >> 11) & 7u);
+            accumulate(act, survivor_sed((unsigned)(32 * slot + owner), en & 0x7ffu), slot, owner);
+            head += navail < 32u ? navail : 32u;
+            __syncwarp();
+        };
+        // pm: bit NB-1-i <-> test i = g * HPT + j of the batch whose first correspondence has position pos0
+        auto push_entries = [&](unsigned pm, unsigned pos0) {
+            unsigned vote;
+            while ((vote = __ballot_sync(full, pm != 0u)) != 0u) {
+                if (pm) {
+                    const int bit = 31 - __clz(pm);
+                    pm ^= 1u << bit;
+                    const unsigned i = (unsigned)(NB - 1 - bit);
+                    qe[(tail + __popc(vote & lt)) & (kRing - 1)] = ((unsigned)lane << 14) | ((i % HPT) << 11) | (pos0 + i / HPT);
                 }
+                tail += __popc(vote);
+                __syncwarp();
+                if (tail - head >= 32u) drain_entries();
             }
         };
 
-        auto drain = [&]() {
-            if constexpr (FS) { drain_entries(); return; }
+        // ---- one-sided bodies: one ring RECORD per (lane, batch) with survivors ------------------------------------
+        // {batch mask pm, owner lane << 27 | item-relative index of the batch's first correspondence}; bit NB-1-i of pm
+        // <-> test i = g*HPT + j.  drain_records() expands the first <= 32 records into <= 32 survivors, one per lane:
+        // prefix sum of the popcounts, then an owner table in shared memory {record, bit position} that every record
+        // fills for the survivor slots it owns (1.3 bits per record at a 1 % survivor rate).
+        auto drain_records = [&]() {
             const unsigned nrec = tail - head;  // 1..63
             uint2 rec = make_uint2(0u, 0u);
             if ((unsigned)lane < nrec) rec = q[(head + lane) & (kRing - 1)];
             const int cnt = __popc(rec.x);
-            int incl, total;
-            if constexpr (MODE == MODE_FULL) {
-                // survivor-rich body: the drain is bound by the MIO queue (shuffles, shared atomics - ncu: short
-                // scoreboard 31 % of its stall samples), so the prefix sum of the per-record counts (<= 32: six bit
-                // planes) is taken with warp votes, which do not go through it.  (In the one-sided body, 1 % survivors,
-                // the same trade costs 1.4 %: there the extra ALU instructions matter more than five shuffles.)
-                incl = 0;
-                total = 0;
-                const unsigned le = lt | (1u << lane);
+            int incl = cnt;
 #pragma unroll
-                for (int b = 0; b < 6; ++b) {
-                    const unsigned v = __ballot_sync(full, (cnt >> b) & 1);
-                    incl += __popc(v & le) << b;
-                    total += __popc(v) << b;
-                }
-            } else {
-                incl = cnt;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) incl = scan_step(incl, d);
-                total = __shfl_sync(full, incl, 31);
-            }
+            for (int d = 1; d < 32; d <<= 1) incl = scan_step(incl, d);
+            const int total = __shfl_sync(full, incl, 31);
             const int m = total < 32 ? total : 32;  // survivors handled now
             const int excl = incl - cnt;
             // ring bookkeeping: records entirely inside the first 32 survivors are retired
             const unsigned done_mask = __ballot_sync(full, (unsigned)lane < nrec && incl <= 32);
             const int ndone = __popc(done_mask);
             const bool act = lane < m;
-            uint2 rj;
-            unsigned o;  // {record (low byte), bit position of this lane's survivor in it}
-            if constexpr (MODE == MODE_FULL) {
-                // Two-sided screen = survivor-rich regime (the AUTO pilot sends > 6.5 % survivors here): records hold
-                // many bits, and handing them out one by one (the table below) was a quarter of all instructions at a
-                // 17 % inlier rate (ncu: 364 M iterations of its loop).  Instead every lane finds its record from a
-                // bit mask of the record starts and its bit by binary search over popcounts: a fixed ~40 instructions.
-                // S = start positions (exclusive counts) of the records inside this drain; every record holds at least
-                // one survivor, so the starts are distinct: survivor t belongs to record #(starts <= t) - 1 and that
-                // record starts at the highest start <= t.  One REDUX, then the record comes from the ring (one LDS).
-                const unsigned S = __reduce_or_sync(full, ((unsigned)lane < nrec && excl < 32) ? (1u << excl) : 0u);
-                const unsigned below = S & ((2u << lane) - 1u);
-                const int j = act ? __popc(below) - 1 : 0;
-                const int before = act ? 31 - __clz(below) : 0;
-                rj = q[(head + (unsigned)j) & (kRing - 1)];
-                o = (unsigned)j | ((unsigned)(act ? nth_set_bit(rj.x, lane - before) : 0) << 8);
-                // the record that straddles the 32-survivor boundary keeps its bits above the last one consumed
-                const int take = 32 - excl;
-                __syncwarp();  // every lane has read its record before the straddling one is rewritten
-                if (lane == ndone && (unsigned)lane < nrec && take > 0)
-                    q[(head + lane) & (kRing - 1)].x = rec.x & ~((2u << nth_set_bit(rec.x, take - 1)) - 1u);
-            } else {
-                // survivor slot t in [excl, incl) of this lane's record -> owner table {record, bit position}: the
-                // record's set bits are handed out lowest first (1.3 bits per record at a 1 % survivor rate), so what
-                // is left in pmw afterwards is exactly what a record that straddles the boundary keeps for the next drain
+            unsigned o = 0u;  // {record (low byte), bit position of this lane's survivor in it}
+            uint2 rj = make_uint2(0u, 0u);
+            if constexpr (!ENTRY) {
+                // the record's set bits are handed out lowest first, so what is left in pmw afterwards is exactly what a
+                // record that straddles the 32-survivor boundary keeps for the next drain
                 unsigned pmw = rec.x;
                 for (int t = excl; pmw && t < 32; ++t) {
                     ws.own[t] = (unsigned short)(lane | ((__ffs(pmw) - 1) << 8));
@@ -584,63 +554,26 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
                 __syncwarp();
                 if (lane == ndone && (unsigned)lane < nrec) q[(head + lane) & (kRing - 1)].x = pmw;  // first record not retired
             }
-            {
-                const int bit = (int)(o >> 8);
-                const int owner = (int)(rj.y >> 27);
-                const int i = NB - 1 - bit;                    // test index in the batch: g * HPT + j
-                const int slot = i % HPT;
-                // FS: the record's low bits are the batch's first position in the tile ring, else its item-relative index
-                const unsigned rel = act ? (rj.y & 0x3fffffu) + (unsigned)(i / HPT) : 0u;
-                // padding hypotheses never survive the screen, so an active entry is a real hypothesis
-                const unsigned hl = act ? (unsigned)(32 * slot + owner) : 0u;
-                double eo[9];
-                Corr c;
-                if constexpr (FS) {
-                    const double2* mp = reinterpret_cast<const double2*>(&ws.model[hl][0]);
-                    const double2 m0 = mp[0], m1 = mp[1], m2 = mp[2], m3 = mp[3];
-                    eo[0] = m0.x; eo[1] = m0.y; eo[2] = m1.x; eo[3] = m1.y;
-                    eo[4] = m2.x; eo[5] = m2.y; eo[6] = m3.x; eo[7] = m3.y;
-                    eo[8] = ws.model[hl][8];
-                    c = (&ws.tile[0][0])[rel];
-                } else {
-                    const ModelRow* er = Rw + hl;
-                    const double4 r0 = er->a, r1 = er->b;
-                    eo[0] = r0.x; eo[1] = r0.y; eo[2] = r0.z; eo[3] = r0.w;
-                    eo[4] = r1.x; eo[5] = r1.y; eo[6] = r1.z; eo[7] = r1.w;
-                    eo[8] = er->c.x;
-                    c = pbeg[rel];
-                }
-                const double sv = sed_exact(eo, c.xa, c.ya, c.xb, c.yb);
-                if (act && (sv <= a.thr)) {  // ransac.py:73  score <= threshold
-                    unsigned ch[kChunks];
-                    // same-address atomics serialise; FS also keeps the two slots of an owner in different banks
-                    unsigned* dst = &ws.sacc[slot][0][FS ? (owner ^ (slot << 4)) : owner];
-                    atomicAdd(dst, 1u);
-                    if (a.sums & SUM_S1) {
-                        chunks21(sv, a.scale1, ch);
-#pragma unroll
-                        for (int kk = 0; kk < kChunks; ++kk) atomicAdd(dst + 32 * (1 + kk), ch[kk]);
-                    }
-                    if (a.sums & SUM_S2) {
-                        chunks21(__dmul_rn(sv, sv), a.scale2, ch);
-#pragma unroll
-                        for (int kk = 0; kk < kChunks; ++kk) atomicAdd(dst + 32 * (1 + kChunks + kk), ch[kk]);
-                    }
-                }
-            }
+            const int i = NB - 1 - (int)(o >> 8);  // test index in the batch: g * HPT + j
+            const int owner = (int)(rj.y >> 27), slot = i % HPT;
+            const unsigned rel = act ? (rj.y & 0x3fffffu) + (unsigned)(i / HPT) : 0u;
+            accumulate(act, survivor_sed(act ? (unsigned)(32 * slot + owner) : 0u, rel), slot, owner);
             head += (unsigned)ndone;
             __syncwarp();
         };
-
         // one record per lane with survivors in this batch (ballot-compacted: no atomics, no loop).  The queue is
         // drained whenever 32 RECORDS are waiting - every record holds at least one survivor, so a drain always finds
         // its 32 survivors, retires at least one record, and the ring (< 32 waiting + <= 32 new) cannot overflow; the
         // trigger needs no reduction over the lanes (a REDUX per batch sat on the critical path before)
-        auto push = [&](unsigned vote, unsigned pm, unsigned rel0) {
+        auto push_records = [&](unsigned vote, unsigned pm, unsigned rel0) {
             if (pm) q[(tail + __popc(vote & lt)) & (kRing - 1)] = make_uint2(pm, ((unsigned)lane << 27) | rel0);
             tail += __popc(vote);
             __syncwarp();
-            while (tail - head >= 32u) drain();
+            while (tail - head >= 32u) drain_records();
+        };
+        auto drain = [&]() {
+            if constexpr (ENTRY) drain_entries();
+            else drain_records();
         };
 
         unsigned mark = tail;  // FS: queue position behind the last record of the previous tile
@@ -693,8 +626,8 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
                 if (v < G) pm &= 0xffffffffu << (NB - v * HPT);
                 const unsigned vote = __ballot_sync(full, pm != 0u);
                 if (vote) {
-                    if constexpr (FS) push_entries(pm, (unsigned)(s * TILE + p));
-                    else push(vote, pm, (unsigned)(first - begin) + (unsigned)p);
+                    if constexpr (ENTRY) push_entries(pm, FS ? (unsigned)(s * TILE + p) : (unsigned)(first - begin) + (unsigned)p);
+                    else push_records(vote, pm, (unsigned)(first - begin) + (unsigned)p);
                 }
             }
             if constexpr (FS) {

@@ -493,25 +493,28 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
         // one-sided body (1 % survivors, 1.3 bits per record) the rounds cost more than they save (-5 %), so it keeps
         // the records.
         unsigned* qe = reinterpret_cast<unsigned*>(ws.ring);
+        constexpr int LH = HPT >= 8 ? 3 : (HPT == 4 ? 2 : (HPT == 2 ? 1 : 0));  // slot bits, kept at the top of an entry
+        const unsigned ln = (unsigned)__popc(lt);  // the lane index again, from a live register (ptxas re-reads SR_TID otherwise)
         auto drain_entries = [&]() {
             const unsigned navail = tail - head;  // 1..63
-            const bool act = (unsigned)lane < navail;
-            const unsigned en = act ? qe[(head + (unsigned)lane) & (kRing - 1)] : 0u;
-            const int owner = (int)(en >> 14), slot = (int)((en >> 11) & 7u);
+            const bool act = ln < navail;
+            const unsigned en = act ? qe[(head + ln) & (kRing - 1)] : 0u;
+            const int owner = (int)((en >> 14) & 31u), slot = LH ? (int)(en >> (32 - (LH ? LH : 1))) : 0;
             accumulate(act, survivor_sed((unsigned)(32 * slot + owner), en & 0x7ffu), slot, owner);
             head += navail < 32u ? navail : 32u;
             __syncwarp();
         };
-        // pm: bit NB-1-i <-> test i = g * HPT + j of the batch whose first correspondence has position pos0
+        // pm: bit NB-1-i <-> test i = g * HPT + j of the batch whose first correspondence has position pos0;
+        // entry = {slot i % HPT at the top | owner lane << 14 | pos0 + i / HPT}: a rotation of i added to a per-batch base
         auto push_entries = [&](unsigned pm, unsigned pos0) {
+            const unsigned base = (ln << 14) | pos0;
             unsigned vote;
             while ((vote = __ballot_sync(full, pm != 0u)) != 0u) {
-                if (pm) {
-                    const int bit = 31 - __clz(pm);
-                    pm ^= 1u << bit;
-                    const unsigned i = (unsigned)(NB - 1 - bit);
-                    qe[(tail + __popc(vote & lt)) & (kRing - 1)] = ((unsigned)lane << 14) | ((i % HPT) << 11) | (pos0 + i / HPT);
-                }
+                const unsigned top = 0x80000000u >> __clz(pm | 1u);           // highest set bit (bit 0 for an empty mask)
+                const unsigned i = (unsigned)(NB - 32) + (unsigned)__clz(pm | 1u);  // NB - 1 - bit
+                const unsigned en = base + __funnelshift_r(i, i, LH);
+                if (pm) qe[(tail + __popc(vote & lt)) & (kRing - 1)] = en;
+                pm &= ~top;
                 tail += __popc(vote);
                 __syncwarp();
                 if (tail - head >= 32u) drain_entries();

@@ -201,13 +201,13 @@ struct __align__(16) Corr32 {
 // fp64 screening copy (xa / s, ya / s, xb, yb) written at the head of every SCREEN scoring call - and, for the AUTO
 // variant, the PILOT that chooses between the two fp64 screens: the first kPilotBlocks blocks also run the one-sided
 // test on a sample (64 hypotheses spread over the range x ~1 000 correspondences of the first pair, 8 tests per thread) and the last of
-// them to finish turns the pass rate into the MODE the scoring kernels check.  Above ~6.5 % survivors the exact
+// them to finish turns the pass rate into the MODE the scoring kernels check.  Above ~9 % survivors the exact
 // evaluation of the survivors dominates and the 21-slot two-sided screen (survivors = inliers) wins; below, the
 // 11-slot one-sided screen does (DESIGN.md, table against the threshold).
 constexpr int kPilotBlocks = 32;
 constexpr int kPilotHyps = 64;
 constexpr int kPilotPts = 1024;
-constexpr double kPilotFullAbove = 0.065;
+constexpr double kPilotFullAbove = 0.09;  // measured crossover of the two bodies (tools/auto_crossover.py): 9.2 % on config 3
 struct PilotArgs {
     const double* E;      // models of the first pair
     long long h;          // hypotheses per pair
@@ -301,7 +301,7 @@ struct alignas(128) ScoreWarpSmem {
     unsigned long long full_bar[kStages];
 };
 
-// Two-sided body, HPT <= 2 (the survivor-rich regime: AUTO sends > 6.5 % survivors here): the drain gathers nothing
+// Two-sided body, HPT <= 2 (the survivor-rich regime: AUTO sends > 9 % survivors here): the drain gathers nothing
 // from global memory.  Its models sit in shared memory (component-major: a gather of 32 models is nine LDS.64) and
 // its correspondences are read from the tile ring itself - the two-sided screen streams the UNSCALED records, and a
 // stage is refilled only after every record that points into it has been drained (one tile of slack: see the tile

@@ -124,6 +124,35 @@ def test_screen_never_drops_an_inlier(engine, thr, escale, variant):
     np.testing.assert_allclose(s2, s2_o, rtol=1e-12, atol=0)
 
 
+@pytest.mark.parametrize("thr", [0.0, 1e-12, 1.5e-6, 1e-4, 1e-3, 0.03, 0.5, 40.0])
+@pytest.mark.parametrize("variant,hpt,group", [("full", 2, 16), ("full", 1, 32), ("full", 4, 8), ("auto", 2, 16), ("auto", 4, 8)])
+def test_two_sided_body_at_every_inlier_rate(engine, thr, variant, hpt, group):
+    """The two-sided body's survivor path (one ring entry per survivor, handed out in rounds; gathers from shared memory
+    for hpt <= 2) from no survivors at all to EVERY test surviving (32 rounds per batch, ring full): counts equal and sums
+    within 1e-12 of the exact oracle scorer; 1 500 correspondences = partial last tile and partial last batch."""
+    n, h = 1500, 200
+    K, x1, x2, *_ = make_scene(n, 0.3, seed=12)
+    nxa, nya, nxb, nyb = _norm(K, x1, x2)
+    rng = np.random.default_rng(10)
+    table = np.stack([rng.choice(n, 8, replace=False) for _ in range(h)]).astype(np.int32)
+    ca, cb = np.stack([nxa, nya], 1), np.stack([nxb, nyb], 1)
+    E = np.stack([o.eight_point(ca[s], cb[s]) for s in table])
+    cnt_o, s1_o, s2_o = csed.score_batch(E, nxa, nya, nxb, nyb, thr, table=table, nthreads=8)
+    engine.upload_pairs(x1, x2, K)
+    engine.set_table(table)
+    engine.set_models(E)
+    engine.set_score_variant(variant, hpt, group)
+    try:
+        cnt, s1, s2, err = engine.score(thr, min_extra=0, aggregation="sum")
+    finally:
+        engine.set_score_variant("auto")
+    assert np.array_equal(cnt, cnt_o)
+    np.testing.assert_allclose(s1, s1_o, rtol=1e-12, atol=0)
+    np.testing.assert_allclose(s2, s2_o, rtol=1e-12, atol=0)
+    if thr >= 40.0:
+        assert cnt_o.min() >= n - 8 - 5  # (nearly) every correspondence is an inlier of every model
+
+
 @pytest.mark.parametrize("agg", ["sum", "square", "mean", "rms"])
 def test_aggregation_methods(engine, agg):
     n, h = 800, 300

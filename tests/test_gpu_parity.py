@@ -150,7 +150,7 @@ def test_two_sided_body_at_every_inlier_rate(engine, thr, variant, hpt, group):
     np.testing.assert_allclose(s1, s1_o, rtol=1e-12, atol=0)
     np.testing.assert_allclose(s2, s2_o, rtol=1e-12, atol=0)
     if thr >= 40.0:
-        assert cnt_o.min() >= n - 8 - 5  # (nearly) every correspondence is an inlier of every model
+        assert cnt_o.mean() > 0.99 * (n - 8)  # (nearly) every correspondence is an inlier of every model
 
 
 @pytest.mark.parametrize("agg", ["sum", "square", "mean", "rms"])

@@ -87,7 +87,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 //   with three fresh 64-bit register operands issues at 2/3 rate on sm_100, measured by
 //   tools/fp64_micro.cu).
 //   FULL: the 21-slot two-sided division-free decision on the unscaled data (survivors ~
-//   inliers); identical results, kept as the like-for-like arithmetic baseline.
+//   inliers); identical results; the like-for-like arithmetic baseline AND the body the AUTO
+//   variant switches to above 9 % survivors.  Its survivor path differs: one ring ENTRY per
+//   survivor (handed out in ballot-compacted rounds) instead of one record per lane and batch,
+//   and - HPT <= 2 - models and correspondences gathered from shared memory (ScoreWarpSmemFS).
 //   SCREEN32 (reported separately, never the fp64 headline): the same 11-slot test in fp32 on
 //   E/|E|_F and fp32 copies of the correspondences — a PRE-FILTER only: every survivor is still
 //   decided and summed by the exact fp64 scorer, so counts, sums and the winner are bit-identical

@@ -160,6 +160,39 @@ def test_config3_winner_count_equals_mask(engine, config3):
     assert np.array_equal(sed, csed.sed_exact_many(E, nxa, nya, nxb, nyb))
 
 
+def test_config3_full_size_inlier_rich_against_oracle(engine, config3):
+    """The same at a threshold where 7 % of the correspondences are inliers of a typical model: the AUTO pilot picks
+    the two-sided body (survivor gathers from shared memory, one ring entry per survivor).  All 65 536 models x 100 000
+    correspondences against the exact C scorer: counts bit-exact, sums to 1e-12, same winner; and bit-identical to the
+    one-sided body's results."""
+    import os
+
+    c = config3
+    thr = 1.5e-4
+    E, valid = engine.get_models()
+    table = engine.get_table()
+    nxa, nya, nxb, nyb = _norm(c["K"], c["x1"], c["x2"])
+    cnt_o, s1_o, s2_o = csed.score_batch(E.reshape(-1, 9), nxa, nya, nxb, nyb, thr, table=table,
+                                         nthreads=os.cpu_count() or 8)
+    assert cnt_o.mean() > 0.05 * c["n"]
+    got = {}
+    try:
+        for variant in ("auto", "screen"):
+            engine.set_score_variant(variant, 2, 16)
+            got[variant] = engine.score(thr, min_extra=10, aggregation="rms") + (engine.get_best().index,)
+    finally:
+        engine.set_score_variant("auto")
+    cnt, s1, s2, err, win = got["auto"]
+    assert np.array_equal(cnt, cnt_o)
+    np.testing.assert_allclose(s2, s2_o, rtol=1e-12, atol=0)
+    err_o = np.where(cnt_o >= 10, np.sqrt(s2_o / (8 + cnt_o)), np.inf)
+    assert win == int(np.argmin(err_o))
+    for a, b in zip(got["auto"][:4], got["screen"][:4]):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert got["screen"][4] == win
+    engine.score(THR, min_extra=10, aggregation="rms", want_arrays=False)  # leave the engine as the fixture left it
+
+
 def test_config3_full_size_counts_against_oracle(engine, config3):
     """BASELINE.json configs[2] at full size against the oracle, not against itself: ALL 65 536 models the GPU fitted
     are scored by the exact C scorer over all 100 000 correspondences (6.5e9 evaluations, threaded): extra-inlier

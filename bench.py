@@ -493,9 +493,10 @@ def run_extras(args, eng, world, rank, barrier, flush_l2, torch, dist, per_gpu_r
         pb[p * n:(p + 1) * n] = base[2][perm]
     offsets = np.arange(P + 1, dtype=np.int64) * n
     Ks = np.stack([base[0]] * P)
-    # four contexts, chunks of up to 512 pairs: H2D of one chunk, kernels of another and D2H of a third overlap
-    # (profiles/r2_pair_pipeline_depth.txt: 0.64e12 against 0.56e12 with two contexts and 256-pair chunks)
-    depth = 4
+    # four to eight contexts, chunks of up to 512 pairs: H2D of one chunk, kernels of another and D2H of a third overlap
+    # (profiles/r2_pair_pipeline_depth.txt: 4 096 pairs 0.634e12 with 4 contexts, 0.663e12 with 8 - one per chunk;
+    #  0.56e12 with two contexts and 256-pair chunks)
+    depth = int(min(8, max(4, P // 512)))
     chunk = int(min(512, max(128, P // depth)))
     pipe = distributed.PairPipeline(depth=depth)
     try:

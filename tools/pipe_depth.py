@@ -21,10 +21,10 @@ for p in range(P):
     pb[p * n:(p + 1) * n] = base[2][perm]
 off = np.arange(P + 1, dtype=np.int64) * n
 Ks = np.stack([base[0]] * P)
-for depth in (1, 2, 3, 4):
+for depth in ([int(a) for a in sys.argv[2].split(",")] if len(sys.argv) > 2 else (1, 2, 3, 4)):
     pipe = PairPipeline(depth=depth)
     try:
-        for chunk in (128, 256, 512, 1024):
+        for chunk in ([int(a) for a in sys.argv[3].split(",")] if len(sys.argv) > 3 else (128, 256, 512, 1024)):
             if chunk * depth > P:
                 continue
             ts = []

@@ -81,7 +81,10 @@ for k in range(cases):
             want[ref["inlier_indices"]] = True
             if ((got != want) & ~band).any():
                 msg = "inlier sets differ"
-            if abs(res.ransac.error - ref["error"]) > 1e-9 * abs(ref["error"]):
+            # a winner supported by its 8 sample points only: its error is the fit's own rounding residual (1e-10 .. 1e-17
+            # here), which two correct solvers reproduce to a few digits at best
+            etol = 1e-9 if len(ref["inlier_indices"]) > 8 else 1e-6
+            if abs(res.ransac.error - ref["error"]) > etol * abs(ref["error"]):
                 msg = f"error {res.ransac.error} vs {ref['error']}"
             # apps/sfm.py:118-133 hands the RANSAC inlier LIST (samples first, ransac.py:76) to recover_r_t_from_e: its
             # position 0 - the correspondence np.count_nonzero never counts (eight_point.py:228-230) - is the first sample

@@ -177,6 +177,34 @@ int check_launch(sfm_ctx* c, const char* what) {
     return 0;
 }
 
+// Launch of a kernel of the per-estimate chain (fit -> screening copy -> score -> select -> tail): programmatic stream
+// serialization lets its blocks be scheduled while the preceding kernel of the chain drains; every chain kernel starts
+// with chain_enter() (griddepcontrol.wait), so the data dependence is the ordinary stream order.
+inline void chain_config(sfm_ctx* c, dim3 grid, dim3 block, size_t smem, cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at) {
+    memset(cfg, 0, sizeof *cfg);
+    cfg->gridDim = grid;
+    cfg->blockDim = block;
+    cfg->dynamicSmemBytes = smem;
+    cfg->stream = c->stream;
+    at->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at->val.programmaticStreamSerializationAllowed = 1;
+    cfg->attrs = at;
+    cfg->numAttrs = SFM_PDL ? 1 : 0;
+}
+template <typename... KArgs, typename... Args>
+cudaError_t chain_launch(sfm_ctx* c, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute at;
+    chain_config(c, grid, block, smem, &cfg, &at);
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+inline cudaError_t chain_launch_ptr(sfm_ctx* c, const void* fn, dim3 grid, dim3 block, size_t smem, void** kargs) {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute at;
+    chain_config(c, grid, block, smem, &cfg, &at);
+    return cudaLaunchKernelExC(&cfg, fn, kargs);
+}
+
 // per-warp shared memory of a scoring body (the two-sided one has its own layout for hpt <= 2)
 size_t score_warp_smem(int hpt, bool full) {
     switch (hpt) {
@@ -519,12 +547,10 @@ static int fit_launch(sfm_ctx* c, bool want_eig) {
         // fast path: Householder null vector in registers; flags the (rare) samples whose validity
         // test is too close to call, which the Y^T Y Jacobi kernel then redoes
         dim3 gq((unsigned)((c->h + kFitQrThreads - 1) / kFitQrThreads), (unsigned)c->npairs);
-        k_fit_qr<<<gq, kFitQrThreads, 0, c->stream>>>(c->pts.as<Corr>(), off, c->table.as<int32_t>(), c->h,
-                                                      c->E.as<double>(), c->valid.as<uint8_t>(),
-                                                      c->fitflag.as<unsigned>(), c->rows.as<ModelRow>(),
-                                                      c->acc.as<unsigned long long>(), kAccWords, (int)((acc_tail + 7) / 8),
-                                                      c->table_pending ? 1 : 0, c->smp_seed, c->smp_stream, c->smp_offset,
-                                                      c->n);
+        CU(chain_launch(c, k_fit_qr, gq, dim3(kFitQrThreads), 0, c->pts.as<Corr>(), off, c->table.as<int32_t>(), c->h,
+                        c->E.as<double>(), c->valid.as<uint8_t>(), c->fitflag.as<unsigned>(), c->rows.as<ModelRow>(),
+                        c->acc.as<unsigned long long>(), kAccWords, (int)((acc_tail + 7) / 8), c->table_pending ? 1 : 0,
+                        c->smp_seed, c->smp_stream, c->smp_offset, c->n));
         if (int r = check_launch(c, "k_fit_qr")) return r;
         c->table_pending = false;  // the fit kernel wrote the rows it drew
         only = c->fitflag.as<unsigned>();
@@ -533,9 +559,9 @@ static int fit_launch(sfm_ctx* c, bool want_eig) {
     } else {
         c->acc_clean = false;
     }
-    k_fit<<<grid, kFitThreads, kFitThreads * kFitSmemDoubles * sizeof(double), c->stream>>>(
-        c->pts.as<Corr>(), off, c->table.as<int32_t>(), c->h, c->E.as<double>(), c->valid.as<uint8_t>(),
-        want_eig ? c->eig.as<double>() : nullptr, only, c->rows.as<ModelRow>());
+    CU(chain_launch(c, k_fit, grid, dim3(kFitThreads), kFitThreads * kFitSmemDoubles * sizeof(double), c->pts.as<Corr>(), off,
+                    c->table.as<int32_t>(), c->h, c->E.as<double>(), c->valid.as<uint8_t>(),
+                    want_eig ? c->eig.as<double>() : nullptr, only, c->rows.as<ModelRow>()));
     if (int r = check_launch(c, "k_fit")) return r;
     c->toc(T_FIT);
     c->has_models = true;
@@ -744,8 +770,8 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
             pa.thr_pre = thr_pre;
             pa.counters = reinterpret_cast<unsigned*>(tailp + 16);
             pa.mode_flag = autov ? reinterpret_cast<int*>(tailp + 32) : nullptr;
-            k_screen_pts64<<<(unsigned)((npts + 255) / 256), 256, 0, c->stream>>>(c->pts.as<Corr>(), npts, 1.0 / s_scale,
-                                                                                  reinterpret_cast<Corr*>(c->spts.p), pa);
+            CU(chain_launch(c, k_screen_pts64, dim3((unsigned)((npts + 255) / 256)), dim3(256), 0, c->pts.as<Corr>(), npts,
+                            1.0 / s_scale, reinterpret_cast<Corr*>(c->spts.p), pa));
             if (int r = check_launch(c, "k_screen_pts64")) return r;
         }
         const long long want_blocks = (total_items + kScoreWarps - 1) / kScoreWarps;
@@ -756,10 +782,10 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
             a2.thr_pre = thr * (1.0 + 1e-9) + 1e-22;
             a2.spts = c->pts.p;
             void* kargs2[] = {(void*)&a, (void*)&a2};
-            CU(cudaLaunchKernel(fn_auto, dim3((unsigned)launch_blocks), dim3(kScoreThreads), kargs2, smem_both, c->stream));
+            CU(chain_launch_ptr(c, fn_auto, dim3((unsigned)launch_blocks), dim3(kScoreThreads), smem_both, kargs2));
             if (int r = check_launch(c, "k_score_auto")) return r;
         } else if (!skip_k2) {
-            CU(cudaLaunchKernel(fn, dim3((unsigned)launch_blocks), dim3(kScoreThreads), kargs, smem, c->stream));
+            CU(chain_launch_ptr(c, fn, dim3((unsigned)launch_blocks), dim3(kScoreThreads), smem, kargs));
             if (int r = check_launch(c, "k_score")) return r;
             if (fn_full) {  // AUTO: the two-sided screen on the unscaled records; exits at once unless the pilot chose it
                 ScoreArgs a2 = a;
@@ -768,7 +794,7 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
                 const long long gb2 = (long long)c->sm_count * occ_full;
                 const long long lb2 = gb2 < want_blocks ? gb2 : want_blocks;
                 void* kargs2[] = {(void*)&a2};
-                CU(cudaLaunchKernel(fn_full, dim3((unsigned)lb2), dim3(kScoreThreads), kargs2, smem_two, c->stream));
+                CU(chain_launch_ptr(c, fn_full, dim3((unsigned)lb2), dim3(kScoreThreads), smem_two, kargs2));
                 if (int r = check_launch(c, "k_score")) return r;
             }
         }
@@ -810,7 +836,7 @@ static int score_launch(sfm_ctx* c, double thr, double min_extra, int agg, int m
     f.invalid_out = c->invalid.as<long long>();
     f.record = c->record.as<SelectRecord>();
     f.fitflag = c->fitflag.as<unsigned>();
-    k_finalise<<<dim3((unsigned)fblocks, (unsigned)P), 256, 0, c->stream>>>(f);
+    CU(chain_launch(c, k_finalise, dim3((unsigned)fblocks, (unsigned)P), dim3(256), 0, f));
     if (int r = check_launch(c, "k_finalise")) return r;
     c->toc(T_SELECT);
     c->has_score = true;
@@ -1118,7 +1144,7 @@ static int pose_tail_launch(sfm_ctx* c, double thr, double dist_thr, const Selec
     a.Ks = c->Ks.as<double>();
     a.X = c->X.as<double>();
     c->tic(T_MASK);
-    k_tail_mask<<<dim3((unsigned)nblk, (unsigned)P), kTailBlock, 0, c->stream>>>(a);
+    CU(chain_launch(c, k_tail_mask, dim3((unsigned)nblk, (unsigned)P), dim3(kTailBlock), 0, a));
     if (int r = check_launch(c, "k_tail_mask")) return r;
     c->toc(T_MASK);
     // the caller's mask is "sed <= thr" (the forced sample points live in the compacted list only)
@@ -1128,11 +1154,11 @@ static int pose_tail_launch(sfm_ctx* c, double thr, double dist_thr, const Selec
     // grids sized for the machine (grid-stride inside): the number of inliers is only known on the device
     const long long cap_blocks = P >= 64 ? 8 : 2ll * c->sm_count;
     const long long g2 = (4 * max_len + 127) / 128, g3 = (max_len + 127) / 128;
-    k_tail_cheirality<<<dim3((unsigned)(g2 < cap_blocks ? g2 : cap_blocks), (unsigned)P), 128, 0, c->stream>>>(a);
+    CU(chain_launch(c, k_tail_cheirality, dim3((unsigned)(g2 < cap_blocks ? g2 : cap_blocks), (unsigned)P), dim3(128), 0, a));
     if (int r = check_launch(c, "k_tail_cheirality")) return r;
     c->toc(T_POSE);
     c->tic(T_TRI);
-    k_tail_triangulate<<<dim3((unsigned)(g3 < cap_blocks ? g3 : cap_blocks), (unsigned)P), 128, 0, c->stream>>>(a);
+    CU(chain_launch(c, k_tail_triangulate, dim3((unsigned)(g3 < cap_blocks ? g3 : cap_blocks), (unsigned)P), dim3(128), 0, a));
     if (int r = check_launch(c, "k_tail_triangulate")) return r;
     c->toc(T_TRI);
     return 0;

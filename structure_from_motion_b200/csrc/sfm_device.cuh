@@ -9,6 +9,22 @@
 
 namespace sfm {
 
+// Programmatic dependent launch (sm_90+): the kernels of one estimate form a chain on one stream, each launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization.  chain_enter() is the first statement of every chain kernel:
+// wait until the preceding grid has completed and its memory is visible (a no-op for an ordinary launch), then let
+// the NEXT kernel of the chain be launched - its blocks become resident as resources free up and sit in their own
+// wait, so the launch latency of a kernel overlaps the execution of its predecessor.
+#ifndef SFM_PDL
+#define SFM_PDL 1
+#endif
+__device__ __forceinline__ void chain_enter() {
+#if SFM_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
+#endif
+}
+
+
 constexpr double kVerySmall = 1e-10;            // lib/epipolar/eight_point.py:415
 constexpr double kCheiralityTolerance = 1e-8;   // lib/epipolar/eight_point.py:477
 

@@ -281,6 +281,7 @@ k_fit_qr(const Corr* __restrict__ pts, const long long* __restrict__ offsets, co
          unsigned* __restrict__ ambiguous_count, ModelRow* __restrict__ rows,
          unsigned long long* __restrict__ acc, int acc_planes, int acc_tail_words,
          int draw, unsigned long long seed, unsigned long long stream0, long long hyp_offset, long long n) {
+    chain_enter();
     const long long li = blockIdx.x * (long long)kFitQrThreads + threadIdx.x;
     if (li >= h) return;
     const long long i = (long long)blockIdx.y * h + li;  // blockIdx.y = image pair
@@ -438,6 +439,7 @@ k_fit(const Corr* __restrict__ pts, const long long* __restrict__ offsets,
       const int32_t* __restrict__ table, long long h, double* __restrict__ E_out,
       uint8_t* __restrict__ valid_out, double* __restrict__ eig_out,
       const unsigned* __restrict__ only_ambiguous /* null = fit everything */, ModelRow* __restrict__ rows) {
+    chain_enter();
     extern __shared__ double fit_smem[];
     if (only_ambiguous && *only_ambiguous == 0u) return;  // the usual case: nothing was flagged
     const long long li = blockIdx.x * (long long)kFitThreads + threadIdx.x;

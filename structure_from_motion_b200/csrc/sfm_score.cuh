@@ -221,6 +221,7 @@ struct PilotArgs {
 };
 __global__ void __launch_bounds__(256) k_screen_pts64(const Corr* __restrict__ pts, long long n, double inv_s,
                                                       Corr* __restrict__ spts, const PilotArgs pa) {
+    chain_enter();
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < n) {
         Corr c = pts[i];
@@ -676,6 +677,7 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a) {
 template <int HPT, int G, int MODE>
 __global__ void __launch_bounds__(kScoreThreads, score_min_blocks(MODE == MODE_SCREEN32 ? HPT / 2 : HPT))
 k_score(const ScoreArgs a) {
+    chain_enter();
     score_body<HPT, G, MODE>(a);
 }
 
@@ -683,6 +685,7 @@ k_score(const ScoreArgs a) {
 // no second (empty) launch is needed; the register budget is the larger of the two.
 template <int HPT, int G>
 __global__ void __launch_bounds__(kScoreThreads, score_min_blocks(HPT)) k_score_auto(const ScoreArgs a, const ScoreArgs a_full) {
+    chain_enter();
     if (*a.mode_flag == MODE_FULL) score_body<HPT, G, MODE_FULL>(a_full);
     else score_body<HPT, G, MODE_SCREEN>(a);
 }
@@ -861,6 +864,7 @@ __device__ __forceinline__ bool finalise_one(const FinalArgs& a, const Corr* pts
 // the result is still independent of scheduling, sharding and scoring variant.  Block arg-min, then the last block of
 // the pair to finish (ticket) reduces the per-block results into the selection record.
 __global__ void __launch_bounds__(256) k_finalise(const FinalArgs a) {
+    chain_enter();
     __shared__ Best sm[32];
     __shared__ int s_list[256];
     __shared__ int s_nlist;

@@ -58,6 +58,7 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
 }
 
 __global__ void __launch_bounds__(kTailBlock) k_tail_mask(const TailArgs a) {
+    chain_enter();
     __shared__ unsigned s_bid;
     __shared__ int warp_cnt[4][8];
     __shared__ long long s_prefix;
@@ -192,6 +193,7 @@ constexpr long long kTailSmallTri = 512;  // up to this many inliers the block t
 // Grid-stride: the grid is sized for the machine, not for the (unknown to the host) number of inliers - a config-3
 // winner has ~100 inliers, and 3 000 blocks that only find that out cost 30 us.
 __global__ void __launch_bounds__(128) k_tail_cheirality(const TailArgs a) {
+    chain_enter();
     __shared__ int s_cnt[4];
     __shared__ int s_last;
     const int pair = blockIdx.y;
@@ -273,6 +275,7 @@ __global__ void __launch_bounds__(128) k_tail_cheirality(const TailArgs a) {
 }
 
 __global__ void __launch_bounds__(128) k_tail_triangulate(const TailArgs a) {
+    chain_enter();
     const int pair = blockIdx.y;
     if (a.poses[pair].pad) return;  // T2 already did it
     const long long pbase = a.offsets ? a.offsets[pair] : 0;

@@ -43,9 +43,11 @@ enum sfm_aggregation { SFM_AGG_SUM = 0, SFM_AGG_SQUARE = 1, SFM_AGG_MEAN = 2, SF
  * (SURVEY.md 8(f) N4): max-inliers; MSAC = minimum of sum_i min(sed_i, threshold) over all correspondences
  * (best.err / err[] then hold that cost). */
 enum sfm_selection { SFM_SELECT_MIN_ERROR = 0, SFM_SELECT_MAX_INLIERS = 1, SFM_SELECT_MSAC = 2 };
-/* scoring kernel variant — all three give bit-identical results (every inlier decision and
+/* scoring kernel variant — all of them give bit-identical results (every inlier decision and
  * every summed value comes from the exact fp64 scorer):
- *   SCREEN    fp64 one-sided screen (11 FP64 slots per evaluation) + exact re-check of survivors (default)
+ *   AUTO      (default) a pilot on the device measures the survivor rate of the one-sided screen and the
+ *             scoring kernel takes SCREEN below 9 % survivors, FULL above
+ *   SCREEN    fp64 one-sided screen (11 FP64 slots per evaluation) + exact re-check of survivors
  *   FULL      fp64 two-sided division-free decision (21 slots) + exact re-check
  *   SCREEN32  the screen evaluated in fp32 as a pre-filter (rigorous guard band, ~2 % more
  *             survivors) + exact fp64 re-check; reported separately from the fp64 headline */
